@@ -1,0 +1,259 @@
+/*
+ * sqgpu.h -- C ABI of libsqgpu.so, the B200 (sm_100a) implementation of the
+ * per-record QC hot path of rhpvorderman/sequali.
+ *
+ * This is the drop-in boundary.  The reference's Python extension
+ * (`sequali._qc`, src/sequali/_qcmodule.c) is the only caller of the hot path;
+ * every entry point below replaces one piece of that file and says which.
+ * All functions are `extern "C"`, take plain pointers and sizes, return 0 on
+ * success and a negative SQ_E_* code on failure (text via sq_last_error()).
+ * No torch / Python types cross this boundary.
+ *
+ * Execution model: everything a collector does is enqueued on the context's
+ * CUDA stream; `*_add` calls return immediately.  Results become observable
+ * through the `*_sync` / `*_read_*` calls, which synchronise first -- the same
+ * observability the reference offers (getters only).
+ */
+#ifndef SQGPU_H
+#define SQGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQ_API __attribute__((visibility("default")))
+
+/* ---- error codes ------------------------------------------------------- */
+enum {
+    SQ_OK = 0,
+    SQ_E_CUDA = -1,      /* CUDA runtime error (see sq_last_error)           */
+    SQ_E_ARG = -2,       /* invalid argument                                  */
+    SQ_E_NOMEM = -3,     /* host or device allocation failed                  */
+    SQ_E_FORMAT = -4,    /* malformed input (details in the out struct)       */
+    SQ_E_NODEVICE = -5,  /* no CUDA device: there is no CPU fallback          */
+    SQ_E_LIMIT = -6,     /* an implementation limit was exceeded              */
+};
+
+/* FASTQ format errors, in the reference's check order (_qcmodule.c:1097-1150) */
+enum {
+    SQ_PARSE_OK = 0,
+    SQ_PARSE_NO_AT = 1,    /* "Record does not start with @ but with %c"  :1098 */
+    SQ_PARSE_NO_PLUS = 2,  /* "Record second header does not start with + ..." :1121 */
+    SQ_PARSE_LEN = 3,      /* "Record sequence and qualities do not have equal length" :1143 */
+    SQ_PARSE_ASCII = 4,    /* "Found non-ASCII character in file: %c" :1062 */
+};
+
+typedef struct sq_ctx sq_ctx;     /* one CUDA device + stream + scratch      */
+typedef struct sq_batch sq_batch; /* a device-resident record array          */
+
+/* Host view of one record: the reference's struct FastqMeta
+ * (_qcmodule.c:337-355) with the pointer replaced by offsets into the batch's
+ * byte buffer (offsets are absolute, not relative to the name). */
+typedef struct {
+    uint32_t name_off, name_len;
+    uint32_t seq_off, seq_len;
+    uint32_t qual_off;
+    uint32_t tags_off, tags_len;
+    uint32_t reserved;
+    double err_sum; /* accumulated_error_rate, valid after sq_qc_add + sync */
+} sq_meta;
+
+typedef struct {
+    uint64_t n_records;   /* complete records parsed (<= max_records)         */
+    uint64_t consumed;    /* bytes of input covered by those records          */
+    uint64_t n_newlines;  /* newlines seen in the whole input                 */
+    uint32_t max_seq_len; /* longest sequence among the parsed records        */
+    int32_t err_code;     /* SQ_PARSE_*                                       */
+    uint64_t err_record;  /* record index of the first format error           */
+    uint64_t err_pos;     /* byte offset of the offending byte / record name  */
+} sq_parse_info;
+
+/* ---- context ----------------------------------------------------------- */
+SQ_API int sq_device_count(void);
+SQ_API const char *sq_last_error(void);
+SQ_API int sq_ctx_create(int device, sq_ctx **out);
+SQ_API void sq_ctx_destroy(sq_ctx *ctx);
+SQ_API int sq_ctx_sync(sq_ctx *ctx);
+/* raw stream handle (cudaStream_t) for callers that time with CUDA events */
+SQ_API void *sq_ctx_stream(sq_ctx *ctx);
+/* number of kernels this library has launched on ctx so far */
+SQ_API uint64_t sq_ctx_launch_count(sq_ctx *ctx);
+/* pinned host staging memory for the parsers' read buffers */
+SQ_API void *sq_pinned_alloc(sq_ctx *ctx, size_t nbytes);
+SQ_API void sq_pinned_free(sq_ctx *ctx, void *p);
+/* plain device memory for callers that keep inputs HBM-resident (bench) */
+SQ_API void *sq_device_alloc(sq_ctx *ctx, size_t nbytes);
+SQ_API void sq_device_free(sq_ctx *ctx, void *p);
+SQ_API int sq_memcpy_h2d(sq_ctx *ctx, void *dst, const void *src, size_t n);
+SQ_API int sq_memcpy_d2h(sq_ctx *ctx, void *dst, const void *src, size_t n);
+
+/* ---- record arrays ------------------------------------------------------ */
+/* FastqParser_create_record_array (_qcmodule.c:965-1184): copy `nbytes` of
+ * FASTQ text to the device (cudaMemcpyAsync; `text` may be pinned), find the
+ * record boundaries there and validate them.  Synchronises, because the
+ * caller needs n_records / consumed to carry the leftover.  On a format error
+ * returns SQ_E_FORMAT with *out == NULL and info filled in. */
+SQ_API int sq_batch_from_fastq(sq_ctx *ctx, const uint8_t *text, uint64_t nbytes,
+                               uint64_t max_records, sq_batch **out, sq_parse_info *info);
+/* Same, for text that already lives in device memory (no copy; the batch
+ * borrows `dev_text`, which must outlive it). */
+SQ_API int sq_batch_from_device_fastq(sq_ctx *ctx, const uint8_t *dev_text, uint64_t nbytes,
+                                      uint64_t max_records, sq_batch **out,
+                                      sq_parse_info *info);
+/* FastqRecordArrayView.__new__ / FastqRecordView (_qcmodule.c:373-482,
+ * 610-687): a packed name|seq|qual|tags buffer with host-built descriptors. */
+SQ_API int sq_batch_from_packed(sq_ctx *ctx, const uint8_t *buf, uint64_t nbytes,
+                                const sq_meta *metas, uint64_t n, sq_batch **out);
+/* BamParser__next__ record decode (_qcmodule.c:1623-1694): `bam` holds
+ * alignment records; rec_off[i] is the offset of the i-th record to keep (the
+ * host walks the block_size chain and drops secondary/supplementary records).
+ * The 4-bit sequence -> ASCII and quality +33 decode runs on the device. */
+SQ_API int sq_batch_from_bam(sq_ctx *ctx, const uint8_t *bam, uint64_t nbytes,
+                             const uint64_t *rec_off, uint64_t n, sq_batch **out,
+                             uint64_t *packed_len);
+SQ_API uint64_t sq_batch_size(const sq_batch *b);
+SQ_API uint64_t sq_batch_nbytes(const sq_batch *b);
+SQ_API uint32_t sq_batch_max_seq_len(const sq_batch *b);
+/* copy descriptors (incl. err_sum) / the byte buffer back to the host */
+SQ_API int sq_batch_get_metas(sq_batch *b, sq_meta *out);
+SQ_API int sq_batch_get_bytes(sq_batch *b, uint8_t *out);
+/* FastqRecordArrayView_is_mate (_qcmodule.c:778-850); *first_mismatch = n when mates */
+SQ_API int sq_batch_is_mate(sq_batch *a, sq_batch *b, uint64_t *first_mismatch);
+SQ_API void sq_batch_free(sq_batch *b);
+
+/* ---- QCMetrics (_qcmodule.c:1966-2139) ---------------------------------- */
+typedef struct sq_qc sq_qc;
+typedef struct {
+    uint64_t number_of_reads;
+    uint64_t max_length;
+    uint64_t end_anchor_length;
+    int32_t bad_phred;       /* 1 when a quality byte outside '!'..'~' was met */
+    uint8_t bad_phred_char;  /* that byte ("Not a valid phred character: %c")  */
+    uint64_t bad_phred_record; /* global index of the record holding it        */
+} sq_qc_info;
+SQ_API int sq_qc_create(sq_ctx *ctx, uint64_t end_anchor_length, sq_qc **out);
+SQ_API void sq_qc_destroy(sq_qc *m);
+SQ_API int sq_qc_add(sq_qc *m, sq_batch *b);
+SQ_API int sq_qc_sync(sq_qc *m, sq_qc_info *info);
+/* tables sized as the reference's getters (_qcmodule.c:2214-2334); NULL skips */
+SQ_API int sq_qc_read(sq_qc *m, uint64_t *base_counts /*max_len*5*/,
+                      uint64_t *phred_counts /*max_len*12*/, uint64_t *ea_base /*ea*5*/,
+                      uint64_t *ea_phred /*ea*12*/, uint64_t *gc_content /*101*/,
+                      uint64_t *phred_scores /*94*/);
+
+/* ---- AdapterCounter (_qcmodule.c:2465-2823) ------------------------------ */
+typedef struct sq_adapters sq_adapters;
+SQ_API int sq_adapters_create(sq_ctx *ctx, const char *const *adapters, uint64_t n,
+                              sq_adapters **out);
+SQ_API void sq_adapters_destroy(sq_adapters *a);
+SQ_API int sq_adapters_add(sq_adapters *a, sq_batch *b);
+SQ_API int sq_adapters_sync(sq_adapters *a, uint64_t *number_of_sequences, uint64_t *max_length);
+SQ_API int sq_adapters_read(sq_adapters *a, uint64_t index, uint64_t *forward, uint64_t *reverse);
+
+/* ---- PerTileQuality (_qcmodule.c:3089-3222, 3307-3359) ------------------- */
+typedef struct sq_pertile sq_pertile;
+typedef struct {
+    uint64_t number_of_reads;
+    uint64_t max_length;
+    uint64_t n_tiles;
+    int32_t skipped;         /* header without a tile id was met               */
+    uint64_t skipped_record; /* global index of that record                    */
+    int32_t bad_phred;
+    uint8_t bad_phred_char;
+} sq_pertile_info;
+SQ_API int sq_pertile_create(sq_ctx *ctx, sq_pertile **out);
+SQ_API void sq_pertile_destroy(sq_pertile *p);
+SQ_API int sq_pertile_add(sq_pertile *p, sq_batch *b);
+SQ_API int sq_pertile_sync(sq_pertile *p, sq_pertile_info *info);
+/* name of the record that switched the module off (for skipped_reason) */
+SQ_API int sq_pertile_skipped_name(sq_pertile *p, uint8_t *out, uint64_t cap, uint64_t *len);
+/* tiles ascending; errors[t*max_len+j] is the ordered sum, counts[..] = reads longer than j */
+SQ_API int sq_pertile_read(sq_pertile *p, uint64_t *tile_ids, double *errors, uint64_t *counts);
+
+/* ---- OverrepresentedSequences (_qcmodule.c:3543-3568, 3830-3942) --------- */
+typedef struct sq_overrep sq_overrep;
+typedef struct {
+    uint64_t number_of_sequences, sampled_sequences, collected_unique_fragments,
+        total_fragments, max_unique_fragments, table_size;
+    uint64_t warn_records;      /* sampled records holding a non-ACGTN letter   */
+    uint64_t first_warn_record; /* global index of the first of them            */
+} sq_overrep_info;
+SQ_API int sq_overrep_create(sq_ctx *ctx, uint64_t max_unique_fragments, uint32_t fragment_length,
+                             uint64_t sample_every, int64_t bases_from_start,
+                             int64_t bases_from_end, sq_overrep **out);
+SQ_API void sq_overrep_destroy(sq_overrep *o);
+SQ_API int sq_overrep_add(sq_overrep *o, sq_batch *b);
+SQ_API int sq_overrep_sync(sq_overrep *o, sq_overrep_info *info);
+/* the stored fragments as 2-bit k-mers (wanghash64_inverse applied) + counts */
+SQ_API int sq_overrep_read(sq_overrep *o, uint64_t *kmers, uint32_t *counts, uint64_t *n);
+
+/* ---- DedupEstimator (_qcmodule.c:4383-4517) ------------------------------- */
+typedef struct sq_dedup sq_dedup;
+typedef struct {
+    uint64_t modulo_bits, hash_table_size, tracked_sequences;
+} sq_dedup_info;
+SQ_API int sq_dedup_create(sq_ctx *ctx, uint64_t max_stored_fingerprints, uint64_t front_len,
+                           uint64_t back_len, uint64_t front_off, uint64_t back_off,
+                           sq_dedup **out);
+SQ_API void sq_dedup_destroy(sq_dedup *d);
+SQ_API int sq_dedup_add(sq_dedup *d, sq_batch *b);
+SQ_API int sq_dedup_add_pair(sq_dedup *d, sq_batch *b1, sq_batch *b2);
+SQ_API int sq_dedup_sync(sq_dedup *d, sq_dedup_info *info);
+/* counts of the occupied slots in slot order, like duplication_counts() */
+SQ_API int sq_dedup_read(sq_dedup *d, uint64_t *counts, uint64_t *n);
+
+/* ---- NanoStats (_qcmodule.c:5006-5324) ------------------------------------ */
+typedef struct sq_nanostats sq_nanostats;
+typedef struct {
+    int64_t start_time;
+    float duration;
+    int32_t channel_id;
+    uint32_t length;
+    uint32_t reserved;
+    double cumulative_error_rate;
+    uint64_t parent_id_hash;
+} sq_nanoinfo; /* struct NanoInfo, _qcmodule.c:4808-4815 */
+typedef struct {
+    uint64_t number_of_reads;
+    int64_t minimum_time, maximum_time;
+    int32_t skipped;
+    uint64_t skipped_record;
+    int32_t tag_error;        /* malformed BAM aux data (the reference raises)   */
+    uint64_t tag_error_record;
+    uint64_t pi_warnings;     /* pi:Z tags that are not 36 characters long        */
+} sq_nanostats_info;
+SQ_API int sq_nanostats_create(sq_ctx *ctx, sq_nanostats **out);
+SQ_API void sq_nanostats_destroy(sq_nanostats *s);
+SQ_API int sq_nanostats_add(sq_nanostats *s, sq_batch *b);
+SQ_API int sq_nanostats_sync(sq_nanostats *s, sq_nanostats_info *info);
+SQ_API int sq_nanostats_skipped_name(sq_nanostats *s, uint8_t *out, uint64_t cap, uint64_t *len);
+SQ_API int sq_nanostats_read(sq_nanostats *s, sq_nanoinfo *out);
+
+/* ---- InsertSizeMetrics (_qcmodule.c:5571-5744) ---------------------------- */
+typedef struct sq_insert sq_insert;
+typedef struct {
+    uint64_t total_reads, number_of_adapters_read1, number_of_adapters_read2;
+    uint64_t max_insert_size, entries_read1, entries_read2;
+} sq_insert_info;
+SQ_API int sq_insert_create(sq_ctx *ctx, uint64_t max_adapters, sq_insert **out);
+SQ_API void sq_insert_destroy(sq_insert *m);
+SQ_API int sq_insert_add_pair(sq_insert *m, sq_batch *b1, sq_batch *b2);
+SQ_API int sq_insert_sync(sq_insert *m, sq_insert_info *info);
+SQ_API int sq_insert_read_sizes(sq_insert *m, uint64_t *sizes /* max_insert_size+1 */);
+/* adapters of read `which` (0/1): seqs[i*32] = length, seqs[i*32+1..] = bytes */
+SQ_API int sq_insert_read_adapters(sq_insert *m, int which, uint8_t *seqs, uint64_t *counts,
+                                   uint64_t *n);
+
+/* ---- synthetic input (bench / tests; SURVEY.md 8d recipe C2) -------------- */
+/* Fill dev_text with `n_reads` NovaSeq-style records generated on the device;
+ * returns the number of bytes written (<= cap) in *nbytes. */
+SQ_API int sq_synth_illumina(sq_ctx *ctx, uint8_t *dev_text, uint64_t cap, uint64_t n_reads,
+                             uint32_t read_length, uint64_t seed, uint64_t *nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQGPU_H */

@@ -1,0 +1,228 @@
+"""ctypes binding of libsqgpu.so (include/sqgpu.h).
+
+There is no CPU fallback: importing this module works anywhere (so that the
+package can be inspected and the symbol table tested on a CPU box), but the
+first call that needs a device raises ``SqGpuError`` when the library or a
+CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsqgpu.so")
+
+SQ_OK, SQ_E_CUDA, SQ_E_ARG, SQ_E_NOMEM, SQ_E_FORMAT, SQ_E_NODEVICE, SQ_E_LIMIT = \
+    0, -1, -2, -3, -4, -5, -6
+PARSE_NO_AT, PARSE_NO_PLUS, PARSE_LEN, PARSE_ASCII = 1, 2, 3, 4
+
+
+class SqGpuError(RuntimeError):
+    pass
+
+
+class Meta(C.Structure):
+    _fields_ = [("name_off", C.c_uint32), ("name_len", C.c_uint32),
+                ("seq_off", C.c_uint32), ("seq_len", C.c_uint32),
+                ("qual_off", C.c_uint32), ("tags_off", C.c_uint32),
+                ("tags_len", C.c_uint32), ("reserved", C.c_uint32),
+                ("err_sum", C.c_double)]
+
+
+class ParseInfo(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("consumed", C.c_uint64),
+                ("n_newlines", C.c_uint64), ("max_seq_len", C.c_uint32),
+                ("err_code", C.c_int32), ("err_record", C.c_uint64),
+                ("err_pos", C.c_uint64)]
+
+
+class QcInfo(C.Structure):
+    _fields_ = [("number_of_reads", C.c_uint64), ("max_length", C.c_uint64),
+                ("end_anchor_length", C.c_uint64), ("bad_phred", C.c_int32),
+                ("bad_phred_char", C.c_uint8), ("bad_phred_record", C.c_uint64)]
+
+
+class PerTileInfo(C.Structure):
+    _fields_ = [("number_of_reads", C.c_uint64), ("max_length", C.c_uint64),
+                ("n_tiles", C.c_uint64), ("skipped", C.c_int32),
+                ("skipped_record", C.c_uint64), ("bad_phred", C.c_int32),
+                ("bad_phred_char", C.c_uint8)]
+
+
+class OverrepInfo(C.Structure):
+    _fields_ = [("number_of_sequences", C.c_uint64), ("sampled_sequences", C.c_uint64),
+                ("collected_unique_fragments", C.c_uint64), ("total_fragments", C.c_uint64),
+                ("max_unique_fragments", C.c_uint64), ("table_size", C.c_uint64),
+                ("warn_records", C.c_uint64), ("first_warn_record", C.c_uint64)]
+
+
+class DedupInfo(C.Structure):
+    _fields_ = [("modulo_bits", C.c_uint64), ("hash_table_size", C.c_uint64),
+                ("tracked_sequences", C.c_uint64)]
+
+
+class NanoInfo(C.Structure):
+    _fields_ = [("start_time", C.c_int64), ("duration", C.c_float),
+                ("channel_id", C.c_int32), ("length", C.c_uint32),
+                ("reserved", C.c_uint32), ("cumulative_error_rate", C.c_double),
+                ("parent_id_hash", C.c_uint64)]
+
+
+class NanoStatsInfo(C.Structure):
+    _fields_ = [("number_of_reads", C.c_uint64), ("minimum_time", C.c_int64),
+                ("maximum_time", C.c_int64), ("skipped", C.c_int32),
+                ("skipped_record", C.c_uint64), ("tag_error", C.c_int32),
+                ("tag_error_record", C.c_uint64), ("pi_warnings", C.c_uint64)]
+
+
+class InsertInfo(C.Structure):
+    _fields_ = [("total_reads", C.c_uint64), ("number_of_adapters_read1", C.c_uint64),
+                ("number_of_adapters_read2", C.c_uint64), ("max_insert_size", C.c_uint64),
+                ("entries_read1", C.c_uint64), ("entries_read2", C.c_uint64)]
+
+
+assert C.sizeof(Meta) == 40 and C.sizeof(NanoInfo) == 40
+
+_vp, _u64, _u32, _i64, _int = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_int
+_P = C.POINTER
+
+# name -> (restype, argtypes); every symbol include/sqgpu.h declares
+SIGNATURES = {
+    "sq_device_count": (_int, []),
+    "sq_last_error": (C.c_char_p, []),
+    "sq_ctx_create": (_int, [_int, _P(_vp)]),
+    "sq_ctx_destroy": (None, [_vp]),
+    "sq_ctx_sync": (_int, [_vp]),
+    "sq_ctx_stream": (_vp, [_vp]),
+    "sq_ctx_launch_count": (_u64, [_vp]),
+    "sq_pinned_alloc": (_vp, [_vp, C.c_size_t]),
+    "sq_pinned_free": (None, [_vp, _vp]),
+    "sq_device_alloc": (_vp, [_vp, C.c_size_t]),
+    "sq_device_free": (None, [_vp, _vp]),
+    "sq_memcpy_h2d": (_int, [_vp, _vp, _vp, C.c_size_t]),
+    "sq_memcpy_d2h": (_int, [_vp, _vp, _vp, C.c_size_t]),
+    "sq_batch_from_fastq": (_int, [_vp, _vp, _u64, _u64, _P(_vp), _P(ParseInfo)]),
+    "sq_batch_from_device_fastq": (_int, [_vp, _vp, _u64, _u64, _P(_vp), _P(ParseInfo)]),
+    "sq_batch_from_packed": (_int, [_vp, _vp, _u64, _vp, _u64, _P(_vp)]),
+    "sq_batch_from_bam": (_int, [_vp, _vp, _u64, _vp, _u64, _P(_vp), _P(_u64)]),
+    "sq_batch_size": (_u64, [_vp]),
+    "sq_batch_nbytes": (_u64, [_vp]),
+    "sq_batch_max_seq_len": (_u32, [_vp]),
+    "sq_batch_get_metas": (_int, [_vp, _vp]),
+    "sq_batch_get_bytes": (_int, [_vp, _vp]),
+    "sq_batch_is_mate": (_int, [_vp, _vp, _P(_u64)]),
+    "sq_batch_free": (None, [_vp]),
+    "sq_qc_create": (_int, [_vp, _u64, _P(_vp)]),
+    "sq_qc_destroy": (None, [_vp]),
+    "sq_qc_add": (_int, [_vp, _vp]),
+    "sq_qc_sync": (_int, [_vp, _P(QcInfo)]),
+    "sq_qc_read": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sq_adapters_create": (_int, [_vp, _P(C.c_char_p), _u64, _P(_vp)]),
+    "sq_adapters_destroy": (None, [_vp]),
+    "sq_adapters_add": (_int, [_vp, _vp]),
+    "sq_adapters_sync": (_int, [_vp, _P(_u64), _P(_u64)]),
+    "sq_adapters_read": (_int, [_vp, _u64, _vp, _vp]),
+    "sq_pertile_create": (_int, [_vp, _P(_vp)]),
+    "sq_pertile_destroy": (None, [_vp]),
+    "sq_pertile_add": (_int, [_vp, _vp]),
+    "sq_pertile_sync": (_int, [_vp, _P(PerTileInfo)]),
+    "sq_pertile_skipped_name": (_int, [_vp, _vp, _u64, _P(_u64)]),
+    "sq_pertile_read": (_int, [_vp, _vp, _vp, _vp]),
+    "sq_overrep_create": (_int, [_vp, _u64, _u32, _u64, _i64, _i64, _P(_vp)]),
+    "sq_overrep_destroy": (None, [_vp]),
+    "sq_overrep_add": (_int, [_vp, _vp]),
+    "sq_overrep_sync": (_int, [_vp, _P(OverrepInfo)]),
+    "sq_overrep_read": (_int, [_vp, _vp, _vp, _P(_u64)]),
+    "sq_dedup_create": (_int, [_vp, _u64, _u64, _u64, _u64, _u64, _P(_vp)]),
+    "sq_dedup_destroy": (None, [_vp]),
+    "sq_dedup_add": (_int, [_vp, _vp]),
+    "sq_dedup_add_pair": (_int, [_vp, _vp, _vp]),
+    "sq_dedup_sync": (_int, [_vp, _P(DedupInfo)]),
+    "sq_dedup_read": (_int, [_vp, _vp, _P(_u64)]),
+    "sq_nanostats_create": (_int, [_vp, _P(_vp)]),
+    "sq_nanostats_destroy": (None, [_vp]),
+    "sq_nanostats_add": (_int, [_vp, _vp]),
+    "sq_nanostats_sync": (_int, [_vp, _P(NanoStatsInfo)]),
+    "sq_nanostats_skipped_name": (_int, [_vp, _vp, _u64, _P(_u64)]),
+    "sq_nanostats_read": (_int, [_vp, _vp]),
+    "sq_insert_create": (_int, [_vp, _u64, _P(_vp)]),
+    "sq_insert_destroy": (None, [_vp]),
+    "sq_insert_add_pair": (_int, [_vp, _vp, _vp]),
+    "sq_insert_sync": (_int, [_vp, _P(InsertInfo)]),
+    "sq_insert_read_sizes": (_int, [_vp, _vp]),
+    "sq_insert_read_adapters": (_int, [_vp, _int, _vp, _vp, _P(_u64)]),
+    "sq_synth_illumina": (_int, [_vp, _vp, _u64, _u64, _u32, _u64, _P(_u64)]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """dlopen libsqgpu.so (built in-tree by sequali_b200/csrc/Makefile)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise SqGpuError(
+                    f"{LIB_PATH} is missing: build it with `make -C sequali_b200/csrc` "
+                    "(or __graft_entry__.build()); sequali_b200 has no CPU fallback")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)  # AttributeError here = ABI drift, fail loudly
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def device_count() -> int:
+    return load().sq_device_count()
+
+
+def last_error() -> str:
+    return (load().sq_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = ""):
+    if rc == SQ_OK:
+        return
+    msg = last_error()
+    if rc == SQ_E_NOMEM:
+        raise MemoryError(f"{what}: {msg}")
+    if rc == SQ_E_ARG:
+        raise ValueError(f"{what}: {msg}")
+    raise SqGpuError(f"{what} failed (code {rc}): {msg}")
+
+
+class Context:
+    """One device context per process (device = $SEQUALI_B200_DEVICE, else
+    $LOCAL_RANK, else 0)."""
+    _instance = None
+
+    def __init__(self, device: int | None = None):
+        lib = load()
+        if device is None:
+            device = int(os.environ.get("SEQUALI_B200_DEVICE",
+                                        os.environ.get("LOCAL_RANK", "0")))
+        if lib.sq_device_count() <= 0:
+            raise SqGpuError("no CUDA device visible: sequali_b200 needs a GPU "
+                             "(there is no CPU fallback)")
+        h = C.c_void_p()
+        check(lib.sq_ctx_create(device % max(lib.sq_device_count(), 1), C.byref(h)),
+              "sq_ctx_create")
+        self.h, self.lib, self.device = h, lib, device
+
+    @classmethod
+    def get(cls) -> "Context":
+        if cls._instance is None:
+            cls._instance = Context()
+        return cls._instance
+
+    def sync(self):
+        check(self.lib.sq_ctx_sync(self.h), "sq_ctx_sync")
+
+    @property
+    def launch_count(self) -> int:
+        return self.lib.sq_ctx_launch_count(self.h)

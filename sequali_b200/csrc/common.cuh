@@ -1,0 +1,237 @@
+// common.cuh -- shared host/device definitions of libsqgpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sqgpu.h"
+
+#define SQ_WARP 32
+constexpr int SQ_NUM_SMS_HINT = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+void sq_set_error(const char *fmt, ...);
+int sq_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define CUDA_TRY(expr)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return sq_cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define SQ_TRY(expr)              \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != SQ_OK) return _rc; \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// context and record arrays
+// ---------------------------------------------------------------------------
+struct sq_ctx {
+    int device = 0;
+    int num_sms = SQ_NUM_SMS_HINT;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    // pinned scratch for small device->host result structs
+    void *h_scratch = nullptr;  // 4 KiB pinned
+    void *d_scratch = nullptr;  // 4 KiB device
+    double *d_err_table = nullptr;      // [94]  10^-(q/10), host libm generated
+    double *d_phred_thresholds = nullptr;  // [94] bucket edges derived from host log10
+    uint32_t func_attr_done = 0;           // bit per kernel family whose smem opt-in was set
+};
+
+// Device-side view of a record array.  Offsets index `text`.
+struct BatchView {
+    const uint8_t *text;
+    const uint32_t *name_off, *seq_off, *seq_len, *qual_off;
+    const uint32_t *name_len, *tags_off, *tags_len;  // nullptr for FASTQ text batches
+    double *err_sum;
+    uint32_t n;
+};
+
+struct sq_batch {
+    sq_ctx *ctx = nullptr;
+    uint8_t *text = nullptr;
+    bool owns_text = true;
+    uint64_t nbytes = 0;
+    uint64_t n = 0;
+    uint32_t max_len = 0;
+    uint32_t *name_off = nullptr, *seq_off = nullptr, *seq_len = nullptr, *qual_off = nullptr;
+    uint32_t *name_len = nullptr, *tags_off = nullptr, *tags_len = nullptr;
+    double *err_sum = nullptr;
+    void *meta_block = nullptr;  // single allocation behind the arrays above
+    bool err_sum_valid = false;  // QCMetrics ran on this array
+
+    BatchView view() const {
+        BatchView v;
+        v.text = text;
+        v.name_off = name_off; v.seq_off = seq_off; v.seq_len = seq_len; v.qual_off = qual_off;
+        v.name_len = name_len; v.tags_off = tags_off; v.tags_len = tags_len;
+        v.err_sum = err_sum;
+        v.n = (uint32_t)n;
+        return v;
+    }
+};
+
+// stream-ordered allocation helpers (cudaMallocAsync on the context stream)
+int sq_dalloc(sq_ctx *ctx, void **p, size_t nbytes, bool zero);
+void sq_dfree(sq_ctx *ctx, void *p);
+
+inline int sq_grid_for(sq_ctx *ctx, uint64_t work_items, int per_block, int max_waves = 8) {
+    uint64_t blocks = (work_items + per_block - 1) / per_block;
+    uint64_t cap = (uint64_t)ctx->num_sms * max_waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+#define SQ_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+    do {                                                                       \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);       \
+        (ctx)->launches++;                                                     \
+        CUDA_TRY(cudaGetLastError());                                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// A/a C/c G/g T/t -> 0..3, everything else 4 (reference LUT _qcmodule.c:1748-1763)
+__device__ __forceinline__ uint32_t nuc5(uint32_t c) {
+    uint32_t u = c | 0x20u;
+    return u == 'a' ? 0u : u == 'c' ? 1u : u == 'g' ? 2u : u == 't' ? 3u : 4u;
+}
+
+// 0x80 in every byte of x that is zero (exact, no cross-byte borrow)
+__device__ __forceinline__ uint32_t zero_bytes80(uint32_t x) {
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+
+// 32-bit little-endian load from an arbitrary byte address (two aligned loads
+// + funnel shift).  Reads up to 7 bytes past `p`; buffers are padded for that.
+__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t *p) {
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t lo = __ldg(w);
+    if (sh == 0) return lo;
+    uint32_t hi = __ldg(w + 1);
+    return __funnelshift_r(lo, hi, sh);
+}
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+__device__ __forceinline__ uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+// MurmurHash3 x64 128, second 64-bit half (reference murmur3.h:49-156), bytes
+// fetched through `get(i)`.
+template <typename GetByte>
+__device__ __forceinline__ uint64_t murmur3_h2(GetByte get, uint64_t len, uint64_t seed) {
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    uint64_t h1 = seed, h2 = seed;
+    uint64_t nb = len >> 4;
+    for (uint64_t b = 0; b < nb; b++) {
+        uint64_t k1 = 0, k2 = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            k1 |= (uint64_t)get(b * 16 + i) << (8 * i);
+            k2 |= (uint64_t)get(b * 16 + 8 + i) << (8 * i);
+        }
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    uint64_t rem = len & 15, base = nb << 4, k1 = 0, k2 = 0;
+    for (uint64_t i = 0; i < rem; i++) {
+        uint64_t v = get(base + i);
+        if (i < 8) k1 |= v << (8 * i);
+        else k2 |= v << (8 * (i - 8));
+    }
+    if (rem > 8) { k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+    if (rem > 0) { k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1; }
+    h1 ^= len; h2 ^= len;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2; h2 += h1;
+    return h2;
+}
+
+// Thomas Wang's 64-bit mix (reference wanghash.h:14-25)
+__device__ __forceinline__ uint64_t wang64(uint64_t k) {
+    k = ~k + (k << 21);
+    k ^= k >> 24;
+    k *= 265;
+    k ^= k >> 14;
+    k *= 21;
+    k ^= k >> 28;
+    k += k << 31;
+    return k;
+}
+
+__host__ __device__ inline uint64_t unxorshift64(uint64_t v, int s) {
+    uint64_t x = v;
+    for (int i = s; i < 64; i += s) x = v ^ (x >> s);
+    return x;
+}
+// inverse of wang64 (each step undone by its modular inverse / xorshift inverse)
+__host__ __device__ inline uint64_t wang64_inverse(uint64_t k) {
+    k *= 0x3fffffff80000001ULL;  // (1 + 2^31)^-1
+    k = unxorshift64(k, 28);
+    k *= 14933078535860113213ULL;  // 21^-1
+    k = unxorshift64(k, 14);
+    k *= 15244667743933553977ULL;  // 265^-1
+    k = unxorshift64(k, 24);
+    return (k + 1) * 0x7ffffbffffdfffffULL;  // (2^21 - 1)^-1
+}
+
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_excl_scan_u32(uint32_t v, uint32_t *total) {
+    uint32_t x = v;
+    uint32_t l = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (l >= (uint32_t)o) x += y;
+    }
+    *total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+}
+
+__device__ __forceinline__ void atomic_add_u64(uint64_t *p, uint64_t v) {
+    atomicAdd((unsigned long long *)p, (unsigned long long)v);
+}
+__device__ __forceinline__ void atomic_min_u64(uint64_t *p, uint64_t v) {
+    atomicMin((unsigned long long *)p, (unsigned long long)v);
+}
+__device__ __forceinline__ void atomic_max_u64(uint64_t *p, uint64_t v) {
+    atomicMax((unsigned long long *)p, (unsigned long long)v);
+}
+
+#endif  // __CUDACC__

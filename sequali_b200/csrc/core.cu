@@ -1,0 +1,662 @@
+// core.cu -- context, memory, record arrays and the FASTQ record-boundary scan.
+//
+// Replaces FastqParser_create_record_array's memchr loop
+// (reference _qcmodule.c:1093-1171) and string_is_ascii (:204-237) with three
+// kernels over text staged in HBM:
+//   k_count_newlines   16-byte vector loads, SWAR newline count per CTA, first
+//                      non-ASCII byte by atomicMin
+//   k_scan_counts      exclusive scan of the per-CTA counts (one CTA)
+//   k_scatter_newlines same traversal, warp-shuffle scans give every newline
+//                      its rank; writes the newline index (u32 offsets)
+//   k_build_records    one thread per record: every 4th newline closes a
+//                      record; validates '@', '+', equal lengths; emits the SoA
+//                      descriptors and the batch's longest sequence
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void sq_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int sq_cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    sq_set_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e),
+                 file, line, what);
+    return e == cudaErrorMemoryAllocation ? SQ_E_NOMEM : SQ_E_CUDA;
+}
+extern "C" const char *sq_last_error(void) { return g_err; }
+
+extern "C" int sq_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// allocation
+// ---------------------------------------------------------------------------
+int sq_dalloc(sq_ctx *ctx, void **p, size_t nbytes, bool zero) {
+    *p = nullptr;
+    if (nbytes == 0) nbytes = 16;
+    CUDA_TRY(cudaMallocAsync(p, nbytes, ctx->stream));
+    if (zero) CUDA_TRY(cudaMemsetAsync(*p, 0, nbytes, ctx->stream));
+    return SQ_OK;
+}
+void sq_dfree(sq_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// Largest x with floor(-10*log10(x)) >= k, found on the bit pattern of the
+// double with the HOST libm, so that the device never has to reproduce glibc's
+// log10 (reference bucket: _qcmodule.c:2127-2137).
+static double phred_bucket_edge(int k) {
+    auto ok = [k](double x) { return floor(-10.0 * log10(x)) >= (double)k; };
+    uint64_t lo_bits, hi_bits;
+    double lo = 1e-300, hi = 1.0;  // ok(lo) is true for every k <= 93, ok(hi) false for k >= 1
+    memcpy(&lo_bits, &lo, 8);
+    memcpy(&hi_bits, &hi, 8);
+    while (hi_bits - lo_bits > 1) {
+        uint64_t mid = lo_bits + (hi_bits - lo_bits) / 2;
+        double x;
+        memcpy(&x, &mid, 8);
+        if (ok(x)) lo_bits = mid;
+        else hi_bits = mid;
+    }
+    double r;
+    memcpy(&r, &lo_bits, 8);
+    return r;
+}
+
+extern "C" int sq_ctx_create(int device, sq_ctx **out) {
+    *out = nullptr;
+    int n = sq_device_count();
+    if (n <= 0) {
+        sq_set_error("no CUDA device visible: libsqgpu has no CPU fallback");
+        return SQ_E_NODEVICE;
+    }
+    if (device < 0 || device >= n) {
+        sq_set_error("device %d out of range (%d devices)", device, n);
+        return SQ_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    sq_ctx *ctx = new sq_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    // keep freed blocks in the pool: record arrays come and go every batch
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    CUDA_TRY(cudaMallocHost(&ctx->h_scratch, 4096));
+    CUDA_TRY(cudaMalloc(&ctx->d_scratch, 4096));
+    double tab[94], edges[94];
+    for (int q = 0; q < 94; q++) tab[q] = pow(10.0, -((double)q / 10.0));
+    edges[0] = 1.0;  // bucket 0 catches everything down to edge 1
+    for (int k = 1; k < 94; k++) edges[k] = phred_bucket_edge(k);
+    CUDA_TRY(cudaMalloc(&ctx->d_err_table, sizeof(tab)));
+    CUDA_TRY(cudaMalloc(&ctx->d_phred_thresholds, sizeof(edges)));
+    CUDA_TRY(cudaMemcpy(ctx->d_err_table, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ctx->d_phred_thresholds, edges, sizeof(edges), cudaMemcpyHostToDevice));
+    *out = ctx;
+    return SQ_OK;
+}
+
+extern "C" void sq_ctx_destroy(sq_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_err_table);
+    cudaFree(ctx->d_phred_thresholds);
+    cudaFree(ctx->d_scratch);
+    cudaFreeHost(ctx->h_scratch);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int sq_ctx_sync(sq_ctx *ctx) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SQ_OK;
+}
+extern "C" void *sq_ctx_stream(sq_ctx *ctx) { return (void *)ctx->stream; }
+extern "C" uint64_t sq_ctx_launch_count(sq_ctx *ctx) { return ctx->launches; }
+
+extern "C" void *sq_pinned_alloc(sq_ctx *ctx, size_t nbytes) {
+    void *p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        sq_set_error("cudaMallocHost(%zu) failed", nbytes);
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void sq_pinned_free(sq_ctx *ctx, void *p) {
+    (void)ctx;
+    if (p) cudaFreeHost(p);
+}
+extern "C" void *sq_device_alloc(sq_ctx *ctx, size_t nbytes) {
+    void *p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaMalloc(&p, nbytes + 64) != cudaSuccess) {  // +64: readable tail for vector loads
+        cudaGetLastError();
+        sq_set_error("cudaMalloc(%zu) failed", nbytes);
+        return nullptr;
+    }
+    cudaMemsetAsync((uint8_t *)p + nbytes, 0, 64, ctx->stream);
+    return p;
+}
+extern "C" void sq_device_free(sq_ctx *ctx, void *p) {
+    if (!p) return;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(p);
+}
+extern "C" int sq_memcpy_h2d(sq_ctx *ctx, void *dst, const void *src, size_t n) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SQ_OK;
+}
+extern "C" int sq_memcpy_d2h(sq_ctx *ctx, void *dst, const void *src, size_t n) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SQ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// record-boundary scan
+// ---------------------------------------------------------------------------
+constexpr int PARSE_THREADS = 256;
+constexpr int PARSE_ITERS = 4;                                      // 16-byte vectors per lane
+constexpr int PARSE_WARP_BYTES = 32 * 16 * PARSE_ITERS;             // 2 KiB per warp
+constexpr int PARSE_CTA_BYTES = (PARSE_THREADS / 32) * PARSE_WARP_BYTES;  // 16 KiB per CTA
+
+struct ParseState {               // lives in device memory, copied back once
+    unsigned long long n_newlines;
+    unsigned long long first_non_ascii;  // byte offset, ULLONG_MAX if none
+    unsigned long long err_key;          // (record << 3) | code, ULLONG_MAX if none
+    unsigned int max_seq_len;
+    unsigned int pad;
+};
+
+// 16 bytes at vector index v (text is 16-byte aligned); bytes past nbytes read as 0
+__device__ __forceinline__ uint4 load_vec16(const uint8_t *text, uint64_t nbytes, uint64_t v) {
+    uint64_t off = v * 16;
+    if (off + 16 <= nbytes) return __ldg((const uint4 *)(text + off));
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (uint64_t i = off; i < nbytes; i++) w[(i - off) >> 2] |= (uint32_t)text[i] << (8 * ((i - off) & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ uint32_t newline_mask(uint32_t w) { return zero_bytes80(w ^ 0x0A0A0A0Au); }
+
+__global__ void __launch_bounds__(PARSE_THREADS)
+k_count_newlines(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t *__restrict__ cta_counts,
+                 ParseState *st) {
+    __shared__ uint32_t warp_tot[PARSE_THREADS / 32];
+    uint64_t warp_base = (uint64_t)blockIdx.x * PARSE_CTA_BYTES + (uint64_t)(threadIdx.x >> 5) * PARSE_WARP_BYTES;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int it = 0; it < PARSE_ITERS; it++) {
+        uint64_t off = warp_base + (uint64_t)(it * 32 + lane_id()) * 16;
+        if (off >= nbytes) continue;
+        uint4 v = load_vec16(text, nbytes, off >> 4);
+        cnt += __popc(newline_mask(v.x)) + __popc(newline_mask(v.y)) + __popc(newline_mask(v.z)) +
+               __popc(newline_mask(v.w));
+        uint32_t hi = (v.x | v.y | v.z | v.w) & 0x80808080u;
+        if (hi) {  // rare: locate the first byte >= 0x80 (reference :1056-1061)
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            for (int j = 0; j < 16; j++)
+                if ((w[j >> 2] >> (8 * (j & 3))) & 0x80u) {
+                    atomicMin(&st->first_non_ascii, (unsigned long long)(off + j));
+                    break;
+                }
+        }
+    }
+    cnt = warp_sum_u32(cnt);
+    if (lane_id() == 0) warp_tot[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int i = 0; i < PARSE_THREADS / 32; i++) s += warp_tot[i];
+        cta_counts[blockIdx.x] = s;
+    }
+}
+
+// in-place exclusive scan of n counts by one CTA; total -> st->n_newlines
+__global__ void __launch_bounds__(1024) k_scan_counts(uint32_t *counts, uint32_t n, ParseState *st) {
+    __shared__ uint32_t warp_pref[32];
+    __shared__ unsigned long long carry_s;
+    __shared__ uint32_t chunk_total_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < n ? counts[i] : 0;
+        uint32_t wtot;
+        uint32_t ex = warp_excl_scan_u32(v, &wtot);
+        if (lane_id() == 0) warp_pref[threadIdx.x >> 5] = wtot;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t tt;
+            uint32_t e = warp_excl_scan_u32(warp_pref[threadIdx.x], &tt);
+            warp_pref[threadIdx.x] = e;
+            if (threadIdx.x == 0) chunk_total_s = tt;
+        }
+        __syncthreads();
+        unsigned long long carry = carry_s;
+        if (i < n) counts[i] = (uint32_t)carry + warp_pref[threadIdx.x >> 5] + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + chunk_total_s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st->n_newlines = carry_s;
+}
+
+__global__ void __launch_bounds__(PARSE_THREADS)
+k_scatter_newlines(const uint8_t *__restrict__ text, uint64_t nbytes,
+                   const uint32_t *__restrict__ cta_offsets, uint32_t *__restrict__ nl_pos) {
+    __shared__ uint32_t warp_tot[PARSE_THREADS / 32];
+    uint32_t warp = threadIdx.x >> 5;
+    uint64_t warp_base = (uint64_t)blockIdx.x * PARSE_CTA_BYTES + (uint64_t)warp * PARSE_WARP_BYTES;
+    uint32_t m[PARSE_ITERS][4];
+    uint32_t cnt[PARSE_ITERS];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int it = 0; it < PARSE_ITERS; it++) {
+        uint64_t off = warp_base + (uint64_t)(it * 32 + lane_id()) * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (off < nbytes) v = load_vec16(text, nbytes, off >> 4);
+        m[it][0] = newline_mask(v.x);
+        m[it][1] = newline_mask(v.y);
+        m[it][2] = newline_mask(v.z);
+        m[it][3] = newline_mask(v.w);
+        cnt[it] = __popc(m[it][0]) + __popc(m[it][1]) + __popc(m[it][2]) + __popc(m[it][3]);
+        mine += cnt[it];
+    }
+    uint32_t wsum = warp_sum_u32(mine);
+    if (lane_id() == 0) warp_tot[warp] = wsum;
+    __syncthreads();
+    uint32_t rank = cta_offsets[blockIdx.x];
+    for (uint32_t i = 0; i < warp; i++) rank += warp_tot[i];
+#pragma unroll
+    for (int it = 0; it < PARSE_ITERS; it++) {
+        uint32_t tot;
+        uint32_t ex = warp_excl_scan_u32(cnt[it], &tot);
+        uint32_t w = rank + ex;
+        uint64_t off = warp_base + (uint64_t)(it * 32 + lane_id()) * 16;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t bits = m[it][j];
+            while (bits) {
+                uint32_t b = __ffs(bits) - 1;  // bit 7 of byte b/8
+                bits &= bits - 1;
+                nl_pos[w++] = (uint32_t)(off + j * 4 + (b >> 3));
+            }
+        }
+        rank += tot;
+    }
+}
+
+// One thread per record (plus one for the partial record that may follow the
+// last complete one).  Checks in the reference's order (:1097, :1119, :1140).
+__global__ void __launch_bounds__(256)
+k_build_records(const uint8_t *__restrict__ text, uint64_t nbytes, const uint32_t *__restrict__ nl,
+                uint64_t n_newlines, uint64_t n_rec, int check_partial, uint32_t *name_off,
+                uint32_t *seq_off, uint32_t *seq_len, uint32_t *qual_off, ParseState *st) {
+    uint32_t local_max = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n_rec;
+         r += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t start = r == 0 ? 0 : (uint64_t)nl[4 * r - 1] + 1;
+        if (r == n_rec) {
+            if (!check_partial) break;
+            if (start + 2 >= nbytes) break;  // :1094
+            if (text[start] != '@') {
+                atomicMin(&st->err_key, (unsigned long long)(r << 3 | SQ_PARSE_NO_AT));
+                break;
+            }
+            uint64_t have = n_newlines - 4 * n_rec;
+            if (have >= 2) {
+                uint64_t plus = (uint64_t)nl[4 * r + 1] + 1;
+                if (plus < nbytes && text[plus] != '+')
+                    atomicMin(&st->err_key, (unsigned long long)(r << 3 | SQ_PARSE_NO_PLUS));
+            }
+            break;
+        }
+        uint32_t e1 = nl[4 * r], e2 = nl[4 * r + 1], e3 = nl[4 * r + 2], e4 = nl[4 * r + 3];
+        uint32_t code = 0;
+        if (text[start] != '@') code = SQ_PARSE_NO_AT;
+        else if (text[(uint64_t)e2 + 1] != '+') code = SQ_PARSE_NO_PLUS;
+        else if (e2 - e1 != e4 - e3) code = SQ_PARSE_LEN;
+        if (code) {
+            atomicMin(&st->err_key, (unsigned long long)(r << 3 | code));
+            continue;
+        }
+        name_off[r] = (uint32_t)start + 1;
+        seq_off[r] = e1 + 1;
+        seq_len[r] = e2 - e1 - 1;
+        qual_off[r] = e3 + 1;
+        local_max = max(local_max, e2 - e1 - 1);
+    }
+    local_max = warp_max_u32(local_max);
+    if (lane_id() == 0 && local_max) atomicMax(&st->max_seq_len, local_max);
+}
+
+static int alloc_fastq_metas(sq_batch *b, uint64_t n) {
+    // name_off | seq_off | seq_len | qual_off | err_sum
+    size_t n4 = (size_t)((n + 3) & ~3ULL);
+    SQ_TRY(sq_dalloc(b->ctx, &b->meta_block, n4 * 4 * 4 + n4 * 8, false));
+    uint32_t *p = (uint32_t *)b->meta_block;
+    b->name_off = p;
+    b->seq_off = p + n4;
+    b->seq_len = p + 2 * n4;
+    b->qual_off = p + 3 * n4;
+    b->err_sum = (double *)(p + 4 * n4);
+    CUDA_TRY(cudaMemsetAsync(b->err_sum, 0, n4 * 8, b->ctx->stream));
+    return SQ_OK;
+}
+
+static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_parse_info *info) {
+    memset(info, 0, sizeof(*info));
+    uint64_t nbytes = b->nbytes;
+    if (nbytes == 0) return SQ_OK;
+    uint32_t n_cta = (uint32_t)((nbytes + PARSE_CTA_BYTES - 1) / PARSE_CTA_BYTES);
+    uint32_t *cta_counts = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&cta_counts, (size_t)n_cta * 4, false));
+    ParseState *st = (ParseState *)ctx->d_scratch;
+    ParseState init;
+    init.n_newlines = 0;
+    init.first_non_ascii = ~0ULL;
+    init.err_key = ~0ULL;
+    init.max_seq_len = 0;
+    init.pad = 0;
+    memcpy(ctx->h_scratch, &init, sizeof(init));
+    CUDA_TRY(cudaMemcpyAsync(st, ctx->h_scratch, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    SQ_LAUNCH(ctx, k_count_newlines, n_cta, PARSE_THREADS, 0, b->text, nbytes, cta_counts, st);
+    SQ_LAUNCH(ctx, k_scan_counts, 1, 1024, 0, cta_counts, n_cta, st);
+    ParseState *hst = (ParseState *)ctx->h_scratch;
+    CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint64_t n_newlines = hst->n_newlines;
+    info->n_newlines = n_newlines;
+    if (hst->first_non_ascii != ~0ULL) {  // checked before any record is looked at (:1055)
+        info->err_code = SQ_PARSE_ASCII;
+        info->err_pos = hst->first_non_ascii;
+        sq_dfree(ctx, cta_counts);
+        return SQ_E_FORMAT;
+    }
+    uint64_t n_rec = n_newlines / 4;
+    int check_partial = 1;
+    if (n_rec >= max_records) {
+        n_rec = max_records;
+        check_partial = 0;
+    }
+    uint32_t *nl = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&nl, (size_t)(n_newlines + 4) * 4, false));
+    if (n_newlines)
+        SQ_LAUNCH(ctx, k_scatter_newlines, n_cta, PARSE_THREADS, 0, b->text, nbytes, cta_counts, nl);
+    SQ_TRY(alloc_fastq_metas(b, n_rec));
+    int grid = sq_grid_for(ctx, n_rec + 1, 256);
+    SQ_LAUNCH(ctx, k_build_records, grid, 256, 0, b->text, nbytes, nl, n_newlines, n_rec, check_partial,
+              b->name_off, b->seq_off, b->seq_len, b->qual_off, st);
+    // the consumed offset is the byte after the last record's 4th newline
+    uint32_t *h_last = (uint32_t *)((char *)ctx->h_scratch + 256);
+    *h_last = 0;
+    if (n_rec)
+        CUDA_TRY(cudaMemcpyAsync(h_last, nl + (4 * n_rec - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    info->n_records = n_rec;
+    info->consumed = n_rec ? (uint64_t)*h_last + 1 : 0;
+    info->max_seq_len = hst->max_seq_len;
+    int rc = SQ_OK;
+    if (hst->err_key != ~0ULL) {
+        uint64_t r = hst->err_key >> 3;
+        info->err_code = (int32_t)(hst->err_key & 7);
+        info->err_record = r;
+        // locate the offending byte for the message (rare path, tiny copies)
+        uint32_t idx[2] = {0, 0};
+        uint64_t start = 0;
+        if (r > 0) {
+            CUDA_TRY(cudaMemcpy(idx, nl + (4 * r - 1), 4, cudaMemcpyDeviceToHost));
+            start = (uint64_t)idx[0] + 1;
+        }
+        if (info->err_code == SQ_PARSE_NO_AT) info->err_pos = start;
+        else if (info->err_code == SQ_PARSE_NO_PLUS) {
+            CUDA_TRY(cudaMemcpy(idx, nl + (4 * r + 1), 4, cudaMemcpyDeviceToHost));
+            info->err_pos = (uint64_t)idx[0] + 1;
+        }
+        else info->err_pos = start + 1;
+        rc = SQ_E_FORMAT;
+    }
+    b->n = n_rec;
+    b->max_len = info->max_seq_len;
+    sq_dfree(ctx, nl);
+    sq_dfree(ctx, cta_counts);
+    return rc;
+}
+
+static int check_size(uint64_t nbytes) {
+    if (nbytes >= 0xFFFFFF00ULL) {
+        sq_set_error("record array of %llu bytes exceeds the 4 GiB offset range",
+                     (unsigned long long)nbytes);
+        return SQ_E_LIMIT;
+    }
+    return SQ_OK;
+}
+
+extern "C" void sq_batch_free(sq_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    if (b->owns_text) sq_dfree(b->ctx, b->text);
+    sq_dfree(b->ctx, b->meta_block);
+    delete b;
+}
+
+extern "C" int sq_batch_from_fastq(sq_ctx *ctx, const uint8_t *text, uint64_t nbytes,
+                                   uint64_t max_records, sq_batch **out, sq_parse_info *info) {
+    *out = nullptr;
+    SQ_TRY(check_size(nbytes));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sq_batch *b = new sq_batch();
+    b->ctx = ctx;
+    b->nbytes = nbytes;
+    int rc = sq_dalloc(ctx, (void **)&b->text, nbytes + 64, false);
+    if (rc == SQ_OK && nbytes)
+        rc = cudaMemcpyAsync(b->text, text, nbytes, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess
+                 ? SQ_OK : sq_cuda_fail(cudaGetLastError(), "H2D text", __FILE__, __LINE__);
+    if (rc == SQ_OK) cudaMemsetAsync(b->text + nbytes, 0, 64, ctx->stream);
+    if (rc == SQ_OK) rc = parse_device_text(ctx, b, max_records, info);
+    if (rc != SQ_OK) {
+        sq_batch_free(b);
+        return rc;
+    }
+    *out = b;
+    return SQ_OK;
+}
+
+extern "C" int sq_batch_from_device_fastq(sq_ctx *ctx, const uint8_t *dev_text, uint64_t nbytes,
+                                          uint64_t max_records, sq_batch **out, sq_parse_info *info) {
+    *out = nullptr;
+    SQ_TRY(check_size(nbytes));
+    if (((uintptr_t)dev_text & 15) != 0) {
+        sq_set_error("device text must be 16-byte aligned");
+        return SQ_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sq_batch *b = new sq_batch();
+    b->ctx = ctx;
+    b->nbytes = nbytes;
+    b->text = (uint8_t *)dev_text;
+    b->owns_text = false;
+    int rc = parse_device_text(ctx, b, max_records, info);
+    if (rc != SQ_OK) {
+        sq_batch_free(b);
+        return rc;
+    }
+    *out = b;
+    return SQ_OK;
+}
+
+extern "C" int sq_batch_from_packed(sq_ctx *ctx, const uint8_t *buf, uint64_t nbytes,
+                                    const sq_meta *metas, uint64_t n, sq_batch **out) {
+    *out = nullptr;
+    SQ_TRY(check_size(nbytes));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sq_batch *b = new sq_batch();
+    b->ctx = ctx;
+    b->nbytes = nbytes;
+    b->n = n;
+    size_t n4 = (size_t)((n + 3) & ~3ULL);
+    size_t meta_bytes = n4 * 4 * 7 + n4 * 8;
+    std::vector<uint8_t> host(meta_bytes ? meta_bytes : 16, 0);
+    uint32_t *p = (uint32_t *)host.data();
+    uint32_t max_len = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const sq_meta &m = metas[i];
+        if ((uint64_t)m.name_off + m.name_len > nbytes || (uint64_t)m.seq_off + m.seq_len > nbytes ||
+            (uint64_t)m.qual_off + m.seq_len > nbytes || (uint64_t)m.tags_off + m.tags_len > nbytes) {
+            delete b;
+            sq_set_error("record %llu points outside the buffer", (unsigned long long)i);
+            return SQ_E_ARG;
+        }
+        p[i] = m.name_off;
+        p[n4 + i] = m.seq_off;
+        p[2 * n4 + i] = m.seq_len;
+        p[3 * n4 + i] = m.qual_off;
+        p[4 * n4 + i] = m.name_len;
+        p[5 * n4 + i] = m.tags_off;
+        p[6 * n4 + i] = m.tags_len;
+        ((double *)(p + 7 * n4))[i] = m.err_sum;
+        if (m.seq_len > max_len) max_len = m.seq_len;
+    }
+    b->max_len = max_len;
+    int rc = sq_dalloc(ctx, (void **)&b->text, nbytes + 64, false);
+    if (rc == SQ_OK) rc = sq_dalloc(ctx, &b->meta_block, meta_bytes, false);
+    if (rc != SQ_OK) {
+        sq_batch_free(b);
+        return rc;
+    }
+    // pageable sources: cudaMemcpyAsync stages them before returning
+    if (nbytes) CUDA_TRY(cudaMemcpyAsync(b->text, buf, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(b->text + nbytes, 0, 64, ctx->stream));
+    if (meta_bytes)
+        CUDA_TRY(cudaMemcpyAsync(b->meta_block, host.data(), meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint32_t *d = (uint32_t *)b->meta_block;
+    b->name_off = d;
+    b->seq_off = d + n4;
+    b->seq_len = d + 2 * n4;
+    b->qual_off = d + 3 * n4;
+    b->name_len = d + 4 * n4;
+    b->tags_off = d + 5 * n4;
+    b->tags_len = d + 6 * n4;
+    b->err_sum = (double *)(d + 7 * n4);
+    *out = b;
+    return SQ_OK;
+}
+
+extern "C" uint64_t sq_batch_size(const sq_batch *b) { return b->n; }
+extern "C" uint64_t sq_batch_nbytes(const sq_batch *b) { return b->nbytes; }
+extern "C" uint32_t sq_batch_max_seq_len(const sq_batch *b) { return b->max_len; }
+
+extern "C" int sq_batch_get_bytes(sq_batch *b, uint8_t *out) {
+    CUDA_TRY(cudaSetDevice(b->ctx->device));
+    if (b->nbytes) CUDA_TRY(cudaMemcpyAsync(out, b->text, b->nbytes, cudaMemcpyDeviceToHost, b->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+    return SQ_OK;
+}
+
+extern "C" int sq_batch_get_metas(sq_batch *b, sq_meta *out) {
+    CUDA_TRY(cudaSetDevice(b->ctx->device));
+    uint64_t n = b->n;
+    if (n == 0) return SQ_OK;
+    size_t n4 = (size_t)((n + 3) & ~3ULL);
+    bool aux = b->name_len != nullptr;
+    size_t bytes = n4 * 4 * (aux ? 7 : 4) + n4 * 8;
+    std::vector<uint8_t> host(bytes);
+    CUDA_TRY(cudaMemcpyAsync(host.data(), b->meta_block, bytes, cudaMemcpyDeviceToHost, b->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+    const uint32_t *p = (const uint32_t *)host.data();
+    const double *es = (const double *)(p + (aux ? 7 : 4) * n4);
+    for (uint64_t i = 0; i < n; i++) {
+        sq_meta &m = out[i];
+        m.name_off = p[i];
+        m.seq_off = p[n4 + i];
+        m.seq_len = p[2 * n4 + i];
+        m.qual_off = p[3 * n4 + i];
+        if (aux) {
+            m.name_len = p[4 * n4 + i];
+            m.tags_off = p[5 * n4 + i];
+            m.tags_len = p[6 * n4 + i];
+        }
+        else {  // FASTQ text: "@name\nSEQ\n+...\nQUAL\n"
+            m.name_len = m.seq_off - 1 - m.name_off;
+            m.tags_off = m.qual_off + m.seq_len;
+            m.tags_len = 0;
+        }
+        m.reserved = 0;
+        m.err_sum = es[i];
+    }
+    return SQ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// mate check (reference _qcmodule.c:778-850)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t view_name_len(const BatchView &v, uint32_t r) {
+    return v.name_len ? v.name_len[r] : v.seq_off[r] - 1 - v.name_off[r];
+}
+
+__global__ void __launch_bounds__(256) k_is_mate(BatchView a, BatchView b, unsigned long long *first_bad) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += gridDim.x * blockDim.x) {
+        const uint8_t *n1 = a.text + a.name_off[r], *n2 = b.text + b.name_off[r];
+        uint32_t l1 = view_name_len(a, r), l2 = view_name_len(b, r);
+        uint32_t id = 0;
+        while (id < l1 && n1[id] != ' ' && n1[id] != '\t') id++;
+        bool ok = l2 >= id;
+        if (ok && l2 > id) ok = n2[id] == ' ' || n2[id] == '\t';
+        if (ok) {
+            uint32_t cmp = id;
+            if (id > 0) {
+                uint8_t c1 = n1[id - 1], c2 = n2[id - 1];
+                if ((c1 == '1' || c1 == '2') && (c2 == '1' || c2 == '2')) cmp--;
+            }
+            for (uint32_t i = 0; i < cmp && ok; i++) ok = n1[i] == n2[i];
+        }
+        if (!ok) atomicMin(first_bad, (unsigned long long)r);
+    }
+}
+
+extern "C" int sq_batch_is_mate(sq_batch *a, sq_batch *b, uint64_t *first_mismatch) {
+    if (a->n != b->n) {
+        sq_set_error("record arrays differ in length: %llu vs %llu", (unsigned long long)a->n,
+                     (unsigned long long)b->n);
+        return SQ_E_ARG;
+    }
+    sq_ctx *ctx = a->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    *first_mismatch = a->n;
+    if (a->n == 0) return SQ_OK;
+    unsigned long long *d = (unsigned long long *)((char *)ctx->d_scratch + 512);
+    unsigned long long *h = (unsigned long long *)((char *)ctx->h_scratch + 512);
+    *h = a->n;
+    CUDA_TRY(cudaMemcpyAsync(d, h, 8, cudaMemcpyHostToDevice, ctx->stream));
+    SQ_LAUNCH(ctx, k_is_mate, sq_grid_for(ctx, a->n, 256), 256, 0, a->view(), b->view(), d);
+    CUDA_TRY(cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *first_mismatch = *h;
+    return SQ_OK;
+}
