@@ -1,0 +1,387 @@
+// nanostats.cu -- NanoStats (reference _qcmodule.c:248-322, 5006-5052, 5078-5259, 5269-5324).
+//
+// One thread per record turns the guppy-style FASTQ header ("... ch=<n>
+// start_time=<iso8601> ...") or the BAM aux fields (ch, st, du, pi) into one
+// 40-byte NanoInfo, in record order, in a device array that grows with the
+// input.  The first FASTQ header that cannot be parsed switches the module off:
+// that record index is taken by atomicMin and everything from it on is ignored
+// at read-out.  The per-read error sum is the one QCMetrics stored on the
+// record array (same stream, so it is already there when this kernel runs).
+#include "common.cuh"
+
+constexpr int NS_TPB = 128;
+
+struct NsState {  // device
+    unsigned long long fail_idx;      // global index of the first unparsable header
+    unsigned long long tag_err_idx;   // global index of the first malformed aux block
+    unsigned long long pi_warnings;
+    long long min_time, max_time;
+    unsigned int nonpositive_time;    // a timestamp <= 0 exists (order-dependent min, see k_ns_minmax_ordered)
+    unsigned int pad;
+};
+
+struct sq_nanostats {
+    sq_ctx *ctx = nullptr;
+    uint64_t n_added = 0, cap = 0;
+    sq_nanoinfo *infos = nullptr;
+    NsState *st = nullptr;
+    bool skipped = false;          // known on the host after a sync
+    uint64_t skipped_record = 0;
+    std::vector<uint8_t> skipped_name;
+    // names of the newest arrays are needed for skipped_reason: keep (batch ptr, base) of pending adds
+    std::vector<std::pair<sq_batch *, uint64_t>> pending;
+};
+
+__device__ __forceinline__ long long dec_field(const uint8_t *s, const uint8_t *end, uint32_t len) {
+    if (len < 1 || len > 18 || s + len > end) return -1;
+    long long v = 0;
+    for (uint32_t i = 0; i < len; i++) {
+        uint32_t d = (uint32_t)s[i] - '0';
+        if (d > 9) return -1;
+        v = v * 10 + d;
+    }
+    return v;
+}
+
+// "YYYY-MM-DDThh:mm:ss[.fff](Z|+hh:mm|-hh:mm)" -> seconds since the epoch, -1 on error (:272-322)
+__device__ long long nanopore_time(const uint8_t *s, const uint8_t *end) {
+    if (s + 20 > end) return -1;
+    long long Y = dec_field(s, end, 4), M = dec_field(s + 5, end, 2), D = dec_field(s + 8, end, 2);
+    long long h = dec_field(s + 11, end, 2), mi = dec_field(s + 14, end, 2), sec = dec_field(s + 17, end, 2);
+    if ((Y | M | D | h | mi | sec) < 0 || s[4] != '-' || s[7] != '-' || s[10] != 'T' || s[13] != ':' ||
+        s[16] != ':')
+        return -1;
+    const uint8_t *tz = s + 19;
+    if (*tz == '.') {
+        tz++;
+        while (tz < end && *tz >= '0' && *tz <= '9') tz++;
+    }
+    if (tz >= end) return -1;
+    if (*tz == '+' || *tz == '-') {
+        long long oh = dec_field(tz + 1, end, 2), om = dec_field(tz + 4, end, 2);
+        if ((oh | om) < 0 || tz[3] != ':') return -1;
+        if (*tz == '+') { h += oh; mi += om; }
+        else { h -= oh; mi -= om; }
+    }
+    else if (*tz != 'Z') return -1;
+    if (Y < 1970 || M < 1 || M > 12) return -1;  // :252
+    const int cum[12] = {0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334};
+    long long y = Y - 1900, yday = cum[M - 1] + D - 1;
+    return sec + mi * 60 + h * 3600 + yday * 86400 + (y - 70) * 31536000 + ((y - 69) / 4) * 86400 -
+           ((y - 1) / 100) * 86400 + ((y + 299) / 400) * 86400;
+}
+
+__device__ __forceinline__ const uint8_t *find_byte(const uint8_t *p, const uint8_t *end, uint8_t c) {
+    while (p < end && *p != c) p++;
+    return p < end ? p : nullptr;
+}
+
+__device__ int nano_header(const uint8_t *h, uint32_t n, int32_t *ch, long long *st) {
+    const uint8_t *end = h + n, *p = find_byte(h, end, ' ');
+    if (!p) return -1;
+    p++;
+    long long channel = -1, start = -1;
+    while (p < end) {
+        const uint8_t *eq = find_byte(p, end, '=');
+        if (!eq) return -1;
+        const uint8_t *val = eq + 1, *ve = find_byte(val, end, ' ');
+        if (!ve) ve = end;
+        uint32_t kl = (uint32_t)(eq - p);
+        if (kl == 2 && p[0] == 'c' && p[1] == 'h')
+            channel = (long long)(int32_t)dec_field(val, end, (uint32_t)(ve - val));
+        else if (kl == 10 && p[0] == 's' && p[1] == 't' && p[2] == 'a' && p[3] == 'r' && p[4] == 't' &&
+                 p[5] == '_' && p[6] == 't' && p[7] == 'i' && p[8] == 'm' && p[9] == 'e')
+            start = nanopore_time(val, end);
+        p = ve + 1;
+    }
+    if (channel == -1 || start == -1) return -1;
+    *ch = (int32_t)channel;
+    *st = start;
+    return 0;
+}
+
+__device__ __forceinline__ uint32_t rd16(const uint8_t *p) { return p[0] | (uint32_t)p[1] << 8; }
+__device__ __forceinline__ uint32_t rd32(const uint8_t *p) {
+    return p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
+}
+
+__device__ long long aux_len(const uint8_t *t, uint64_t avail) {  // :5078-5140
+    if (avail < 4) return -1;
+    uint8_t ty = t[2];
+    uint64_t head = 3, count = 1, width;
+    if (ty == 'B') {
+        if (avail < 8) return -1;
+        ty = t[3];
+        count = rd32(t + 4);
+        head = 8;
+        if (ty == 'Z' || ty == 'H') return -1;
+    }
+    switch (ty) {
+        case 'A': case 'c': case 'C': width = 1; break;
+        case 's': case 'S': width = 2; break;
+        case 'i': case 'I': case 'f': width = 4; break;
+        case 'Z': case 'H': {
+            const uint8_t *z = find_byte(t + 3, t + avail, 0);
+            if (!z) return -1;
+            width = (uint64_t)(z - (t + 3)) + 1;
+            break;
+        }
+        default: return -1;
+    }
+    uint64_t len = head + count * width;
+    return len > avail ? -1 : (long long)len;
+}
+
+// strtoull(s, &end, 16) consuming exactly 8 bytes (blanks, sign, 0x prefix accepted like libc)
+__device__ bool hex8_like_strtoull(const uint8_t *s, uint64_t *out) {
+    int i = 0;
+    bool neg = false;
+    while (i < 8 && (s[i] == ' ' || (s[i] >= 9 && s[i] <= 13))) i++;
+    if (i < 8 && (s[i] == '+' || s[i] == '-')) neg = s[i++] == '-';
+    int digits_at = i;
+    if (i + 1 < 8 && s[i] == '0' && (s[i + 1] | 0x20) == 'x') {
+        uint8_t c = i + 2 < 8 ? s[i + 2] : 0;
+        bool hexd = (c >= '0' && c <= '9') || ((c | 0x20) >= 'a' && (c | 0x20) <= 'f');
+        if (hexd) digits_at = i + 2;
+    }
+    uint64_t v = 0;
+    int j = digits_at;
+    for (; j < 8; j++) {
+        uint8_t c = s[j];
+        int d = (c >= '0' && c <= '9') ? c - '0' : ((c | 0x20) >= 'a' && (c | 0x20) <= 'f') ? (c | 0x20) - 'a' + 10 : -1;
+        if (d < 0) break;
+        v = v << 4 | (uint64_t)d;
+    }
+    if (j != 8 || j == digits_at) return false;
+    *out = neg ? 0ULL - v : v;
+    return true;
+}
+__device__ uint64_t uuid4_hash(const uint8_t *u) {  // :5153-5179
+    if (u[8] != '-' || u[13] != '-' || u[14] != '4' || u[18] != '-' || u[23] != '-' || u[36] != 0) return 0;
+    uint64_t a, b;
+    if (!hex8_like_strtoull(u, &a) || !hex8_like_strtoull(u + 28, &b)) return 0;
+    return a << 32 | (b & 0xffffffffULL);
+}
+
+__device__ int nano_tags(const uint8_t *t, uint64_t n, sq_nanoinfo *o, unsigned long long *pi_warn) {
+    o->channel_id = -1;
+    o->duration = 0.0f;
+    o->start_time = 0;
+    o->parent_id_hash = 0;
+    while (n) {
+        long long len = aux_len(t, n);
+        if (len < 0) return -1;
+        uint8_t ty = t[2];
+        if (t[0] == 'c' && t[1] == 'h') {
+            const uint8_t *v = t + 3;
+            switch (ty) {
+                case 'c': o->channel_id = (int8_t)v[0]; break;
+                case 'C': o->channel_id = v[0]; break;
+                case 's': o->channel_id = (int16_t)rd16(v); break;
+                case 'S': o->channel_id = (int32_t)rd16(v); break;
+                case 'i': case 'I': o->channel_id = (int32_t)rd32(v); break;
+                default: return -1;
+            }
+        }
+        else if (t[0] == 's' && t[1] == 't') {
+            if (ty != 'Z') return -1;
+            o->start_time = nanopore_time(t + 3, t + len);
+        }
+        else if (t[0] == 'd' && t[1] == 'u') {
+            if (ty != 'f') return -1;
+            o->duration = __uint_as_float(rd32(t + 3));
+        }
+        else if (t[0] == 'p' && t[1] == 'i') {
+            if (ty != 'Z') return -1;
+            if (len - 4 != 36) atomicAdd(pi_warn, 1ULL);
+            else o->parent_id_hash = uuid4_hash(t + 3);
+        }
+        t += len;
+        n -= (uint64_t)len;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(NS_TPB)
+k_ns_parse(BatchView bv, sq_nanoinfo *out, uint64_t base, NsState *st) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < bv.n; r += gridDim.x * blockDim.x) {
+        sq_nanoinfo info;
+        info.start_time = 0;
+        info.duration = 0.0f;
+        info.channel_id = 0;
+        info.length = bv.seq_len[r];
+        info.reserved = 0;
+        info.parent_id_hash = 0;
+        const uint32_t tl = bv.tags_len ? bv.tags_len[r] : 0;
+        if (tl) {
+            if (nano_tags(bv.text + bv.tags_off[r], tl, &info, &st->pi_warnings))
+                atomicMin(&st->tag_err_idx, (unsigned long long)(base + r));
+        }
+        else {
+            const uint32_t nl = bv.name_len ? bv.name_len[r] : bv.seq_off[r] - 1 - bv.name_off[r];
+            int32_t ch;
+            long long t0;
+            if (nano_header(bv.text + bv.name_off[r], nl, &ch, &t0)) {
+                atomicMin(&st->fail_idx, (unsigned long long)(base + r));
+            }
+            else {
+                info.channel_id = ch;
+                info.start_time = t0;
+            }
+        }
+        info.cumulative_error_rate = bv.err_sum[r];
+        out[base + r] = info;
+    }
+}
+
+// min/max start time over the first n kept records
+__global__ void __launch_bounds__(256) k_ns_minmax(const sq_nanoinfo *infos, uint64_t n, NsState *st) {
+    long long lo = 0x7fffffffffffffffLL, hi = 0;
+    unsigned int nonpos = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        long long t = infos[i].start_time;
+        lo = min(lo, t);
+        hi = max(hi, t);
+        nonpos |= t <= 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        nonpos |= __shfl_xor_sync(0xffffffffu, nonpos, o);
+    }
+    if (lane_id() == 0) {
+        atomicMin(&st->min_time, lo);
+        atomicMax(&st->max_time, hi);
+        if (nonpos) atomicOr(&st->nonpositive_time, 1u);
+    }
+}
+// The reference treats min_time == 0 as "unset" (:5319), which makes the fold
+// order-dependent once a timestamp <= 0 shows up.  Replay it in order (rare).
+__global__ void k_ns_minmax_ordered(const sq_nanoinfo *infos, uint64_t n, NsState *st) {
+    if (blockIdx.x || threadIdx.x) return;
+    long long lo = 0, hi = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        long long t = infos[i].start_time;
+        if (t > hi) hi = t;
+        if (lo == 0 || t < lo) lo = t;
+    }
+    st->min_time = lo;
+    st->max_time = hi;
+}
+
+extern "C" int sq_nanostats_create(sq_ctx *ctx, sq_nanostats **out) {
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sq_nanostats *s = new sq_nanostats();
+    s->ctx = ctx;
+    int rc = sq_dalloc(ctx, (void **)&s->st, sizeof(NsState), true);
+    if (rc == SQ_OK) {
+        NsState init;
+        memset(&init, 0, sizeof(init));
+        init.fail_idx = ~0ULL;
+        init.tag_err_idx = ~0ULL;
+        rc = cudaMemcpy(s->st, &init, sizeof(init), cudaMemcpyHostToDevice) == cudaSuccess ? SQ_OK : SQ_E_CUDA;
+    }
+    if (rc != SQ_OK) {
+        sq_nanostats_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return SQ_OK;
+}
+
+extern "C" void sq_nanostats_destroy(sq_nanostats *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    sq_dfree(s->ctx, s->infos);
+    sq_dfree(s->ctx, s->st);
+    delete s;
+}
+
+extern "C" int sq_nanostats_add(sq_nanostats *s, sq_batch *b) {
+    sq_ctx *ctx = s->ctx;
+    if (b->ctx != ctx) {
+        sq_set_error("record array belongs to another context");
+        return SQ_E_ARG;
+    }
+    if (s->skipped || b->n == 0) return SQ_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // Cheap early out for non-nanopore input: once the device has reported an
+    // unparsable header there is nothing left to do.  Peek without blocking.
+    if (s->n_added + b->n > s->cap) {
+        uint64_t cap = s->cap ? s->cap : 16384;
+        while (cap < s->n_added + b->n) cap *= 2;
+        sq_nanoinfo *ni = nullptr;
+        SQ_TRY(sq_dalloc(ctx, (void **)&ni, cap * sizeof(sq_nanoinfo), false));
+        if (s->n_added)
+            CUDA_TRY(cudaMemcpyAsync(ni, s->infos, s->n_added * sizeof(sq_nanoinfo), cudaMemcpyDeviceToDevice, ctx->stream));
+        sq_dfree(ctx, s->infos);
+        s->infos = ni;
+        s->cap = cap;
+    }
+    SQ_LAUNCH(ctx, k_ns_parse, sq_grid_for(ctx, b->n, NS_TPB, 16), NS_TPB, 0, b->view(), s->infos, s->n_added, s->st);
+    // the name of the record that switches the module off is wanted for
+    // skipped_reason: find out now while the array is still alive
+    NsState *h = (NsState *)((char *)ctx->h_scratch + 2560);
+    CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h->fail_idx != ~0ULL) {
+        s->skipped = true;
+        s->skipped_record = h->fail_idx;
+        uint64_t r = h->fail_idx - s->n_added;
+        std::vector<sq_meta> metas(b->n);
+        SQ_TRY(sq_batch_get_metas(b, metas.data()));
+        s->skipped_name.resize(metas[r].name_len);
+        if (metas[r].name_len)
+            CUDA_TRY(cudaMemcpy(s->skipped_name.data(), b->text + metas[r].name_off, metas[r].name_len,
+                                cudaMemcpyDeviceToHost));
+    }
+    s->n_added += b->n;
+    return SQ_OK;
+}
+
+extern "C" int sq_nanostats_sync(sq_nanostats *s, sq_nanostats_info *info) {
+    sq_ctx *ctx = s->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    memset(info, 0, sizeof(*info));
+    const uint64_t n = s->skipped ? s->skipped_record : s->n_added;
+    NsState *h = (NsState *)((char *)ctx->h_scratch + 2560);
+    // recompute min/max over the kept prefix
+    CUDA_TRY(cudaMemsetAsync(&s->st->max_time, 0, 8, ctx->stream));
+    long long big = 0x7fffffffffffffffLL;
+    CUDA_TRY(cudaMemcpyAsync(&s->st->min_time, &big, 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(&s->st->nonpositive_time, 0, 4, ctx->stream));
+    if (n) SQ_LAUNCH(ctx, k_ns_minmax, sq_grid_for(ctx, n, 256, 8), 256, 0, s->infos, n, s->st);
+    CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (n && h->nonpositive_time) {
+        SQ_LAUNCH(ctx, k_ns_minmax_ordered, 1, 32, 0, s->infos, n, s->st);
+        CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    info->number_of_reads = n;
+    info->minimum_time = n ? h->min_time : 0;
+    info->maximum_time = n ? h->max_time : 0;
+    info->skipped = s->skipped;
+    info->skipped_record = s->skipped_record;
+    info->tag_error = h->tag_err_idx != ~0ULL;
+    info->tag_error_record = h->tag_err_idx;
+    info->pi_warnings = h->pi_warnings;
+    return SQ_OK;
+}
+
+extern "C" int sq_nanostats_skipped_name(sq_nanostats *s, uint8_t *out, uint64_t cap, uint64_t *len) {
+    uint64_t n = s->skipped_name.size() < cap ? s->skipped_name.size() : cap;
+    if (n) memcpy(out, s->skipped_name.data(), n);
+    *len = n;
+    return SQ_OK;
+}
+
+extern "C" int sq_nanostats_read(sq_nanostats *s, sq_nanoinfo *out) {
+    sq_ctx *ctx = s->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t n = s->skipped ? s->skipped_record : s->n_added;
+    if (n) CUDA_TRY(cudaMemcpyAsync(out, s->infos, n * sizeof(sq_nanoinfo), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SQ_OK;
+}

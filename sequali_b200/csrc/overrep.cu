@@ -1,0 +1,410 @@
+// overrep.cu -- OverrepresentedSequences (reference _qcmodule.c:3543-3568, 3589-3608,
+// 3635-3694, 3830-3942).
+//
+// Every `sample_every`-th read (by running read count) contributes the
+// canonical 2-bit k-mers of a few non-overlapping fragments from both ends,
+// de-duplicated within the read, to a capped open-addressing count table keyed
+// by Thomas Wang's hash of the k-mer.
+//
+//   k_ov_fragments   one thread per sampled read: k-mers, reverse complement,
+//                    hash, and the reference's per-read staging table (its slot
+//                    order is the tie-break when the cap is hit mid-read)
+//   k_ov_count       insert-or-increment with atomicCAS (table below the cap:
+//                    content is order-free), or lookup-only (table full)
+//   k_ov_classify / k_ov_flags / scan / k_ov_admit   the one batch that crosses
+//                    the cap: the first (max - unique) new hashes in (read,
+//                    staging slot) order are admitted, the rest dropped
+#include <math.h>
+
+#include "common.cuh"
+
+constexpr int OV_TPB = 128;
+constexpr int OV_STAGE_MAX = 128;  // per-read staging slots kept in local memory
+
+struct OvCounters {
+    unsigned long long total_frags;
+    unsigned long long warn_records;
+    unsigned long long first_warn;
+    unsigned int n_unique;
+    unsigned int n_new;
+};
+
+struct sq_overrep {
+    sq_ctx *ctx = nullptr;
+    uint64_t max_unique = 0, k = 0, sample_every = 0, frags_front = 0, frags_back = 0;
+    uint64_t n_seqs = 0, n_sampled = 0, table_size = 0;
+    uint64_t unique_known = 0;   // exact unique count at the last synchronisation
+    uint64_t unique_upper = 0;   // upper bound since then
+    bool full = false;
+    uint64_t *keys = nullptr;    // wang hash, 0 = empty
+    uint32_t *counts = nullptr;
+    OvCounters *cnt = nullptr;
+};
+
+// canonical k-mer of s[0..k): 0 ok, 1 holds N/n, 2 holds another non-ACGT letter (:3612-3694)
+__device__ __forceinline__ int canonical_kmer(const uint8_t *s, uint32_t k, uint64_t *out) {
+    uint64_t fw = 0, rc = 0;
+    uint32_t flags = 0;
+    for (uint32_t i = 0; i < k; i++) {
+        uint32_t ch = s[i] | 0x20u;
+        uint32_t c = ch == 'a' ? 0u : ch == 'c' ? 1u : ch == 'g' ? 2u : ch == 't' ? 3u : 4u;
+        if (c == 4) {
+            flags |= ch == 'n' ? 1u : 2u;
+            c = 0;
+        }
+        fw = (fw << 2) | c;
+        rc |= (uint64_t)(3 - c) << (2 * i);
+    }
+    if (flags & 2) return 2;
+    if (flags & 1) return 1;
+    *out = rc < fw ? rc : fw;
+    return 0;
+}
+
+__global__ void __launch_bounds__(OV_TPB)
+k_ov_fragments(BatchView bv, uint32_t first_sampled, uint32_t sample_every, uint32_t n_sampled, uint32_t k,
+               uint64_t frags_front, uint64_t frags_back, uint32_t fcap, uint64_t *__restrict__ frag_hash,
+               uint32_t *__restrict__ frag_n, OvCounters *cnt, uint64_t record_base) {
+    unsigned long long valid_total = 0;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_sampled; s += gridDim.x * blockDim.x) {
+        const uint32_t r = first_sampled + s * sample_every;
+        const uint64_t L = bv.seq_len[r];
+        uint32_t emitted = 0;
+        if (L >= k) {
+            const uint8_t *seq = bv.text + bv.seq_off[r];
+            const uint64_t maxf = (L + k - 1) / k, back_cap = maxf / 2, front_cap = maxf - back_cap;
+            const uint64_t nf = min(frags_front, front_cap), nb = min(frags_back, back_cap);
+            const uint32_t total = (uint32_t)(nf + nb);
+            if (total) {
+                uint32_t ssize = 1;  // 2^ceil(log2(1.5*total)); 3*total is never a power of two
+                while (2 * ssize < 3 * total) ssize <<= 1;
+                uint64_t stage[OV_STAGE_MAX];
+                for (uint32_t i = 0; i < ssize; i++) stage[i] = 0;
+                bool warn = false;
+                uint32_t valid = 0;
+                for (uint32_t f = 0; f < total; f++) {
+                    const uint64_t off = f < nf ? (uint64_t)f * k : L - (nb - (f - nf)) * k;
+                    uint64_t kmer;
+                    int rc = canonical_kmer(seq + off, k, &kmer);
+                    if (rc) {
+                        warn |= rc == 2;
+                        continue;
+                    }
+                    valid++;
+                    const uint64_t h = wang64(kmer);
+                    uint32_t i = (uint32_t)h & (ssize - 1);
+                    while (stage[i] != 0 && stage[i] != h) i = (i + 1) & (ssize - 1);
+                    stage[i] = h;
+                }
+                for (uint32_t i = 0; i < ssize; i++)
+                    if (stage[i]) frag_hash[(size_t)s * fcap + emitted++] = stage[i];
+                valid_total += valid;
+                if (warn) {
+                    atomicAdd(&cnt->warn_records, 1ULL);
+                    atomicMin(&cnt->first_warn, (unsigned long long)(record_base + r));
+                }
+            }
+        }
+        frag_n[s] = emitted;
+    }
+    // block-level aggregation of the (non de-duplicated) fragment count
+    for (int o = 16; o > 0; o >>= 1) valid_total += __shfl_xor_sync(0xffffffffu, valid_total, o);
+    if (lane_id() == 0 && valid_total) atomicAdd(&cnt->total_frags, valid_total);
+}
+
+__device__ __forceinline__ void ov_insert_or_count(uint64_t *keys, uint32_t *counts, uint64_t mask, uint64_t h,
+                                                   bool may_insert, unsigned int *n_unique) {
+    uint64_t i = h & mask;
+    for (;;) {
+        uint64_t kk = keys[i];
+        if (kk == h) {
+            atomicAdd(&counts[i], 1u);
+            return;
+        }
+        if (kk == 0) {
+            if (!may_insert) return;  // table full: unknown hashes are dropped (:3553)
+            uint64_t old = atomicCAS((unsigned long long *)&keys[i], 0ULL, (unsigned long long)h);
+            if (old == 0) {
+                atomicAdd(n_unique, 1u);
+                atomicAdd(&counts[i], 1u);
+                return;
+            }
+            if (old == h) {
+                atomicAdd(&counts[i], 1u);
+                return;
+            }
+        }
+        i = (i + 1) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ov_count(const uint64_t *__restrict__ frag_hash, const uint32_t *__restrict__ frag_n, uint32_t n_sampled,
+           uint32_t fcap, uint64_t *keys, uint32_t *counts, uint64_t mask, int may_insert, OvCounters *cnt) {
+    const uint64_t total = (uint64_t)n_sampled * fcap;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = (uint32_t)(t / fcap), i = (uint32_t)(t % fcap);
+        if (i >= frag_n[s]) continue;
+        ov_insert_or_count(keys, counts, mask, frag_hash[t], may_insert != 0, &cnt->n_unique);
+    }
+}
+
+// ---- the batch that crosses the cap ---------------------------------------------------------
+struct OvScratch {
+    uint64_t *key;    // ~0 = free
+    uint32_t *first;  // smallest occurrence index t holding the key
+    uint32_t mask;
+};
+__device__ __forceinline__ uint32_t ov_scratch_slot(const OvScratch &S, uint64_t h, bool insert) {
+    uint32_t i = (uint32_t)(h ^ (h >> 29)) & S.mask;
+    for (;;) {
+        uint64_t kk = S.key[i];
+        if (kk == h) return i;
+        if (kk == ~0ULL) {
+            if (!insert) return 0xFFFFFFFFu;
+            uint64_t old = atomicCAS((unsigned long long *)&S.key[i], ~0ULL, (unsigned long long)h);
+            if (old == ~0ULL || old == h) return i;
+        }
+        i = (i + 1) & S.mask;
+    }
+}
+// cls[t]: 0 = slot unused, 1 = hash already in the table, 2 = new hash
+__global__ void __launch_bounds__(256)
+k_ov_classify(const uint64_t *__restrict__ frag_hash, const uint32_t *__restrict__ frag_n, uint32_t n_sampled,
+              uint32_t fcap, const uint64_t *__restrict__ keys, uint64_t mask, uint8_t *__restrict__ cls,
+              OvScratch S) {
+    const uint64_t total = (uint64_t)n_sampled * fcap;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = (uint32_t)(t / fcap), i = (uint32_t)(t % fcap);
+        if (i >= frag_n[s]) {
+            cls[t] = 0;
+            continue;
+        }
+        const uint64_t h = frag_hash[t];
+        uint64_t p = h & mask;
+        uint8_t c = 2;
+        for (;;) {
+            uint64_t kk = keys[p];
+            if (kk == 0) break;
+            if (kk == h) {
+                c = 1;
+                break;
+            }
+            p = (p + 1) & mask;
+        }
+        cls[t] = c;
+        if (c == 2) atomicMin(&S.first[ov_scratch_slot(S, h, true)], (uint32_t)t);
+    }
+}
+__global__ void __launch_bounds__(256)
+k_ov_flags(const uint64_t *__restrict__ frag_hash, const uint8_t *__restrict__ cls, uint64_t total, OvScratch S,
+           uint32_t *__restrict__ flag) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t f = 0;
+        if (cls[t] == 2) f = S.first[ov_scratch_slot(S, frag_hash[t], false)] == (uint32_t)t;
+        flag[t] = f;
+    }
+}
+// admit the first K new hashes in occurrence order; count every occurrence of
+// table hashes and of admitted hashes
+__global__ void __launch_bounds__(256)
+k_ov_admit(const uint64_t *__restrict__ frag_hash, const uint8_t *__restrict__ cls, uint64_t total,
+           OvScratch S, const uint32_t *__restrict__ rank, uint32_t K, uint64_t *keys, uint32_t *counts,
+           uint64_t mask, OvCounters *cnt) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t c = cls[t];
+        if (c == 0) continue;
+        const uint64_t h = frag_hash[t];
+        bool ok = c == 1;
+        if (c == 2) {
+            uint32_t first = S.first[ov_scratch_slot(S, h, false)];
+            ok = rank[first] < K;  // rank of the hash's first occurrence among new hashes
+        }
+        if (ok) ov_insert_or_count(keys, counts, mask, h, true, &cnt->n_unique);
+    }
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int sq_overrep_create(sq_ctx *ctx, uint64_t max_unique_fragments, uint32_t fragment_length,
+                                 uint64_t sample_every, int64_t bases_from_start, int64_t bases_from_end,
+                                 sq_overrep **out) {
+    *out = nullptr;
+    if (max_unique_fragments < 1 || (fragment_length & 1) == 0 || fragment_length > 31 ||
+        fragment_length < 3 || sample_every < 1) {
+        sq_set_error("invalid OverrepresentedSequences parameters");
+        return SQ_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sq_overrep *o = new sq_overrep();
+    o->ctx = ctx;
+    o->max_unique = max_unique_fragments;
+    o->k = fragment_length;
+    o->sample_every = sample_every;
+    if (bases_from_start < 0) bases_from_start = UINT32_MAX;  // :3499-3504
+    if (bases_from_end < 0) bases_from_end = UINT32_MAX;
+    o->frags_front = ((uint64_t)bases_from_start + fragment_length - 1) / fragment_length;
+    o->frags_back = ((uint64_t)bases_from_end + fragment_length - 1) / fragment_length;
+    uint64_t bits = (uint64_t)(log2((double)max_unique_fragments * 1.5) + 1);  // :3508
+    o->table_size = 1ULL << bits;
+    int rc = sq_dalloc(ctx, (void **)&o->keys, o->table_size * 8, true);
+    if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&o->counts, o->table_size * 4, true);
+    if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&o->cnt, sizeof(OvCounters), true);
+    if (rc == SQ_OK)
+        rc = cudaMemsetAsync(&o->cnt->first_warn, 0xFF, 8, ctx->stream) == cudaSuccess ? SQ_OK : SQ_E_CUDA;
+    if (rc != SQ_OK) {
+        sq_overrep_destroy(o);
+        return rc;
+    }
+    *out = o;
+    return SQ_OK;
+}
+
+extern "C" void sq_overrep_destroy(sq_overrep *o) {
+    if (!o) return;
+    cudaSetDevice(o->ctx->device);
+    sq_dfree(o->ctx, o->keys);
+    sq_dfree(o->ctx, o->counts);
+    sq_dfree(o->ctx, o->cnt);
+    delete o;
+}
+
+static int ov_refresh_unique(sq_overrep *o) {
+    sq_ctx *ctx = o->ctx;
+    OvCounters *h = (OvCounters *)((char *)ctx->h_scratch + 1536);
+    CUDA_TRY(cudaMemcpyAsync(h, o->cnt, sizeof(OvCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    o->unique_known = o->unique_upper = h->n_unique;
+    o->full = o->unique_known >= o->max_unique;
+    return SQ_OK;
+}
+
+extern "C" int sq_overrep_add(sq_overrep *o, sq_batch *b) {
+    sq_ctx *ctx = o->ctx;
+    if (b->ctx != ctx) {
+        sq_set_error("record array belongs to another context");
+        return SQ_E_ARG;
+    }
+    const uint64_t n = b->n;
+    if (n == 0) return SQ_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // reads whose running index is a multiple of sample_every (:3833)
+    const uint64_t se = o->sample_every;
+    const uint64_t first = (se - o->n_seqs % se) % se;
+    const uint64_t n_sampled = first < n ? (n - first + se - 1) / se : 0;
+    const uint64_t record_base = o->n_seqs;
+    o->n_seqs += n;
+    o->n_sampled += n_sampled;
+    if (n_sampled == 0 || b->max_len < o->k) return SQ_OK;
+    // staging capacity needed by the longest read of this array
+    const uint64_t maxf = (b->max_len + o->k - 1) / o->k;
+    const uint64_t nf = std::min(o->frags_front, maxf - maxf / 2), nb = std::min(o->frags_back, maxf / 2);
+    const uint64_t total = nf + nb;
+    if (total == 0) return SQ_OK;
+    uint32_t fcap = 1;
+    while (2 * (uint64_t)fcap < 3 * total) fcap <<= 1;
+    if (fcap > OV_STAGE_MAX) {
+        sq_set_error("more than %d fragments per read are not supported yet (got %llu)",
+                     OV_STAGE_MAX * 2 / 3, (unsigned long long)total);
+        return SQ_E_LIMIT;
+    }
+    const uint64_t occ = n_sampled * fcap;
+    if (occ >= 0xFFFFFFFFULL) {
+        sq_set_error("record array too large for the fragment index");
+        return SQ_E_LIMIT;
+    }
+    uint64_t *frag_hash = nullptr;
+    uint32_t *frag_n = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&frag_hash, occ * 8, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&frag_n, n_sampled * 4, false));
+    SQ_LAUNCH(ctx, k_ov_fragments, sq_grid_for(ctx, n_sampled, OV_TPB, 16), OV_TPB, 0, b->view(), (uint32_t)first,
+              (uint32_t)se, (uint32_t)n_sampled, (uint32_t)o->k, o->frags_front, o->frags_back, fcap, frag_hash,
+              frag_n, o->cnt, record_base);
+    const uint64_t mask = o->table_size - 1;
+    const int grid = sq_grid_for(ctx, occ, 256, 16);
+    int rc = SQ_OK;
+    if (!o->full && o->unique_upper + n_sampled * total > o->max_unique) rc = ov_refresh_unique(o);
+    if (rc == SQ_OK) {
+        if (o->full) {
+            SQ_LAUNCH(ctx, k_ov_count, grid, 256, 0, frag_hash, frag_n, (uint32_t)n_sampled, fcap, o->keys,
+                      o->counts, mask, 0, o->cnt);
+        }
+        else if (o->unique_upper + n_sampled * total <= o->max_unique) {
+            SQ_LAUNCH(ctx, k_ov_count, grid, 256, 0, frag_hash, frag_n, (uint32_t)n_sampled, fcap, o->keys,
+                      o->counts, mask, 1, o->cnt);
+            o->unique_upper += n_sampled * total;
+        }
+        else {
+            // this array may cross the cap: admission in (read, staging slot) order
+            uint8_t *cls = nullptr;
+            uint32_t *flag = nullptr, *rank = nullptr;
+            OvScratch S;
+            uint32_t scap = 1024;
+            while (scap < 2 * occ) scap <<= 1;
+            S.mask = scap - 1;
+            rc = sq_dalloc(ctx, (void **)&cls, occ, false);
+            if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&flag, occ * 4, false);
+            if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&rank, occ * 4, false);
+            if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&S.key, (size_t)scap * 8, false);
+            if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&S.first, (size_t)scap * 4, false);
+            if (rc == SQ_OK) {
+                CUDA_TRY(cudaMemsetAsync(S.key, 0xFF, (size_t)scap * 8, ctx->stream));
+                CUDA_TRY(cudaMemsetAsync(S.first, 0xFF, (size_t)scap * 4, ctx->stream));
+                SQ_LAUNCH(ctx, k_ov_classify, grid, 256, 0, frag_hash, frag_n, (uint32_t)n_sampled, fcap, o->keys,
+                          mask, cls, S);
+                SQ_LAUNCH(ctx, k_ov_flags, grid, 256, 0, frag_hash, cls, occ, S, flag);
+                rc = sq_scan_exclusive_u32(ctx, flag, rank, (uint32_t)occ, nullptr);
+            }
+            if (rc == SQ_OK) {
+                const uint32_t K = (uint32_t)(o->max_unique - o->unique_known);
+                SQ_LAUNCH(ctx, k_ov_admit, grid, 256, 0, frag_hash, cls, occ, S, rank, K, o->keys, o->counts, mask,
+                          o->cnt);
+                rc = ov_refresh_unique(o);
+            }
+            sq_dfree(ctx, cls);
+            sq_dfree(ctx, flag);
+            sq_dfree(ctx, rank);
+            sq_dfree(ctx, S.key);
+            sq_dfree(ctx, S.first);
+        }
+    }
+    sq_dfree(ctx, frag_hash);
+    sq_dfree(ctx, frag_n);
+    return rc;
+}
+
+extern "C" int sq_overrep_sync(sq_overrep *o, sq_overrep_info *info) {
+    sq_ctx *ctx = o->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    OvCounters *h = (OvCounters *)((char *)ctx->h_scratch + 1536);
+    CUDA_TRY(cudaMemcpyAsync(h, o->cnt, sizeof(OvCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    o->unique_known = o->unique_upper = h->n_unique;
+    o->full = o->unique_known >= o->max_unique;
+    info->number_of_sequences = o->n_seqs;
+    info->sampled_sequences = o->n_sampled;
+    info->collected_unique_fragments = h->n_unique;
+    info->total_fragments = h->total_frags;
+    info->max_unique_fragments = o->max_unique;
+    info->table_size = o->table_size;
+    info->warn_records = h->warn_records;
+    info->first_warn_record = h->first_warn;
+    return SQ_OK;
+}
+
+extern "C" int sq_overrep_read(sq_overrep *o, uint64_t *kmers, uint32_t *counts, uint64_t *n) {
+    sq_ctx *ctx = o->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> hk(o->table_size);
+    std::vector<uint32_t> hc(o->table_size);
+    CUDA_TRY(cudaMemcpyAsync(hk.data(), o->keys, o->table_size * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(hc.data(), o->counts, o->table_size * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < o->table_size; i++)
+        if (hk[i]) {
+            kmers[w] = wang64_inverse(hk[i]);  // key -> sequence, as the getter does (:4042)
+            counts[w++] = hc[i];
+        }
+    *n = w;
+    return SQ_OK;
+}

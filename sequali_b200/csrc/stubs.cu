@@ -9,11 +9,6 @@
 extern "C" {
 int sq_batch_from_bam(sq_ctx *, const uint8_t *, uint64_t, const uint64_t *, uint64_t, sq_batch **out, uint64_t *) { *out = nullptr; NOT_YET("sq_batch_from_bam"); }
 
-int sq_adapters_create(sq_ctx *, const char *const *, uint64_t, sq_adapters **out) { *out = nullptr; NOT_YET("sq_adapters_create"); }
-void sq_adapters_destroy(sq_adapters *) {}
-int sq_adapters_add(sq_adapters *, sq_batch *) { NOT_YET("sq_adapters_add"); }
-int sq_adapters_sync(sq_adapters *, uint64_t *, uint64_t *) { NOT_YET("sq_adapters_sync"); }
-int sq_adapters_read(sq_adapters *, uint64_t, uint64_t *, uint64_t *) { NOT_YET("sq_adapters_read"); }
 
 int sq_pertile_create(sq_ctx *, sq_pertile **out) { *out = nullptr; NOT_YET("sq_pertile_create"); }
 void sq_pertile_destroy(sq_pertile *) {}
@@ -22,18 +17,7 @@ int sq_pertile_sync(sq_pertile *, sq_pertile_info *) { NOT_YET("sq_pertile_sync"
 int sq_pertile_skipped_name(sq_pertile *, uint8_t *, uint64_t, uint64_t *) { NOT_YET("sq_pertile_skipped_name"); }
 int sq_pertile_read(sq_pertile *, uint64_t *, double *, uint64_t *) { NOT_YET("sq_pertile_read"); }
 
-int sq_overrep_create(sq_ctx *, uint64_t, uint32_t, uint64_t, int64_t, int64_t, sq_overrep **out) { *out = nullptr; NOT_YET("sq_overrep_create"); }
-void sq_overrep_destroy(sq_overrep *) {}
-int sq_overrep_add(sq_overrep *, sq_batch *) { NOT_YET("sq_overrep_add"); }
-int sq_overrep_sync(sq_overrep *, sq_overrep_info *) { NOT_YET("sq_overrep_sync"); }
-int sq_overrep_read(sq_overrep *, uint64_t *, uint32_t *, uint64_t *) { NOT_YET("sq_overrep_read"); }
 
-int sq_dedup_create(sq_ctx *, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, sq_dedup **out) { *out = nullptr; NOT_YET("sq_dedup_create"); }
-void sq_dedup_destroy(sq_dedup *) {}
-int sq_dedup_add(sq_dedup *, sq_batch *) { NOT_YET("sq_dedup_add"); }
-int sq_dedup_add_pair(sq_dedup *, sq_batch *, sq_batch *) { NOT_YET("sq_dedup_add_pair"); }
-int sq_dedup_sync(sq_dedup *, sq_dedup_info *) { NOT_YET("sq_dedup_sync"); }
-int sq_dedup_read(sq_dedup *, uint64_t *, uint64_t *) { NOT_YET("sq_dedup_read"); }
 
 int sq_nanostats_create(sq_ctx *, sq_nanostats **out) { *out = nullptr; NOT_YET("sq_nanostats_create"); }
 void sq_nanostats_destroy(sq_nanostats *) {}

@@ -99,3 +99,100 @@ def test_qc_lowercase_and_iupac(sq):
         qual = "".join(chr(int(x)) for x in rng.integers(33, 127, size=ln))
         recs.append(f"@r{i}\n{seq}\n+\n{qual}\n")
     _qc_case(sq, "".join(recs).encode())
+
+
+# ----------------------------------------------------------------------------
+# adapters / dedup / overrepresented
+# ----------------------------------------------------------------------------
+def _run_modules(sq, text, adapters, bufsize, mods, dedup_kwargs=None, overrep_kwargs=None):
+    """Selected single-end modules through the GPU API and the oracle."""
+    recs, _ = orc.parse_fastq(text)
+    buf = np.frombuffer(text, np.uint8)
+    out_g, out_o = {}, {}
+    g = {}
+    if "adapters" in mods:
+        g["adapters"] = sq.AdapterCounter(adapters)
+    if "dedup" in mods:
+        g["dedup"] = sq.DedupEstimator(**(dedup_kwargs or dict(front_sequence_offset=64,
+                                                                back_sequence_offset=0)))
+    if "overrep" in mods:
+        g["overrep"] = sq.OverrepresentedSequences(**(overrep_kwargs or {}))
+    for arr in sq.FastqParser(io.BytesIO(text), bufsize):
+        for m in g.values():
+            m.add_record_array(arr)
+    if "adapters" in mods:
+        o = orc.AdapterCounter(adapters)
+        o.add(buf, recs)
+        H.assert_same(H.dump_adapters(g["adapters"]), H.odump_adapters(o))
+    if "dedup" in mods:
+        o = orc.DedupEstimator(**(dedup_kwargs or dict(front_sequence_offset=64,
+                                                        back_sequence_offset=0)))
+        o.add(buf, recs)
+        H.assert_same(H.dump_dedup(g["dedup"]), H.odump_dedup(o))
+    if "overrep" in mods:
+        o = orc.OverrepresentedSequences(**(overrep_kwargs or {}))
+        o.add(buf, recs)
+        H.assert_same(H.dump_overrep(g["overrep"]), H.odump_overrep(o))
+
+
+def test_adapters_illumina(sq):
+    text = synth.illumina_fastq(20000, seed=11, n_tiles=5, adapter_frac=0.3)
+    _run_modules(sq, text, H.ILLUMINA_ADAPTERS, 1 << 26, {"adapters"})
+
+
+def test_adapters_long_reads_many_words(sq):
+    text = synth.nanopore_fastq(300, mean_length=4000, max_length=60000, seed=12)
+    _run_modules(sq, text, H.NANOPORE_ADAPTERS, 1 << 26, {"adapters"})
+
+
+def test_adapters_odd_patterns(sq):
+    # long adapters, N letters (match any non-ACGT), lower case, repeats at chunk borders
+    adapters = ["A" * 64, "ACGTN", "GATTACAGATTACAGATTACAGATTACA", "nnnn", "T", "CCGGTTAA" * 8]
+    rng = np.random.default_rng(13)
+    recs = []
+    for i in range(400):
+        ln = int(rng.integers(0, 700))
+        seq = "".join(rng.choice(list("ACGTacgtNX"), p=[.2, .2, .2, .2, .03, .03, .03, .03, .04, .04])
+                      for _ in range(ln))
+        if ln > 300 and i % 3 == 0:
+            at = int(rng.integers(180, 260))
+            ins = adapters[i % len(adapters)]
+            seq = (seq[:at] + ins + seq[at:])[:max(ln, at + len(ins))]
+        recs.append(f"@r{i}\n{seq}\n+\n{'I' * len(seq)}\n")
+    _run_modules(sq, "".join(recs).encode(), adapters, 1 << 26, {"adapters"})
+
+
+def test_dedup_no_escalation(sq):
+    text = synth.illumina_fastq(20000, seed=21, n_tiles=5, dup_frac=0.2)
+    _run_modules(sq, text, [], 1 << 26, {"dedup"})
+
+
+@pytest.mark.parametrize("bufsize", [1 << 26, 200_000])
+def test_dedup_escalations(sq, bufsize):
+    # 200 slots -> several escalations inside and across record arrays
+    text = synth.illumina_fastq(30000, seed=22, n_tiles=5, dup_frac=0.3)
+    _run_modules(sq, text, [], bufsize, {"dedup"}, dedup_kwargs=dict(max_stored_fingerprints=200))
+
+
+def test_dedup_short_and_odd_fingerprints(sq):
+    text = synth.illumina_fastq(5000, length=40, seed=23, n_tiles=5, variable_length=True, dup_frac=0.3)
+    for kw in (dict(max_stored_fingerprints=150, front_sequence_length=3, back_sequence_length=5,
+                    front_sequence_offset=2, back_sequence_offset=1),
+               dict(max_stored_fingerprints=100, front_sequence_length=20, back_sequence_length=1,
+                    front_sequence_offset=0, back_sequence_offset=64)):
+        _run_modules(sq, text, [], 1 << 26, {"dedup"}, dedup_kwargs=kw)
+
+
+def test_overrep_default(sq):
+    text = synth.illumina_fastq(20000, seed=31, n_tiles=5, dup_frac=0.2)
+    _run_modules(sq, text, [], 1 << 26, {"overrep"})
+
+
+@pytest.mark.parametrize("bufsize", [1 << 26, 150_000])
+@pytest.mark.parametrize("kw", [dict(max_unique_fragments=300, sample_every=2),
+                                dict(max_unique_fragments=5000, sample_every=1, fragment_length=7),
+                                dict(max_unique_fragments=77, sample_every=3, fragment_length=5,
+                                     bases_from_start=12, bases_from_end=30)])
+def test_overrep_cap_crossing(sq, kw, bufsize):
+    text = synth.illumina_fastq(6000, length=90, seed=32, n_tiles=5, variable_length=True)
+    _run_modules(sq, text, [], bufsize, {"overrep"}, overrep_kwargs=kw)
