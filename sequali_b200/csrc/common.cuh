@@ -87,6 +87,10 @@ void sq_dfree(sq_ctx *ctx, void *p);
 // device-wide exclusive scan (scan.cu)
 int sq_scan_exclusive_u32(sq_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total_dev);
 
+// stable radix sort of (key, value) pairs by the low key_bits of the key (sort.cu)
+int sq_radix_sort_pairs(sq_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *tmp_keys, uint32_t *tmp_vals,
+                        uint32_t n, uint32_t key_bits);
+
 inline int sq_grid_for(sq_ctx *ctx, uint64_t work_items, int per_block, int max_waves = 8) {
     uint64_t blocks = (work_items + per_block - 1) / per_block;
     uint64_t cap = (uint64_t)ctx->num_sms * max_waves;

@@ -430,12 +430,12 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
         uint32_t idx[2] = {0, 0};
         uint64_t start = 0;
         if (r > 0) {
-            CUDA_TRY(cudaMemcpy(idx, nl + (4 * r - 1), 4, cudaMemcpyDeviceToHost));
+            SQ_TRY(sq_memcpy_d2h(ctx, idx, nl + (4 * r - 1), 4));
             start = (uint64_t)idx[0] + 1;
         }
         if (info->err_code == SQ_PARSE_NO_AT) info->err_pos = start;
         else if (info->err_code == SQ_PARSE_NO_PLUS) {
-            CUDA_TRY(cudaMemcpy(idx, nl + (4 * r + 1), 4, cudaMemcpyDeviceToHost));
+            SQ_TRY(sq_memcpy_d2h(ctx, idx, nl + (4 * r + 1), 4));
             info->err_pos = (uint64_t)idx[0] + 1;
         }
         else info->err_pos = start + 1;

@@ -280,7 +280,10 @@ extern "C" int sq_nanostats_create(sq_ctx *ctx, sq_nanostats **out) {
         memset(&init, 0, sizeof(init));
         init.fail_idx = ~0ULL;
         init.tag_err_idx = ~0ULL;
-        rc = cudaMemcpy(s->st, &init, sizeof(init), cudaMemcpyHostToDevice) == cudaSuccess ? SQ_OK : SQ_E_CUDA;
+        // same stream as the zero-fill above, so the two cannot swap
+        rc = cudaMemcpyAsync(s->st, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+                     cudaStreamSynchronize(ctx->stream) == cudaSuccess
+                 ? SQ_OK : SQ_E_CUDA;
     }
     if (rc != SQ_OK) {
         sq_nanostats_destroy(s);
@@ -333,8 +336,7 @@ extern "C" int sq_nanostats_add(sq_nanostats *s, sq_batch *b) {
         SQ_TRY(sq_batch_get_metas(b, metas.data()));
         s->skipped_name.resize(metas[r].name_len);
         if (metas[r].name_len)
-            CUDA_TRY(cudaMemcpy(s->skipped_name.data(), b->text + metas[r].name_off, metas[r].name_len,
-                                cudaMemcpyDeviceToHost));
+            SQ_TRY(sq_memcpy_d2h(ctx, s->skipped_name.data(), b->text + metas[r].name_off, metas[r].name_len));
     }
     s->n_added += b->n;
     return SQ_OK;

@@ -196,3 +196,87 @@ def test_overrep_default(sq):
 def test_overrep_cap_crossing(sq, kw, bufsize):
     text = synth.illumina_fastq(6000, length=90, seed=32, n_tiles=5, variable_length=True)
     _run_modules(sq, text, [], bufsize, {"overrep"}, overrep_kwargs=kw)
+
+
+# ----------------------------------------------------------------------------
+# whole pipelines, shaped like src/sequali/__main__.py:279-306
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("bufsize", [1 << 26, 250_000])
+def test_single_end_all_modules_illumina(sq, bufsize):
+    text = synth.illumina_fastq(30000, seed=41, n_tiles=40)
+    got = H.api_single_end(sq, text, H.ILLUMINA_ADAPTERS, buffersize=bufsize)
+    want = H.oracle_single_end(text, H.ILLUMINA_ADAPTERS, chunk_records=997)
+    H.assert_same(got, want)
+
+
+def test_single_end_random_tiles_variable_length(sq):
+    text = synth.illumina_fastq(20000, length=120, seed=42, n_tiles=150, tile_runs=False,
+                                variable_length=True)
+    got = H.api_single_end(sq, text, H.ILLUMINA_ADAPTERS, buffersize=400_000,
+                           dedup_kwargs=dict(max_stored_fingerprints=500),
+                           overrep_kwargs=dict(max_unique_fragments=2000, sample_every=3))
+    want = H.oracle_single_end(text, H.ILLUMINA_ADAPTERS,
+                               dedup_kwargs=dict(max_stored_fingerprints=500),
+                               overrep_kwargs=dict(max_unique_fragments=2000, sample_every=3))
+    H.assert_same(got, want)
+
+
+def test_single_end_nanopore(sq):
+    text = synth.nanopore_fastq(400, mean_length=5000, max_length=150_000, seed=43)
+    got = H.api_single_end(sq, text, H.NANOPORE_ADAPTERS, buffersize=1 << 21)
+    want = H.oracle_single_end(text, H.NANOPORE_ADAPTERS)
+    H.assert_same(got, want)
+
+
+def test_pertile_skips_mid_stream(sq):
+    good = synth.illumina_fastq(3000, length=50, seed=44, n_tiles=9)
+    bad = b"@not_an_illumina_header\nACGT\n+\nIIII\n"
+    more = synth.illumina_fastq(500, length=50, seed=45, n_tiles=9)
+    text = good + bad + more
+    got = H.api_single_end(sq, text, H.ILLUMINA_ADAPTERS, buffersize=60_000)
+    want = H.oracle_single_end(text, H.ILLUMINA_ADAPTERS)
+    H.assert_same(got, want)
+
+
+@pytest.mark.parametrize("bufsize", [1 << 26, 300_000])
+def test_paired_end(sq, bufsize):
+    t1, t2 = synth.paired_fastq(20000, seed=46)
+    got = H.api_paired(sq, t1, t2, buffersize=bufsize)
+    want = H.oracle_paired(t1, t2)
+    H.assert_same(got, want)
+
+
+def test_paired_adapter_table_cap(sq):
+    t1, t2 = synth.paired_fastq(8000, seed=47, error_rate=0.03)
+    r1, _ = orc.parse_fastq(t1)
+    r2, _ = orc.parse_fastq(t2)
+    o = orc.InsertSizeMetrics(max_adapters=150)
+    o.add_pair(np.frombuffer(t1, np.uint8), r1, np.frombuffer(t2, np.uint8), r2)
+    g = sq.InsertSizeMetrics(max_adapters=150)
+    p1, p2 = sq.FastqParser(io.BytesIO(t1), 200_000), sq.FastqParser(io.BytesIO(t2), 200_000)
+    for a in p1:
+        g.add_record_array_pair(a, p2.read(len(a)))
+    H.assert_same(H.dump_insert(g), H.odump_insert(o))
+
+
+def test_bam_nanopore(sq):
+    bam = synth.nanopore_ubam(300, mean_length=3000, max_length=80_000, seed=48)
+    stream = bam[len(synth.bam_header()):]
+    packed, recs, consumed, skipped = orc.decode_bam(stream)
+    assert consumed == len(stream)
+    oq, ons, oad = orc.QCMetrics(), orc.NanoStats(), orc.AdapterCounter(H.NANOPORE_ADAPTERS)
+    oq.add(packed, recs)
+    ons.add(packed, recs)
+    oad.add(packed, recs)
+    gq, gns, gad = sq.QCMetrics(), sq.NanoStats(), sq.AdapterCounter(H.NANOPORE_ADAPTERS)
+    got_bytes = b""
+    for arr in sq.BamParser(io.BytesIO(bam), 1 << 20):
+        gq.add_record_array(arr)
+        gns.add_record_array(arr)
+        gad.add_record_array(arr)
+        got_bytes += arr.obj
+        assert arr[0].tags().startswith(b"qsC")
+    assert got_bytes == packed.tobytes()
+    H.assert_same(H.dump_qc(gq), H.odump_qc(oq))
+    H.assert_same(H.dump_nano(gns), H.odump_nano(ons))
+    H.assert_same(H.dump_adapters(gad), H.odump_adapters(oad))
