@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- all-module QC throughput of the sequali hot path on B200.
+
+Metric (BASELINE.json): Gbases/s (and reads/s) of all default modules over
+synthetic NovaSeq-style 150 bp single-end reads (recipe C2).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3          # this repo (CUDA path)
+  python bench.py --impl reference --gpus 1 ...          # the reference's CPU path
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the whole hot loop (src/sequali/__main__.py:279-306:
+QCMetrics, PerTileQuality, OverrepresentedSequences, NanoStats, AdapterCounter,
+DedupEstimator) over the full input with fresh collectors.
+
+  value     input resident in HBM when the timed region starts (device parse +
+            all collectors + table read-back), CUDA events on the launch stream
+  e2e       the same loop through the public API with HOST text: FastqParser
+            .readinto -> pinned staging -> H2D -> kernels -> getters (D2H)
+  roofline  dominant kernel: algorithmic bytes (record text, read once) per
+            launch / its mean launch time (CUDA events), against MEASURED_PEAKS
+  cpu_baseline  the unmodified reference (oracle/_ref) on one host core over a
+            bounded prefix of the same input
+
+Multi-GPU: reads shard across ranks (each rank owns an equal, contiguous slice
+of the record stream: weak scaling), no data-path collective; the additive
+count tables are merged with one NCCL all-reduce inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ILLUMINA_ADAPTERS = ["AGATCGGAAGAG", "TGGAATTCTCGG", "GATCGTCGGACT", "CTGTCTCTTATA",
+                     "GGGGGGGGGGGG", "AAAAAAAAAAAA"]
+READ_LENGTH = 150
+METRIC = "gbases_per_s_all_module_qc"
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self._halt = index, [], set(), threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=5)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------
+# the hot loop, shaped like src/sequali/__main__.py:214-306 (single end)
+# ----------------------------------------------------------------------------
+def make_modules(mod):
+    return dict(
+        qc=mod.QCMetrics(), ptq=mod.PerTileQuality(), ov=mod.OverrepresentedSequences(),
+        ns=mod.NanoStats(), ad=mod.AdapterCounter(ILLUMINA_ADAPTERS),
+        dd=mod.DedupEstimator(front_sequence_offset=64, back_sequence_offset=0))
+
+
+def feed(mods, arr):
+    mods["qc"].add_record_array(arr)
+    mods["ptq"].add_record_array(arr)
+    mods["ov"].add_record_array(arr)
+    mods["ns"].add_record_array(arr)
+    mods["ad"].add_record_array(arr)
+    mods["dd"].add_record_array(arr)
+
+
+def read_results(mods):
+    """The getters the report calls (report_modules.py:2537-2605); returns the
+    additive tables as numpy arrays (merged across ranks) and result bytes."""
+    qc = mods["qc"]
+    t = [np.frombuffer(x, dtype=np.uint64) for x in (
+        qc.base_count_table(), qc.phred_count_table(), qc.end_anchored_base_count_table(),
+        qc.end_anchored_phred_count_table(), qc.gc_content(), qc.phred_scores())]
+    for _, f, r in mods["ad"].get_counts():
+        t += [np.frombuffer(f, dtype=np.uint64), np.frombuffer(r, dtype=np.uint64)]
+    tiles = mods["ptq"].get_tile_counts()
+    dups = mods["dd"].duplication_counts()
+    ov = mods["ov"].overrepresented_sequences(threshold_fraction=0.001, min_threshold=100)
+    nbytes = sum(x.nbytes for x in t) + len(dups) * 8 + len(tiles) * 16 * max(qc.max_length, 1)
+    return np.concatenate(t), nbytes, dict(tiles=len(tiles), dups=len(dups), overrep=len(ov),
+                                           reads=qc.number_of_reads)
+
+
+class HostText(io.RawIOBase):
+    """File-like over host memory: what a decompressor thread hands the parser."""
+
+    def __init__(self, arr: np.ndarray):
+        self._mv, self._pos = memoryview(arr), 0
+
+    def readinto(self, b):
+        n = min(len(b), len(self._mv) - self._pos)
+        b[:n] = self._mv[self._pos:self._pos + n]
+        self._pos += n
+        return n
+
+    def readable(self):
+        return True
+
+
+# ----------------------------------------------------------------------------
+def run_cuda(args):
+    import sequali_b200 as sq
+    from sequali_b200 import _lib
+    from sequali_b200.device import DeviceFastq
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    os.environ.setdefault("SEQUALI_B200_DEVICE", str(local))
+    ctx = _lib.Context.get()
+
+    n_reads = args.reads  # per GPU (weak scaling)
+    data = DeviceFastq.synth_illumina(n_reads, READ_LENGTH, seed=2, chunk_reads=args.chunk_reads,
+                                      first_read=rank * n_reads, total_reads=n_reads * world)
+    text_bytes = data.nbytes
+    bases = n_reads * READ_LENGTH
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def merge(tables: np.ndarray):
+        if dist is None:
+            return tables
+        import torch
+        t = torch.from_numpy(tables.astype(np.int64)).cuda()
+        # ranks may have seen different max lengths only for ragged input; C2 is fixed length
+        dist.all_reduce(t)
+        return t.cpu().numpy().astype(np.uint64)
+
+    def step_resident():
+        mods = make_modules(sq)
+        for arr in data.record_arrays():
+            feed(mods, arr)
+        tables, nbytes, summary = read_results(mods)
+        merge(tables)
+        return nbytes, summary
+
+    # ---- HBM-resident timing -------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d2h, summary = step_resident()
+    barrier()
+    ms = ctx.timer_stop()
+    wall = time.perf_counter() - t0
+    clocks = sampler.finish()
+    launches = ctx.launch_count - launches0
+    if dist is not None:
+        import torch
+        tm = torch.tensor([ms], dtype=torch.float64).cuda()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+    ms_per_step = ms / args.steps
+    value = world * bases / (ms_per_step * 1e-3) / 1e9
+
+    # ---- per-kernel times of one step (CUDA events around every launch) --------
+    ctx.profile(True)
+    step_resident()
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    kernel_ms = sum(v[1] for v in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1][1])
+    peak, peak_src = measured_peak_gbs()
+    n_chunks = len(data.chunks)
+    top_launch_bytes = text_bytes / n_chunks  # one launch per chunk reads that chunk's text once
+    top_ms_per_launch = top[1][1] / top[1][0]
+    achieved = top_launch_bytes / (top_ms_per_launch * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": top[0], "achieved": round(achieved, 1), "peak": peak,
+        "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": int(top_launch_bytes),
+        "launches_per_step": top[1][0], "ms_per_launch": round(top_ms_per_launch, 4),
+        "share_of_kernel_time": round(top[1][1] / kernel_ms, 3),
+        "all_kernels_gbs": round(text_bytes / (kernel_ms * 1e-3) / 1e9, 1),
+        "all_kernels_frac": round(text_bytes / (kernel_ms * 1e-3) / 1e9 / peak, 4),
+        "kernels_ms_per_step": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]},
+    }
+
+    # ---- end to end: host text -> parser -> collectors -> getters --------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_reads = min(n_reads, args.e2e_reads)
+        host, e2e_reads = data.to_host(e2e_reads)
+
+        def step_e2e():
+            mods = make_modules(sq)
+            for arr in sq.FastqParser(HostText(host), args.buffersize):
+                feed(mods, arr)
+            tables, nbytes, _ = read_results(mods)
+            merge(tables)
+            return nbytes
+
+        step_e2e()
+        barrier()
+        e2e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out_bytes = step_e2e()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        if dist is not None:
+            import torch
+            tm = torch.tensor([dt], dtype=torch.float64).cuda()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dt = float(tm.item())
+        e2e = {"value": round(world * e2e_reads * READ_LENGTH / dt / 1e9, 4), "unit": "Gbases/s",
+               "h2d_bytes_per_step": int(host.nbytes), "d2h_bytes_per_step": int(out_bytes),
+               "reads_per_step_per_gpu": int(e2e_reads), "steps": e2e_steps,
+               "buffersize": args.buffersize,
+               "path": "FastqParser(host file object).readinto -> pinned staging -> cudaMemcpyAsync "
+                       "-> kernels -> getters"}
+
+    # ---- CPU baseline: the unmodified reference on one core, bounded sample ----
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cpu = cpu_baseline(data, args.cpu_reads)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 4), "unit": "Gbases/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 (+f64 ordered sums)",
+            "data": "synthetic",
+            "config": {"workload": f"{n_reads} synthetic NovaSeq {READ_LENGTH} bp single-end reads per GPU, "
+                                   "936 tiles in runs, all default modules (QCMetrics, PerTileQuality, "
+                                   "OverrepresentedSequences, NanoStats, AdapterCounter, DedupEstimator)",
+                       "reads_per_gpu": n_reads, "read_length": READ_LENGTH,
+                       "text_bytes_per_gpu": int(text_bytes), "record_arrays_per_step": n_chunks,
+                       "l2": "inputs larger than L2" if text_bytes > 200e6 else "input smaller than L2",
+                       "parallelism": f"{world} x contiguous read shards, NCCL all-reduce of count tables"},
+            "reads_per_s": round(world * n_reads / (ms_per_step * 1e-3), 1),
+            "wall_ms_per_step": round(wall * 1e3 / args.steps, 3),
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "result_summary": summary,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own extension, built from
+# /root/reference into oracle/_ref by oracle/build_ref.sh (falls back to the
+# oracle port when that build is absent)
+# ----------------------------------------------------------------------------
+def import_cpu_impl():
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.exists(os.path.join(ref_dir, "sequali", "_qc.abi3.so")):
+        sys.path.insert(0, ref_dir)
+        import sequali  # type: ignore
+        return sequali, "reference"
+    return None, "port"
+
+
+def cpu_all_modules(text: bytes) -> float:
+    """Seconds for one pass of the reference's hot loop over `text` (1 thread)."""
+    ref, kind = import_cpu_impl()
+    t0 = time.perf_counter()
+    if ref is not None:
+        mods = make_modules(ref)
+        for arr in ref.FastqParser(io.BytesIO(text)):
+            feed(mods, arr)
+        mods["qc"].base_count_table()
+    else:
+        from tests import helpers as H
+        H.oracle_single_end(text, ILLUMINA_ADAPTERS, chunk_records=384)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(data, reads: int):
+    arr, n = data.to_host(reads)
+    host = arr.tobytes()
+    del arr
+    dt = cpu_all_modules(host)
+    _, kind = import_cpu_impl()
+    return {"value": round(n * READ_LENGTH / dt / 1e9, 5), "unit": "Gbases/s", "cores": 1,
+            "kind": kind, "reads_per_s": round(n / dt, 1),
+            "sample": f"first {n} reads of the same synthetic input, uncompressed in RAM, default "
+                      "128 KiB record arrays, one QC thread (the reference's QC loop is single-threaded)"}
+
+
+def _ref_worker(args):
+    seed, n, steps = args
+    from sequali_b200 import synth
+    text = synth.illumina_fastq(n, READ_LENGTH, seed=seed, n_tiles=936)
+    return [cpu_all_modules(text) for _ in range(steps)]
+
+
+def run_reference(args):
+    """The reference's CPU path on all host cores: one independent process per
+    core over its own shard (the usage README.rst:160-166 recommends), each step
+    a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n = args.ref_reads
+    _, kind = import_cpu_impl()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        times = pool.map(_ref_worker, [(1000 + i, n, args.warmup + args.steps) for i in range(cores)])
+        total_wall = time.perf_counter() - t0
+    per_step = [max(t[args.warmup + s] for t in times) for s in range(args.steps)]
+    dt = float(np.mean(per_step))
+    value = cores * n * READ_LENGTH / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": "Gbases/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/u64 (+f64 ordered sums)", "data": "synthetic",
+        "config": {"workload": f"bounded sample: {cores} processes x {n} synthetic NovaSeq {READ_LENGTH} bp "
+                               "reads per step, all default modules"},
+        "reads_per_s": round(cores * n / dt, 1),
+        "cpu_baseline": {"value": round(value, 5), "unit": "Gbases/s", "cores": cores, "kind": kind,
+                         "sample": f"{cores} independent single-threaded processes x {n} reads per step "
+                                   f"(the reference's QC loop has no internal threading); total wall {total_wall:.1f}s"},
+        "e2e": {"value": round(value, 5), "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU")
+    ap.add_argument("--chunk-reads", type=int, default=1 << 18, help="reads per record array")
+    ap.add_argument("--buffersize", type=int, default=64 << 20, help="e2e parser staging size")
+    ap.add_argument("--e2e-reads", type=int, default=20_000_000)
+    ap.add_argument("--cpu-reads", type=int, default=8_000_000)
+    ap.add_argument("--ref-reads", type=int, default=500_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

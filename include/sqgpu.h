@@ -81,6 +81,13 @@ SQ_API int sq_ctx_sync(sq_ctx *ctx);
 SQ_API void *sq_ctx_stream(sq_ctx *ctx);
 /* number of kernels this library has launched on ctx so far */
 SQ_API uint64_t sq_ctx_launch_count(sq_ctx *ctx);
+/* per-kernel device time (CUDA events around every launch on the context
+ * stream); report = "kernel launches total_ms" lines, most expensive first */
+SQ_API int sq_ctx_profile(sq_ctx *ctx, int enable);
+SQ_API int sq_ctx_profile_report(sq_ctx *ctx, char *buf, size_t cap);
+/* stopwatch: CUDA events recorded on the context stream */
+SQ_API int sq_timer_start(sq_ctx *ctx);
+SQ_API int sq_timer_stop(sq_ctx *ctx, double *elapsed_ms);
 /* pinned host staging memory for the parsers' read buffers */
 SQ_API void *sq_pinned_alloc(sq_ctx *ctx, size_t nbytes);
 SQ_API void sq_pinned_free(sq_ctx *ctx, void *p);

@@ -97,6 +97,10 @@ SIGNATURES = {
     "sq_ctx_sync": (_int, [_vp]),
     "sq_ctx_stream": (_vp, [_vp]),
     "sq_ctx_launch_count": (_u64, [_vp]),
+    "sq_ctx_profile": (_int, [_vp, _int]),
+    "sq_ctx_profile_report": (_int, [_vp, C.c_char_p, C.c_size_t]),
+    "sq_timer_start": (_int, [_vp]),
+    "sq_timer_stop": (_int, [_vp, _P(C.c_double)]),
     "sq_pinned_alloc": (_vp, [_vp, C.c_size_t]),
     "sq_pinned_free": (None, [_vp, _vp]),
     "sq_device_alloc": (_vp, [_vp, C.c_size_t]),
@@ -226,3 +230,24 @@ class Context:
     @property
     def launch_count(self) -> int:
         return self.lib.sq_ctx_launch_count(self.h)
+
+    def timer_start(self):
+        check(self.lib.sq_timer_start(self.h), "sq_timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        check(self.lib.sq_timer_stop(self.h, C.byref(ms)), "sq_timer_stop")
+        return ms.value
+
+    def profile(self, enable: bool):
+        check(self.lib.sq_ctx_profile(self.h, 1 if enable else 0), "sq_ctx_profile")
+
+    def profile_report(self) -> dict:
+        """{kernel: (launches, total_ms)} measured with CUDA events on the launch stream."""
+        buf = C.create_string_buffer(1 << 16)
+        check(self.lib.sq_ctx_profile_report(self.h, buf, len(buf)), "sq_ctx_profile_report")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split()
+            out[name] = (int(n), float(ms))
+        return out

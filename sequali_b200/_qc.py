@@ -155,12 +155,19 @@ class FastqRecordView:
 
 
 class _PinnedBuffer:
-    """A pinned staging buffer; returned to the allocator when released."""
+    """A pinned staging buffer.  cudaMallocHost is slow (it page-locks), so
+    released buffers go back to a small per-size pool instead of the driver."""
     __slots__ = ("ptr", "size", "_ctx")
+    _pool: dict = {}
+    _POOL_BYTES = 1 << 30
 
     def __init__(self, ctx: Context, size: int):
         self._ctx = ctx
         self.size = size
+        free = _PinnedBuffer._pool.get(size)
+        if free:
+            self.ptr = free.pop()
+            return
         self.ptr = ctx.lib.sq_pinned_alloc(ctx.h, size)
         if not self.ptr:
             raise MemoryError(_lib.last_error())
@@ -170,9 +177,15 @@ class _PinnedBuffer:
         return memoryview((_C.c_char * (stop - start)).from_address(self.ptr + start)).cast("B")
 
     def __del__(self):
-        if getattr(self, "ptr", None):
-            self._ctx.lib.sq_pinned_free(self._ctx.h, self.ptr)
-            self.ptr = None
+        ptr = getattr(self, "ptr", None)
+        if not ptr:
+            return
+        self.ptr = None
+        pool = _PinnedBuffer._pool.setdefault(self.size, [])
+        if (len(pool) + 1) * self.size <= _PinnedBuffer._POOL_BYTES or not pool:
+            pool.append(ptr)
+        else:
+            self._ctx.lib.sq_pinned_free(self._ctx.h, ptr)
 
 
 class FastqRecordArrayView:

@@ -45,7 +45,14 @@ struct sq_ctx {
     double *d_err_table = nullptr;      // [94]  10^-(q/10), host libm generated
     double *d_phred_thresholds = nullptr;  // [94] bucket edges derived from host log10
     uint32_t func_attr_done = 0;           // bit per kernel family whose smem opt-in was set
+    // optional per-kernel timing (CUDA events on the launch stream), see sq_ctx_profile
+    bool profile = false;
+    struct ProfEvent { const char *name; cudaEvent_t start, stop; };
+    std::vector<ProfEvent> prof_events;
+    cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
 };
+void sq_prof_begin(sq_ctx *ctx, const char *name);
+void sq_prof_end(sq_ctx *ctx);
 
 // Device-side view of a record array.  Offsets index `text`.
 struct BatchView {
@@ -101,7 +108,9 @@ inline int sq_grid_for(sq_ctx *ctx, uint64_t work_items, int per_block, int max_
 
 #define SQ_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
     do {                                                                       \
+        if ((ctx)->profile) sq_prof_begin((ctx), #kernel);                     \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);       \
+        if ((ctx)->profile) sq_prof_end((ctx));                                \
         (ctx)->launches++;                                                     \
         CUDA_TRY(cudaGetLastError());                                          \
     } while (0)

@@ -127,6 +127,75 @@ extern "C" void sq_ctx_destroy(sq_ctx *ctx) {
     delete ctx;
 }
 
+// ---- per-kernel timing: CUDA events around every launch on the launch stream ----
+void sq_prof_begin(sq_ctx *ctx, const char *name) {
+    sq_ctx::ProfEvent e;
+    e.name = name;
+    cudaEventCreate(&e.start);
+    cudaEventCreate(&e.stop);
+    cudaEventRecord(e.start, ctx->stream);
+    ctx->prof_events.push_back(e);
+}
+void sq_prof_end(sq_ctx *ctx) { cudaEventRecord(ctx->prof_events.back().stop, ctx->stream); }
+
+extern "C" int sq_ctx_profile(sq_ctx *ctx, int enable) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (auto &e : ctx->prof_events) {
+        cudaEventDestroy(e.start);
+        cudaEventDestroy(e.stop);
+    }
+    ctx->prof_events.clear();
+    ctx->profile = enable != 0;
+    return SQ_OK;
+}
+// "kernel launches total_ms\n" per kernel, most expensive first
+extern "C" int sq_ctx_profile_report(sq_ctx *ctx, char *buf, size_t cap) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    struct Row { std::string name; uint64_t n; double ms; };
+    std::vector<Row> rows;
+    for (auto &e : ctx->prof_events) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e.start, e.stop);
+        bool found = false;
+        for (auto &r : rows)
+            if (r.name == e.name) { r.n++; r.ms += ms; found = true; break; }
+        if (!found) rows.push_back({e.name, 1, ms});
+    }
+    for (size_t i = 0; i < rows.size(); i++)
+        for (size_t j = i + 1; j < rows.size(); j++)
+            if (rows[j].ms > rows[i].ms) std::swap(rows[i], rows[j]);
+    std::string out;
+    char line[256];
+    for (auto &r : rows) {
+        snprintf(line, sizeof(line), "%s %llu %.6f\n", r.name.c_str(), (unsigned long long)r.n, r.ms);
+        out += line;
+    }
+    if (cap) {
+        size_t k = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), k);
+        buf[k] = 0;
+    }
+    return SQ_OK;
+}
+
+// device-side stopwatch on the launch stream (bench.py times steps with it)
+extern "C" int sq_timer_start(sq_ctx *ctx) {
+    if (!ctx->timer_start) {
+        CUDA_TRY(cudaEventCreate(&ctx->timer_start));
+        CUDA_TRY(cudaEventCreate(&ctx->timer_stop));
+    }
+    CUDA_TRY(cudaEventRecord(ctx->timer_start, ctx->stream));
+    return SQ_OK;
+}
+extern "C" int sq_timer_stop(sq_ctx *ctx, double *ms) {
+    CUDA_TRY(cudaEventRecord(ctx->timer_stop, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(ctx->timer_stop));
+    float f = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, ctx->timer_start, ctx->timer_stop));
+    *ms = f;
+    return SQ_OK;
+}
+
 extern "C" int sq_ctx_sync(sq_ctx *ctx) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return SQ_OK;
