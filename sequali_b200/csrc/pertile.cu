@@ -10,6 +10,8 @@
 //                    order and extends the chain that lives in HBM; consecutive
 //                    threads read consecutive quality bytes of the same read
 //   k_pt_lengths     length_counts[tile][L-1]++ (order free)
+#include <math.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -37,6 +39,7 @@ struct sq_pertile {
     double *errors = nullptr;       // [slot_cap][len_cap]
     uint64_t *lengths = nullptr;    // [slot_cap][len_cap]
     PtState *st = nullptr;
+    uint64_t *lut = nullptr;        // [PT_LUT_NK][94] in-binade increments r_k(10^-(q/10))
     bool skipped = false;
     uint64_t skipped_record = 0;
     std::vector<uint8_t> skipped_name;
@@ -147,34 +150,272 @@ k_pt_segments(const uint32_t *__restrict__ sorted_slot, uint32_t n, uint32_t *se
     }
 }
 
+// ---------------------------------------------------------------------------
+// Ordered double sums without a serial pass over the reads.
+//
+// The reference extends total_errors[tile][pos] by one rounded double addition
+// per read (:3199-3219).  While the running sum s stays inside one binade
+// [2^k, 2^(k+1)) every such addition moves s by a whole number of ulps:
+// fl(s + e) = s + round_to_nearest(e / ulp_k) * ulp_k, and on the IEEE bit
+// pattern that is the integer addition bits(s) += r_k(e).  Integer additions
+// are associative, so a run of reads that keeps s inside its binade (and meets
+// no round-half tie, whose direction would depend on the parity of s) can be
+// summed in any order and applied at once; only the few additions that cross
+// a power of two or tie are executed as real, ordered double additions.
+//
+//   k_pt_approx   per (segment of consecutive reads of one tile, position):
+//                 approximate (float) sum of the error rates
+//   k_pt_guess    per chain: prefix of those sums from the chain's exact state
+//                 -> the binade each segment is expected to start in
+//   k_pt_incr     per (segment, position): exact integer sum of r_k(e) for the
+//                 guessed binade k (poisoned by a tie or an increment that
+//                 cannot stay in the binade)
+//   k_pt_chain    one warp per chain walks its segments 32 at a time, verifies
+//                 the guess against the exact state and applies the integer
+//                 sums; a segment that fails the check is replayed read by read
+//                 (32 reads per step, same integer rule, real additions at the
+//                 crossing points).  Guesses are hints: every accepted step is
+//                 verified exactly, so the result is bit-identical to the serial
+//                 chain whatever the guess was.
+// ---------------------------------------------------------------------------
+constexpr uint64_t PT_HARD = 1ULL << 53;          // no valid in-binade increment reaches this
+constexpr uint64_t PT_MANT = (1ULL << 52) - 1;
+constexpr int PT_LUT_KMIN = 1023 - 30;            // binades 2^-30 .. 2^25 are tabulated
+constexpr int PT_LUT_NK = 56;
+
+// r_k(e): e in ulps of binade k (biased exponent), round to nearest; PT_HARD when
+// the addition cannot be expressed that way (tie, e >= 2^k, s == 0)
+__host__ __device__ inline uint64_t pt_increment(uint32_t k, uint64_t ebits) {
+    const int d = (int)k - (int)(ebits >> 52);
+    if (k == 0 || d < 1) return PT_HARD;
+    if (d >= 64) return 0;
+    const uint64_t m = (ebits & PT_MANT) | (1ULL << 52);
+    uint64_t r = m >> d;
+    const uint64_t rem = m & ((1ULL << d) - 1), half = 1ULL << (d - 1);
+    if (rem > half) r++;
+    else if (rem == half) return PT_HARD;
+    return r;
+}
+
+struct PtSeg {  // a run of consecutive (tile-sorted) reads of one tile
+    uint32_t lo, hi, slot, pad;
+};
+
 __global__ void __launch_bounds__(PT_TPB)
-k_pt_accumulate(BatchView bv, const uint32_t *__restrict__ order, const uint32_t *__restrict__ seg_lo,
-                const uint32_t *__restrict__ seg_hi, uint32_t n_slots, uint32_t width, double *errors,
-                uint64_t len_cap, const double *__restrict__ err_tab, uint64_t base, PtState *st) {
+k_pt_seg_counts(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_hi, uint32_t n_slots,
+                uint32_t seg_rows, uint32_t *__restrict__ nseg) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x)
+        nseg[s] = (seg_hi[s] - seg_lo[s] + seg_rows - 1) / seg_rows;
+}
+__global__ void __launch_bounds__(PT_TPB)
+k_pt_seg_fill(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_hi,
+              const uint32_t *__restrict__ seg_first, uint32_t n_slots, uint32_t seg_rows, PtSeg *__restrict__ segs) {
+    // one warp per tile: lanes write that tile's segment descriptors
+    const uint32_t warps = gridDim.x * (PT_TPB / 32);
+    for (uint32_t s = blockIdx.x * (PT_TPB / 32) + (threadIdx.x >> 5); s < n_slots; s += warps) {
+        const uint32_t lo = seg_lo[s], hi = seg_hi[s], first = seg_first[s];
+        const uint32_t cnt = (hi - lo + seg_rows - 1) / seg_rows;
+        for (uint32_t j = lane_id(); j < cnt; j += 32) {
+            PtSeg g;
+            g.lo = lo + j * seg_rows;
+            g.hi = min(hi, g.lo + seg_rows);
+            g.slot = s;
+            g.pad = 0;
+            segs[first + j] = g;
+        }
+    }
+}
+
+// Vertical walk shared by k_pt_approx / k_pt_incr: a thread owns four positions
+// (col0..col0+3) of one segment; the CG threads of a row group read consecutive
+// words of the same quality line.
+template <bool EXACT>
+__global__ void __launch_bounds__(PT_TPB)
+k_pt_segment_sums(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__restrict__ segs,
+                  const uint32_t *__restrict__ n_segs_p, uint32_t CG, uint32_t RG, uint32_t width4,
+                  const double *__restrict__ err_tab, const uint64_t *__restrict__ lut,
+                  const uint16_t *__restrict__ kguess, float *__restrict__ approx, uint64_t *__restrict__ incr,
+                  uint64_t base, PtState *st) {
+    __shared__ float s_errf[96];
+    extern __shared__ uint64_t s_lut[];  // [PT_LUT_NK][94] when EXACT
+    if (EXACT) {
+        for (uint32_t i = threadIdx.x; i < PT_LUT_NK * 94; i += PT_TPB) s_lut[i] = lut[i];
+    }
+    else {
+        for (uint32_t i = threadIdx.x; i < 94; i += PT_TPB) s_errf[i] = (float)err_tab[i];
+    }
+    __syncthreads();
+    const uint32_t n_segs = *n_segs_p;
+    const uint32_t rg = threadIdx.x / CG, cg = threadIdx.x - rg * CG;
+    if (rg >= RG) return;
+    const uint32_t col0 = blockIdx.y * CG * 4 + cg * 4;
+    if (col0 >= width4) return;
+    for (uint32_t g = blockIdx.x * RG + rg; g < n_segs; g += gridDim.x * RG) {
+        const PtSeg sg = segs[g];
+        float fa[4] = {0.f, 0.f, 0.f, 0.f};
+        uint64_t ia[4] = {0, 0, 0, 0};
+        const uint64_t *lrow[4];
+        if (EXACT) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int k = (int)kguess[(uint64_t)g * width4 + col0 + j] - PT_LUT_KMIN;
+                if (k < 0 || k >= PT_LUT_NK) {
+                    lrow[j] = s_lut;
+                    ia[j] = PT_HARD;
+                }
+                else lrow[j] = s_lut + k * 94;
+            }
+        }
+        for (uint32_t i = sg.lo; i < sg.hi; i++) {
+            const uint32_t r = order[i];
+            const uint32_t L = bv.seq_len[r];
+            if (L <= col0) continue;
+            const uint32_t nvalid = min(4u, L - col0);
+            const uint32_t w = load_u32_unaligned(bv.text + bv.qual_off[r] + col0) - 0x21212121u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if ((uint32_t)j < nvalid) {
+                    const uint32_t q = (w >> (8 * j)) & 0xFF;
+                    if (q > 93) {
+                        if (!EXACT)
+                            atomicMin(&st->err_key, (unsigned long long)((base + r) << 8 | ((q + 33) & 0xFF)));
+                    }
+                    else if (EXACT) ia[j] += lrow[j][q];
+                    else fa[j] += s_errf[q];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (EXACT) incr[(uint64_t)g * width4 + col0 + j] = ia[j] < PT_HARD ? ia[j] : PT_HARD;
+            else approx[(uint64_t)g * width4 + col0 + j] = fa[j];
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t y = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= (uint32_t)o) v += y;
+    }
+    return v;
+}
+
+// one warp per chain (tile slot, position): expected binade at the start of every segment
+__global__ void __launch_bounds__(PT_TPB)
+k_pt_guess(const uint32_t *__restrict__ seg_first, const uint32_t *__restrict__ nseg, uint32_t n_slots,
+           uint32_t width, uint32_t width4, const float *__restrict__ approx, const double *__restrict__ errors,
+           uint64_t len_cap, uint16_t *__restrict__ kguess) {
+    const uint64_t chains = (uint64_t)n_slots * width;
+    const uint64_t warps = (uint64_t)gridDim.x * (PT_TPB / 32);
+    for (uint64_t c = (uint64_t)blockIdx.x * (PT_TPB / 32) + (threadIdx.x >> 5); c < chains; c += warps) {
+        const uint32_t s = (uint32_t)(c / width), pos = (uint32_t)(c % width);
+        const uint32_t cnt = nseg[s];
+        if (cnt == 0) continue;
+        const uint32_t first = seg_first[s];
+        double run = errors[(uint64_t)s * len_cap + pos];
+        for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+            const uint32_t j = j0 + lane_id();
+            double v = j < cnt ? (double)approx[(uint64_t)(first + j) * width4 + pos] : 0.0;
+            double x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                double y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane_id() >= (uint32_t)o) x += y;
+            }
+            const double start = run + (x - v);
+            if (j < cnt)
+                kguess[(uint64_t)(first + j) * width4 + pos] = (uint16_t)((uint64_t)__double_as_longlong(start) >> 52);
+            run += __shfl_sync(0xffffffffu, x, 31);
+        }
+    }
+}
+
+// replay rows [lo, hi) of the tile-sorted order on chain `pos`, bit-exact
+__device__ uint64_t pt_replay_rows(uint64_t sbits, const BatchView &bv, const uint32_t *__restrict__ order,
+                                   uint32_t lo, uint32_t hi, uint32_t pos, const double *s_err) {
+    uint32_t i = lo;
+    while (i < hi) {
+        const uint32_t ii = i + lane_id();
+        uint64_t ebits = 0;
+        bool has = false;
+        if (ii < hi) {
+            const uint32_t r = order[ii];
+            if (pos < bv.seq_len[r]) {
+                const uint32_t q = (uint8_t)(bv.text[bv.qual_off[r] + pos] - 33);
+                if (q <= 93) {
+                    has = true;
+                    ebits = (uint64_t)__double_as_longlong(s_err[q]);
+                }
+            }
+        }
+        const uint32_t k = (uint32_t)(sbits >> 52);
+        uint64_t inc = has ? pt_increment(k, ebits) : 0;
+        const bool hard = inc >= PT_HARD;
+        if (hard) inc = 0;
+        const uint64_t incl = warp_incl_scan_u64(inc);
+        const bool stays = (uint32_t)((sbits + incl) >> 52) == k;
+        const uint32_t nv = min(32u, hi - i);
+        const uint32_t bad = __ballot_sync(0xffffffffu, ii < hi && (hard || !stays));
+        const uint32_t f = bad ? (uint32_t)__ffs(bad) - 1 : 32u;
+        const uint32_t nacc = min(f, nv);
+        if (nacc) sbits += __shfl_sync(0xffffffffu, incl, nacc - 1);
+        i += nacc;
+        if (f < nv) {  // a real, ordered addition: crosses a power of two, ties, or starts from 0.0
+            const uint64_t eb = __shfl_sync(0xffffffffu, ebits, f);
+            const double s = __longlong_as_double((long long)sbits) + __longlong_as_double((long long)eb);
+            sbits = (uint64_t)__double_as_longlong(s);
+            i += 1;
+        }
+    }
+    return sbits;
+}
+
+__global__ void __launch_bounds__(PT_TPB)
+k_pt_chain(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__restrict__ segs,
+           const uint32_t *__restrict__ seg_first, const uint32_t *__restrict__ nseg, uint32_t n_slots,
+           uint32_t width, uint32_t width4, const uint16_t *__restrict__ kguess, const uint64_t *__restrict__ incr,
+           double *errors, uint64_t len_cap, const double *__restrict__ err_tab) {
     __shared__ double s_err[94];
     for (uint32_t i = threadIdx.x; i < 94; i += PT_TPB) s_err[i] = err_tab[i];
     __syncthreads();
-    const uint64_t total = (uint64_t)n_slots * width;
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t s = (uint32_t)(t / width), pos = (uint32_t)(t % width);
-        const uint32_t lo = seg_lo[s], hi = seg_hi[s];
-        if (lo >= hi) continue;
+    const uint64_t chains = (uint64_t)n_slots * width;
+    const uint64_t warps = (uint64_t)gridDim.x * (PT_TPB / 32);
+    for (uint64_t c = (uint64_t)blockIdx.x * (PT_TPB / 32) + (threadIdx.x >> 5); c < chains; c += warps) {
+        const uint32_t s = (uint32_t)(c / width), pos = (uint32_t)(c % width);
+        const uint32_t cnt = nseg[s];
+        if (cnt == 0) continue;
+        const uint32_t first = seg_first[s];
         double *cell = errors + (uint64_t)s * len_cap + pos;
-        double acc = *cell;
-        bool touched = false;
-        for (uint32_t i = lo; i < hi; i++) {
-            const uint32_t r = order[i];
-            if (pos >= bv.seq_len[r]) continue;
-            const uint8_t c = bv.text[bv.qual_off[r] + pos];
-            const uint32_t q = (uint8_t)(c - 33);
-            if (q > 93) {
-                atomicMin(&st->err_key, (unsigned long long)((base + r) << 8 | c));
-                continue;
+        uint64_t sbits = (uint64_t)__double_as_longlong(*cell);
+        uint32_t j = 0;
+        while (j < cnt) {
+            const uint32_t jj = j + lane_id();
+            uint64_t inc = 0;
+            uint32_t kg = 0;
+            if (jj < cnt) {
+                inc = incr[(uint64_t)(first + jj) * width4 + pos];
+                kg = kguess[(uint64_t)(first + jj) * width4 + pos];
             }
-            acc += s_err[q];  // read order within the tile: the reference's chain (:3199-3219)
-            touched = true;
+            const uint32_t k = (uint32_t)(sbits >> 52);
+            const bool hard = inc >= PT_HARD || kg != k;
+            if (hard) inc = 0;
+            const uint64_t incl = warp_incl_scan_u64(inc);
+            const bool stays = (uint32_t)((sbits + incl) >> 52) == k;
+            const uint32_t nv = min(32u, cnt - j);
+            const uint32_t bad = __ballot_sync(0xffffffffu, jj < cnt && (hard || !stays));
+            const uint32_t f = bad ? (uint32_t)__ffs(bad) - 1 : 32u;
+            const uint32_t nacc = min(f, nv);
+            if (nacc) sbits += __shfl_sync(0xffffffffu, incl, nacc - 1);
+            j += nacc;
+            if (f < nv) {
+                const PtSeg sg = segs[first + j];
+                sbits = pt_replay_rows(sbits, bv, order, sg.lo, sg.hi, pos, s_err);
+                j += 1;
+            }
         }
-        if (touched) *cell = acc;
+        if (lane_id() == 0) *cell = __longlong_as_double((long long)sbits);
     }
 }
 
@@ -187,7 +428,18 @@ extern "C" int sq_pertile_create(sq_ctx *ctx, sq_pertile **out) {
     int rc = sq_dalloc(ctx, (void **)&p->map_keys, (size_t)PT_MAP_CAP * 8, false);
     if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&p->map_vals, (size_t)PT_MAP_CAP * 4, true);
     if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&p->st, sizeof(PtState), true);
+    if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&p->lut, (size_t)PT_LUT_NK * 94 * 8, false);
     if (rc == SQ_OK) {
+        std::vector<uint64_t> lut((size_t)PT_LUT_NK * 94);
+        for (int k = 0; k < PT_LUT_NK; k++)
+            for (int q = 0; q < 94; q++) {
+                const double e = pow(10.0, -((double)q / 10.0));  // same table as sq_ctx::d_err_table
+                uint64_t eb;
+                memcpy(&eb, &e, 8);
+                lut[(size_t)k * 94 + q] = pt_increment((uint32_t)(PT_LUT_KMIN + k), eb);
+            }
+        CUDA_TRY(cudaMemcpyAsync(p->lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         CUDA_TRY(cudaMemsetAsync(p->map_keys, 0xFF, (size_t)PT_MAP_CAP * 8, ctx->stream));
         CUDA_TRY(cudaMemsetAsync(&p->st->fail_idx, 0xFF, 16, ctx->stream));
     }
@@ -208,6 +460,7 @@ extern "C" void sq_pertile_destroy(sq_pertile *p) {
     sq_dfree(p->ctx, p->errors);
     sq_dfree(p->ctx, p->lengths);
     sq_dfree(p->ctx, p->st);
+    sq_dfree(p->ctx, p->lut);
     delete p;
 }
 
@@ -238,6 +491,59 @@ static int pt_grow(sq_pertile *p, uint64_t slots, uint64_t len) {
     p->slot_tile = nt;
     p->slot_cap = nsc;
     p->len_cap = nlc;
+    return SQ_OK;
+}
+
+// ordered per-(tile, position) sums for one tile-sorted record array (see the note above k_pt_approx)
+static int pt_accumulate(sq_pertile *p, sq_batch *b, const uint32_t *order, const uint32_t *seg_lo,
+                         const uint32_t *seg_hi, uint32_t n_slots, uint32_t width, uint64_t base) {
+    sq_ctx *ctx = p->ctx;
+    const uint32_t n = (uint32_t)b->n;
+    uint32_t CG = (width + 3) / 4;
+    const uint32_t width4 = CG * 4;
+    if (CG > PT_TPB) CG = PT_TPB;
+    const uint32_t RG = PT_TPB / CG;
+    const uint32_t windows = (width4 + CG * 4 - 1) / (CG * 4);
+    // segment length: enough (segment, 4-position) threads to fill the machine twice over
+    uint64_t want = (uint64_t)n * (width4 / 4) / ((uint64_t)ctx->num_sms * 4096);
+    uint32_t seg_rows = 32;
+    while (seg_rows < 1024 && seg_rows * 2 <= want) seg_rows *= 2;
+    const uint32_t seg_cap = n / seg_rows + n_slots + 1;
+    uint32_t *nseg = nullptr, *seg_first = nullptr, *n_segs_dev = nullptr;
+    PtSeg *segs = nullptr;
+    float *approx = nullptr;
+    uint64_t *incr = nullptr;
+    uint16_t *kguess = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&nseg, (size_t)n_slots * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&seg_first, (size_t)n_slots * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&n_segs_dev, 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&segs, (size_t)seg_cap * sizeof(PtSeg), false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&approx, (size_t)seg_cap * width4 * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&incr, (size_t)seg_cap * width4 * 8, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&kguess, (size_t)seg_cap * width4 * 2, false));
+    const int slot_grid = sq_grid_for(ctx, n_slots, PT_TPB, 8);
+    SQ_LAUNCH(ctx, k_pt_seg_counts, slot_grid, PT_TPB, 0, seg_lo, seg_hi, n_slots, seg_rows, nseg);
+    SQ_TRY(sq_scan_exclusive_u32(ctx, nseg, seg_first, n_slots, n_segs_dev));
+    SQ_LAUNCH(ctx, k_pt_seg_fill, sq_grid_for(ctx, (uint64_t)n_slots * 32, PT_TPB, 8), PT_TPB, 0, seg_lo, seg_hi,
+              seg_first, n_slots, seg_rows, segs);
+    dim3 sgrid((unsigned)sq_grid_for(ctx, (uint64_t)seg_cap, (int)RG, 64), windows);
+    const BatchView bv = b->view();
+    SQ_LAUNCH(ctx, k_pt_segment_sums<false>, sgrid, PT_TPB, 0, bv, order, segs, n_segs_dev, CG, RG, width4,
+              ctx->d_err_table, p->lut, kguess, approx, incr, base, p->st);
+    const int chain_grid = sq_grid_for(ctx, (uint64_t)n_slots * width * 32, PT_TPB, 32);
+    SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, seg_first, nseg, n_slots, width, width4, approx, p->errors,
+              p->len_cap, kguess);
+    SQ_LAUNCH(ctx, k_pt_segment_sums<true>, sgrid, PT_TPB, (size_t)PT_LUT_NK * 94 * 8, bv, order, segs, n_segs_dev,
+              CG, RG, width4, ctx->d_err_table, p->lut, kguess, approx, incr, base, p->st);
+    SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, bv, order, segs, seg_first, nseg, n_slots, width, width4,
+              kguess, incr, p->errors, p->len_cap, ctx->d_err_table);
+    sq_dfree(ctx, nseg);
+    sq_dfree(ctx, seg_first);
+    sq_dfree(ctx, n_segs_dev);
+    sq_dfree(ctx, segs);
+    sq_dfree(ctx, approx);
+    sq_dfree(ctx, incr);
+    sq_dfree(ctx, kguess);
     return SQ_OK;
 }
 
@@ -303,12 +609,7 @@ extern "C" int sq_pertile_add(sq_pertile *p, sq_batch *b) {
             uint32_t *seg_lo = seg, *seg_hi = seg + h->n_slots;
             SQ_LAUNCH(ctx, k_pt_segments, grid, PT_TPB, 0, slot, n, seg_lo, seg_hi);
             const uint32_t width = b->max_len;
-            if (width) {
-                const uint64_t work = (uint64_t)h->n_slots * width;
-                SQ_LAUNCH(ctx, k_pt_accumulate, sq_grid_for(ctx, work, PT_TPB, 32), PT_TPB, 0, b->view(), idx,
-                          seg_lo, seg_hi, h->n_slots, width, p->errors, p->len_cap, ctx->d_err_table, base,
-                          p->st);
-            }
+            if (width) rc = pt_accumulate(p, b, idx, seg_lo, seg_hi, h->n_slots, width, base);
         }
     }
     if (rc == SQ_OK && h->fail_idx != ~0ULL) {

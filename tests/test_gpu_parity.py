@@ -280,3 +280,44 @@ def test_bam_nanopore(sq):
     H.assert_same(H.dump_qc(gq), H.odump_qc(oq))
     H.assert_same(H.dump_nano(gns), H.odump_nano(ons))
     H.assert_same(H.dump_adapters(gad), H.odump_adapters(oad))
+
+
+# ----------------------------------------------------------------------------
+# PerTileQuality: long ordered chains (many reads per tile), power-of-two
+# crossings, round-half ties (phred 0..3 against sums in [1, 4)), several arrays
+# ----------------------------------------------------------------------------
+def _pertile_case(sq, text, bufsize):
+    recs, _ = orc.parse_fastq(text)
+    o = orc.PerTileQuality()
+    o.add(np.frombuffer(text, np.uint8), recs)
+    g = sq.PerTileQuality()
+    for arr in sq.FastqParser(io.BytesIO(text), bufsize):
+        g.add_record_array(arr)
+    H.assert_same(H.dump_ptq(g), H.odump_ptq(o))
+
+
+def _tile_fastq(n, length, n_tiles, qlo, qhi, seed, runs=True, variable=False):
+    rng = np.random.default_rng(seed)
+    tiles = synth.novaseq_tiles()[:n_tiles]
+    t = rng.integers(0, n_tiles, size=n)
+    if runs:
+        t = np.sort(t)
+    qual = (rng.integers(qlo, qhi + 1, size=(n, length)) + 33).astype(np.uint8)
+    seq = np.full((n, length), ord("A"), dtype=np.uint8)
+    lens = rng.integers(0, length + 1, size=n) if variable else np.full(n, length)
+    out = io.BytesIO()
+    for i in range(n):
+        ln = int(lens[i])
+        out.write(b"@SIM:1:FCX:1:%d:%d:%d 1:N:0:ATCACG\n" % (tiles[t[i]], i, i))
+        out.write(seq[i, :ln].tobytes() + b"\n+\n" + qual[i, :ln].tobytes() + b"\n")
+    return out.getvalue()
+
+
+@pytest.mark.parametrize("qlo,qhi", [(2, 41), (0, 3), (30, 93), (0, 93)])
+@pytest.mark.parametrize("bufsize", [1 << 27, 3_000_000])
+def test_pertile_long_chains(sq, qlo, qhi, bufsize):
+    _pertile_case(sq, _tile_fastq(120_000, 24, 3, qlo, qhi, seed=qlo * 100 + qhi), bufsize)
+
+
+def test_pertile_random_tiles_variable_length(sq):
+    _pertile_case(sq, _tile_fastq(60_000, 37, 11, 2, 41, seed=7, runs=False, variable=True), 1_000_000)
