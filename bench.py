@@ -212,6 +212,27 @@ def run_cuda(args):
     ms_per_step = ms / args.steps
     value = world * bases / (ms_per_step * 1e-3) / 1e9
 
+    # ---- where one step's wall time goes (host view; outside the timed region) ---
+    t0 = time.perf_counter()
+    mods = make_modules(sq)
+    t1 = time.perf_counter()
+    arrays = list(data.record_arrays())
+    ctx.sync()
+    t2 = time.perf_counter()
+    per_mod = {}
+    for key in ("qc", "ptq", "ov", "ns", "ad", "dd"):
+        ta = time.perf_counter()
+        for arr in arrays:
+            mods[key].add_record_array(arr)
+        ctx.sync()
+        per_mod[key] = round((time.perf_counter() - ta) * 1e3, 3)
+    t3 = time.perf_counter()
+    read_results(mods)
+    t4 = time.perf_counter()
+    del arrays, mods
+    host_ms = {"create_modules": round((t1 - t0) * 1e3, 3), "parse": round((t2 - t1) * 1e3, 3),
+               "add_record_array": per_mod, "getters": round((t4 - t3) * 1e3, 3)}
+
     # ---- per-kernel times of one step (CUDA events around every launch) --------
     ctx.profile(True)
     step_resident()
@@ -290,7 +311,7 @@ def run_cuda(args):
             "reads_per_s": round(world * n_reads / (ms_per_step * 1e-3), 1),
             "wall_ms_per_step": round(wall * 1e3 / args.steps, 3),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "result_summary": summary,
+            "result_summary": summary, "host_ms_one_step": host_ms,
         }
         if e2e:
             line["e2e"] = e2e

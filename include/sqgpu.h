@@ -196,6 +196,11 @@ SQ_API int sq_overrep_add(sq_overrep *o, sq_batch *b);
 SQ_API int sq_overrep_sync(sq_overrep *o, sq_overrep_info *info);
 /* the stored fragments as 2-bit k-mers (wanghash64_inverse applied) + counts */
 SQ_API int sq_overrep_read(sq_overrep *o, uint64_t *kmers, uint32_t *counts, uint64_t *n);
+/* only fragments seen at least min_count times (the filter of
+ * OverrepresentedSequences_overrepresented_sequences, _qcmodule.c:4100-4180),
+ * compacted on the device; *n > cap means "call again with room for *n" */
+SQ_API int sq_overrep_read_min(sq_overrep *o, uint32_t min_count, uint64_t *kmers, uint32_t *counts,
+                               uint64_t cap, uint64_t *n);
 
 /* ---- DedupEstimator (_qcmodule.c:4383-4517) ------------------------------- */
 typedef struct sq_dedup sq_dedup;

@@ -139,6 +139,7 @@ SIGNATURES = {
     "sq_overrep_add": (_int, [_vp, _vp]),
     "sq_overrep_sync": (_int, [_vp, _P(OverrepInfo)]),
     "sq_overrep_read": (_int, [_vp, _vp, _vp, _P(_u64)]),
+    "sq_overrep_read_min": (_int, [_vp, _u32, _vp, _vp, _u64, _P(_u64)]),
     "sq_dedup_create": (_int, [_vp, _u64, _u64, _u64, _u64, _u64, _P(_vp)]),
     "sq_dedup_destroy": (None, [_vp]),
     "sq_dedup_add": (_int, [_vp, _vp]),

@@ -798,14 +798,25 @@ class OverrepresentedSequences(_Collector):
             raise ValueError(f"min_threshold must be at least 1, got {min_threshold}")
         if max_threshold < 1:
             raise ValueError(f"max_threshold must be at least 1, got {max_threshold}")
-        info, km, ct = self._entries()
+        info = self._sync()
         sampled = info.sampled_sequences
         hits = math.ceil(threshold_fraction * sampled)
         hits = min(max_threshold, max(min_threshold, hits))
         k = self.fragment_length
-        keep = ct >= hits
+        # the table is filtered on the device; only the hits cross PCIe
+        cap = 4096
+        while True:
+            km, ct = np.zeros(cap, "<u8"), np.zeros(cap, "<u4")
+            got = _C.c_uint64()
+            check(self._ctx.lib.sq_overrep_read_min(self._h, min(hits, 0xFFFFFFFF), _void(km),
+                                                    _void(ct), cap, _C.byref(got)),
+                  "sq_overrep_read_min")
+            if got.value <= cap:
+                break
+            cap = got.value
+        km, ct = km[:got.value], ct[:got.value]
         result = [(int(c), int(c) / sampled, _kmer_to_sequence(int(a), k))
-                  for a, c in zip(km[keep].tolist(), ct[keep].tolist())]
+                  for a, c in zip(km.tolist(), ct.tolist())]
         result.sort(reverse=True)
         return result
 

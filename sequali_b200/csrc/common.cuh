@@ -87,6 +87,9 @@ struct sq_batch {
     }
 };
 
+// name bytes of record r of a record array (host copy; rare paths only)
+int sq_batch_get_name(sq_batch *b, uint64_t r, std::vector<uint8_t> &out);
+
 // stream-ordered allocation helpers (cudaMallocAsync on the context stream)
 int sq_dalloc(sq_ctx *ctx, void **p, size_t nbytes, bool zero);
 void sq_dfree(sq_ctx *ctx, void *p);

@@ -682,6 +682,21 @@ extern "C" int sq_batch_get_metas(sq_batch *b, sq_meta *out) {
     return SQ_OK;
 }
 
+// name of record r (for skipped_reason messages): three 4-byte reads + the name bytes
+int sq_batch_get_name(sq_batch *b, uint64_t r, std::vector<uint8_t> &out) {
+    sq_ctx *ctx = b->ctx;
+    uint32_t name_off = 0, name_len = 0, seq_off = 0;
+    SQ_TRY(sq_memcpy_d2h(ctx, &name_off, b->name_off + r, 4));
+    if (b->name_len) SQ_TRY(sq_memcpy_d2h(ctx, &name_len, b->name_len + r, 4));
+    else {
+        SQ_TRY(sq_memcpy_d2h(ctx, &seq_off, b->seq_off + r, 4));
+        name_len = seq_off - 1 - name_off;
+    }
+    out.resize(name_len);
+    if (name_len) SQ_TRY(sq_memcpy_d2h(ctx, out.data(), b->text + name_off, name_len));
+    return SQ_OK;
+}
+
 // ---------------------------------------------------------------------------
 // mate check (reference _qcmodule.c:778-850)
 // ---------------------------------------------------------------------------

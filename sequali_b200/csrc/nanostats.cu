@@ -332,11 +332,7 @@ extern "C" int sq_nanostats_add(sq_nanostats *s, sq_batch *b) {
         s->skipped = true;
         s->skipped_record = h->fail_idx;
         uint64_t r = h->fail_idx - s->n_added;
-        std::vector<sq_meta> metas(b->n);
-        SQ_TRY(sq_batch_get_metas(b, metas.data()));
-        s->skipped_name.resize(metas[r].name_len);
-        if (metas[r].name_len)
-            SQ_TRY(sq_memcpy_d2h(ctx, s->skipped_name.data(), b->text + metas[r].name_off, metas[r].name_len));
+        SQ_TRY(sq_batch_get_name(b, r, s->skipped_name));
     }
     s->n_added += b->n;
     return SQ_OK;

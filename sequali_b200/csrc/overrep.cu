@@ -391,20 +391,68 @@ extern "C" int sq_overrep_sync(sq_overrep *o, sq_overrep_info *info) {
     return SQ_OK;
 }
 
-extern "C" int sq_overrep_read(sq_overrep *o, uint64_t *kmers, uint32_t *counts, uint64_t *n) {
+// table entries with count >= min_count, compacted on the device (slot order is
+// not observable: the getters return a dict / a sorted list, :4020-4062, :4169-4175)
+__global__ void __launch_bounds__(256)
+k_ov_compact(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ counts, uint64_t table_size,
+             uint32_t min_count, uint64_t cap, uint64_t *__restrict__ out_kmer, uint32_t *__restrict__ out_count,
+             unsigned long long *n_out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < table_size + 31;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t h = 0;
+        uint32_t c = 0;
+        if (i < table_size) {
+            h = keys[i];
+            c = counts[i];
+        }
+        const bool take = h != 0 && c >= min_count;
+        const uint32_t m = __ballot_sync(0xffffffffu, take);
+        if (!m) continue;
+        unsigned long long base = 0;
+        if (lane_id() == 0) base = atomicAdd(n_out, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) {
+            const uint64_t w = base + __popc(m & ((1u << lane_id()) - 1));
+            if (w < cap) {
+                out_kmer[w] = wang64_inverse(h);  // key -> sequence, as the getter does (:4042)
+                out_count[w] = c;
+            }
+        }
+    }
+}
+
+extern "C" int sq_overrep_read_min(sq_overrep *o, uint32_t min_count, uint64_t *kmers, uint32_t *counts,
+                                   uint64_t cap, uint64_t *n) {
     sq_ctx *ctx = o->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    std::vector<uint64_t> hk(o->table_size);
-    std::vector<uint32_t> hc(o->table_size);
-    CUDA_TRY(cudaMemcpyAsync(hk.data(), o->keys, o->table_size * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(hc.data(), o->counts, o->table_size * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    *n = 0;
+    uint64_t *dk = nullptr;
+    uint32_t *dc = nullptr;
+    unsigned long long *dn = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&dk, cap * 8, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&dc, cap * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&dn, 8, true));
+    SQ_LAUNCH(ctx, k_ov_compact, sq_grid_for(ctx, o->table_size + 31, 256, 16), 256, 0, o->keys, o->counts,
+              o->table_size, min_count, cap, dk, dc, dn);
+    unsigned long long *hn = (unsigned long long *)((char *)ctx->h_scratch + 1792);
+    CUDA_TRY(cudaMemcpyAsync(hn, dn, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    uint64_t w = 0;
-    for (uint64_t i = 0; i < o->table_size; i++)
-        if (hk[i]) {
-            kmers[w] = wang64_inverse(hk[i]);  // key -> sequence, as the getter does (:4042)
-            counts[w++] = hc[i];
-        }
-    *n = w;
+    const uint64_t got = *hn < cap ? *hn : cap;
+    if (got) {
+        CUDA_TRY(cudaMemcpyAsync(kmers, dk, got * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(counts, dc, got * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    *n = *hn;  // > cap tells the caller to retry with a larger buffer
+    sq_dfree(ctx, dk);
+    sq_dfree(ctx, dc);
+    sq_dfree(ctx, dn);
     return SQ_OK;
+}
+
+extern "C" int sq_overrep_read(sq_overrep *o, uint64_t *kmers, uint32_t *counts, uint64_t *n) {
+    // every stored fragment; the caller sized the buffers from collected_unique_fragments
+    sq_overrep_info info;
+    SQ_TRY(sq_overrep_sync(o, &info));
+    return sq_overrep_read_min(o, 0, kmers, counts, info.collected_unique_fragments, n);
 }

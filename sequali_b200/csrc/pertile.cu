@@ -616,13 +616,7 @@ extern "C" int sq_pertile_add(sq_pertile *p, sq_batch *b) {
         p->skipped = true;
         p->skipped_record = h->fail_idx;
         const uint64_t r = h->fail_idx - base;
-        std::vector<sq_meta> metas(b->n);
-        rc = sq_batch_get_metas(b, metas.data());
-        if (rc == SQ_OK) {
-            p->skipped_name.resize(metas[r].name_len);
-            if (metas[r].name_len)
-                rc = sq_memcpy_d2h(ctx, p->skipped_name.data(), b->text + metas[r].name_off, metas[r].name_len);
-        }
+        rc = sq_batch_get_name(b, r, p->skipped_name);
     }
     p->n_added += n;
     sq_dfree(ctx, tile);
