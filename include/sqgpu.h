@@ -259,6 +259,15 @@ SQ_API int sq_insert_read_sizes(sq_insert *m, uint64_t *sizes /* max_insert_size
 SQ_API int sq_insert_read_adapters(sq_insert *m, int which, uint8_t *seqs, uint64_t *counts,
                                    uint64_t *n);
 
+/* ---- fused add ------------------------------------------------------------ */
+/* One call for the whole hot loop body of src/sequali/__main__.py:280-306:
+ * equivalent to calling the *_add of every non-NULL collector on `b` in the
+ * reference's order (QCMetrics, PerTileQuality, OverrepresentedSequences,
+ * NanoStats, AdapterCounter, DedupEstimator), but short-read FASTQ arrays are
+ * walked once for all per-read quantities instead of once per collector. */
+SQ_API int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt, sq_overrep *ov,
+                        sq_nanostats *ns, sq_adapters *ad, sq_dedup *dd);
+
 /* ---- synthetic input (bench / tests; SURVEY.md 8d recipe C2) -------------- */
 /* Fill dev_text with `n_reads` NovaSeq-style records generated on the device;
  * returns the number of bytes written (<= cap) in *nbytes. */

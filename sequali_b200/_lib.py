@@ -158,11 +158,13 @@ SIGNATURES = {
     "sq_insert_sync": (_int, [_vp, _P(InsertInfo)]),
     "sq_insert_read_sizes": (_int, [_vp, _vp]),
     "sq_insert_read_adapters": (_int, [_vp, _int, _vp, _vp, _P(_u64)]),
+    "sq_fused_add": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sq_synth_illumina": (_int, [_vp, _vp, _u64, _u64, _u32, _u64, _P(_u64)]),
 }
 
 _lib = None
 _lock = threading.Lock()
+FLUSH_HOOKS: list = []  # callables run before Context.sync() (deferred adds of the _qc layer)
 
 
 def load() -> C.CDLL:
@@ -226,6 +228,8 @@ class Context:
         return cls._instance
 
     def sync(self):
+        for hook in FLUSH_HOOKS:
+            hook()
         check(self.lib.sq_ctx_sync(self.h), "sq_ctx_sync")
 
     @property

@@ -188,6 +188,51 @@ class _PinnedBuffer:
             self._ctx.lib.sq_pinned_free(self._ctx.h, ptr)
 
 
+# ------------------------------------------------------------------------------
+# deferred add_record_array
+# ------------------------------------------------------------------------------
+# Results of the collectors are observable only through getters and members
+# (SURVEY.md 8b), so `add_record_array` may be deferred: the collectors fed with
+# the same record array are gathered and handed to the device in ONE call
+# (sq_fused_add), which walks the text once for all of them.  Anything that
+# could observe state -- a getter, a member, add_read, another record array --
+# flushes first; per collector the arrays are applied in call order.
+_ROLES = ("qc", "pt", "ov", "ns", "ad", "dd")
+
+
+class _Pending:
+    array = None      # the record array being gathered (keeps it alive)
+    mods: dict = {}   # role -> collector
+
+
+def _flush() -> None:
+    arr, mods = _Pending.array, _Pending.mods
+    if arr is None:
+        return
+    _Pending.array, _Pending.mods = None, {}
+    ctx = Context.get()
+    hs = [mods[r]._h if r in mods else None for r in _ROLES]
+    if "qc" in mods:
+        arr._metas_stale = True
+    check(ctx.lib.sq_fused_add(ctx.h, arr._handle(), *hs), "sq_fused_add")
+
+
+_lib.FLUSH_HOOKS.append(_flush)  # Context.sync() drains the pending adds first
+
+
+def _defer(role: str, mod, arr) -> None:
+    if _Pending.array is not None:
+        clash = (_Pending.array is not arr or role in _Pending.mods
+                 # NanoStats copies the error sum QCMetrics left in the array (:5314): if it
+                 # was fed before QCMetrics, keep that order
+                 or (role == "qc" and "ns" in _Pending.mods))
+        if clash:
+            _flush()
+    if _Pending.array is None:
+        _Pending.array, _Pending.mods = arr, {}
+    _Pending.mods[role] = mod
+
+
 class FastqRecordArrayView:
     """A record array: bytes buffer + descriptors (reference :575-883), plus the
     handle of its device-resident copy."""
@@ -244,6 +289,8 @@ class FastqRecordArrayView:
         return self._h
 
     def _fetch_metas(self):
+        if _Pending.array is self:
+            _flush()
         if self._metas is None or self._metas_stale:
             m = np.zeros(self._n, dtype=META_DTYPE)
             if self._n:
@@ -286,6 +333,7 @@ class FastqRecordArrayView:
                              f"This length: {len(self)}, other length: {len(other)}")
         if self._n == 0:
             return True
+        _flush()
         ctx = Context.get()
         first = _C.c_uint64()
         check(ctx.lib.sq_batch_is_mate(self._handle(), other._handle(), _C.byref(first)),
@@ -518,6 +566,10 @@ class BamParser:
 class _Collector:
     _destroy = None
 
+    @staticmethod
+    def _flush_pending():
+        _flush()
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and self._destroy:
@@ -548,6 +600,7 @@ class QCMetrics(_Collector):
         self._h = h
 
     def _sync(self) -> _lib.QcInfo:
+        _flush()
         info = _lib.QcInfo()
         check(self._ctx.lib.sq_qc_sync(self._h, _C.byref(info)), "sq_qc_sync")
         if info.bad_phred:
@@ -566,8 +619,7 @@ class QCMetrics(_Collector):
         arr = _check_array(record_array)
         if len(arr) == 0:
             return
-        check(self._ctx.lib.sq_qc_add(self._h, arr._handle()), "sq_qc_add")
-        arr._metas_stale = True
+        _defer("qc", self, arr)
 
     max_length = property(lambda self: self._sync().max_length)
     number_of_reads = property(lambda self: self._sync().number_of_reads)
@@ -626,6 +678,7 @@ class AdapterCounter(_Collector):
         self._h = h
 
     def _sync(self):
+        _flush()
         n, ml = _C.c_uint64(), _C.c_uint64()
         check(self._ctx.lib.sq_adapters_sync(self._h, _C.byref(n), _C.byref(ml)),
               "sq_adapters_sync")
@@ -642,7 +695,7 @@ class AdapterCounter(_Collector):
     def add_record_array(self, record_array: FastqRecordArrayView) -> None:
         arr = _check_array(record_array)
         if len(arr):
-            check(self._ctx.lib.sq_adapters_add(self._h, arr._handle()), "sq_adapters_add")
+            _defer("ad", self, arr)
 
     def get_counts(self):
         _, ml = self._sync()
@@ -667,6 +720,7 @@ class PerTileQuality(_Collector):
         self._reason = None
 
     def _sync(self) -> _lib.PerTileInfo:
+        _flush()
         info = _lib.PerTileInfo()
         check(self._ctx.lib.sq_pertile_sync(self._h, _C.byref(info)), "sq_pertile_sync")
         if info.bad_phred:
@@ -700,7 +754,7 @@ class PerTileQuality(_Collector):
             return
         arr = _check_array(record_array)
         if len(arr):
-            check(self._ctx.lib.sq_pertile_add(self._h, arr._handle()), "sq_pertile_add")
+            _defer("pt", self, arr)
 
     def get_tile_counts(self):
         info = self._sync()
@@ -746,6 +800,7 @@ class OverrepresentedSequences(_Collector):
         self._warned = 0
 
     def _sync(self, source: Optional[FastqRecordArrayView] = None) -> _lib.OverrepInfo:
+        _flush()
         info = _lib.OverrepInfo()
         check(self._ctx.lib.sq_overrep_sync(self._h, _C.byref(info)), "sq_overrep_sync")
         if info.warn_records > self._warned:
@@ -772,7 +827,7 @@ class OverrepresentedSequences(_Collector):
     def add_record_array(self, record_array: FastqRecordArrayView) -> None:
         arr = _check_array(record_array)
         if len(arr):
-            check(self._ctx.lib.sq_overrep_add(self._h, arr._handle()), "sq_overrep_add")
+            _defer("ov", self, arr)
 
     def _entries(self):
         info = self._sync()
@@ -855,6 +910,7 @@ class DedupEstimator(_Collector):
         self._h = h
 
     def _sync(self) -> _lib.DedupInfo:
+        _flush()
         info = _lib.DedupInfo()
         check(self._ctx.lib.sq_dedup_sync(self._h, _C.byref(info)), "sq_dedup_sync")
         return info
@@ -884,7 +940,7 @@ class DedupEstimator(_Collector):
     def add_record_array(self, record_array: FastqRecordArrayView) -> None:
         arr = _check_array(record_array)
         if len(arr):
-            check(self._ctx.lib.sq_dedup_add(self._h, arr._handle()), "sq_dedup_add")
+            _defer("dd", self, arr)
 
     def add_record_array_pair(self, record_array1, record_array2) -> None:
         a1 = _check_array(record_array1, "record_array1")
@@ -893,6 +949,7 @@ class DedupEstimator(_Collector):
             raise ValueError("record_array1 and record_array2 must be of the same size. "
                              f"Got {len(a1)} and {len(a2)} respectively.")
         if len(a1):
+            _flush()
             check(self._ctx.lib.sq_dedup_add_pair(self._h, a1._handle(), a2._handle()),
                   "sq_dedup_add_pair")
 
@@ -951,6 +1008,7 @@ class NanoStats(_Collector):
         self._pi_warned = 0
 
     def _sync(self) -> _lib.NanoStatsInfo:
+        _flush()
         info = _lib.NanoStatsInfo()
         check(self._ctx.lib.sq_nanostats_sync(self._h, _C.byref(info)), "sq_nanostats_sync")
         if info.tag_error:
@@ -988,7 +1046,7 @@ class NanoStats(_Collector):
         if self._reason is not None:
             return
         if len(arr):
-            check(self._ctx.lib.sq_nanostats_add(self._h, arr._handle()), "sq_nanostats_add")
+            _defer("ns", self, arr)
 
     def nano_info_iterator(self) -> NanoStatsIterator:
         info = self._sync()
@@ -1012,6 +1070,7 @@ class InsertSizeMetrics(_Collector):
         self._h = h
 
     def _sync(self) -> _lib.InsertInfo:
+        _flush()
         info = _lib.InsertInfo()
         check(self._ctx.lib.sq_insert_sync(self._h, _C.byref(info)), "sq_insert_sync")
         return info
@@ -1036,6 +1095,7 @@ class InsertSizeMetrics(_Collector):
             raise ValueError("record_array1 and record_array2 must be of the same size. "
                              f"Got {len(a1)} and {len(a2)} respectively.")
         if len(a1):
+            _flush()
             check(self._ctx.lib.sq_insert_add_pair(self._h, a1._handle(), a2._handle()),
                   "sq_insert_add_pair")
 

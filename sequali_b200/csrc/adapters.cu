@@ -9,19 +9,9 @@
 // present), and an adapter matches where the AND of its letters' planes,
 // shifted by the letter's offset, leaves a bit.  Mismatches kill all bits
 // after a few letters, so most adapters cost ~4 plane operations per chunk.
-#include "common.cuh"
+#include "modules.cuh"
 
-constexpr int AD_TPB = 128;
-constexpr int AD_MAXLEN = 64;
 
-struct sq_adapters {
-    sq_ctx *ctx = nullptr;
-    uint32_t n_adapters = 0, max_pat_len = 0;
-    uint64_t n_seqs = 0, max_len = 0, cap_len = 0;
-    uint8_t *pat = nullptr;      // device [n_adapters][64] letter classes 0..4
-    uint32_t *plen = nullptr;    // device [n_adapters]
-    uint64_t *counts = nullptr;  // device [n_adapters][2][cap_len]: forward, reverse
-};
 
 // bit i of the result = bit 0 of byte i of x (x has only bit 0 of each byte set)
 __device__ __forceinline__ uint32_t pack_bytes_lsb(uint32_t x) { return (x * 0x00204081u) >> 21 & 0xFu; }
@@ -179,7 +169,7 @@ extern "C" void sq_adapters_destroy(sq_adapters *a) {
     delete a;
 }
 
-static int adapters_grow(sq_adapters *a, uint64_t len) {
+int adapters_grow(sq_adapters *a, uint64_t len) {
     if (len <= a->cap_len) return SQ_OK;
     uint64_t cap = a->cap_len * 2 > len ? a->cap_len * 2 : len;
     if (cap < 256) cap = 256;

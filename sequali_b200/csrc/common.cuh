@@ -70,6 +70,8 @@ struct sq_batch {
     uint64_t nbytes = 0;
     uint64_t n = 0;
     uint32_t max_len = 0;
+    uint32_t max_rec_bytes = 0;  // FASTQ text arrays: longest record in bytes (0 = unknown)
+    uint64_t text_end = 0;       // FASTQ text arrays: byte after the last complete record
     uint32_t *name_off = nullptr, *seq_off = nullptr, *seq_len = nullptr, *qual_off = nullptr;
     uint32_t *name_len = nullptr, *tags_off = nullptr, *tags_len = nullptr;
     double *err_sum = nullptr;

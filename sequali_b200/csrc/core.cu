@@ -257,7 +257,7 @@ struct ParseState {               // lives in device memory, copied back once
     unsigned long long first_non_ascii;  // byte offset, ULLONG_MAX if none
     unsigned long long err_key;          // (record << 3) | code, ULLONG_MAX if none
     unsigned int max_seq_len;
-    unsigned int pad;
+    unsigned int max_rec_bytes;  // longest record, '@' through the final newline
 };
 
 // 16 bytes at vector index v (text is 16-byte aligned); bytes past nbytes read as 0
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256)
 k_build_records(const uint8_t *__restrict__ text, uint64_t nbytes, const uint32_t *__restrict__ nl,
                 uint64_t n_newlines, uint64_t n_rec, int check_partial, uint32_t *name_off,
                 uint32_t *seq_off, uint32_t *seq_len, uint32_t *qual_off, ParseState *st) {
-    uint32_t local_max = 0;
+    uint32_t local_max = 0, local_rec = 0;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n_rec;
          r += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t start = r == 0 ? 0 : (uint64_t)nl[4 * r - 1] + 1;
@@ -418,9 +418,12 @@ k_build_records(const uint8_t *__restrict__ text, uint64_t nbytes, const uint32_
         seq_len[r] = e2 - e1 - 1;
         qual_off[r] = e3 + 1;
         local_max = max(local_max, e2 - e1 - 1);
+        local_rec = max(local_rec, e4 + 1 - (uint32_t)start);
     }
     local_max = warp_max_u32(local_max);
+    local_rec = warp_max_u32(local_rec);
     if (lane_id() == 0 && local_max) atomicMax(&st->max_seq_len, local_max);
+    if (lane_id() == 0 && local_rec) atomicMax(&st->max_rec_bytes, local_rec);
 }
 
 static int alloc_fastq_metas(sq_batch *b, uint64_t n) {
@@ -450,7 +453,7 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
     init.first_non_ascii = ~0ULL;
     init.err_key = ~0ULL;
     init.max_seq_len = 0;
-    init.pad = 0;
+    init.max_rec_bytes = 0;
     memcpy(ctx->h_scratch, &init, sizeof(init));
     CUDA_TRY(cudaMemcpyAsync(st, ctx->h_scratch, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     SQ_LAUNCH(ctx, k_count_newlines, n_cta, PARSE_THREADS, 0, b->text, nbytes, cta_counts, st);
@@ -512,6 +515,8 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
     }
     b->n = n_rec;
     b->max_len = info->max_seq_len;
+    b->max_rec_bytes = hst->max_rec_bytes;
+    b->text_end = info->consumed;
     sq_dfree(ctx, nl);
     sq_dfree(ctx, cta_counts);
     return rc;

@@ -23,37 +23,11 @@
 //   k_dd_rebuild_* / k_dd_insert_one    escalation (rare: ~log2(reads/max))
 #include <math.h>
 
-#include "common.cuh"
+#include "modules.cuh"
 
-constexpr int DD_TPB = 256;
-constexpr uint32_t DD_NEW = 0xFFFFFFFFu;     // sampled, not in the table
-constexpr uint32_t DD_NOPASS = 0xFFFFFFFEu;  // not sampled at this level
-constexpr uint64_t DD_EMPTY = ~0ULL;
 
-struct DdTable {
-    uint64_t *hash = nullptr;   // [size]
-    uint32_t *count = nullptr;  // [size], 0 = empty
-    uint64_t *prio = nullptr;   // [size], DD_EMPTY = empty; arrival priority of the occupant
-};
 
-struct DdCounters {  // device
-    unsigned long long r_full;   // record index of the K-th first occurrence
-    unsigned long long r_star;   // the add that triggers the escalation
-    unsigned int n_new;          // distinct new keys in the segment
-    unsigned int kept;           // entries surviving a rebuild
-    unsigned int inserted_one;   // k_dd_insert_one created an entry
-    unsigned int pad;
-};
 
-struct sq_dedup {
-    sq_ctx *ctx = nullptr;
-    uint64_t max_stored = 0, table_size = 0, stored = 0, mod_bits = 0;
-    uint64_t front_len = 0, back_len = 0, front_off = 0, back_off = 0;
-    uint64_t n_records = 0;  // records added so far (global index base)
-    DdTable tab, spare;
-    DdCounters *cnt = nullptr;
-    uint8_t *stale_fp = nullptr;  // pair path: persistent fingerprint scratch of the reference
-};
 
 // ---------------------------------------------------------------------------
 // hashing (reference :4463-4517)
@@ -368,7 +342,7 @@ extern "C" void sq_dedup_destroy(sq_dedup *d) {
 }
 
 // Process hashes[0..n) in record order.
-static int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n) {
+int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n) {
     sq_ctx *ctx = d->ctx;
     const uint64_t tmask = d->table_size - 1;
     const uint64_t prio_base = d->table_size + 1 + d->n_records;  // above every rebuild priority

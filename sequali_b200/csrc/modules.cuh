@@ -1,0 +1,102 @@
+// modules.cuh -- collector state shared between the per-module entry points
+// (qc.cu, adapters.cu, pertile.cu, dedup.cu) and the fused short-read pass
+// (fused.cu), which feeds several collectors from one walk over the text.
+#pragma once
+#include "common.cuh"
+
+// ---- QCMetrics (qc.cu) -------------------------------------------------------
+struct sq_qc {
+    sq_ctx *ctx = nullptr;
+    uint64_t ea_len = 0, n_reads = 0, max_len = 0, cap_len = 0;
+    uint64_t *base = nullptr, *phred = nullptr;        // [cap_len][5], [cap_len][12]
+    uint64_t *ea_base = nullptr, *ea_phred = nullptr;  // [ea_len][5], [ea_len][12]
+    uint64_t *gc = nullptr, *mean_phred = nullptr;     // [101], [94]
+    unsigned long long *err_key = nullptr;             // (global record << 8 | byte), min
+};
+
+int qc_grow(sq_qc *m, uint64_t len);
+// per-position tables only (base / phred / end-anchored); the per-read part is the caller's
+int qc_add_vertical(sq_qc *m, sq_batch *b);
+
+// ---- AdapterCounter (adapters.cu) ---------------------------------------------
+constexpr int AD_TPB = 128;
+constexpr int AD_MAXLEN = 64;
+
+struct sq_adapters {
+    sq_ctx *ctx = nullptr;
+    uint32_t n_adapters = 0, max_pat_len = 0;
+    uint64_t n_seqs = 0, max_len = 0, cap_len = 0;
+    uint8_t *pat = nullptr;      // device [n_adapters][64] letter classes 0..4
+    uint32_t *plen = nullptr;    // device [n_adapters]
+    uint64_t *counts = nullptr;  // device [n_adapters][2][cap_len]: forward, reverse
+};
+
+int adapters_grow(sq_adapters *a, uint64_t len);
+
+// ---- PerTileQuality (pertile.cu) ----------------------------------------------
+constexpr int PT_TPB = 256;
+constexpr uint64_t PT_EMPTY = ~0ULL;
+constexpr uint32_t PT_MAP_CAP = 1u << 18;   // open addressing, <= 2^17 distinct tiles
+constexpr uint32_t PT_NONE = 0xFFFFFFFFu;
+
+struct PtState {  // device
+    unsigned long long fail_idx;   // global index of the first header without a tile id
+    unsigned long long err_key;    // (global record << 8 | byte) of an invalid phred
+    unsigned int n_slots;
+    unsigned int max_len;          // longest kept read
+    unsigned long long n_kept;     // kept reads (before fail_idx)
+};
+
+struct sq_pertile {
+    sq_ctx *ctx = nullptr;
+    uint64_t n_added = 0;
+    uint64_t slot_cap = 0, len_cap = 0;
+    uint64_t *map_keys = nullptr;  // [PT_MAP_CAP]
+    uint32_t *map_vals = nullptr;
+    uint64_t *slot_tile = nullptr;  // [slot_cap]
+    double *errors = nullptr;       // [slot_cap][len_cap]
+    uint64_t *lengths = nullptr;    // [slot_cap][len_cap]
+    PtState *st = nullptr;
+    uint64_t *lut = nullptr;        // [PT_LUT_NK][94] in-binade increments r_k(10^-(q/10))
+    bool skipped = false;
+    uint64_t skipped_record = 0;
+    std::vector<uint8_t> skipped_name;
+    // host mirror after the last sync
+    uint64_t n_slots = 0, max_len = 0;
+};
+
+// everything after the tile ids are known (tile[r] < 0: unparsable header, already folded into st->fail_idx)
+int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile);
+
+// ---- DedupEstimator (dedup.cu) -------------------------------------------------
+constexpr int DD_TPB = 256;
+constexpr uint32_t DD_NEW = 0xFFFFFFFFu;     // sampled, not in the table
+constexpr uint32_t DD_NOPASS = 0xFFFFFFFEu;  // not sampled at this level
+constexpr uint64_t DD_EMPTY = ~0ULL;
+
+struct DdTable {
+    uint64_t *hash = nullptr;   // [size]
+    uint32_t *count = nullptr;  // [size], 0 = empty
+    uint64_t *prio = nullptr;   // [size], DD_EMPTY = empty; arrival priority of the occupant
+};
+
+struct DdCounters {  // device
+    unsigned long long r_full;   // record index of the K-th first occurrence
+    unsigned long long r_star;   // the add that triggers the escalation
+    unsigned int n_new;          // distinct new keys in the segment
+    unsigned int kept;           // entries surviving a rebuild
+    unsigned int inserted_one;   // k_dd_insert_one created an entry
+    unsigned int pad;
+};
+
+struct sq_dedup {
+    sq_ctx *ctx = nullptr;
+    uint64_t max_stored = 0, table_size = 0, stored = 0, mod_bits = 0;
+    uint64_t front_len = 0, back_len = 0, front_off = 0, back_off = 0;
+    uint64_t n_records = 0;  // records added so far (global index base)
+    DdTable tab, spare;
+    DdCounters *cnt = nullptr;
+    uint8_t *stale_fp = nullptr;  // pair path: persistent fingerprint scratch of the reference
+};
+
+int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n);

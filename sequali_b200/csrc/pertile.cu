@@ -14,38 +14,10 @@
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "modules.cuh"
 
-constexpr int PT_TPB = 256;
-constexpr uint64_t PT_EMPTY = ~0ULL;
-constexpr uint32_t PT_MAP_CAP = 1u << 18;   // open addressing, <= 2^17 distinct tiles
-constexpr uint32_t PT_NONE = 0xFFFFFFFFu;
 
-struct PtState {  // device
-    unsigned long long fail_idx;   // global index of the first header without a tile id
-    unsigned long long err_key;    // (global record << 8 | byte) of an invalid phred
-    unsigned int n_slots;
-    unsigned int max_len;          // longest kept read
-    unsigned long long n_kept;     // kept reads (before fail_idx)
-};
 
-struct sq_pertile {
-    sq_ctx *ctx = nullptr;
-    uint64_t n_added = 0;
-    uint64_t slot_cap = 0, len_cap = 0;
-    uint64_t *map_keys = nullptr;  // [PT_MAP_CAP]
-    uint32_t *map_vals = nullptr;
-    uint64_t *slot_tile = nullptr;  // [slot_cap]
-    double *errors = nullptr;       // [slot_cap][len_cap]
-    uint64_t *lengths = nullptr;    // [slot_cap][len_cap]
-    PtState *st = nullptr;
-    uint64_t *lut = nullptr;        // [PT_LUT_NK][94] in-binade increments r_k(10^-(q/10))
-    bool skipped = false;
-    uint64_t skipped_record = 0;
-    std::vector<uint8_t> skipped_name;
-    // host mirror after the last sync
-    uint64_t n_slots = 0, max_len = 0;
-};
 
 __device__ long long tile_id_of(const uint8_t *h, uint32_t n) {  // :3089-3121, :160-180
     uint32_t i = 0, colons = 0;
@@ -556,17 +528,25 @@ extern "C" int sq_pertile_add(sq_pertile *p, sq_batch *b) {
     if (p->skipped || b->n == 0) return SQ_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
     const uint32_t n = (uint32_t)b->n;
+    long long *tile = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&tile, (size_t)n * 8, false));
+    SQ_LAUNCH(ctx, k_pt_tile, sq_grid_for(ctx, n, PT_TPB, 16), PT_TPB, 0, b->view(), tile, p->n_added, p->st);
+    int rc = pt_add_with_tiles(p, b, tile);
+    sq_dfree(ctx, tile);
+    return rc;
+}
+
+int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile) {
+    sq_ctx *ctx = p->ctx;
+    const uint32_t n = (uint32_t)b->n;
     const uint64_t base = p->n_added;
     const int grid = sq_grid_for(ctx, n, PT_TPB, 16);
-    long long *tile = nullptr;
     uint32_t *slot = nullptr, *idx = nullptr, *tmpk = nullptr, *tmpv = nullptr, *seg = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&tile, (size_t)n * 8, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&slot, (size_t)n * 4, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&idx, (size_t)n * 4, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&tmpk, (size_t)n * 4, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&tmpv, (size_t)n * 4, false));
     SQ_TRY(pt_grow(p, p->n_slots ? p->n_slots : 1, b->max_len ? b->max_len : 1));
-    SQ_LAUNCH(ctx, k_pt_tile, grid, PT_TPB, 0, b->view(), tile, base, p->st);
     // slot ids of new tiles may exceed slot_cap: slot_tile writes are guarded, and the
     // map is re-read after growing
     SQ_LAUNCH(ctx, k_pt_map_insert, grid, PT_TPB, 0, tile, n, base, p->map_keys, p->map_vals, p->slot_tile,
@@ -619,7 +599,6 @@ extern "C" int sq_pertile_add(sq_pertile *p, sq_batch *b) {
         rc = sq_batch_get_name(b, r, p->skipped_name);
     }
     p->n_added += n;
-    sq_dfree(ctx, tile);
     sq_dfree(ctx, slot);
     sq_dfree(ctx, idx);
     sq_dfree(ctx, tmpk);

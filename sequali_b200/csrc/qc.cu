@@ -16,16 +16,8 @@
 //  k_qc_horizontal  per-read quantities: GC bucket, the four-chain ordered
 //                   error sum (bit-exact evaluation order of :2059-2112), the
 //                   mean-phred bucket.  Four lanes per read, one per chain.
-#include "common.cuh"
+#include "modules.cuh"
 
-struct sq_qc {
-    sq_ctx *ctx = nullptr;
-    uint64_t ea_len = 0, n_reads = 0, max_len = 0, cap_len = 0;
-    uint64_t *base = nullptr, *phred = nullptr;        // [cap_len][5], [cap_len][12]
-    uint64_t *ea_base = nullptr, *ea_phred = nullptr;  // [ea_len][5], [ea_len][12]
-    uint64_t *gc = nullptr, *mean_phred = nullptr;     // [101], [94]
-    unsigned long long *err_key = nullptr;             // (global record << 8 | byte), min
-};
 
 constexpr int QC_TPB = 256;
 constexpr int QC_BINS = 17;  // 5 base classes + 12 phred bins
@@ -360,7 +352,7 @@ extern "C" void sq_qc_destroy(sq_qc *m) {
     delete m;
 }
 
-static int qc_grow(sq_qc *m, uint64_t len) {
+int qc_grow(sq_qc *m, uint64_t len) {
     if (len <= m->cap_len) return SQ_OK;
     uint64_t cap = m->cap_len * 2 > len ? m->cap_len * 2 : len;
     if (cap < 256) cap = 256;
@@ -379,14 +371,8 @@ static int qc_grow(sq_qc *m, uint64_t len) {
     return SQ_OK;
 }
 
-extern "C" int sq_qc_add(sq_qc *m, sq_batch *b) {
+int qc_add_vertical(sq_qc *m, sq_batch *b) {
     sq_ctx *ctx = m->ctx;
-    if (b->ctx != ctx) {
-        sq_set_error("record array belongs to another context");
-        return SQ_E_ARG;
-    }
-    if (b->n == 0) return SQ_OK;
-    CUDA_TRY(cudaSetDevice(ctx->device));
     SQ_TRY(qc_grow(m, b->max_len));
     BatchView bv = b->view();
     uint32_t n = (uint32_t)b->n;
@@ -423,8 +409,21 @@ extern "C" int sq_qc_add(sq_qc *m, sq_batch *b) {
         }
         sq_dfree(ctx, mixed);
     }
+    return SQ_OK;
+}
+
+extern "C" int sq_qc_add(sq_qc *m, sq_batch *b) {
+    sq_ctx *ctx = m->ctx;
+    if (b->ctx != ctx) {
+        sq_set_error("record array belongs to another context");
+        return SQ_E_ARG;
+    }
+    if (b->n == 0) return SQ_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    SQ_TRY(qc_add_vertical(m, b));
+    const uint32_t n = (uint32_t)b->n;
     int grid_h = sq_grid_for(ctx, (uint64_t)n * 4, QC_TPB, 8);
-    SQ_LAUNCH(ctx, k_qc_horizontal, grid_h, QC_TPB, 0, bv, ctx->d_err_table, ctx->d_phred_thresholds, m->gc,
+    SQ_LAUNCH(ctx, k_qc_horizontal, grid_h, QC_TPB, 0, b->view(), ctx->d_err_table, ctx->d_phred_thresholds, m->gc,
               m->mean_phred, m->err_key, m->n_reads);
     m->n_reads += n;
     if (b->max_len > m->max_len) m->max_len = b->max_len;

@@ -321,3 +321,85 @@ def test_pertile_long_chains(sq, qlo, qhi, bufsize):
 
 def test_pertile_random_tiles_variable_length(sq):
     _pertile_case(sq, _tile_fastq(60_000, 37, 11, 2, 41, seed=7, runs=False, variable=True), 1_000_000)
+
+
+# ----------------------------------------------------------------------------
+# fused short-read pass (csrc/fused.cu): odd content through the one-walk kernel
+# ----------------------------------------------------------------------------
+def _odd_short_fastq(n, max_len, seed, good_headers=True):
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTacgtNnRYKM-.*X", np.uint8)
+    probs = np.array([.2, .2, .2, .2, .03, .03, .03, .03, .02, .01] + [.00625] * 8)
+    probs /= probs.sum()
+    ins = [b"AGATCGGAAGAG", b"ACGTN", b"nnnn", b"T", b"GATTACAGATTACAGATTACAGATTACA", b"CTGTCTCTTATA"]
+    tiles = synth.novaseq_tiles()[:9]
+    out = io.BytesIO()
+    for i in range(n):
+        ln = int(rng.integers(0, max_len + 1))
+        seq = alphabet[rng.choice(len(alphabet), size=ln, p=probs)].tobytes()
+        if ln > 40 and i % 3 == 0:
+            a = ins[i % len(ins)]
+            at = int(rng.integers(0, ln - len(a) + 1)) if ln >= len(a) else 0
+            seq = (seq[:at] + a + seq[at + len(a):])[:ln]
+        qual = (rng.integers(0, 94, size=ln) + 33).astype(np.uint8).tobytes()
+        if good_headers:
+            name = b"SIM:1:FCX:1:%d:%d:%d 1:N:0:ATCACG" % (tiles[int(rng.integers(0, 9))], i, i * 7)
+        else:
+            name = [b"r%d" % i, b"a:b:c:d:%d:x" % i, b"a:b:c:d::x", b"a:b:c:d:12", b"::::7:",
+                    b"a:b:c:d:1234567890123456789:x", b"a:b:c:d:12a:x"][i % 7]
+        out.write(b"@" + name + b"\n" + seq + b"\n+\n" + qual + b"\n")
+    return out.getvalue()
+
+
+FUSED_ADAPTERS = ["AGATCGGAAGAG", "ACGTN", "nnnn", "T", "GATTACAGATTACAGATTACAGATTACA", "A" * 32,
+                  "CTGTCTCTTATA"]
+
+
+@pytest.mark.parametrize("max_len", [40, 150, 250, 320])
+@pytest.mark.parametrize("bufsize", [1 << 26, 70_000])
+def test_fused_odd_content(sq, max_len, bufsize):
+    text = _odd_short_fastq(6000, max_len, seed=max_len)
+    kw = dict(dedup_kwargs=dict(max_stored_fingerprints=700),
+              overrep_kwargs=dict(max_unique_fragments=3000, sample_every=2))
+    got = H.api_single_end(sq, text, FUSED_ADAPTERS, buffersize=bufsize, **kw)
+    want = H.oracle_single_end(text, FUSED_ADAPTERS, **kw)
+    H.assert_same(got, want)
+
+
+def test_fused_header_variants_switch_pertile_off(sq):
+    good = _odd_short_fastq(700, 100, seed=5)
+    text = good + _odd_short_fastq(300, 100, seed=6, good_headers=False)
+    got = H.api_single_end(sq, text, FUSED_ADAPTERS, buffersize=50_000)
+    want = H.oracle_single_end(text, FUSED_ADAPTERS)
+    H.assert_same(got, want)
+
+
+def test_fused_invalid_phred_raises(sq):
+    text = b"@SIM:1:FCX:1:1101:1:1 1:N:0:A\nACGTACGTAC\n+\nIIII\x1fIIIII\n" * 3
+    qc = sq.QCMetrics()
+    for arr in sq.FastqParser(io.BytesIO(text), 1 << 20):
+        qc.add_record_array(arr)
+    with pytest.raises(ValueError, match="Not a valid phred character"):
+        qc.base_count_table()
+
+
+def test_deferred_adds_keep_call_order(sq):
+    # the same collector fed with two arrays before any getter, and NanoStats fed before
+    # QCMetrics (it must then see error sums of 0.0, like the reference: _qcmodule.c:5314)
+    text = synth.nanopore_fastq(40, mean_length=200, max_length=300, seed=3)
+    recs, _ = orc.parse_fastq(text)
+    buf = np.frombuffer(text, np.uint8)
+    ons, oq = orc.NanoStats(), orc.QCMetrics()
+    gns, gq = sq.NanoStats(), sq.QCMetrics()
+    arrays = list(sq.FastqParser(io.BytesIO(text), 3000))
+    assert len(arrays) > 2
+    start = 0
+    for arr in arrays:
+        part = recs[start:start + len(arr)]
+        start += len(arr)
+        ons.add(buf, part)
+        oq.add(buf, part)
+        gns.add_record_array(arr)
+        gq.add_record_array(arr)
+    H.assert_same(H.dump_nano(gns), H.odump_nano(ons))
+    H.assert_same(H.dump_qc(gq), H.odump_qc(oq))
