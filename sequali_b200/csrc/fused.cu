@@ -350,6 +350,351 @@ k_fused_reads(const FusedArgs A) {
     }
 }
 
+// ===========================================================================
+// Per-position pass ("columns"): a thread owns four read positions and walks
+// the records of a tile that a TMA bulk copy staged in shared memory.
+//
+//   k_fused_columns<false>  QCMetrics base / phred-bin histograms (:2004-2031,
+//                           :2068-2124) with the counters of qc.cu's vertical
+//                           kernel (byte-sliced registers, byte counters in
+//                           shared memory, no atomics in the loop), and, for
+//                           PerTileQuality, the approximate per-(tile of 128
+//                           records, position) error sums that pertile.cu's
+//                           chain needs as binade hints
+//   k_fused_columns<true>   PerTileQuality's exact in-binade integer sums for
+//                           the hinted binades (see pertile.cu)
+// ===========================================================================
+constexpr int FC_TPB = 128;
+constexpr int FC_BINS = 17;       // 5 base classes + 12 phred bins
+constexpr int FC_LUT_WINDOW = 8;  // binades tabulated per tile in the exact pass
+
+struct ColumnArgs {
+    BatchView bv;
+    uint32_t recs_per_tile, n_tiles;
+    uint64_t text_end;
+    uint32_t CG, RG, W;  // column groups (4 positions each), row groups, W = 4*CG >= longest read
+    uint32_t buf_bytes;  // shared-memory tile buffer
+    // QCMetrics tables
+    int do_qc;
+    uint64_t *base, *phred, *ea_base, *ea_phred;
+    uint32_t ea_len;
+    uint8_t *cta_mixed;  // [grid] CTAs that met reads of different lengths
+    // PerTileQuality
+    int do_pt;
+    const double *err_tab;
+    float *approx;            // [W][n_tiles]  (position-major: a chain reads consecutive tiles)
+    const uint16_t *kguess;   // [W][n_tiles]
+    uint64_t *incr;           // [W][n_tiles]
+    const uint8_t *tile_uniform;  // [n_tiles] 1: all records of the tile belong to one flow-cell tile
+    PtState *pt_st;
+    uint64_t pt_base;
+};
+
+template <bool EXACT>
+__global__ void __launch_bounds__(FC_TPB)
+k_fused_columns(const ColumnArgs A) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float s_errf[128];  // by raw quality byte; 0 outside '!'..'~' (0x7F marks padding)
+    __shared__ double s_errd[94];
+    __shared__ uint32_t s_lmin, s_lmax, s_kmin;
+    const uint32_t tid = threadIdx.x, R = A.recs_per_tile, W = A.W;
+    uint8_t *buf = smem_raw;
+    uint32_t *s_qo = (uint32_t *)(smem_raw + A.buf_bytes + 16);
+    uint32_t *s_so = s_qo + R;
+    uint32_t *s_L = s_so + R;
+    uint32_t *hist = s_L + R;                    // [W][17]            (!EXACT, do_qc)
+    uint32_t *priv = hist + W * FC_BINS;         // [13][FC_TPB] words (!EXACT, do_qc); row 12 = padding
+    float *partf = (float *)(priv + 13 * FC_TPB);  // [RG][W]          (!EXACT, do_pt)
+    uint64_t *s_lut = (uint64_t *)(s_L + R + ((R & 1) ? 1 : 0));  // [WINDOW + 1][128] by raw byte; last row zero
+    uint64_t *parti = s_lut + (FC_LUT_WINDOW + 1) * 128;           // [RG][W]       (EXACT)
+
+    if (!EXACT) {
+        for (uint32_t i = tid; i < 128; i += FC_TPB) s_errf[i] = (i >= 33 && i < 127) ? (float)A.err_tab[i - 33] : 0.f;
+        if (A.do_qc)
+            for (uint32_t i = tid; i < W * FC_BINS + 13 * FC_TPB; i += FC_TPB) hist[i] = 0;
+    }
+    else {
+        for (uint32_t i = tid; i < 94; i += FC_TPB) s_errd[i] = A.err_tab[i];
+    }
+    if (tid == 0) {
+        s_lmin = 0xFFFFFFFFu;
+        s_lmax = 0;
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const BatchView &bv = A.bv;
+    const uint32_t CG = A.CG, RG = A.RG;
+    const uint32_t rg = tid / CG, cg = tid - rg * CG;
+    const bool worker = rg < RG;
+    const uint32_t col0 = cg * 4;
+    uint8_t *priv8 = (uint8_t *)priv + tid * 4;
+    uint32_t acc_v = 0, acc_h = 0, acc_g = 0, acc_hg = 0, acc_n = 0, rows = 0;
+    uint32_t lmin = 0xFFFFFFFFu, lmax = 0;
+
+    auto spill = [&]() {
+        // registers -> CTA histogram; per column: A = v-h-g+hg, C = h-hg, G = hg, T = g-hg
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t v = (acc_v >> (8 * j)) & 0xFF, h = (acc_h >> (8 * j)) & 0xFF;
+            const uint32_t g = (acc_g >> (8 * j)) & 0xFF, hg = (acc_hg >> (8 * j)) & 0xFF;
+            const uint32_t nn = (acc_n >> (8 * j)) & 0xFF;
+            uint32_t *hrow = hist + (col0 + j) * FC_BINS;
+            if (v | nn) {
+                const uint32_t a = v - h - g + hg, c = h - hg, t = g - hg;
+                if (a) atomicAdd(hrow + 0, a);
+                if (c) atomicAdd(hrow + 1, c);
+                if (hg) atomicAdd(hrow + 2, hg);
+                if (t) atomicAdd(hrow + 3, t);
+                if (nn) atomicAdd(hrow + 4, nn);
+            }
+        }
+        acc_v = acc_h = acc_g = acc_hg = acc_n = 0;
+#pragma unroll
+        for (int b = 0; b < 12; b++) {
+            const uint32_t wv = priv[b * FC_TPB + tid];
+            if (wv) {
+                priv[b * FC_TPB + tid] = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t c = (wv >> (8 * j)) & 0xFF;
+                    if (c) atomicAdd(hist + (col0 + j) * FC_BINS + 5 + b, c);
+                }
+            }
+        }
+        rows = 0;
+    };
+
+    uint32_t parity = 0;
+    for (uint32_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
+        const uint32_t r0 = t * R, r1 = min(r0 + R, bv.n), nrec = r1 - r0;
+        const bool skip = EXACT && !A.tile_uniform[t];  // replayed read by read in the chain kernel
+        if (!skip) {
+            const uint64_t start = (uint64_t)bv.name_off[r0] - 1;
+            const uint64_t end = r1 < bv.n ? (uint64_t)bv.name_off[r1] - 1 : A.text_end;
+            const uint64_t gstart = start & ~15ULL;
+            const uint32_t bytes = (uint32_t)(((end + 15) & ~15ULL) - gstart);
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&bar, bytes);
+                bulk_g2s(buf, bv.text + gstart, bytes, &bar);
+                if (EXACT) s_kmin = 0xFFFFFFFFu;
+            }
+            for (uint32_t i = tid; i < nrec; i += FC_TPB) {
+                const uint32_t L = bv.seq_len[r0 + i];
+                s_so[i] = bv.seq_off[r0 + i] - (uint32_t)gstart;
+                s_qo[i] = bv.qual_off[r0 + i] - (uint32_t)gstart;
+                s_L[i] = L;
+                lmin = min(lmin, L);
+                lmax = max(lmax, L);
+            }
+        }
+        __syncthreads();
+        if (skip) continue;
+        // ---- exact pass: this tile's window of binades ----------------------------------------
+        uint32_t kg[4] = {0, 0, 0, 0};
+        if (EXACT) {
+            uint32_t kmin = 0xFFFFFFFFu;
+            if (worker && rg == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    kg[j] = col0 + j < W ? A.kguess[(uint64_t)(col0 + j) * A.n_tiles + t] : 0;
+                    if (kg[j]) kmin = min(kmin, kg[j]);
+                }
+            }
+            kmin = ~warp_max_u32(~kmin);
+            if (lane_id() == 0 && kmin != 0xFFFFFFFFu) atomicMin(&s_kmin, kmin);
+            __syncthreads();
+            kmin = s_kmin;
+            for (uint32_t i = tid; i < (FC_LUT_WINDOW + 1) * 128; i += FC_TPB) {
+                const uint32_t row = i >> 7, byte = i & 127;
+                s_lut[i] = (row < FC_LUT_WINDOW && byte >= 33 && byte < 127)
+                               ? pt_increment(kmin + row, (uint64_t)__double_as_longlong(s_errd[byte - 33]))
+                               : 0;
+            }
+            if (worker && rg != 0) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) kg[j] = col0 + j < W ? A.kguess[(uint64_t)(col0 + j) * A.n_tiles + t] : 0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; j++) kg[j] = (kg[j] && kg[j] - kmin < FC_LUT_WINDOW) ? kg[j] - kmin + 1 : 0;  // 0: no table
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        float fa[4] = {0.f, 0.f, 0.f, 0.f};
+        uint64_t ia[4] = {0, 0, 0, 0};
+        if (worker) {
+            // kg[j] == 0 (no table for that column): read the all-zero row, marked PT_HARD below
+            const uint64_t *lrow0 = s_lut + (kg[0] ? kg[0] - 1 : FC_LUT_WINDOW) * 128;
+            const uint64_t *lrow1 = s_lut + (kg[1] ? kg[1] - 1 : FC_LUT_WINDOW) * 128;
+            const uint64_t *lrow2 = s_lut + (kg[2] ? kg[2] - 1 : FC_LUT_WINDOW) * 128;
+            const uint64_t *lrow3 = s_lut + (kg[3] ? kg[3] - 1 : FC_LUT_WINDOW) * 128;
+            uint32_t badw = 0;
+            for (uint32_t i = rg; i < nrec; i += RG) {
+                const uint32_t L = s_L[i];
+                if (L <= col0) continue;
+                const uint32_t nvalid = min(4u, L - col0);
+                // bytes past the end of the read become 0x7F: zero in every table, own trash bin
+                const uint32_t keep = 0xFFFFFFFFu >> (8 * (4 - nvalid));
+                const uint32_t raw = fh_word(buf, s_qo[i], cg);
+                const uint32_t q = (raw & keep) | (0x7F7F7F7Fu & ~keep);
+                const uint32_t q0 = q & 0xFF, q1 = (q >> 8) & 0xFF, q2 = (q >> 16) & 0xFF, q3 = q >> 24;
+                if (!EXACT) {
+                    if (A.do_qc) {
+                        const uint32_t w = fh_word(buf, s_so[i], cg);
+                        const uint32_t pm = keep & 0x01010101u;
+                        const uint32_t vb = fh_acgt_bytes(w) & pm;
+                        const uint32_t hb = (w >> 1) & vb, gb = (w >> 2) & vb;
+                        acc_v += vb;
+                        acc_h += hb;
+                        acc_g += gb;
+                        acc_hg += hb & gb;
+                        acc_n += pm & ~vb;
+                        // phred bins min(q,47)>>2 as byte counters at bin*FC_TPB*4 + tid*4 + j; the
+                        // padding byte is counted in the spare 13th row that nobody reads
+                        priv8[(q0 == 0x7F ? 12u : min(q0 - 33u, 47u) >> 2) * (FC_TPB * 4) + 0] += 1;
+                        priv8[(q1 == 0x7F ? 12u : min(q1 - 33u, 47u) >> 2) * (FC_TPB * 4) + 1] += 1;
+                        priv8[(q2 == 0x7F ? 12u : min(q2 - 33u, 47u) >> 2) * (FC_TPB * 4) + 2] += 1;
+                        priv8[(q3 == 0x7F ? 12u : min(q3 - 33u, 47u) >> 2) * (FC_TPB * 4) + 3] += 1;
+                        if (++rows == 255) spill();
+                    }
+                    if (A.do_pt) {
+                        badw |= ((raw - 0x21212121u) | (raw + 0x01010101u)) & keep;
+                        fa[0] += s_errf[q0];
+                        fa[1] += s_errf[q1];
+                        fa[2] += s_errf[q2];
+                        fa[3] += s_errf[q3];
+                    }
+                }
+                else {
+                    ia[0] += lrow0[q0];
+                    ia[1] += lrow1[q1];
+                    ia[2] += lrow2[q2];
+                    ia[3] += lrow3[q3];
+                }
+            }
+            if (!EXACT && A.do_pt && (badw & 0x80808080u)) {
+                // a quality byte outside '!'..'~' (PerTileQuality raises for it, :3213): find it
+                for (uint32_t i = rg; i < nrec; i += RG) {
+                    const uint32_t L = s_L[i];
+                    for (uint32_t j = 0; j < 4 && col0 + j < L; j++) {
+                        const uint32_t c = buf[s_qo[i] + col0 + j];
+                        if (c - 33u > 93u)
+                            atomicMin(&A.pt_st->err_key, (unsigned long long)((A.pt_base + r0 + i) << 8 | c));
+                    }
+                }
+            }
+        }
+        // ---- per-tile column sums: combine the row groups -------------------------------------
+        if (A.do_pt) {
+            if (worker) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (EXACT) parti[rg * W + col0 + j] = kg[j] ? (ia[j] < PT_HARD ? ia[j] : PT_HARD) : PT_HARD;
+                    else partf[rg * W + col0 + j] = fa[j];
+                }
+            }
+            __syncthreads();
+            for (uint32_t c = tid; c < W; c += FC_TPB) {
+                if (EXACT) {
+                    uint64_t s = 0;
+                    for (uint32_t g = 0; g < RG; g++) s += parti[g * W + c];
+                    A.incr[(uint64_t)c * A.n_tiles + t] = s < PT_HARD ? s : PT_HARD;
+                }
+                else {
+                    float s = 0.f;
+                    for (uint32_t g = 0; g < RG; g++) s += partf[g * W + c];
+                    A.approx[(uint64_t)c * A.n_tiles + t] = s;
+                }
+            }
+        }
+        __syncthreads();  // tile buffer, offsets and partial sums are free again
+    }
+    if (EXACT || !A.do_qc) return;
+    if (worker) spill();
+    lmax = warp_max_u32(lmax);
+    lmin = ~warp_max_u32(~lmin);
+    if (lane_id() == 0) {
+        atomicMin(&s_lmin, lmin);
+        atomicMax(&s_lmax, lmax);
+    }
+    __syncthreads();
+    // CTA histogram -> global tables
+    for (uint32_t i = tid; i < W * FC_BINS; i += FC_TPB) {
+        const uint32_t c = hist[i];
+        if (!c) continue;
+        const uint32_t pos = i / FC_BINS, k = i % FC_BINS;
+        if (k < 5) atomic_add_u64(A.base + (uint64_t)pos * 5 + k, c);
+        else atomic_add_u64(A.phred + (uint64_t)pos * 12 + (k - 5), c);
+    }
+    if (s_lmax == 0 && s_lmin == 0xFFFFFFFFu) return;  // this CTA had no tile
+    if (s_lmin == s_lmax) {
+        // every record had length L0: the end-anchored rows are a shifted window of hist
+        const uint32_t L0 = s_lmin, ea_n = min(L0, A.ea_len);
+        const uint32_t lo = L0 - ea_n, hi = L0;
+        const uint32_t span = (hi - lo) * FC_BINS;
+        for (uint32_t i = tid; i < span; i += FC_TPB) {
+            const uint32_t pos = lo + i / FC_BINS, k = i % FC_BINS;
+            const uint32_t c = hist[pos * FC_BINS + k];
+            if (!c) continue;
+            const uint64_t row = (uint64_t)A.ea_len - (L0 - pos);
+            if (k < 5) atomic_add_u64(A.ea_base + row * 5 + k, c);
+            else atomic_add_u64(A.ea_phred + row * 12 + (k - 5), c);
+        }
+    }
+    else if (tid == 0) A.cta_mixed[blockIdx.x] = 1;
+}
+
+// end-anchored tables for the CTAs of k_fused_columns that met reads of different
+// lengths (:2034-2043, :2115-2124): same tile assignment, one warp per read
+__global__ void __launch_bounds__(FC_TPB)
+k_fused_ea_fallback(BatchView bv, uint32_t R, uint32_t n_tiles, const uint8_t *cta_mixed, uint64_t *g_ea_base,
+                    uint64_t *g_ea_phred, uint32_t ea_len, int smem_hist) {
+    extern __shared__ uint32_t ea_hist[];  // [ea_len][17] when smem_hist
+    if (!cta_mixed[blockIdx.x]) return;
+    if (smem_hist) {
+        for (uint32_t i = threadIdx.x; i < ea_len * FC_BINS; i += FC_TPB) ea_hist[i] = 0;
+        __syncthreads();
+    }
+    const uint32_t warp = threadIdx.x >> 5, nwarps = FC_TPB / 32;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint32_t r0 = t * R, r1 = min(r0 + R, bv.n);
+        for (uint32_t r = r0 + warp; r < r1; r += nwarps) {
+            const uint32_t L = bv.seq_len[r], ea_n = min(L, ea_len);
+            const uint8_t *s = bv.text + bv.seq_off[r] + (L - ea_n);
+            const uint8_t *q = bv.text + bv.qual_off[r] + (L - ea_n);
+            const uint32_t row0 = ea_len - ea_n;
+            for (uint32_t k = lane_id(); k < ea_n; k += 32) {
+                const uint32_t bcls = nuc5(s[k]);
+                const uint32_t p = min((uint32_t)(uint8_t)(q[k] - 33), 47u) >> 2;
+                if (smem_hist) {
+                    atomicAdd(ea_hist + (row0 + k) * FC_BINS + bcls, 1u);
+                    atomicAdd(ea_hist + (row0 + k) * FC_BINS + 5 + p, 1u);
+                }
+                else {
+                    atomic_add_u64(g_ea_base + (uint64_t)(row0 + k) * 5 + bcls, 1);
+                    atomic_add_u64(g_ea_phred + (uint64_t)(row0 + k) * 12 + p, 1);
+                }
+            }
+        }
+    }
+    if (smem_hist) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < ea_len * FC_BINS; i += FC_TPB) {
+            const uint32_t c = ea_hist[i];
+            if (!c) continue;
+            const uint32_t row = i / FC_BINS, k = i % FC_BINS;
+            if (k < 5) atomic_add_u64(g_ea_base + (uint64_t)row * 5 + k, c);
+            else atomic_add_u64(g_ea_phred + (uint64_t)row * 12 + (k - 5), c);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
 template <int NW>
 static int launch_fused(sq_ctx *ctx, const FusedArgs &A) {
     CUDA_TRY(cudaFuncSetAttribute(k_fused_reads<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_BUF + 16));
@@ -368,6 +713,67 @@ static bool fused_eligible(const sq_batch *b, const sq_adapters *ad) {
     if ((uint64_t)b->max_rec_bytes * 8 + 32 > FH_BUF) return false;  // at least 8 records per tile
     if (ad && (ad->n_adapters > FH_MAX_ADAPTERS || ad->max_pat_len > FH_MAX_PAT)) return false;
     return true;
+}
+
+// shared-memory plan of k_fused_columns: four CTAs per SM
+constexpr uint32_t FC_SMEM = 55 * 1024;
+struct ColGeom {
+    uint32_t R, n_tiles, CG, RG, W, buf_bytes, grid;
+    size_t smem;
+    bool ok;
+};
+static ColGeom col_geometry(sq_ctx *ctx, const sq_batch *b) {
+    ColGeom g;
+    memset(&g, 0, sizeof(g));
+    if (b->max_len == 0) return g;
+    g.CG = (b->max_len + 3) / 4;
+    if (g.CG > FC_TPB) return g;
+    g.RG = FC_TPB / g.CG;
+    g.W = g.CG * 4;
+    const uint32_t hist = g.W * FC_BINS * 4 + 13 * FC_TPB * 4 + g.RG * g.W * 4;
+    const uint32_t exact = (FC_LUT_WINDOW + 1) * 128 * 8 + g.RG * g.W * 8 + 8;
+    const uint32_t fixed = (hist > exact ? hist : exact) + 64;
+    if (fixed + 8 * (b->max_rec_bytes + 12) > FC_SMEM) return g;
+    g.R = (FC_SMEM - fixed) / (b->max_rec_bytes + 12);
+    if (g.R > 255) g.R = 255;
+    g.buf_bytes = (g.R * b->max_rec_bytes + 32 + 15) & ~15u;
+    g.smem = (size_t)g.buf_bytes + 16 + (size_t)(3 * g.R + 1) * 4 + fixed;
+    g.n_tiles = (uint32_t)((b->n + g.R - 1) / g.R);
+    g.grid = (uint32_t)ctx->num_sms * 4;
+    if (g.grid > g.n_tiles) g.grid = g.n_tiles;
+    g.ok = true;
+    return g;
+}
+
+static void col_args_common(ColumnArgs &A, sq_ctx *ctx, sq_batch *b, const ColGeom &g) {
+    memset(&A, 0, sizeof(A));
+    A.bv = b->view();
+    A.recs_per_tile = g.R;
+    A.n_tiles = g.n_tiles;
+    A.text_end = b->text_end;
+    A.CG = g.CG;
+    A.RG = g.RG;
+    A.W = g.W;
+    A.buf_bytes = g.buf_bytes;
+    A.err_tab = ctx->d_err_table;
+}
+
+int fused_exact_sums(sq_ctx *ctx, sq_batch *b, uint32_t R, uint32_t n_ftiles, uint32_t W, const uint16_t *kguess,
+                     uint64_t *incr, const uint8_t *tile_uniform) {
+    const ColGeom g = col_geometry(ctx, b);
+    if (!g.ok || g.R != R || g.n_tiles != n_ftiles || g.W != W) {
+        sq_set_error("fused_exact_sums: tile geometry changed between the passes");
+        return SQ_E_ARG;
+    }
+    ColumnArgs A;
+    col_args_common(A, ctx, b, g);
+    A.do_pt = 1;
+    A.kguess = kguess;
+    A.incr = incr;
+    A.tile_uniform = tile_uniform;
+    CUDA_TRY(cudaFuncSetAttribute(k_fused_columns<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    SQ_LAUNCH(ctx, k_fused_columns<true>, g.grid, FC_TPB, g.smem, A);
+    return SQ_OK;
 }
 
 extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt, sq_overrep *ov,
@@ -403,6 +809,8 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     A.edges = ctx->d_phred_thresholds;
     long long *tile = nullptr;
     uint64_t *hashes = nullptr;
+    float *approx = nullptr;
+    uint8_t *cta_mixed = nullptr;
     if (qc) {
         A.do_qc = 1;
         A.gc = qc->gc;
@@ -440,14 +848,53 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     else if (b->max_len <= 160) rc = launch_fused<5>(ctx, A);
     else if (b->max_len <= 256) rc = launch_fused<8>(ctx, A);
     else rc = launch_fused<10>(ctx, A);
-    // per-position tables and table maintenance, in the reference's module order
-    if (rc == SQ_OK && qc) {
-        rc = qc_add_vertical(qc, b);
+
+    // ---- per-position pass: QCMetrics histograms + PerTileQuality hints ----------------------
+    const ColGeom g = col_geometry(ctx, b);
+    if (rc == SQ_OK && g.ok && (qc || pt)) {
+        ColumnArgs C;
+        col_args_common(C, ctx, b, g);
+        if (qc) {
+            rc = qc_grow(qc, b->max_len);
+            if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&cta_mixed, g.grid, true);
+            C.do_qc = 1;
+            C.base = qc->base;
+            C.phred = qc->phred;
+            C.ea_base = qc->ea_base;
+            C.ea_phred = qc->ea_phred;
+            C.ea_len = (uint32_t)qc->ea_len;
+            C.cta_mixed = cta_mixed;
+        }
+        if (pt && rc == SQ_OK) {
+            rc = sq_dalloc(ctx, (void **)&approx, (size_t)g.n_tiles * g.W * 4, false);
+            C.do_pt = 1;
+            C.approx = approx;
+            C.pt_st = pt->st;
+            C.pt_base = pt->n_added;
+        }
+        if (rc == SQ_OK) {
+            CUDA_TRY(cudaFuncSetAttribute(k_fused_columns<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)g.smem));
+            SQ_LAUNCH(ctx, k_fused_columns<false>, g.grid, FC_TPB, g.smem, C);
+            if (qc && qc->ea_len) {
+                const size_t ea_smem = (size_t)qc->ea_len * FC_BINS * 4;
+                const int use_smem = ea_smem <= 96 * 1024;
+                if (use_smem)
+                    CUDA_TRY(cudaFuncSetAttribute(k_fused_ea_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  96 * 1024));
+                SQ_LAUNCH(ctx, k_fused_ea_fallback, g.grid, FC_TPB, use_smem ? ea_smem : 0, b->view(), g.R, g.n_tiles,
+                          cta_mixed, qc->ea_base, qc->ea_phred, (uint32_t)qc->ea_len, use_smem);
+            }
+        }
+    }
+    else if (rc == SQ_OK && qc) rc = qc_add_vertical(qc, b);
+    if (qc) {
         qc->n_reads += n;
         if (b->max_len > qc->max_len) qc->max_len = b->max_len;
         b->err_sum_valid = true;
     }
-    if (rc == SQ_OK && pt) rc = pt_add_with_tiles(pt, b, tile);
+    // ---- table maintenance, in the reference's module order ------------------------------------
+    if (rc == SQ_OK && pt) rc = pt_add_with_tiles(pt, b, tile, approx, g.R, g.n_tiles, g.W);
     if (rc == SQ_OK && ov) rc = sq_overrep_add(ov, b);
     if (rc == SQ_OK && ns) rc = sq_nanostats_add(ns, b);
     if (ad) {
@@ -457,5 +904,7 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     if (rc == SQ_OK && dd) rc = dedup_consume(dd, hashes, n);
     sq_dfree(ctx, tile);
     sq_dfree(ctx, hashes);
+    sq_dfree(ctx, approx);
+    sq_dfree(ctx, cta_mixed);
     return rc;
 }

@@ -45,6 +45,8 @@ struct PtState {  // device
     unsigned int n_slots;
     unsigned int max_len;          // longest kept read
     unsigned long long n_kept;     // kept reads (before fail_idx)
+    unsigned int n_changes;        // this array: reads whose tile differs from the previous read's
+    unsigned int pad;
 };
 
 struct sq_pertile {
@@ -65,8 +67,40 @@ struct sq_pertile {
     uint64_t n_slots = 0, max_len = 0;
 };
 
-// everything after the tile ids are known (tile[r] < 0: unparsable header, already folded into st->fail_idx)
-int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile);
+constexpr uint64_t PT_HARD = 1ULL << 53;          // no valid in-binade increment reaches this
+constexpr uint64_t PT_MANT = (1ULL << 52) - 1;
+constexpr int PT_LUT_KMIN = 1023 - 30;            // binades 2^-30 .. 2^25 are tabulated
+constexpr int PT_LUT_NK = 56;
+
+// r_k(e): e in ulps of binade k (biased exponent), round to nearest; PT_HARD when
+// the addition cannot be expressed that way (tie, e >= 2^k, s == 0)
+__host__ __device__ inline uint64_t pt_increment(uint32_t k, uint64_t ebits) {
+    const int d = (int)k - (int)(ebits >> 52);
+    if (k == 0 || d < 1) return PT_HARD;
+    if (d >= 64) return 0;
+    const uint64_t m = (ebits & PT_MANT) | (1ULL << 52);
+    uint64_t r = m >> d;
+    const uint64_t rem = m & ((1ULL << d) - 1), half = 1ULL << (d - 1);
+    if (rem > half) r++;
+    else if (rem == half) return PT_HARD;
+    return r;
+}
+
+struct PtSeg {  // a run of consecutive reads of one tile: rows [lo, hi) of `order` (or of the array)
+    uint32_t lo, hi, slot;
+    uint32_t data;  // row of approx / kguess / incr holding this segment's sums, PT_NONE: replay the reads
+};
+
+
+// Everything after the tile ids are known (tile[r] < 0: unparsable header, already folded
+// into st->fail_idx).  `approx` != nullptr: [n_ftiles][W] approximate error sums of fixed
+// tiles of R records (k_fused_columns<false>), which lets reads that arrive in tile runs
+// skip the sort and the segment passes over the text.
+int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile, const float *approx, uint32_t R,
+                      uint32_t n_ftiles, uint32_t W);
+// exact in-binade integer sums of the uniform tiles (fused.cu)
+int fused_exact_sums(sq_ctx *ctx, sq_batch *b, uint32_t R, uint32_t n_ftiles, uint32_t W,
+                     const uint16_t *kguess, uint64_t *incr, const uint8_t *tile_uniform);
 
 // ---- DedupEstimator (dedup.cu) -------------------------------------------------
 constexpr int DD_TPB = 256;

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(PT_TPB)
 k_pt_map_lookup(BatchView bv, const long long *__restrict__ tile, uint64_t base, const uint64_t *map_keys,
                 const uint32_t *map_vals, uint32_t *__restrict__ slot, uint32_t *__restrict__ idx, PtState *st) {
     const unsigned long long fail = st->fail_idx;
-    uint32_t lmax = 0, kept = 0;
+    uint32_t lmax = 0, kept = 0, changes = 0;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < bv.n; r += gridDim.x * blockDim.x) {
         idx[r] = r;
         if (base + r >= fail) {
@@ -89,6 +89,7 @@ k_pt_map_lookup(BatchView bv, const long long *__restrict__ tile, uint64_t base,
             continue;
         }
         const uint64_t t = (uint64_t)tile[r];
+        changes += r == 0 || tile[r - 1] != tile[r];
         uint32_t i = pt_hash(t) & (PT_MAP_CAP - 1);
         while (map_keys[i] != t) i = (i + 1) & (PT_MAP_CAP - 1);
         slot[r] = map_vals[i];
@@ -97,17 +98,29 @@ k_pt_map_lookup(BatchView bv, const long long *__restrict__ tile, uint64_t base,
     }
     lmax = warp_max_u32(lmax);
     kept = warp_sum_u32(kept);
+    changes = warp_sum_u32(changes);
     if (lane_id() == 0) {
         if (lmax) atomicMax(&st->max_len, lmax);
         if (kept) atomicAdd(&st->n_kept, (unsigned long long)kept);
+        if (changes) atomicAdd(&st->n_changes, changes);
     }
 }
 
 __global__ void __launch_bounds__(PT_TPB)
 k_pt_lengths(BatchView bv, const uint32_t *__restrict__ slot, uint64_t *lengths, uint64_t len_cap) {
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < bv.n; r += gridDim.x * blockDim.x) {
-        const uint32_t s = slot[r], L = bv.seq_len[r];
-        if (s != PT_NONE && L) atomic_add_u64(lengths + (uint64_t)s * len_cap + (L - 1), 1);
+    // neighbouring reads share tile and length: one atomic per distinct (tile, length) in a warp
+    const uint32_t n_round = (bv.n + 31) & ~31u;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_round; r += gridDim.x * blockDim.x) {
+        uint32_t s = PT_NONE, L = 0;
+        if (r < bv.n) {
+            s = slot[r];
+            L = bv.seq_len[r];
+        }
+        const bool take = s != PT_NONE && L;
+        const uint64_t key = take ? ((uint64_t)s << 32 | L) : ~0ULL;
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (take && lane_id() == (uint32_t)__ffs(peers) - 1)
+            atomic_add_u64(lengths + (uint64_t)s * len_cap + (L - 1), __popc(peers));
     }
 }
 
@@ -150,29 +163,6 @@ k_pt_segments(const uint32_t *__restrict__ sorted_slot, uint32_t n, uint32_t *se
 //                 verified exactly, so the result is bit-identical to the serial
 //                 chain whatever the guess was.
 // ---------------------------------------------------------------------------
-constexpr uint64_t PT_HARD = 1ULL << 53;          // no valid in-binade increment reaches this
-constexpr uint64_t PT_MANT = (1ULL << 52) - 1;
-constexpr int PT_LUT_KMIN = 1023 - 30;            // binades 2^-30 .. 2^25 are tabulated
-constexpr int PT_LUT_NK = 56;
-
-// r_k(e): e in ulps of binade k (biased exponent), round to nearest; PT_HARD when
-// the addition cannot be expressed that way (tie, e >= 2^k, s == 0)
-__host__ __device__ inline uint64_t pt_increment(uint32_t k, uint64_t ebits) {
-    const int d = (int)k - (int)(ebits >> 52);
-    if (k == 0 || d < 1) return PT_HARD;
-    if (d >= 64) return 0;
-    const uint64_t m = (ebits & PT_MANT) | (1ULL << 52);
-    uint64_t r = m >> d;
-    const uint64_t rem = m & ((1ULL << d) - 1), half = 1ULL << (d - 1);
-    if (rem > half) r++;
-    else if (rem == half) return PT_HARD;
-    return r;
-}
-
-struct PtSeg {  // a run of consecutive (tile-sorted) reads of one tile
-    uint32_t lo, hi, slot, pad;
-};
-
 __global__ void __launch_bounds__(PT_TPB)
 k_pt_seg_counts(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_hi, uint32_t n_slots,
                 uint32_t seg_rows, uint32_t *__restrict__ nseg) {
@@ -192,7 +182,7 @@ k_pt_seg_fill(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ 
             g.lo = lo + j * seg_rows;
             g.hi = min(hi, g.lo + seg_rows);
             g.slot = s;
-            g.pad = 0;
+            g.data = first + j;
             segs[first + j] = g;
         }
     }
@@ -204,7 +194,7 @@ k_pt_seg_fill(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ 
 template <bool EXACT>
 __global__ void __launch_bounds__(PT_TPB)
 k_pt_segment_sums(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__restrict__ segs,
-                  const uint32_t *__restrict__ n_segs_p, uint32_t CG, uint32_t RG, uint32_t width4,
+                  const uint32_t *__restrict__ n_segs_p, uint32_t CG, uint32_t RG, uint32_t width4, uint32_t stride,
                   const double *__restrict__ err_tab, const uint64_t *__restrict__ lut,
                   const uint16_t *__restrict__ kguess, float *__restrict__ approx, uint64_t *__restrict__ incr,
                   uint64_t base, PtState *st) {
@@ -230,7 +220,7 @@ k_pt_segment_sums(BatchView bv, const uint32_t *__restrict__ order, const PtSeg 
         if (EXACT) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int k = (int)kguess[(uint64_t)g * width4 + col0 + j] - PT_LUT_KMIN;
+                const int k = (int)kguess[(uint64_t)(col0 + j) * stride + g] - PT_LUT_KMIN;
                 if (k < 0 || k >= PT_LUT_NK) {
                     lrow[j] = s_lut;
                     ia[j] = PT_HARD;
@@ -259,8 +249,8 @@ k_pt_segment_sums(BatchView bv, const uint32_t *__restrict__ order, const PtSeg 
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (EXACT) incr[(uint64_t)g * width4 + col0 + j] = ia[j] < PT_HARD ? ia[j] : PT_HARD;
-            else approx[(uint64_t)g * width4 + col0 + j] = fa[j];
+            if (EXACT) incr[(uint64_t)(col0 + j) * stride + g] = ia[j] < PT_HARD ? ia[j] : PT_HARD;
+            else approx[(uint64_t)(col0 + j) * stride + g] = fa[j];
         }
     }
 }
@@ -274,11 +264,27 @@ __device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v) {
     return v;
 }
 
-// one warp per chain (tile slot, position): expected binade at the start of every segment
+// float sum of the error rates of rows [lo, hi) at `pos` (segments without precomputed sums)
+__device__ double pt_rows_sum(const BatchView &bv, const uint32_t *__restrict__ order, uint32_t lo, uint32_t hi,
+                              uint32_t pos, const double *__restrict__ err_tab) {
+    double s = 0.0;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t r = order ? order[i] : i;
+        if (pos >= bv.seq_len[r]) continue;
+        const uint32_t q = (uint8_t)(bv.text[bv.qual_off[r] + pos] - 33);
+        if (q <= 93) s += err_tab[q];
+    }
+    return s;
+}
+
+// one warp per chain (tile slot, position): expected binade at the start of every segment.
+// A tile's segments are segs[perm[first .. first+cnt)] (perm == nullptr: identity).
 __global__ void __launch_bounds__(PT_TPB)
-k_pt_guess(const uint32_t *__restrict__ seg_first, const uint32_t *__restrict__ nseg, uint32_t n_slots,
-           uint32_t width, uint32_t width4, const float *__restrict__ approx, const double *__restrict__ errors,
-           uint64_t len_cap, uint16_t *__restrict__ kguess) {
+k_pt_guess(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__restrict__ segs,
+           const uint32_t *__restrict__ perm, const uint32_t *__restrict__ seg_first,
+           const uint32_t *__restrict__ nseg, uint32_t n_slots, uint32_t width, uint32_t stride,
+           const float *__restrict__ approx, const double *__restrict__ errors, uint64_t len_cap,
+           const double *__restrict__ err_tab, uint16_t *__restrict__ kguess) {
     const uint64_t chains = (uint64_t)n_slots * width;
     const uint64_t warps = (uint64_t)gridDim.x * (PT_TPB / 32);
     for (uint64_t c = (uint64_t)blockIdx.x * (PT_TPB / 32) + (threadIdx.x >> 5); c < chains; c += warps) {
@@ -289,7 +295,14 @@ k_pt_guess(const uint32_t *__restrict__ seg_first, const uint32_t *__restrict__ 
         double run = errors[(uint64_t)s * len_cap + pos];
         for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
             const uint32_t j = j0 + lane_id();
-            double v = j < cnt ? (double)approx[(uint64_t)(first + j) * width4 + pos] : 0.0;
+            double v = 0.0;
+            uint32_t data = PT_NONE;
+            if (j < cnt) {
+                const PtSeg sg = segs[perm ? perm[first + j] : first + j];
+                data = sg.data;
+                v = data != PT_NONE ? (double)approx[(uint64_t)pos * stride + data]
+                                    : pt_rows_sum(bv, order, sg.lo, sg.hi, pos, err_tab);
+            }
             double x = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -297,8 +310,8 @@ k_pt_guess(const uint32_t *__restrict__ seg_first, const uint32_t *__restrict__ 
                 if (lane_id() >= (uint32_t)o) x += y;
             }
             const double start = run + (x - v);
-            if (j < cnt)
-                kguess[(uint64_t)(first + j) * width4 + pos] = (uint16_t)((uint64_t)__double_as_longlong(start) >> 52);
+            if (data != PT_NONE)
+                kguess[(uint64_t)pos * stride + data] = (uint16_t)((uint64_t)__double_as_longlong(start) >> 52);
             run += __shfl_sync(0xffffffffu, x, 31);
         }
     }
@@ -313,7 +326,7 @@ __device__ uint64_t pt_replay_rows(uint64_t sbits, const BatchView &bv, const ui
         uint64_t ebits = 0;
         bool has = false;
         if (ii < hi) {
-            const uint32_t r = order[ii];
+            const uint32_t r = order ? order[ii] : ii;
             if (pos < bv.seq_len[r]) {
                 const uint32_t q = (uint8_t)(bv.text[bv.qual_off[r] + pos] - 33);
                 if (q <= 93) {
@@ -346,9 +359,10 @@ __device__ uint64_t pt_replay_rows(uint64_t sbits, const BatchView &bv, const ui
 
 __global__ void __launch_bounds__(PT_TPB)
 k_pt_chain(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__restrict__ segs,
-           const uint32_t *__restrict__ seg_first, const uint32_t *__restrict__ nseg, uint32_t n_slots,
-           uint32_t width, uint32_t width4, const uint16_t *__restrict__ kguess, const uint64_t *__restrict__ incr,
-           double *errors, uint64_t len_cap, const double *__restrict__ err_tab) {
+           const uint32_t *__restrict__ perm, const uint32_t *__restrict__ seg_first,
+           const uint32_t *__restrict__ nseg, uint32_t n_slots, uint32_t width, uint32_t stride,
+           const uint16_t *__restrict__ kguess, const uint64_t *__restrict__ incr, double *errors,
+           uint64_t len_cap, const double *__restrict__ err_tab) {
     __shared__ double s_err[94];
     for (uint32_t i = threadIdx.x; i < 94; i += PT_TPB) s_err[i] = err_tab[i];
     __syncthreads();
@@ -364,11 +378,15 @@ k_pt_chain(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__rest
         uint32_t j = 0;
         while (j < cnt) {
             const uint32_t jj = j + lane_id();
-            uint64_t inc = 0;
-            uint32_t kg = 0;
+            uint64_t inc = PT_HARD;
+            uint32_t kg = 0, seg_id = 0;
             if (jj < cnt) {
-                inc = incr[(uint64_t)(first + jj) * width4 + pos];
-                kg = kguess[(uint64_t)(first + jj) * width4 + pos];
+                seg_id = perm ? perm[first + jj] : first + jj;
+                const uint32_t data = segs[seg_id].data;
+                if (data != PT_NONE) {
+                    inc = incr[(uint64_t)pos * stride + data];
+                    kg = kguess[(uint64_t)pos * stride + data];
+                }
             }
             const uint32_t k = (uint32_t)(sbits >> 52);
             const bool hard = inc >= PT_HARD || kg != k;
@@ -382,12 +400,59 @@ k_pt_chain(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__rest
             if (nacc) sbits += __shfl_sync(0xffffffffu, incl, nacc - 1);
             j += nacc;
             if (f < nv) {
-                const PtSeg sg = segs[first + j];
+                const PtSeg sg = segs[__shfl_sync(0xffffffffu, seg_id, f)];
                 sbits = pt_replay_rows(sbits, bv, order, sg.lo, sg.hi, pos, s_err);
                 j += 1;
             }
         }
         if (lane_id() == 0) *cell = __longlong_as_double((long long)sbits);
+    }
+}
+
+// ---- segments of the fused path: the record array is cut into fixed tiles of R
+// ---- records (the tiles k_fused_columns sums over); a tile whose records all
+// ---- belong to one flow-cell tile is one segment with precomputed sums, any
+// ---- other tile is split into runs that the chain replays read by read.
+__global__ void __launch_bounds__(PT_TPB)
+k_pt_ftile_runs(const uint32_t *__restrict__ slot, uint32_t n, uint32_t R, uint32_t n_ftiles,
+                uint32_t *__restrict__ runs, uint8_t *__restrict__ uniform) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_ftiles; t += gridDim.x * blockDim.x) {
+        const uint32_t r0 = t * R, r1 = min(n, r0 + R);
+        uint32_t cnt = 0, prev = PT_NONE;
+        for (uint32_t r = r0; r < r1; r++) {
+            const uint32_t s = slot[r];
+            if (s != prev && s != PT_NONE) cnt++;
+            prev = s;
+        }
+        runs[t] = cnt;
+        uniform[t] = cnt == 1 && slot[r0] != PT_NONE && slot[r1 - 1] == slot[r0];
+    }
+}
+__global__ void __launch_bounds__(PT_TPB)
+k_pt_ftile_segs(const uint32_t *__restrict__ slot, uint32_t n, uint32_t R, uint32_t n_ftiles,
+                const uint32_t *__restrict__ seg_off, const uint8_t *__restrict__ uniform,
+                PtSeg *__restrict__ segs, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_ftiles; t += gridDim.x * blockDim.x) {
+        const uint32_t r0 = t * R, r1 = min(n, r0 + R);
+        uint32_t w = seg_off[t], prev = PT_NONE, lo = r0;
+        for (uint32_t r = r0; r <= r1; r++) {
+            const uint32_t s = r < r1 ? slot[r] : PT_NONE;
+            if (s != prev || r == r1) {
+                if (prev != PT_NONE) {
+                    PtSeg g;
+                    g.lo = lo;
+                    g.hi = r;
+                    g.slot = prev;
+                    g.data = uniform[t] ? t : PT_NONE;
+                    segs[w] = g;
+                    keys[w] = prev;
+                    vals[w] = w;
+                    w++;
+                }
+                lo = r;
+            }
+            prev = s;
+        }
     }
 }
 
@@ -500,20 +565,77 @@ static int pt_accumulate(sq_pertile *p, sq_batch *b, const uint32_t *order, cons
               seg_first, n_slots, seg_rows, segs);
     dim3 sgrid((unsigned)sq_grid_for(ctx, (uint64_t)seg_cap, (int)RG, 64), windows);
     const BatchView bv = b->view();
-    SQ_LAUNCH(ctx, k_pt_segment_sums<false>, sgrid, PT_TPB, 0, bv, order, segs, n_segs_dev, CG, RG, width4,
+    SQ_LAUNCH(ctx, k_pt_segment_sums<false>, sgrid, PT_TPB, 0, bv, order, segs, n_segs_dev, CG, RG, width4, seg_cap,
               ctx->d_err_table, p->lut, kguess, approx, incr, base, p->st);
     const int chain_grid = sq_grid_for(ctx, (uint64_t)n_slots * width * 32, PT_TPB, 32);
-    SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, seg_first, nseg, n_slots, width, width4, approx, p->errors,
-              p->len_cap, kguess);
+    SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, bv, order, segs, (const uint32_t *)nullptr, seg_first, nseg,
+              n_slots, width, seg_cap, approx, p->errors, p->len_cap, ctx->d_err_table, kguess);
     SQ_LAUNCH(ctx, k_pt_segment_sums<true>, sgrid, PT_TPB, (size_t)PT_LUT_NK * 94 * 8, bv, order, segs, n_segs_dev,
-              CG, RG, width4, ctx->d_err_table, p->lut, kguess, approx, incr, base, p->st);
-    SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, bv, order, segs, seg_first, nseg, n_slots, width, width4,
-              kguess, incr, p->errors, p->len_cap, ctx->d_err_table);
+              CG, RG, width4, seg_cap, ctx->d_err_table, p->lut, kguess, approx, incr, base, p->st);
+    SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, bv, order, segs, (const uint32_t *)nullptr, seg_first, nseg,
+              n_slots, width, seg_cap, kguess, incr, p->errors, p->len_cap, ctx->d_err_table);
     sq_dfree(ctx, nseg);
     sq_dfree(ctx, seg_first);
     sq_dfree(ctx, n_segs_dev);
     sq_dfree(ctx, segs);
     sq_dfree(ctx, approx);
+    sq_dfree(ctx, incr);
+    sq_dfree(ctx, kguess);
+    return SQ_OK;
+}
+
+// Reads that arrive in tile runs (every real Illumina file): no sort, no extra
+// passes for the approximate sums (k_fused_columns<false> produced them per fixed
+// tile of R records), one TMA-staged pass for the exact integer sums.
+static int pt_accumulate_runs(sq_pertile *p, sq_batch *b, const uint32_t *slot, const float *approx, uint32_t R,
+                              uint32_t n_ftiles, uint32_t W, uint32_t n_slots, uint32_t seg_cap, uint32_t width,
+                              uint32_t *tmpk, uint32_t *tmpv) {
+    sq_ctx *ctx = p->ctx;
+    const uint32_t n = (uint32_t)b->n;
+    uint32_t *runs = nullptr, *seg_off = nullptr, *keys = nullptr, *vals = nullptr, *seg = nullptr, *nseg = nullptr;
+    uint8_t *uniform = nullptr;
+    PtSeg *segs = nullptr;
+    uint64_t *incr = nullptr;
+    uint16_t *kguess = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&runs, (size_t)n_ftiles * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&seg_off, (size_t)n_ftiles * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&uniform, n_ftiles, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&segs, (size_t)seg_cap * sizeof(PtSeg), false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&keys, (size_t)seg_cap * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&vals, (size_t)seg_cap * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&seg, (size_t)n_slots * 8, true));
+    SQ_TRY(sq_dalloc(ctx, (void **)&nseg, (size_t)n_slots * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&incr, (size_t)n_ftiles * W * 8, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&kguess, (size_t)n_ftiles * W * 2, true));
+    CUDA_TRY(cudaMemsetAsync(keys, 0xFF, (size_t)seg_cap * 4, ctx->stream));  // unused tail sorts last
+    const int tgrid = sq_grid_for(ctx, n_ftiles, PT_TPB, 8);
+    SQ_LAUNCH(ctx, k_pt_ftile_runs, tgrid, PT_TPB, 0, slot, n, R, n_ftiles, runs, uniform);
+    SQ_TRY(sq_scan_exclusive_u32(ctx, runs, seg_off, n_ftiles, nullptr));
+    SQ_LAUNCH(ctx, k_pt_ftile_segs, tgrid, PT_TPB, 0, slot, n, R, n_ftiles, seg_off, uniform, segs, keys, vals);
+    uint32_t key_bits = 1;
+    while ((1ull << key_bits) < n_slots) key_bits++;
+    // stable: a tile's segments stay in read order; the 0xFFFFFFFF padding shares the low
+    // bits of the largest slot ids at worst, and is cut off by the per-slot ranges below
+    SQ_TRY(sq_radix_sort_pairs(ctx, keys, vals, tmpk, tmpv, seg_cap, 32));
+    uint32_t *seg_lo = seg, *seg_hi = seg + n_slots;
+    SQ_LAUNCH(ctx, k_pt_segments, sq_grid_for(ctx, seg_cap, PT_TPB, 8), PT_TPB, 0, keys, seg_cap, seg_lo, seg_hi);
+    SQ_LAUNCH(ctx, k_pt_seg_counts, sq_grid_for(ctx, n_slots, PT_TPB, 8), PT_TPB, 0, seg_lo, seg_hi, n_slots, 1u, nseg);
+    const BatchView bv = b->view();
+    const int chain_grid = sq_grid_for(ctx, (uint64_t)n_slots * width * 32, PT_TPB, 32);
+    SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, bv, (const uint32_t *)nullptr, segs, vals, seg_lo, nseg, n_slots,
+              width, n_ftiles, approx, p->errors, p->len_cap, ctx->d_err_table, kguess);
+    SQ_TRY(fused_exact_sums(ctx, b, R, n_ftiles, W, kguess, incr, uniform));
+    SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, bv, (const uint32_t *)nullptr, segs, vals, seg_lo, nseg, n_slots,
+              width, n_ftiles, kguess, incr, p->errors, p->len_cap, ctx->d_err_table);
+    (void)key_bits;
+    sq_dfree(ctx, runs);
+    sq_dfree(ctx, seg_off);
+    sq_dfree(ctx, uniform);
+    sq_dfree(ctx, segs);
+    sq_dfree(ctx, keys);
+    sq_dfree(ctx, vals);
+    sq_dfree(ctx, seg);
+    sq_dfree(ctx, nseg);
     sq_dfree(ctx, incr);
     sq_dfree(ctx, kguess);
     return SQ_OK;
@@ -531,12 +653,13 @@ extern "C" int sq_pertile_add(sq_pertile *p, sq_batch *b) {
     long long *tile = nullptr;
     SQ_TRY(sq_dalloc(ctx, (void **)&tile, (size_t)n * 8, false));
     SQ_LAUNCH(ctx, k_pt_tile, sq_grid_for(ctx, n, PT_TPB, 16), PT_TPB, 0, b->view(), tile, p->n_added, p->st);
-    int rc = pt_add_with_tiles(p, b, tile);
+    int rc = pt_add_with_tiles(p, b, tile, nullptr, 0, 0, 0);
     sq_dfree(ctx, tile);
     return rc;
 }
 
-int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile) {
+int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile, const float *approx, uint32_t R,
+                      uint32_t n_ftiles, uint32_t W) {
     sq_ctx *ctx = p->ctx;
     const uint32_t n = (uint32_t)b->n;
     const uint64_t base = p->n_added;
@@ -549,6 +672,7 @@ int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile) {
     SQ_TRY(pt_grow(p, p->n_slots ? p->n_slots : 1, b->max_len ? b->max_len : 1));
     // slot ids of new tiles may exceed slot_cap: slot_tile writes are guarded, and the
     // map is re-read after growing
+    CUDA_TRY(cudaMemsetAsync(&p->st->n_changes, 0, 4, ctx->stream));
     SQ_LAUNCH(ctx, k_pt_map_insert, grid, PT_TPB, 0, tile, n, base, p->map_keys, p->map_vals, p->slot_tile,
               p->slot_cap, p->st);
     SQ_LAUNCH(ctx, k_pt_map_lookup, grid, PT_TPB, 0, b->view(), tile, base, p->map_keys, p->map_vals, slot, idx,
@@ -583,6 +707,13 @@ int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile) {
         while ((1ull << key_bits) < h->n_slots) key_bits++;
         // PT_NONE (skipped reads) carries all-ones low bits, so it sorts last within those bits
         SQ_LAUNCH(ctx, k_pt_lengths, grid, PT_TPB, 0, b->view(), slot, p->lengths, p->len_cap);
+        // reads in tile runs: at most one extra segment per change of tile
+        const uint64_t seg_cap = (uint64_t)n_ftiles + h->n_changes + 2;
+        if (approx && b->max_len && seg_cap <= n / 16 + 64 && seg_cap <= n) {
+            rc = pt_accumulate_runs(p, b, slot, approx, R, n_ftiles, W, h->n_slots, (uint32_t)seg_cap, b->max_len,
+                                    tmpk, tmpv);
+        }
+        else {
         rc = sq_radix_sort_pairs(ctx, slot, idx, tmpk, tmpv, n, h->fail_idx != ~0ULL ? 32 : key_bits);
         if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&seg, (size_t)h->n_slots * 8, true);
         if (rc == SQ_OK) {
@@ -590,6 +721,7 @@ int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile) {
             SQ_LAUNCH(ctx, k_pt_segments, grid, PT_TPB, 0, slot, n, seg_lo, seg_hi);
             const uint32_t width = b->max_len;
             if (width) rc = pt_accumulate(p, b, idx, seg_lo, seg_hi, h->n_slots, width, base);
+        }
         }
     }
     if (rc == SQ_OK && h->fail_idx != ~0ULL) {
