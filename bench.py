@@ -253,7 +253,7 @@ def run_cuda(args):
         "share_of_kernel_time": round(top[1][1] / kernel_ms, 3),
         "all_kernels_gbs": round(text_bytes / (kernel_ms * 1e-3) / 1e9, 1),
         "all_kernels_frac": round(text_bytes / (kernel_ms * 1e-3) / 1e9 / peak, 4),
-        "kernels_ms_per_step": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]},
+        "kernels_ms_per_step": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:48]},
     }
 
     # ---- end to end: host text -> parser -> collectors -> getters --------------

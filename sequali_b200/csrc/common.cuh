@@ -76,6 +76,7 @@ struct sq_batch {
     uint32_t *name_len = nullptr, *tags_off = nullptr, *tags_len = nullptr;
     double *err_sum = nullptr;
     void *meta_block = nullptr;  // single allocation behind the arrays above
+    uint64_t meta_stride = 0;    // elements per array inside meta_block (0: (n + 3) & ~3)
     bool err_sum_valid = false;  // QCMetrics ran on this array
 
     BatchView view() const {

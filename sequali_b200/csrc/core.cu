@@ -6,11 +6,11 @@
 //   k_count_newlines   16-byte vector loads, SWAR newline count per CTA, first
 //                      non-ASCII byte by atomicMin
 //   k_scan_counts      exclusive scan of the per-CTA counts (one CTA)
-//   k_scatter_newlines same traversal, warp-shuffle scans give every newline
-//                      its rank; writes the newline index (u32 offsets)
-//   k_build_records    one thread per record: every 4th newline closes a
-//                      record; validates '@', '+', equal lengths; emits the SoA
-//                      descriptors and the batch's longest sequence
+//   k_scatter_fields   same traversal, warp-shuffle scans give every newline
+//                      its rank k; the newline writes the descriptor field it
+//                      closes (record k/4, line k%4) and checks '@' / '+'
+//   k_finish_records   one thread per record: sequence length, equal-length
+//                      check, longest sequence / record of the array
 #include <math.h>
 #include <stdarg.h>
 
@@ -334,91 +334,98 @@ __global__ void __launch_bounds__(1024) k_scan_counts(uint32_t *counts, uint32_t
     if (threadIdx.x == 0) st->n_newlines = carry_s;
 }
 
+// Second pass over the text: every newline learns its global rank k (CTA offset
+// from the scan + warp/CTA prefix) and writes the descriptor field it closes
+// straight into the record arrays: record k/4, line k%4.
+//   line 0 (name)  -> seq_off[rec]  = p + 1
+//   line 1 (seq)   -> seq_len[rec]  = p   (end of the sequence; turned into a length by k_finish_records),
+//                     and the '+' check on the byte that follows (:1119-1127)
+//   line 2 ('+')   -> qual_off[rec] = p + 1
+//   line 3 (qual)  -> name_off[rec + 1] = p + 2, and the '@' check on the next record (:1097)
+// A lane owns 64 consecutive bytes, so one warp scan ranks 2 KiB of text.
+constexpr int SCAT_LANE_VECS = 4;  // 16-byte vectors per lane, consecutive
+
 __global__ void __launch_bounds__(PARSE_THREADS)
-k_scatter_newlines(const uint8_t *__restrict__ text, uint64_t nbytes,
-                   const uint32_t *__restrict__ cta_offsets, uint32_t *__restrict__ nl_pos) {
+k_scatter_fields(const uint8_t *__restrict__ text, uint64_t nbytes, const uint32_t *__restrict__ cta_offsets,
+                 uint64_t n_rec, int check_partial, uint32_t *__restrict__ name_off, uint32_t *__restrict__ seq_off,
+                 uint32_t *__restrict__ seq_len, uint32_t *__restrict__ qual_off, ParseState *st) {
     __shared__ uint32_t warp_tot[PARSE_THREADS / 32];
-    uint32_t warp = threadIdx.x >> 5;
-    uint64_t warp_base = (uint64_t)blockIdx.x * PARSE_CTA_BYTES + (uint64_t)warp * PARSE_WARP_BYTES;
-    uint32_t m[PARSE_ITERS][4];
-    uint32_t cnt[PARSE_ITERS];
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint64_t lane_base = (uint64_t)blockIdx.x * PARSE_CTA_BYTES + (uint64_t)warp * PARSE_WARP_BYTES +
+                               (uint64_t)lane_id() * (16 * SCAT_LANE_VECS);
+    uint32_t m[SCAT_LANE_VECS][4];
     uint32_t mine = 0;
 #pragma unroll
-    for (int it = 0; it < PARSE_ITERS; it++) {
-        uint64_t off = warp_base + (uint64_t)(it * 32 + lane_id()) * 16;
+    for (int it = 0; it < SCAT_LANE_VECS; it++) {
+        const uint64_t off = lane_base + (uint64_t)it * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (off < nbytes) v = load_vec16(text, nbytes, off >> 4);
         m[it][0] = newline_mask(v.x);
         m[it][1] = newline_mask(v.y);
         m[it][2] = newline_mask(v.z);
         m[it][3] = newline_mask(v.w);
-        cnt[it] = __popc(m[it][0]) + __popc(m[it][1]) + __popc(m[it][2]) + __popc(m[it][3]);
-        mine += cnt[it];
+        mine += __popc(m[it][0]) + __popc(m[it][1]) + __popc(m[it][2]) + __popc(m[it][3]);
     }
-    uint32_t wsum = warp_sum_u32(mine);
+    uint32_t wsum;
+    const uint32_t ex = warp_excl_scan_u32(mine, &wsum);
     if (lane_id() == 0) warp_tot[warp] = wsum;
     __syncthreads();
-    uint32_t rank = cta_offsets[blockIdx.x];
-    for (uint32_t i = 0; i < warp; i++) rank += warp_tot[i];
+    if (mine == 0) return;
+    uint64_t k = (uint64_t)cta_offsets[blockIdx.x] + ex;
+    for (uint32_t i = 0; i < warp; i++) k += warp_tot[i];
 #pragma unroll
-    for (int it = 0; it < PARSE_ITERS; it++) {
-        uint32_t tot;
-        uint32_t ex = warp_excl_scan_u32(cnt[it], &tot);
-        uint32_t w = rank + ex;
-        uint64_t off = warp_base + (uint64_t)(it * 32 + lane_id()) * 16;
+    for (int it = 0; it < SCAT_LANE_VECS; it++) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             uint32_t bits = m[it][j];
             while (bits) {
-                uint32_t b = __ffs(bits) - 1;  // bit 7 of byte b/8
+                const uint32_t b = __ffs(bits) - 1;  // bit 7 of byte b/8
                 bits &= bits - 1;
-                nl_pos[w++] = (uint32_t)(off + j * 4 + (b >> 3));
+                const uint64_t p = lane_base + it * 16 + j * 4 + (b >> 3);
+                const uint64_t rec = k >> 2;
+                const uint32_t line = (uint32_t)k & 3;
+                k++;
+                if (rec > n_rec || (rec == n_rec && !check_partial)) continue;
+                if (line == 0) seq_off[rec] = (uint32_t)p + 1;
+                else if (line == 1) {
+                    seq_len[rec] = (uint32_t)p;
+                    if (p + 1 < nbytes && text[p + 1] != '+')
+                        atomicMin(&st->err_key, (unsigned long long)(rec << 3 | SQ_PARSE_NO_PLUS));
+                }
+                else if (line == 2) qual_off[rec] = (uint32_t)p + 1;
+                else if (rec < n_rec) {
+                    name_off[rec + 1] = (uint32_t)p + 2;
+                    // the record that starts behind this newline: complete, or the partial tail (:1094)
+                    const uint64_t start = p + 1;
+                    const bool look = rec + 1 < n_rec || (check_partial && start + 2 < nbytes);
+                    if (look && text[start] != '@')
+                        atomicMin(&st->err_key, (unsigned long long)((rec + 1) << 3 | SQ_PARSE_NO_AT));
+                }
             }
         }
-        rank += tot;
     }
 }
 
-// One thread per record (plus one for the partial record that may follow the
-// last complete one).  Checks in the reference's order (:1097, :1119, :1140).
+// One thread per record: sequence length, the equal-length check (:1140), longest
+// sequence / record.  Thread 0 also looks at the very first byte of the text.
 __global__ void __launch_bounds__(256)
-k_build_records(const uint8_t *__restrict__ text, uint64_t nbytes, const uint32_t *__restrict__ nl,
-                uint64_t n_newlines, uint64_t n_rec, int check_partial, uint32_t *name_off,
-                uint32_t *seq_off, uint32_t *seq_len, uint32_t *qual_off, ParseState *st) {
+k_finish_records(const uint8_t *__restrict__ text, uint64_t nbytes, uint64_t n_rec, int check_partial,
+                 const uint32_t *__restrict__ name_off, const uint32_t *__restrict__ seq_off,
+                 uint32_t *__restrict__ seq_len, const uint32_t *__restrict__ qual_off, ParseState *st) {
     uint32_t local_max = 0, local_rec = 0;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n_rec;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec;
          r += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t start = r == 0 ? 0 : (uint64_t)nl[4 * r - 1] + 1;
-        if (r == n_rec) {
-            if (!check_partial) break;
-            if (start + 2 >= nbytes) break;  // :1094
-            if (text[start] != '@') {
-                atomicMin(&st->err_key, (unsigned long long)(r << 3 | SQ_PARSE_NO_AT));
-                break;
-            }
-            uint64_t have = n_newlines - 4 * n_rec;
-            if (have >= 2) {
-                uint64_t plus = (uint64_t)nl[4 * r + 1] + 1;
-                if (plus < nbytes && text[plus] != '+')
-                    atomicMin(&st->err_key, (unsigned long long)(r << 3 | SQ_PARSE_NO_PLUS));
-            }
-            break;
-        }
-        uint32_t e1 = nl[4 * r], e2 = nl[4 * r + 1], e3 = nl[4 * r + 2], e4 = nl[4 * r + 3];
-        uint32_t code = 0;
-        if (text[start] != '@') code = SQ_PARSE_NO_AT;
-        else if (text[(uint64_t)e2 + 1] != '+') code = SQ_PARSE_NO_PLUS;
-        else if (e2 - e1 != e4 - e3) code = SQ_PARSE_LEN;
-        if (code) {
-            atomicMin(&st->err_key, (unsigned long long)(r << 3 | code));
-            continue;
-        }
-        name_off[r] = (uint32_t)start + 1;
-        seq_off[r] = e1 + 1;
-        seq_len[r] = e2 - e1 - 1;
-        qual_off[r] = e3 + 1;
-        local_max = max(local_max, e2 - e1 - 1);
-        local_rec = max(local_rec, e4 + 1 - (uint32_t)start);
+        const uint32_t start = name_off[r] - 1, so = seq_off[r], se = seq_len[r], qo = qual_off[r];
+        const uint32_t e4 = name_off[r + 1] - 2;
+        const uint32_t L = se - so;
+        if (L != e4 - qo) atomicMin(&st->err_key, (unsigned long long)(r << 3 | SQ_PARSE_LEN));
+        seq_len[r] = L;
+        local_max = max(local_max, L);
+        local_rec = max(local_rec, e4 + 1 - start);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const bool look = n_rec > 0 || (check_partial && 2 < nbytes);
+        if (look && text[0] != '@') atomicMin(&st->err_key, (unsigned long long)(0ULL << 3 | SQ_PARSE_NO_AT));
     }
     local_max = warp_max_u32(local_max);
     local_rec = warp_max_u32(local_rec);
@@ -428,7 +435,8 @@ k_build_records(const uint8_t *__restrict__ text, uint64_t nbytes, const uint32_
 
 static int alloc_fastq_metas(sq_batch *b, uint64_t n) {
     // name_off | seq_off | seq_len | qual_off | err_sum
-    size_t n4 = (size_t)((n + 3) & ~3ULL);
+    size_t n4 = (size_t)((n + 1 + 3) & ~3ULL);
+    b->meta_stride = n4;
     SQ_TRY(sq_dalloc(b->ctx, &b->meta_block, n4 * 4 * 4 + n4 * 8, false));
     uint32_t *p = (uint32_t *)b->meta_block;
     b->name_off = p;
@@ -475,23 +483,26 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
         n_rec = max_records;
         check_partial = 0;
     }
-    uint32_t *nl = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&nl, (size_t)(n_newlines + 4) * 4, false));
-    if (n_newlines)
-        SQ_LAUNCH(ctx, k_scatter_newlines, n_cta, PARSE_THREADS, 0, b->text, nbytes, cta_counts, nl);
     SQ_TRY(alloc_fastq_metas(b, n_rec));
+    // name_off[0]: the first record starts at byte 0; slot n_rec of the other arrays is only
+    // written when a partial record follows (and only read to word an error message)
+    uint32_t *h_one = (uint32_t *)((char *)ctx->h_scratch + 256);
+    *h_one = 1;
+    CUDA_TRY(cudaMemcpyAsync(b->name_off, h_one, 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_newlines)
+        SQ_LAUNCH(ctx, k_scatter_fields, n_cta, PARSE_THREADS, 0, b->text, nbytes, cta_counts, n_rec, check_partial,
+                  b->name_off, b->seq_off, b->seq_len, b->qual_off, st);
     int grid = sq_grid_for(ctx, n_rec + 1, 256);
-    SQ_LAUNCH(ctx, k_build_records, grid, 256, 0, b->text, nbytes, nl, n_newlines, n_rec, check_partial,
-              b->name_off, b->seq_off, b->seq_len, b->qual_off, st);
-    // the consumed offset is the byte after the last record's 4th newline
-    uint32_t *h_last = (uint32_t *)((char *)ctx->h_scratch + 256);
-    *h_last = 0;
-    if (n_rec)
-        CUDA_TRY(cudaMemcpyAsync(h_last, nl + (4 * n_rec - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SQ_LAUNCH(ctx, k_finish_records, grid, 256, 0, b->text, nbytes, n_rec, check_partial, b->name_off, b->seq_off,
+              b->seq_len, b->qual_off, st);
+    // the consumed offset is the byte after the last record's 4th newline = name_off[n_rec] - 1
+    uint32_t *h_last = (uint32_t *)((char *)ctx->h_scratch + 260);
+    *h_last = 1;
+    if (n_rec) CUDA_TRY(cudaMemcpyAsync(h_last, b->name_off + n_rec, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     info->n_records = n_rec;
-    info->consumed = n_rec ? (uint64_t)*h_last + 1 : 0;
+    info->consumed = n_rec ? (uint64_t)*h_last - 1 : 0;
     info->max_seq_len = hst->max_seq_len;
     int rc = SQ_OK;
     if (hst->err_key != ~0ULL) {
@@ -499,16 +510,14 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
         info->err_code = (int32_t)(hst->err_key & 7);
         info->err_record = r;
         // locate the offending byte for the message (rare path, tiny copies)
-        uint32_t idx[2] = {0, 0};
-        uint64_t start = 0;
-        if (r > 0) {
-            SQ_TRY(sq_memcpy_d2h(ctx, idx, nl + (4 * r - 1), 4));
-            start = (uint64_t)idx[0] + 1;
-        }
+        uint32_t v[3] = {1, 0, 0};  // name_off, seq_off, seq_len (or, for the partial tail, the sequence end)
+        if (r > 0) SQ_TRY(sq_memcpy_d2h(ctx, &v[0], b->name_off + r, 4));
+        const uint64_t start = (uint64_t)v[0] - 1;
         if (info->err_code == SQ_PARSE_NO_AT) info->err_pos = start;
         else if (info->err_code == SQ_PARSE_NO_PLUS) {
-            SQ_TRY(sq_memcpy_d2h(ctx, idx, nl + (4 * r + 1), 4));
-            info->err_pos = (uint64_t)idx[0] + 1;
+            SQ_TRY(sq_memcpy_d2h(ctx, &v[1], b->seq_off + r, 4));
+            SQ_TRY(sq_memcpy_d2h(ctx, &v[2], b->seq_len + r, 4));
+            info->err_pos = (r < n_rec ? (uint64_t)v[1] + v[2] : (uint64_t)v[2]) + 1;
         }
         else info->err_pos = start + 1;
         rc = SQ_E_FORMAT;
@@ -517,7 +526,6 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
     b->max_len = info->max_seq_len;
     b->max_rec_bytes = hst->max_rec_bytes;
     b->text_end = info->consumed;
-    sq_dfree(ctx, nl);
     sq_dfree(ctx, cta_counts);
     return rc;
 }
@@ -657,7 +665,7 @@ extern "C" int sq_batch_get_metas(sq_batch *b, sq_meta *out) {
     CUDA_TRY(cudaSetDevice(b->ctx->device));
     uint64_t n = b->n;
     if (n == 0) return SQ_OK;
-    size_t n4 = (size_t)((n + 3) & ~3ULL);
+    size_t n4 = b->meta_stride ? (size_t)b->meta_stride : (size_t)((n + 3) & ~3ULL);
     bool aux = b->name_len != nullptr;
     size_t bytes = n4 * 4 * (aux ? 7 : 4) + n4 * 8;
     std::vector<uint8_t> host(bytes);

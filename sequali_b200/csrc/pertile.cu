@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(PT_TPB)
 k_pt_seg_counts(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_hi, uint32_t n_slots,
                 uint32_t seg_rows, uint32_t *__restrict__ nseg) {
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x)
-        nseg[s] = (seg_hi[s] - seg_lo[s] + seg_rows - 1) / seg_rows;
+        nseg[s] = seg_hi[s] > seg_lo[s] ? (seg_hi[s] - seg_lo[s] + seg_rows - 1) / seg_rows : 0;
 }
 __global__ void __launch_bounds__(PT_TPB)
 k_pt_seg_fill(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_hi,
@@ -278,13 +278,13 @@ __device__ double pt_rows_sum(const BatchView &bv, const uint32_t *__restrict__ 
 }
 
 // one warp per chain (tile slot, position): expected binade at the start of every segment.
-// A tile's segments are segs[perm[first .. first+cnt)] (perm == nullptr: identity).
+// A tile's segments are those of segs[first .. first+cnt) that carry its slot (the general
+// path groups them; the tile-run path leaves foreign segments of a mixed tile in between).
 __global__ void __launch_bounds__(PT_TPB)
 k_pt_guess(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__restrict__ segs,
-           const uint32_t *__restrict__ perm, const uint32_t *__restrict__ seg_first,
-           const uint32_t *__restrict__ nseg, uint32_t n_slots, uint32_t width, uint32_t stride,
-           const float *__restrict__ approx, const double *__restrict__ errors, uint64_t len_cap,
-           const double *__restrict__ err_tab, uint16_t *__restrict__ kguess) {
+           const uint32_t *__restrict__ seg_first, const uint32_t *__restrict__ nseg, uint32_t n_slots,
+           uint32_t width, uint32_t stride, const float *__restrict__ approx, const double *__restrict__ errors,
+           uint64_t len_cap, const double *__restrict__ err_tab, uint16_t *__restrict__ kguess) {
     const uint64_t chains = (uint64_t)n_slots * width;
     const uint64_t warps = (uint64_t)gridDim.x * (PT_TPB / 32);
     for (uint64_t c = (uint64_t)blockIdx.x * (PT_TPB / 32) + (threadIdx.x >> 5); c < chains; c += warps) {
@@ -296,12 +296,29 @@ k_pt_guess(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__rest
         for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
             const uint32_t j = j0 + lane_id();
             double v = 0.0;
-            uint32_t data = PT_NONE;
+            uint32_t data = PT_NONE, lo = 0, hi = 0;
+            bool replayed = false;
             if (j < cnt) {
-                const PtSeg sg = segs[perm ? perm[first + j] : first + j];
-                data = sg.data;
-                v = data != PT_NONE ? (double)approx[(uint64_t)pos * stride + data]
-                                    : pt_rows_sum(bv, order, sg.lo, sg.hi, pos, err_tab);
+                const PtSeg sg = segs[first + j];
+                if (sg.slot == s) {
+                    data = sg.data;
+                    lo = sg.lo;
+                    hi = sg.hi;
+                    if (data != PT_NONE) v = (double)approx[(uint64_t)pos * stride + data];
+                    else replayed = true;
+                }
+            }
+            // segments without precomputed sums (pieces of a mixed tile): the warp sums their rows together
+            uint32_t todo = __ballot_sync(0xffffffffu, replayed);
+            while (todo) {
+                const uint32_t l = (uint32_t)__ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t rlo = __shfl_sync(0xffffffffu, lo, l), rhi = __shfl_sync(0xffffffffu, hi, l);
+                double part = 0.0;
+                for (uint32_t i = rlo + lane_id(); i < rhi; i += 32) part += pt_rows_sum(bv, order, i, i + 1, pos, err_tab);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                if (lane_id() == l) v = part;
             }
             double x = v;
 #pragma unroll
@@ -317,41 +334,65 @@ k_pt_guess(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__rest
     }
 }
 
-// replay rows [lo, hi) of the tile-sorted order on chain `pos`, bit-exact
+// Replay rows [lo, hi) of `order` (or of the array) on chain `pos`, bit-exact.  128 rows
+// are gathered at a time (four per lane, all loads in flight together); within a
+// block of 32 rows the in-binade integer rule is applied to as many rows as stay
+// in the binade, the row that does not gets a real addition, and the block is
+// resumed behind it.
 __device__ uint64_t pt_replay_rows(uint64_t sbits, const BatchView &bv, const uint32_t *__restrict__ order,
                                    uint32_t lo, uint32_t hi, uint32_t pos, const double *s_err) {
-    uint32_t i = lo;
-    while (i < hi) {
-        const uint32_t ii = i + lane_id();
-        uint64_t ebits = 0;
-        bool has = false;
-        if (ii < hi) {
-            const uint32_t r = order ? order[ii] : ii;
-            if (pos < bv.seq_len[r]) {
-                const uint32_t q = (uint8_t)(bv.text[bv.qual_off[r] + pos] - 33);
-                if (q <= 93) {
-                    has = true;
-                    ebits = (uint64_t)__double_as_longlong(s_err[q]);
-                }
+    for (uint32_t c0 = lo; c0 < hi; c0 += 128) {
+        uint64_t eb[4];
+        uint32_t rr[4], off[4];
+        bool ok[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t ii = c0 + b * 32 + lane_id();
+            ok[b] = ii < hi;
+            rr[b] = ok[b] ? (order ? order[ii] : ii) : 0;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            if (ok[b]) {
+                ok[b] = pos < bv.seq_len[rr[b]];
+                off[b] = bv.qual_off[rr[b]];
             }
         }
-        const uint32_t k = (uint32_t)(sbits >> 52);
-        uint64_t inc = has ? pt_increment(k, ebits) : 0;
-        const bool hard = inc >= PT_HARD;
-        if (hard) inc = 0;
-        const uint64_t incl = warp_incl_scan_u64(inc);
-        const bool stays = (uint32_t)((sbits + incl) >> 52) == k;
-        const uint32_t nv = min(32u, hi - i);
-        const uint32_t bad = __ballot_sync(0xffffffffu, ii < hi && (hard || !stays));
-        const uint32_t f = bad ? (uint32_t)__ffs(bad) - 1 : 32u;
-        const uint32_t nacc = min(f, nv);
-        if (nacc) sbits += __shfl_sync(0xffffffffu, incl, nacc - 1);
-        i += nacc;
-        if (f < nv) {  // a real, ordered addition: crosses a power of two, ties, or starts from 0.0
-            const uint64_t eb = __shfl_sync(0xffffffffu, ebits, f);
-            const double s = __longlong_as_double((long long)sbits) + __longlong_as_double((long long)eb);
-            sbits = (uint64_t)__double_as_longlong(s);
-            i += 1;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            eb[b] = 0;
+            if (ok[b]) {
+                const uint32_t q = (uint8_t)(bv.text[off[b] + pos] - 33);
+                if (q <= 93) eb[b] = (uint64_t)__double_as_longlong(s_err[q]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t base = c0 + b * 32;
+            if (base >= hi) break;
+            const uint32_t nv = min(32u, hi - base);
+            uint32_t s0 = 0;  // rows of this block already applied
+            while (s0 < nv) {
+                const uint32_t k = (uint32_t)(sbits >> 52);
+                const bool mine = lane_id() >= s0 && lane_id() < nv && eb[b] != 0;
+                uint64_t inc = mine ? pt_increment(k, eb[b]) : 0;
+                const bool hard = inc >= PT_HARD;
+                if (hard) inc = 0;
+                const uint64_t incl = warp_incl_scan_u64(inc);
+                const bool stays = (uint32_t)((sbits + incl) >> 52) == k;
+                const uint32_t bad = __ballot_sync(0xffffffffu, mine && (hard || !stays));
+                const uint32_t f = bad ? (uint32_t)__ffs(bad) - 1 : 32u;
+                if (f >= nv) {  // every remaining row of the block stays in the binade
+                    sbits += __shfl_sync(0xffffffffu, incl, 31);
+                    break;
+                }
+                if (f > 0) sbits += __shfl_sync(0xffffffffu, incl, f - 1);
+                // a real, ordered addition: crosses a power of two, ties, or starts from 0.0
+                const uint64_t e = __shfl_sync(0xffffffffu, eb[b], f);
+                const double sum = __longlong_as_double((long long)sbits) + __longlong_as_double((long long)e);
+                sbits = (uint64_t)__double_as_longlong(sum);
+                s0 = f + 1;
+            }
         }
     }
     return sbits;
@@ -359,10 +400,10 @@ __device__ uint64_t pt_replay_rows(uint64_t sbits, const BatchView &bv, const ui
 
 __global__ void __launch_bounds__(PT_TPB)
 k_pt_chain(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__restrict__ segs,
-           const uint32_t *__restrict__ perm, const uint32_t *__restrict__ seg_first,
-           const uint32_t *__restrict__ nseg, uint32_t n_slots, uint32_t width, uint32_t stride,
-           const uint16_t *__restrict__ kguess, const uint64_t *__restrict__ incr, double *errors,
-           uint64_t len_cap, const double *__restrict__ err_tab) {
+           const uint32_t *__restrict__ seg_first, const uint32_t *__restrict__ nseg, uint32_t n_slots,
+           uint32_t width, uint32_t stride, const uint16_t *__restrict__ kguess,
+           const uint64_t *__restrict__ incr, double *errors, uint64_t len_cap,
+           const double *__restrict__ err_tab) {
     __shared__ double s_err[94];
     for (uint32_t i = threadIdx.x; i < 94; i += PT_TPB) s_err[i] = err_tab[i];
     __syncthreads();
@@ -378,30 +419,36 @@ k_pt_chain(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__rest
         uint32_t j = 0;
         while (j < cnt) {
             const uint32_t jj = j + lane_id();
-            uint64_t inc = PT_HARD;
-            uint32_t kg = 0, seg_id = 0;
+            uint64_t inc = 0;
+            uint32_t kg = 0, lo = 0, hi = 0;
+            bool mine = false;
             if (jj < cnt) {
-                seg_id = perm ? perm[first + jj] : first + jj;
-                const uint32_t data = segs[seg_id].data;
-                if (data != PT_NONE) {
-                    inc = incr[(uint64_t)pos * stride + data];
-                    kg = kguess[(uint64_t)pos * stride + data];
+                const PtSeg sg = segs[first + jj];
+                if (sg.slot == s) {  // a foreign segment adds nothing
+                    mine = true;
+                    lo = sg.lo;
+                    hi = sg.hi;
+                    inc = PT_HARD;
+                    if (sg.data != PT_NONE) {
+                        inc = incr[(uint64_t)pos * stride + sg.data];
+                        kg = kguess[(uint64_t)pos * stride + sg.data];
+                    }
                 }
             }
             const uint32_t k = (uint32_t)(sbits >> 52);
-            const bool hard = inc >= PT_HARD || kg != k;
+            const bool hard = mine && (inc >= PT_HARD || kg != k);
             if (hard) inc = 0;
             const uint64_t incl = warp_incl_scan_u64(inc);
             const bool stays = (uint32_t)((sbits + incl) >> 52) == k;
             const uint32_t nv = min(32u, cnt - j);
-            const uint32_t bad = __ballot_sync(0xffffffffu, jj < cnt && (hard || !stays));
+            const uint32_t bad = __ballot_sync(0xffffffffu, mine && (hard || !stays));
             const uint32_t f = bad ? (uint32_t)__ffs(bad) - 1 : 32u;
             const uint32_t nacc = min(f, nv);
             if (nacc) sbits += __shfl_sync(0xffffffffu, incl, nacc - 1);
             j += nacc;
             if (f < nv) {
-                const PtSeg sg = segs[__shfl_sync(0xffffffffu, seg_id, f)];
-                sbits = pt_replay_rows(sbits, bv, order, sg.lo, sg.hi, pos, s_err);
+                const uint32_t rlo = __shfl_sync(0xffffffffu, lo, f), rhi = __shfl_sync(0xffffffffu, hi, f);
+                sbits = pt_replay_rows(sbits, bv, order, rlo, rhi, pos, s_err);
                 j += 1;
             }
         }
@@ -431,7 +478,7 @@ k_pt_ftile_runs(const uint32_t *__restrict__ slot, uint32_t n, uint32_t R, uint3
 __global__ void __launch_bounds__(PT_TPB)
 k_pt_ftile_segs(const uint32_t *__restrict__ slot, uint32_t n, uint32_t R, uint32_t n_ftiles,
                 const uint32_t *__restrict__ seg_off, const uint8_t *__restrict__ uniform,
-                PtSeg *__restrict__ segs, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                PtSeg *__restrict__ segs, uint32_t *__restrict__ seg_lo, uint32_t *__restrict__ seg_hi) {
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_ftiles; t += gridDim.x * blockDim.x) {
         const uint32_t r0 = t * R, r1 = min(n, r0 + R);
         uint32_t w = seg_off[t], prev = PT_NONE, lo = r0;
@@ -445,8 +492,9 @@ k_pt_ftile_segs(const uint32_t *__restrict__ slot, uint32_t n, uint32_t R, uint3
                     g.slot = prev;
                     g.data = uniform[t] ? t : PT_NONE;
                     segs[w] = g;
-                    keys[w] = prev;
-                    vals[w] = w;
+                    // segments are numbered in read order: a tile's run is [min, max] of its numbers
+                    atomicMin(seg_lo + prev, w);
+                    atomicMax(seg_hi + prev, w + 1);
                     w++;
                 }
                 lo = r;
@@ -568,11 +616,11 @@ static int pt_accumulate(sq_pertile *p, sq_batch *b, const uint32_t *order, cons
     SQ_LAUNCH(ctx, k_pt_segment_sums<false>, sgrid, PT_TPB, 0, bv, order, segs, n_segs_dev, CG, RG, width4, seg_cap,
               ctx->d_err_table, p->lut, kguess, approx, incr, base, p->st);
     const int chain_grid = sq_grid_for(ctx, (uint64_t)n_slots * width * 32, PT_TPB, 32);
-    SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, bv, order, segs, (const uint32_t *)nullptr, seg_first, nseg,
+    SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, bv, order, segs, seg_first, nseg,
               n_slots, width, seg_cap, approx, p->errors, p->len_cap, ctx->d_err_table, kguess);
     SQ_LAUNCH(ctx, k_pt_segment_sums<true>, sgrid, PT_TPB, (size_t)PT_LUT_NK * 94 * 8, bv, order, segs, n_segs_dev,
               CG, RG, width4, seg_cap, ctx->d_err_table, p->lut, kguess, approx, incr, base, p->st);
-    SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, bv, order, segs, (const uint32_t *)nullptr, seg_first, nseg,
+    SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, bv, order, segs, seg_first, nseg,
               n_slots, width, seg_cap, kguess, incr, p->errors, p->len_cap, ctx->d_err_table);
     sq_dfree(ctx, nseg);
     sq_dfree(ctx, seg_first);
@@ -588,11 +636,10 @@ static int pt_accumulate(sq_pertile *p, sq_batch *b, const uint32_t *order, cons
 // passes for the approximate sums (k_fused_columns<false> produced them per fixed
 // tile of R records), one TMA-staged pass for the exact integer sums.
 static int pt_accumulate_runs(sq_pertile *p, sq_batch *b, const uint32_t *slot, const float *approx, uint32_t R,
-                              uint32_t n_ftiles, uint32_t W, uint32_t n_slots, uint32_t seg_cap, uint32_t width,
-                              uint32_t *tmpk, uint32_t *tmpv) {
+                              uint32_t n_ftiles, uint32_t W, uint32_t n_slots, uint32_t seg_cap, uint32_t width) {
     sq_ctx *ctx = p->ctx;
     const uint32_t n = (uint32_t)b->n;
-    uint32_t *runs = nullptr, *seg_off = nullptr, *keys = nullptr, *vals = nullptr, *seg = nullptr, *nseg = nullptr;
+    uint32_t *runs = nullptr, *seg_off = nullptr, *seg = nullptr, *nseg = nullptr;
     uint8_t *uniform = nullptr;
     PtSeg *segs = nullptr;
     uint64_t *incr = nullptr;
@@ -601,39 +648,29 @@ static int pt_accumulate_runs(sq_pertile *p, sq_batch *b, const uint32_t *slot, 
     SQ_TRY(sq_dalloc(ctx, (void **)&seg_off, (size_t)n_ftiles * 4, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&uniform, n_ftiles, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&segs, (size_t)seg_cap * sizeof(PtSeg), false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&keys, (size_t)seg_cap * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&vals, (size_t)seg_cap * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&seg, (size_t)n_slots * 8, true));
+    SQ_TRY(sq_dalloc(ctx, (void **)&seg, (size_t)n_slots * 8, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&nseg, (size_t)n_slots * 4, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&incr, (size_t)n_ftiles * W * 8, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&kguess, (size_t)n_ftiles * W * 2, true));
-    CUDA_TRY(cudaMemsetAsync(keys, 0xFF, (size_t)seg_cap * 4, ctx->stream));  // unused tail sorts last
+    uint32_t *seg_lo = seg, *seg_hi = seg + n_slots;
+    CUDA_TRY(cudaMemsetAsync(seg_lo, 0xFF, (size_t)n_slots * 4, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(seg_hi, 0, (size_t)n_slots * 4, ctx->stream));
     const int tgrid = sq_grid_for(ctx, n_ftiles, PT_TPB, 8);
     SQ_LAUNCH(ctx, k_pt_ftile_runs, tgrid, PT_TPB, 0, slot, n, R, n_ftiles, runs, uniform);
     SQ_TRY(sq_scan_exclusive_u32(ctx, runs, seg_off, n_ftiles, nullptr));
-    SQ_LAUNCH(ctx, k_pt_ftile_segs, tgrid, PT_TPB, 0, slot, n, R, n_ftiles, seg_off, uniform, segs, keys, vals);
-    uint32_t key_bits = 1;
-    while ((1ull << key_bits) < n_slots) key_bits++;
-    // stable: a tile's segments stay in read order; the 0xFFFFFFFF padding shares the low
-    // bits of the largest slot ids at worst, and is cut off by the per-slot ranges below
-    SQ_TRY(sq_radix_sort_pairs(ctx, keys, vals, tmpk, tmpv, seg_cap, 32));
-    uint32_t *seg_lo = seg, *seg_hi = seg + n_slots;
-    SQ_LAUNCH(ctx, k_pt_segments, sq_grid_for(ctx, seg_cap, PT_TPB, 8), PT_TPB, 0, keys, seg_cap, seg_lo, seg_hi);
+    SQ_LAUNCH(ctx, k_pt_ftile_segs, tgrid, PT_TPB, 0, slot, n, R, n_ftiles, seg_off, uniform, segs, seg_lo, seg_hi);
     SQ_LAUNCH(ctx, k_pt_seg_counts, sq_grid_for(ctx, n_slots, PT_TPB, 8), PT_TPB, 0, seg_lo, seg_hi, n_slots, 1u, nseg);
     const BatchView bv = b->view();
     const int chain_grid = sq_grid_for(ctx, (uint64_t)n_slots * width * 32, PT_TPB, 32);
-    SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, bv, (const uint32_t *)nullptr, segs, vals, seg_lo, nseg, n_slots,
+    SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, bv, (const uint32_t *)nullptr, segs, seg_lo, nseg, n_slots,
               width, n_ftiles, approx, p->errors, p->len_cap, ctx->d_err_table, kguess);
     SQ_TRY(fused_exact_sums(ctx, b, R, n_ftiles, W, kguess, incr, uniform));
-    SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, bv, (const uint32_t *)nullptr, segs, vals, seg_lo, nseg, n_slots,
+    SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, bv, (const uint32_t *)nullptr, segs, seg_lo, nseg, n_slots,
               width, n_ftiles, kguess, incr, p->errors, p->len_cap, ctx->d_err_table);
-    (void)key_bits;
     sq_dfree(ctx, runs);
     sq_dfree(ctx, seg_off);
     sq_dfree(ctx, uniform);
     sq_dfree(ctx, segs);
-    sq_dfree(ctx, keys);
-    sq_dfree(ctx, vals);
     sq_dfree(ctx, seg);
     sq_dfree(ctx, nseg);
     sq_dfree(ctx, incr);
@@ -709,9 +746,8 @@ int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile, const float *
         SQ_LAUNCH(ctx, k_pt_lengths, grid, PT_TPB, 0, b->view(), slot, p->lengths, p->len_cap);
         // reads in tile runs: at most one extra segment per change of tile
         const uint64_t seg_cap = (uint64_t)n_ftiles + h->n_changes + 2;
-        if (approx && b->max_len && seg_cap <= n / 16 + 64 && seg_cap <= n) {
-            rc = pt_accumulate_runs(p, b, slot, approx, R, n_ftiles, W, h->n_slots, (uint32_t)seg_cap, b->max_len,
-                                    tmpk, tmpv);
+        if (approx && b->max_len && seg_cap <= n / 16 + 64) {
+            rc = pt_accumulate_runs(p, b, slot, approx, R, n_ftiles, W, h->n_slots, (uint32_t)seg_cap, b->max_len);
         }
         else {
         rc = sq_radix_sort_pairs(ctx, slot, idx, tmpk, tmpv, n, h->fail_idx != ~0ULL ? 32 : key_bits);
