@@ -342,30 +342,32 @@ __global__ void __launch_bounds__(1024) k_scan_counts(uint32_t *counts, uint32_t
 //                     and the '+' check on the byte that follows (:1119-1127)
 //   line 2 ('+')   -> qual_off[rec] = p + 1
 //   line 3 (qual)  -> name_off[rec + 1] = p + 2, and the '@' check on the next record (:1097)
-// A lane owns 64 consecutive bytes, so one warp scan ranks 2 KiB of text.
-constexpr int SCAT_LANE_VECS = 4;  // 16-byte vectors per lane, consecutive
+// Loads stay coalesced; a lane ranks 64 consecutive bytes, so one warp scan covers 2 KiB of text.
+// bit i of the result = bit 7 of byte i of m (m has at most bit 7 of each byte set)
+__device__ __forceinline__ uint32_t pack_msb4(uint32_t m) { return ((m >> 7) * 0x00204081u) >> 21 & 0xFu; }
 
 __global__ void __launch_bounds__(PARSE_THREADS)
 k_scatter_fields(const uint8_t *__restrict__ text, uint64_t nbytes, const uint32_t *__restrict__ cta_offsets,
                  uint64_t n_rec, int check_partial, uint32_t *__restrict__ name_off, uint32_t *__restrict__ seq_off,
                  uint32_t *__restrict__ seq_len, uint32_t *__restrict__ qual_off, ParseState *st) {
     __shared__ uint32_t warp_tot[PARSE_THREADS / 32];
+    __shared__ __align__(8) uint16_t vec_mask[PARSE_THREADS / 32][32 * PARSE_ITERS];  // newline bits per 16-byte vector
     const uint32_t warp = threadIdx.x >> 5;
-    const uint64_t lane_base = (uint64_t)blockIdx.x * PARSE_CTA_BYTES + (uint64_t)warp * PARSE_WARP_BYTES +
-                               (uint64_t)lane_id() * (16 * SCAT_LANE_VECS);
-    uint32_t m[SCAT_LANE_VECS][4];
-    uint32_t mine = 0;
+    const uint64_t warp_base = (uint64_t)blockIdx.x * PARSE_CTA_BYTES + (uint64_t)warp * PARSE_WARP_BYTES;
+    // coalesced loads: lane l takes vector it*32 + l; one 16-bit newline mask per vector goes to
+    // shared memory, from where every lane picks up the four masks of its own 64 consecutive bytes
 #pragma unroll
-    for (int it = 0; it < SCAT_LANE_VECS; it++) {
-        const uint64_t off = lane_base + (uint64_t)it * 16;
+    for (int it = 0; it < PARSE_ITERS; it++) {
+        const uint64_t off = warp_base + (uint64_t)(it * 32 + lane_id()) * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (off < nbytes) v = load_vec16(text, nbytes, off >> 4);
-        m[it][0] = newline_mask(v.x);
-        m[it][1] = newline_mask(v.y);
-        m[it][2] = newline_mask(v.z);
-        m[it][3] = newline_mask(v.w);
-        mine += __popc(m[it][0]) + __popc(m[it][1]) + __popc(m[it][2]) + __popc(m[it][3]);
+        const uint32_t bits = pack_msb4(newline_mask(v.x)) | pack_msb4(newline_mask(v.y)) << 4 |
+                              pack_msb4(newline_mask(v.z)) << 8 | pack_msb4(newline_mask(v.w)) << 12;
+        vec_mask[warp][it * 32 + lane_id()] = (uint16_t)bits;
     }
+    __syncwarp();
+    uint64_t mask = *(const uint64_t *)&vec_mask[warp][lane_id() * 4];  // bit i = byte i of this lane's 64 bytes
+    const uint32_t mine = __popcll(mask);
     uint32_t wsum;
     const uint32_t ex = warp_excl_scan_u32(mine, &wsum);
     if (lane_id() == 0) warp_tot[warp] = wsum;
@@ -373,35 +375,28 @@ k_scatter_fields(const uint8_t *__restrict__ text, uint64_t nbytes, const uint32
     if (mine == 0) return;
     uint64_t k = (uint64_t)cta_offsets[blockIdx.x] + ex;
     for (uint32_t i = 0; i < warp; i++) k += warp_tot[i];
-#pragma unroll
-    for (int it = 0; it < SCAT_LANE_VECS; it++) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t bits = m[it][j];
-            while (bits) {
-                const uint32_t b = __ffs(bits) - 1;  // bit 7 of byte b/8
-                bits &= bits - 1;
-                const uint64_t p = lane_base + it * 16 + j * 4 + (b >> 3);
-                const uint64_t rec = k >> 2;
-                const uint32_t line = (uint32_t)k & 3;
-                k++;
-                if (rec > n_rec || (rec == n_rec && !check_partial)) continue;
-                if (line == 0) seq_off[rec] = (uint32_t)p + 1;
-                else if (line == 1) {
-                    seq_len[rec] = (uint32_t)p;
-                    if (p + 1 < nbytes && text[p + 1] != '+')
-                        atomicMin(&st->err_key, (unsigned long long)(rec << 3 | SQ_PARSE_NO_PLUS));
-                }
-                else if (line == 2) qual_off[rec] = (uint32_t)p + 1;
-                else if (rec < n_rec) {
-                    name_off[rec + 1] = (uint32_t)p + 2;
-                    // the record that starts behind this newline: complete, or the partial tail (:1094)
-                    const uint64_t start = p + 1;
-                    const bool look = rec + 1 < n_rec || (check_partial && start + 2 < nbytes);
-                    if (look && text[start] != '@')
-                        atomicMin(&st->err_key, (unsigned long long)((rec + 1) << 3 | SQ_PARSE_NO_AT));
-                }
-            }
+    const uint64_t lane_base = warp_base + (uint64_t)lane_id() * 64;
+    while (mask) {
+        const uint64_t p = lane_base + (uint32_t)(__ffsll((long long)mask) - 1);
+        mask &= mask - 1;
+        const uint64_t rec = k >> 2;
+        const uint32_t line = (uint32_t)k & 3;
+        k++;
+        if (rec > n_rec || (rec == n_rec && !check_partial)) continue;
+        if (line == 0) seq_off[rec] = (uint32_t)p + 1;
+        else if (line == 1) {
+            seq_len[rec] = (uint32_t)p;
+            if (p + 1 < nbytes && text[p + 1] != '+')
+                atomicMin(&st->err_key, (unsigned long long)(rec << 3 | SQ_PARSE_NO_PLUS));
+        }
+        else if (line == 2) qual_off[rec] = (uint32_t)p + 1;
+        else if (rec < n_rec) {
+            name_off[rec + 1] = (uint32_t)p + 2;
+            // the record that starts behind this newline: complete, or the partial tail (:1094)
+            const uint64_t start = p + 1;
+            const bool look = rec + 1 < n_rec || (check_partial && start + 2 < nbytes);
+            if (look && text[start] != '@')
+                atomicMin(&st->err_key, (unsigned long long)((rec + 1) << 3 | SQ_PARSE_NO_AT));
         }
     }
 }

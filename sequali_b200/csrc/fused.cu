@@ -554,10 +554,16 @@ k_fused_columns(const ColumnArgs A) {
                         acc_n += pm & ~vb;
                         // phred bins min(q,47)>>2 as byte counters at bin*FC_TPB*4 + tid*4 + j; the
                         // padding byte is counted in the spare 13th row that nobody reads
-                        priv8[(q0 == 0x7F ? 12u : min(q0 - 33u, 47u) >> 2) * (FC_TPB * 4) + 0] += 1;
-                        priv8[(q1 == 0x7F ? 12u : min(q1 - 33u, 47u) >> 2) * (FC_TPB * 4) + 1] += 1;
-                        priv8[(q2 == 0x7F ? 12u : min(q2 - 33u, 47u) >> 2) * (FC_TPB * 4) + 2] += 1;
-                        priv8[(q3 == 0x7F ? 12u : min(q3 - 33u, 47u) >> 2) * (FC_TPB * 4) + 3] += 1;
+                        // four bins at once: 4*min(q,47)>>2 per byte (q >= 48 saturates to bin 11,
+                        // padding goes to row 12)
+                        const uint32_t t = q - 0x21212121u;
+                        const uint32_t sat = (((t + 0x50505050u) >> 7) & 0x01010101u) * 0xFFu;
+                        uint32_t bin4 = ((t & 0x3C3C3C3Cu) & ~sat) | (0x2C2C2C2Cu & sat);
+                        bin4 = (bin4 & keep) | (0x30303030u & ~keep);
+                        priv8[(bin4 & 0xFF) * (FC_TPB) + 0] += 1;
+                        priv8[((bin4 >> 8) & 0xFF) * (FC_TPB) + 1] += 1;
+                        priv8[((bin4 >> 16) & 0xFF) * (FC_TPB) + 2] += 1;
+                        priv8[(bin4 >> 24) * (FC_TPB) + 3] += 1;
                         if (++rows == 255) spill();
                     }
                     if (A.do_pt) {

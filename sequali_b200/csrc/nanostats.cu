@@ -205,6 +205,9 @@ __device__ int nano_tags(const uint8_t *t, uint64_t n, sq_nanoinfo *o, unsigned 
 __global__ void __launch_bounds__(NS_TPB)
 k_ns_parse(BatchView bv, sq_nanoinfo *out, uint64_t base, NsState *st) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < bv.n; r += gridDim.x * blockDim.x) {
+        // records behind an unparsable header are never looked at again (the module switches
+        // itself off, :5302-5313): once one is known, later records need no work
+        if (*(volatile unsigned long long *)&st->fail_idx < base + r) continue;
         sq_nanoinfo info;
         info.start_time = 0;
         info.duration = 0.0f;

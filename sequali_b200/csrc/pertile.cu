@@ -59,6 +59,8 @@ k_pt_map_insert(const long long *__restrict__ tile, uint32_t n, uint64_t base, u
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
         if (base + r >= fail) continue;
         const uint64_t t = (uint64_t)tile[r];
+        // reads come in runs of one tile: only the first read of a run has to look at the map
+        if (r > 0 && base + r - 1 < fail && (uint64_t)tile[r - 1] == t) continue;
         uint32_t i = pt_hash(t) & (PT_MAP_CAP - 1);
         for (;;) {
             uint64_t k = map_keys[i];
@@ -82,19 +84,28 @@ k_pt_map_lookup(BatchView bv, const long long *__restrict__ tile, uint64_t base,
                 const uint32_t *map_vals, uint32_t *__restrict__ slot, uint32_t *__restrict__ idx, PtState *st) {
     const unsigned long long fail = st->fail_idx;
     uint32_t lmax = 0, kept = 0, changes = 0;
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < bv.n; r += gridDim.x * blockDim.x) {
-        idx[r] = r;
-        if (base + r >= fail) {
-            slot[r] = PT_NONE;
-            continue;
+    const uint32_t n_round = (bv.n + 31) & ~31u;  // whole warps stay in the loop for the match below
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_round; r += gridDim.x * blockDim.x) {
+        const bool in = r < bv.n;
+        const bool keep = in && base + r < fail;
+        if (in) idx[r] = r;
+        const uint64_t t = keep ? (uint64_t)tile[r] : ~0ULL;
+        // one probe per distinct tile in the warp
+        const uint32_t peers = __match_any_sync(0xffffffffu, t);
+        const uint32_t leader = (uint32_t)__ffs(peers) - 1;
+        uint32_t sl = PT_NONE;
+        if (keep && lane_id() == leader) {
+            uint32_t i = pt_hash(t) & (PT_MAP_CAP - 1);
+            while (map_keys[i] != t) i = (i + 1) & (PT_MAP_CAP - 1);
+            sl = map_vals[i];
         }
-        const uint64_t t = (uint64_t)tile[r];
-        changes += r == 0 || tile[r - 1] != tile[r];
-        uint32_t i = pt_hash(t) & (PT_MAP_CAP - 1);
-        while (map_keys[i] != t) i = (i + 1) & (PT_MAP_CAP - 1);
-        slot[r] = map_vals[i];
-        lmax = max(lmax, bv.seq_len[r]);
-        kept++;
+        sl = __shfl_sync(0xffffffffu, sl, leader);
+        if (in) slot[r] = keep ? sl : PT_NONE;
+        if (keep) {
+            changes += r == 0 || tile[r - 1] != tile[r];
+            lmax = max(lmax, bv.seq_len[r]);
+            kept++;
+        }
     }
     lmax = warp_max_u32(lmax);
     kept = warp_sum_u32(kept);
