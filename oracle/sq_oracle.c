@@ -8,7 +8,7 @@
  * cpu_baseline / --impl reference legs may load this library; the product
  * (sequali_b200) never does.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks every
+ * Parity status: PINNED.  tests/test_oracle.py checks every
  * function below against the reference's own compiled extension
  * (oracle/_ref, built by oracle/build_ref.sh from /root/reference) and
  * against the golden vectors committed under tests/golden/.

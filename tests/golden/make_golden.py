@@ -5,7 +5,7 @@ Run once in the build container:   python tests/golden/make_golden.py
 The inputs are committed next to the outputs so that the fixtures do not depend
 on the numpy version that produced them.  Doubles are stored as u64 bit
 patterns.  The reference's own known-answer cases (tests/test_*.py of the
-reference) that fit a table are restated in tests/test_known_answers.py.
+reference) that fit a table are restated in tests/test_oracle.py.
 """
 import gzip
 import json
