@@ -14,8 +14,9 @@ DedupEstimator) over the full input with fresh collectors.
 
   value     input resident in HBM when the timed region starts (device parse +
             all collectors + table read-back), CUDA events on the launch stream
-  e2e       the same loop through the public API with HOST text: FastqParser
-            .readinto -> pinned staging -> H2D -> kernels -> getters (D2H)
+  e2e       the same loop with HOST text in pinned memory through the C ABI
+            (sq_batch_from_fastq copies H2D inside the call) -> kernels ->
+            getters (D2H); e2e.fileobj_api = through FastqParser(file object)
   roofline  dominant kernel: algorithmic bytes (record text, read once) per
             launch / its mean launch time (CUDA events), against MEASURED_PEAKS
   cpu_baseline  the unmodified reference (oracle/_ref) on one host core over a
@@ -172,13 +173,9 @@ def run_cuda(args):
             dist.barrier()
 
     def merge(tables: np.ndarray):
-        if dist is None:
-            return tables
-        import torch
-        t = torch.from_numpy(tables.astype(np.int64)).cuda()
-        # ranks may have seen different max lengths only for ragged input; C2 is fixed length
-        dist.all_reduce(t)
-        return t.cpu().numpy().astype(np.uint64)
+        # additive count tables of all ranks: one all-reduce (NCCL over NVLink when world > 1)
+        from sequali_b200 import sharded
+        return sharded.allreduce_sum_tables([tables])[0]
 
     def step_resident():
         mods = make_modules(sq)
@@ -272,10 +269,51 @@ def run_cuda(args):
     # ---- end to end: host text -> parser -> collectors -> getters --------------
     e2e = None
     if not args.no_e2e:
+        from sequali_b200.device import HostFastq
         e2e_reads = min(n_reads, args.e2e_reads)
-        host, e2e_reads = data.to_host(e2e_reads)
+        hostq, e2e_reads = HostFastq.from_device(data, e2e_reads)
 
+        def max_over_ranks(dt):
+            if dist is None:
+                return dt
+            import torch
+            tm = torch.tensor([dt], dtype=torch.float64).cuda()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            return float(tm.item())
+
+        def timed(step_fn, steps):
+            step_fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                out = step_fn()
+            barrier()
+            return max_over_ranks((time.perf_counter() - t0) / steps), out
+
+        # (1) the C-ABI with HOST buffers: pinned host text -> sq_batch_from_fastq (H2D inside the call)
+        #     -> sq_fused_add -> getters (D2H)
         def step_e2e():
+            mods = make_modules(sq)
+            for arr in hostq.record_arrays(args.e2e_window):
+                feed(mods, arr)
+            tables, nbytes, _ = read_results(mods)
+            merge(tables)
+            return nbytes
+
+        e2e_steps = max(1, min(args.steps, 3))
+        dt, out_bytes = timed(step_e2e, e2e_steps)
+        e2e = {"value": round(world * e2e_reads * READ_LENGTH / dt / 1e9, 4), "unit": "Gbases/s",
+               "h2d_bytes_per_step": int(hostq.nbytes), "d2h_bytes_per_step": int(out_bytes),
+               "reads_per_step_per_gpu": int(e2e_reads), "steps": e2e_steps, "window_bytes": args.e2e_window,
+               "h2d_gbs": round(hostq.nbytes / dt / 1e9, 2),
+               "path": "pinned host text -> sq_batch_from_fastq (cudaMemcpyAsync H2D inside) -> sq_fused_add "
+                       "-> getters"}
+
+        # (2) the reference-shaped Python API with a host FILE OBJECT (readinto into pinned staging first:
+        #     one extra host copy by the Python file object, as with the reference's xopen stream)
+        host = np.frombuffer(hostq.view(), dtype=np.uint8)
+
+        def step_fileobj():
             mods = make_modules(sq)
             for arr in sq.FastqParser(HostText(host), args.buffersize):
                 feed(mods, arr)
@@ -283,25 +321,13 @@ def run_cuda(args):
             merge(tables)
             return nbytes
 
-        step_e2e()
-        barrier()
-        e2e_steps = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            out_bytes = step_e2e()
-        barrier()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        if dist is not None:
-            import torch
-            tm = torch.tensor([dt], dtype=torch.float64).cuda()
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dt = float(tm.item())
-        e2e = {"value": round(world * e2e_reads * READ_LENGTH / dt / 1e9, 4), "unit": "Gbases/s",
-               "h2d_bytes_per_step": int(host.nbytes), "d2h_bytes_per_step": int(out_bytes),
-               "reads_per_step_per_gpu": int(e2e_reads), "steps": e2e_steps,
-               "buffersize": args.buffersize,
-               "path": "FastqParser(host file object).readinto -> pinned staging -> cudaMemcpyAsync "
-                       "-> kernels -> getters"}
+        dt2, _ = timed(step_fileobj, 1)
+        e2e["fileobj_api"] = {"value": round(world * e2e_reads * READ_LENGTH / dt2 / 1e9, 4), "unit": "Gbases/s",
+                              "buffersize": args.buffersize,
+                              "path": "FastqParser(host file object).readinto -> pinned staging -> H2D -> kernels "
+                                      "-> getters"}
+        del host
+        hostq.free()
 
     # ---- CPU baseline: the unmodified reference on one core, bounded sample ----
     cpu = None
@@ -428,6 +454,7 @@ def main():
     ap.add_argument("--chunk-reads", type=int, default=1 << 22, help="reads per record array")
     ap.add_argument("--buffersize", type=int, default=64 << 20, help="e2e parser staging size")
     ap.add_argument("--e2e-reads", type=int, default=20_000_000)
+    ap.add_argument("--e2e-window", type=int, default=512 << 20, help="bytes of host text per record array (e2e)")
     ap.add_argument("--cpu-reads", type=int, default=8_000_000)
     ap.add_argument("--ref-reads", type=int, default=500_000)
     ap.add_argument("--no-e2e", action="store_true")

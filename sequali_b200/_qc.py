@@ -763,8 +763,11 @@ class PerTileQuality(_Collector):
         if nt:
             check(self._ctx.lib.sq_pertile_read(self._h, _void(ids), _void(err), _void(cnt)),
                   "sq_pertile_read")
-        return [(int(ids[i]), err[i * ml:(i + 1) * ml].tolist(),
-                 cnt[i * ml:(i + 1) * ml].tolist()) for i in range(nt)]
+        if nt == 0:
+            return []
+        if ml == 0:
+            return [(t, [], []) for t in ids.tolist()]
+        return list(zip(ids.tolist(), err.reshape(nt, ml).tolist(), cnt.reshape(nt, ml).tolist()))
 
 
 def _kmer_to_sequence(kmer: int, k: int) -> str:

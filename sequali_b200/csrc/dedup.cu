@@ -498,15 +498,48 @@ extern "C" int sq_dedup_sync(sq_dedup *d, sq_dedup_info *info) {
     return SQ_OK;
 }
 
+// counts of the occupied slots, in slot order (the reference getter, :4736-4744), compacted on the device
+__global__ void __launch_bounds__(DD_TPB)
+k_dd_occupied(const uint32_t *__restrict__ count, uint32_t size, uint32_t *__restrict__ flag) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < size; i += gridDim.x * blockDim.x)
+        flag[i] = count[i] != 0;
+}
+__global__ void __launch_bounds__(DD_TPB)
+k_dd_compact(const uint32_t *__restrict__ count, const uint32_t *__restrict__ rank, uint32_t size,
+             uint64_t *__restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < size; i += gridDim.x * blockDim.x)
+        if (count[i]) out[rank[i]] = count[i];
+}
+
 extern "C" int sq_dedup_read(sq_dedup *d, uint64_t *counts, uint64_t *n) {
     sq_ctx *ctx = d->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    std::vector<uint32_t> host(d->table_size);
-    CUDA_TRY(cudaMemcpyAsync(host.data(), d->tab.count, d->table_size * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    *n = 0;
+    const uint32_t size = (uint32_t)d->table_size;
+    uint32_t *flag = nullptr, *rank = nullptr, *total = nullptr;
+    uint64_t *out = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&flag, (size_t)size * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&rank, (size_t)size * 4 + 4, false));
+    total = rank + size;
+    SQ_TRY(sq_dalloc(ctx, (void **)&out, (size_t)(d->stored + 1) * 8, false));
+    const int grid = sq_grid_for(ctx, size, DD_TPB, 16);
+    SQ_LAUNCH(ctx, k_dd_occupied, grid, DD_TPB, 0, d->tab.count, size, flag);
+    SQ_TRY(sq_scan_exclusive_u32(ctx, flag, rank, size, total));
+    SQ_LAUNCH(ctx, k_dd_compact, grid, DD_TPB, 0, d->tab.count, rank, size, out);
+    uint32_t *h_total = (uint32_t *)((char *)ctx->h_scratch + 3080);
+    CUDA_TRY(cudaMemcpyAsync(h_total, total, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    uint64_t w = 0;
-    for (uint64_t i = 0; i < d->table_size; i++)  // slot order, like the reference getter (:4736-4744)
-        if (host[i]) counts[w++] = host[i];
-    *n = w;
+    const uint64_t got = *h_total;
+    if (got > d->stored) {
+        sq_set_error("dedup table holds %llu entries, expected at most %llu", (unsigned long long)got,
+                     (unsigned long long)d->stored);
+        return SQ_E_CUDA;
+    }
+    if (got) CUDA_TRY(cudaMemcpyAsync(counts, out, got * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *n = got;
+    sq_dfree(ctx, flag);
+    sq_dfree(ctx, rank);
+    sq_dfree(ctx, out);
     return SQ_OK;
 }

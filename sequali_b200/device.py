@@ -95,3 +95,63 @@ class DeviceFastq:
             self.free()
         except Exception:
             pass
+
+
+class HostFastq:
+    """Uncompressed FASTQ text in PINNED host memory, fed to the device in windows.
+
+    What a decompressor thread with a pinned output buffer hands over: every
+    record array is one ``sq_batch_from_fastq`` call on a window of the host
+    text (the H2D copy happens inside the call), the next window starts at the
+    first byte the previous one did not consume.  No extra host copy."""
+
+    def __init__(self, ctx: Context, nbytes: int):
+        self._ctx = ctx
+        self.nbytes = nbytes
+        self.ptr = ctx.lib.sq_pinned_alloc(ctx.h, nbytes + 64)
+        if not self.ptr:
+            raise MemoryError(_lib.last_error())
+
+    @classmethod
+    def from_device(cls, data: "DeviceFastq", max_reads: int | None = None) -> tuple["HostFastq", int]:
+        ctx = data._ctx
+        take, reads = [], 0
+        for ch in data.chunks:
+            take.append(ch)
+            reads += ch[2]
+            if max_reads is not None and reads >= max_reads:
+                break
+        self = cls(ctx, sum(c[1] for c in take))
+        off = 0
+        for ptr, nbytes, _ in take:
+            check(ctx.lib.sq_memcpy_d2h(ctx.h, self.ptr + off, ptr, nbytes), "d2h")
+            off += nbytes
+        return self, reads
+
+    def view(self) -> memoryview:
+        return memoryview((C.c_char * self.nbytes).from_address(self.ptr)).cast("B")
+
+    def record_arrays(self, window: int = 256 << 20):
+        ctx = self._ctx
+        pos = 0
+        while pos < self.nbytes:
+            size = min(window, self.nbytes - pos)
+            h, info = C.c_void_p(), _lib.ParseInfo()
+            check(ctx.lib.sq_batch_from_fastq(ctx.h, self.ptr + pos, size, 2 ** 63, C.byref(h), C.byref(info)),
+                  "sq_batch_from_fastq")
+            if info.n_records == 0:
+                ctx.lib.sq_batch_free(h)
+                raise ValueError("window smaller than one record")
+            yield FastqRecordArrayView._from_parser(h, info.n_records, None, size)
+            pos += info.consumed
+
+    def free(self):
+        if self.ptr:
+            self._ctx.lib.sq_pinned_free(self._ctx.h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
