@@ -44,6 +44,8 @@ struct sq_ctx {
     void *d_scratch = nullptr;  // 4 KiB device
     double *d_err_table = nullptr;      // [94]  10^-(q/10), host libm generated
     double *d_phred_thresholds = nullptr;  // [94] bucket edges derived from host log10
+    void *parse_masks = nullptr;        // newline bit masks of the record array being parsed (grow-only)
+    size_t parse_masks_cap = 0;
     uint32_t func_attr_done = 0;           // bit per kernel family whose smem opt-in was set
     // optional per-kernel timing (CUDA events on the launch stream), see sq_ctx_profile
     bool profile = false;

@@ -5,7 +5,7 @@
 // kernels over text staged in HBM:
 //   k_count_newlines   16-byte vector loads, SWAR newline count per CTA, first
 //                      non-ASCII byte by atomicMin
-//   k_scan_counts      exclusive scan of the per-CTA counts (one CTA)
+//   sq_scan_exclusive  exclusive scan of the per-CTA counts (scan.cu)
 //   k_scatter_fields   same traversal, warp-shuffle scans give every newline
 //                      its rank k; the newline writes the descriptor field it
 //                      closes (record k/4, line k%4) and checks '@' / '+'
@@ -122,6 +122,7 @@ extern "C" void sq_ctx_destroy(sq_ctx *ctx) {
     cudaFree(ctx->d_err_table);
     cudaFree(ctx->d_phred_thresholds);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->parse_masks);
     cudaFreeHost(ctx->h_scratch);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -271,9 +272,12 @@ __device__ __forceinline__ uint4 load_vec16(const uint8_t *text, uint64_t nbytes
 
 __device__ __forceinline__ uint32_t newline_mask(uint32_t w) { return zero_bytes80(w ^ 0x0A0A0A0Au); }
 
+// bit i of the result = bit 7 of byte i of m (m has at most bit 7 of each byte set)
+__device__ __forceinline__ uint32_t pack_msb4(uint32_t m) { return ((m >> 7) * 0x00204081u) >> 21 & 0xFu; }
+
 __global__ void __launch_bounds__(PARSE_THREADS)
 k_count_newlines(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t *__restrict__ cta_counts,
-                 ParseState *st) {
+                 uint16_t *__restrict__ vec_masks, ParseState *st) {
     __shared__ uint32_t warp_tot[PARSE_THREADS / 32];
     uint64_t warp_base = (uint64_t)blockIdx.x * PARSE_CTA_BYTES + (uint64_t)(threadIdx.x >> 5) * PARSE_WARP_BYTES;
     uint32_t cnt = 0;
@@ -282,8 +286,11 @@ k_count_newlines(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t *__
         uint64_t off = warp_base + (uint64_t)(it * 32 + lane_id()) * 16;
         if (off >= nbytes) continue;
         uint4 v = load_vec16(text, nbytes, off >> 4);
-        cnt += __popc(newline_mask(v.x)) + __popc(newline_mask(v.y)) + __popc(newline_mask(v.z)) +
-               __popc(newline_mask(v.w));
+        // one bit per byte: the second pass ranks newlines from these masks (1/8 of the text)
+        const uint32_t bits = pack_msb4(newline_mask(v.x)) | pack_msb4(newline_mask(v.y)) << 4 |
+                              pack_msb4(newline_mask(v.z)) << 8 | pack_msb4(newline_mask(v.w)) << 12;
+        vec_masks[off >> 4] = (uint16_t)bits;
+        cnt += __popc(bits);
         uint32_t hi = (v.x | v.y | v.z | v.w) & 0x80808080u;
         if (hi) {  // rare: locate the first byte >= 0x80 (reference :1056-1061)
             uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -304,36 +311,6 @@ k_count_newlines(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t *__
     }
 }
 
-// in-place exclusive scan of n counts by one CTA; total -> st->n_newlines
-__global__ void __launch_bounds__(1024) k_scan_counts(uint32_t *counts, uint32_t n, ParseState *st) {
-    __shared__ uint32_t warp_pref[32];
-    __shared__ unsigned long long carry_s;
-    __shared__ uint32_t chunk_total_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n; base += 1024) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < n ? counts[i] : 0;
-        uint32_t wtot;
-        uint32_t ex = warp_excl_scan_u32(v, &wtot);
-        if (lane_id() == 0) warp_pref[threadIdx.x >> 5] = wtot;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t tt;
-            uint32_t e = warp_excl_scan_u32(warp_pref[threadIdx.x], &tt);
-            warp_pref[threadIdx.x] = e;
-            if (threadIdx.x == 0) chunk_total_s = tt;
-        }
-        __syncthreads();
-        unsigned long long carry = carry_s;
-        if (i < n) counts[i] = (uint32_t)carry + warp_pref[threadIdx.x >> 5] + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + chunk_total_s;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) st->n_newlines = carry_s;
-}
-
 // Second pass over the text: every newline learns its global rank k (CTA offset
 // from the scan + warp/CTA prefix) and writes the descriptor field it closes
 // straight into the record arrays: record k/4, line k%4.
@@ -343,30 +320,23 @@ __global__ void __launch_bounds__(1024) k_scan_counts(uint32_t *counts, uint32_t
 //   line 2 ('+')   -> qual_off[rec] = p + 1
 //   line 3 (qual)  -> name_off[rec + 1] = p + 2, and the '@' check on the next record (:1097)
 // Loads stay coalesced; a lane ranks 64 consecutive bytes, so one warp scan covers 2 KiB of text.
-// bit i of the result = bit 7 of byte i of m (m has at most bit 7 of each byte set)
-__device__ __forceinline__ uint32_t pack_msb4(uint32_t m) { return ((m >> 7) * 0x00204081u) >> 21 & 0xFu; }
-
 __global__ void __launch_bounds__(PARSE_THREADS)
-k_scatter_fields(const uint8_t *__restrict__ text, uint64_t nbytes, const uint32_t *__restrict__ cta_offsets,
-                 uint64_t n_rec, int check_partial, uint32_t *__restrict__ name_off, uint32_t *__restrict__ seq_off,
-                 uint32_t *__restrict__ seq_len, uint32_t *__restrict__ qual_off, ParseState *st) {
+k_scatter_fields(const uint8_t *__restrict__ text, uint64_t nbytes, const uint16_t *__restrict__ vec_masks,
+                 const uint32_t *__restrict__ cta_offsets, uint64_t n_rec, int check_partial,
+                 uint32_t *__restrict__ name_off, uint32_t *__restrict__ seq_off, uint32_t *__restrict__ seq_len,
+                 uint32_t *__restrict__ qual_off, ParseState *st) {
     __shared__ uint32_t warp_tot[PARSE_THREADS / 32];
-    __shared__ __align__(8) uint16_t vec_mask[PARSE_THREADS / 32][32 * PARSE_ITERS];  // newline bits per 16-byte vector
     const uint32_t warp = threadIdx.x >> 5;
     const uint64_t warp_base = (uint64_t)blockIdx.x * PARSE_CTA_BYTES + (uint64_t)warp * PARSE_WARP_BYTES;
-    // coalesced loads: lane l takes vector it*32 + l; one 16-bit newline mask per vector goes to
-    // shared memory, from where every lane picks up the four masks of its own 64 consecutive bytes
-#pragma unroll
-    for (int it = 0; it < PARSE_ITERS; it++) {
-        const uint64_t off = warp_base + (uint64_t)(it * 32 + lane_id()) * 16;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (off < nbytes) v = load_vec16(text, nbytes, off >> 4);
-        const uint32_t bits = pack_msb4(newline_mask(v.x)) | pack_msb4(newline_mask(v.y)) << 4 |
-                              pack_msb4(newline_mask(v.z)) << 8 | pack_msb4(newline_mask(v.w)) << 12;
-        vec_mask[warp][it * 32 + lane_id()] = (uint16_t)bits;
+    const uint64_t lane_base = warp_base + (uint64_t)lane_id() * 64;
+    // four 16-bit vector masks = the newline bits of this lane's 64 consecutive bytes
+    uint64_t mask = 0;
+    if (lane_base < nbytes) {
+        const uint64_t n_vec = (nbytes + 15) >> 4, v0 = lane_base >> 4;
+        if (v0 + 4 <= n_vec) mask = *(const uint64_t *)(vec_masks + v0);
+        else
+            for (uint64_t v = v0; v < n_vec; v++) mask |= (uint64_t)vec_masks[v] << (16 * (v - v0));
     }
-    __syncwarp();
-    uint64_t mask = *(const uint64_t *)&vec_mask[warp][lane_id() * 4];  // bit i = byte i of this lane's 64 bytes
     const uint32_t mine = __popcll(mask);
     uint32_t wsum;
     const uint32_t ex = warp_excl_scan_u32(mine, &wsum);
@@ -375,7 +345,6 @@ k_scatter_fields(const uint8_t *__restrict__ text, uint64_t nbytes, const uint32
     if (mine == 0) return;
     uint64_t k = (uint64_t)cta_offsets[blockIdx.x] + ex;
     for (uint32_t i = 0; i < warp; i++) k += warp_tot[i];
-    const uint64_t lane_base = warp_base + (uint64_t)lane_id() * 64;
     while (mask) {
         const uint64_t p = lane_base + (uint32_t)(__ffsll((long long)mask) - 1);
         mask &= mask - 1;
@@ -459,12 +428,28 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
     init.max_rec_bytes = 0;
     memcpy(ctx->h_scratch, &init, sizeof(init));
     CUDA_TRY(cudaMemcpyAsync(st, ctx->h_scratch, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    SQ_LAUNCH(ctx, k_count_newlines, n_cta, PARSE_THREADS, 0, b->text, nbytes, cta_counts, st);
-    SQ_LAUNCH(ctx, k_scan_counts, 1, 1024, 0, cta_counts, n_cta, st);
+    // one bit per text byte; a grow-only scratch of the context (a fresh 100+ MB stream-ordered
+    // allocation per record array makes the pool re-map memory every time)
+    const size_t mask_bytes = (size_t)(((nbytes + 15) >> 4) + 4) * 2;
+    if (mask_bytes > ctx->parse_masks_cap) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->parse_masks) CUDA_TRY(cudaFree(ctx->parse_masks));
+        ctx->parse_masks = nullptr;
+        ctx->parse_masks_cap = 0;
+        CUDA_TRY(cudaMalloc(&ctx->parse_masks, mask_bytes + mask_bytes / 8));
+        ctx->parse_masks_cap = mask_bytes + mask_bytes / 8;
+    }
+    uint16_t *vec_masks = (uint16_t *)ctx->parse_masks;
+    SQ_LAUNCH(ctx, k_count_newlines, n_cta, PARSE_THREADS, 0, b->text, nbytes, cta_counts, vec_masks, st);
+    // exclusive scan of the per-CTA counts (in place); the total is the number of newlines
+    uint32_t *d_total = (uint32_t *)((char *)ctx->d_scratch + 128);
+    uint32_t *h_total = (uint32_t *)((char *)ctx->h_scratch + 128);
+    SQ_TRY(sq_scan_exclusive_u32(ctx, cta_counts, cta_counts, n_cta, d_total));
     ParseState *hst = (ParseState *)ctx->h_scratch;
     CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    uint64_t n_newlines = hst->n_newlines;
+    uint64_t n_newlines = *h_total;
     info->n_newlines = n_newlines;
     if (hst->first_non_ascii != ~0ULL) {  // checked before any record is looked at (:1055)
         info->err_code = SQ_PARSE_ASCII;
@@ -485,7 +470,7 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
     *h_one = 1;
     CUDA_TRY(cudaMemcpyAsync(b->name_off, h_one, 4, cudaMemcpyHostToDevice, ctx->stream));
     if (n_newlines)
-        SQ_LAUNCH(ctx, k_scatter_fields, n_cta, PARSE_THREADS, 0, b->text, nbytes, cta_counts, n_rec, check_partial,
+        SQ_LAUNCH(ctx, k_scatter_fields, n_cta, PARSE_THREADS, 0, b->text, nbytes, vec_masks, cta_counts, n_rec, check_partial,
                   b->name_off, b->seq_off, b->seq_len, b->qual_off, st);
     int grid = sq_grid_for(ctx, n_rec + 1, 256);
     SQ_LAUNCH(ctx, k_finish_records, grid, 256, 0, b->text, nbytes, n_rec, check_partial, b->name_off, b->seq_off,

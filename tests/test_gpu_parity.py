@@ -403,3 +403,28 @@ def test_deferred_adds_keep_call_order(sq):
         gq.add_record_array(arr)
     H.assert_same(H.dump_nano(gns), H.odump_nano(ons))
     H.assert_same(H.dump_qc(gq), H.odump_qc(oq))
+
+
+# ----------------------------------------------------------------------------
+# the bench input itself (device-generated NovaSeq recipe C2), at a size that
+# crosses the 5 M unique-fragment cap of OverrepresentedSequences and makes
+# DedupEstimator escalate, through the HBM-resident path bench.py times
+# ----------------------------------------------------------------------------
+def test_bench_input_prefix_all_modules(sq):
+    from sequali_b200.device import DeviceFastq
+    n = 6_500_000
+    data = DeviceFastq.synth_illumina(n, 150, seed=2, chunk_reads=1 << 21, total_reads=100_000_000)
+    mods = dict(qc=sq.QCMetrics(), ptq=sq.PerTileQuality(), ov=sq.OverrepresentedSequences(),
+                ns=sq.NanoStats(), ad=sq.AdapterCounter(H.ILLUMINA_ADAPTERS),
+                dd=sq.DedupEstimator(front_sequence_offset=64, back_sequence_offset=0))
+    for arr in data.record_arrays():
+        for key in ("qc", "ptq", "ov", "ns", "ad", "dd"):
+            mods[key].add_record_array(arr)
+    got = dict(qc=H.dump_qc(mods["qc"]), adapters=H.dump_adapters(mods["ad"]), ptq=H.dump_ptq(mods["ptq"]),
+               overrep=H.dump_overrep(mods["ov"]), dedup=H.dump_dedup(mods["dd"]), nano=H.dump_nano(mods["ns"]))
+    host, reads = data.to_host()
+    assert reads == n
+    want = H.oracle_single_end(host.tobytes(), H.ILLUMINA_ADAPTERS, chunk_records=1 << 20)
+    assert want["overrep"]["collected_unique_fragments"] == 5_000_000   # the cap was hit
+    assert want["dedup"]["modulo_bits"] >= 1                               # at least one escalation
+    H.assert_same(got, want)
