@@ -15,8 +15,9 @@ DedupEstimator) over the full input with fresh collectors.
   value     input resident in HBM when the timed region starts (device parse +
             all collectors + table read-back), CUDA events on the launch stream
   e2e       the same loop with HOST text in pinned memory through the C ABI
-            (sq_batch_from_fastq copies H2D inside the call) -> kernels ->
-            getters (D2H); e2e.fileobj_api = through FastqParser(file object)
+            (sq_fastq_stream_*: windows copied H2D ahead of the parser on a
+            copy stream) -> kernels -> getters (D2H); e2e.fileobj_api = through
+            FastqParser(file object)
   roofline  dominant kernel: algorithmic bytes (record text, read once) per
             launch / its mean launch time (CUDA events), against MEASURED_PEAKS
   cpu_baseline  the unmodified reference (oracle/_ref) on one host core over a
@@ -290,8 +291,8 @@ def run_cuda(args):
             barrier()
             return max_over_ranks((time.perf_counter() - t0) / steps), out
 
-        # (1) the C-ABI with HOST buffers: pinned host text -> sq_batch_from_fastq (H2D inside the call)
-        #     -> sq_fused_add -> getters (D2H)
+        # (1) the C-ABI with HOST buffers: pinned host text -> sq_fastq_stream_next (windows copied H2D on a
+        #     copy stream ahead of the parser, inside the timed region) -> sq_fused_add -> getters (D2H)
         def step_e2e():
             mods = make_modules(sq)
             for arr in hostq.record_arrays(args.e2e_window):
@@ -306,8 +307,8 @@ def run_cuda(args):
                "h2d_bytes_per_step": int(hostq.nbytes), "d2h_bytes_per_step": int(out_bytes),
                "reads_per_step_per_gpu": int(e2e_reads), "steps": e2e_steps, "window_bytes": args.e2e_window,
                "h2d_gbs": round(hostq.nbytes / dt / 1e9, 2),
-               "path": "pinned host text -> sq_batch_from_fastq (cudaMemcpyAsync H2D inside) -> sq_fused_add "
-                       "-> getters"}
+               "path": "pinned host text -> sq_fastq_stream_next (triple-buffered cudaMemcpyAsync H2D on a copy "
+                       "stream, overlapped with the kernels) -> sq_fused_add -> getters"}
 
         # (2) the reference-shaped Python API with a host FILE OBJECT (readinto into pinned staging first:
         #     one extra host copy by the Python file object, as with the reference's xopen stream)

@@ -121,6 +121,19 @@ SQ_API int sq_batch_from_packed(sq_ctx *ctx, const uint8_t *buf, uint64_t nbytes
 SQ_API int sq_batch_from_bam(sq_ctx *ctx, const uint8_t *bam, uint64_t nbytes,
                              const uint64_t *rec_off, uint64_t n, sq_batch **out,
                              uint64_t *packed_len);
+/* FastqParser's read loop (_qcmodule.c:985-1029: readinto + leftover carry,
+ * :1187 __next__) for uncompressed text in (pinned) HOST memory: windows of
+ * `window` bytes are copied host->device on a separate copy stream ahead of
+ * the boundary scan (triple-buffered), each record array is [leftover of the
+ * previous array | next window].  sq_fastq_stream_next returns the next record
+ * array, or *out == NULL when the text is exhausted; a trailing partial record
+ * is reported by sq_fastq_stream_leftover (the caller raises EOFError :1073). */
+typedef struct sq_fastq_stream sq_fastq_stream;
+SQ_API int sq_fastq_stream_create(sq_ctx *ctx, const uint8_t *host_text, uint64_t nbytes,
+                                  uint64_t window, sq_fastq_stream **out);
+SQ_API int sq_fastq_stream_next(sq_fastq_stream *s, sq_batch **out, sq_parse_info *info);
+SQ_API uint64_t sq_fastq_stream_leftover(const sq_fastq_stream *s);
+SQ_API void sq_fastq_stream_destroy(sq_fastq_stream *s);
 SQ_API uint64_t sq_batch_size(const sq_batch *b);
 SQ_API uint64_t sq_batch_nbytes(const sq_batch *b);
 SQ_API uint32_t sq_batch_max_seq_len(const sq_batch *b);

@@ -111,6 +111,10 @@ SIGNATURES = {
     "sq_batch_from_device_fastq": (_int, [_vp, _vp, _u64, _u64, _P(_vp), _P(ParseInfo)]),
     "sq_batch_from_packed": (_int, [_vp, _vp, _u64, _vp, _u64, _P(_vp)]),
     "sq_batch_from_bam": (_int, [_vp, _vp, _u64, _vp, _u64, _P(_vp), _P(_u64)]),
+    "sq_fastq_stream_create": (_int, [_vp, _vp, _u64, _u64, _P(_vp)]),
+    "sq_fastq_stream_next": (_int, [_vp, _P(_vp), _P(ParseInfo)]),
+    "sq_fastq_stream_leftover": (_u64, [_vp]),
+    "sq_fastq_stream_destroy": (None, [_vp]),
     "sq_batch_size": (_u64, [_vp]),
     "sq_batch_nbytes": (_u64, [_vp]),
     "sq_batch_max_seq_len": (_u32, [_vp]),

@@ -46,6 +46,10 @@ struct sq_ctx {
     double *d_phred_thresholds = nullptr;  // [94] bucket edges derived from host log10
     void *parse_masks = nullptr;        // newline bit masks of the record array being parsed (grow-only)
     size_t parse_masks_cap = 0;
+    // staging ring of the host reader (sq_fastq_stream), kept between readers
+    void *stage_slot[3] = {nullptr, nullptr, nullptr};
+    size_t stage_cap = 0;
+    bool stage_in_use = false;
     uint32_t func_attr_done = 0;           // bit per kernel family whose smem opt-in was set
     // optional per-kernel timing (CUDA events on the launch stream), see sq_ctx_profile
     bool profile = false;

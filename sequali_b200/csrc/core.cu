@@ -123,6 +123,7 @@ extern "C" void sq_ctx_destroy(sq_ctx *ctx) {
     cudaFree(ctx->d_phred_thresholds);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->parse_masks);
+    for (int k = 0; k < 3; k++) cudaFree(ctx->stage_slot[k]);
     cudaFreeHost(ctx->h_scratch);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -627,6 +628,195 @@ extern "C" int sq_batch_from_packed(sq_ctx *ctx, const uint8_t *buf, uint64_t nb
     b->tags_len = d + 6 * n4;
     b->err_sum = (double *)(d + 7 * n4);
     *out = b;
+    return SQ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Double-buffered host reader: the device-side stand-in for the reference's
+// read loop (FastqParser__next__ -> readinto -> leftover copy,
+// _qcmodule.c:985-1029, 1175-1180) when the uncompressed text sits in (pinned)
+// host memory.  Fixed-size windows of raw bytes go host -> device on a COPY
+// stream into a ring of staging slots, ahead of the parser; the parser's
+// stream only waits for the window it is about to scan, then places
+// [leftover of the previous array | window] in a fresh 16-byte aligned text
+// buffer with two device-to-device copies.  H2D of the next windows overlaps
+// with the boundary scan and the collectors of the current record array.
+// ---------------------------------------------------------------------------
+// dst[0..n) = src[0..n) for any alignment of either side, on the SMs: the copy engines
+// stay free for the host->device windows that are in flight on the copy stream
+__global__ void __launch_bounds__(256)
+k_copy_bytes(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint64_t n) {
+    const uint64_t head = min(n, (uint64_t)((16 - ((uintptr_t)dst & 15)) & 15));
+    const uint64_t n_vec = (n - head) >> 4, tail0 = head + (n_vec << 4);
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+    if (tid < head) dst[tid] = src[tid];
+    if (tid < n - tail0) dst[tail0 + tid] = src[tail0 + tid];
+    const uint8_t *s0 = src + head;
+    const uint32_t sh = (uint32_t)((uintptr_t)s0 & 3) * 8;
+    const uint32_t *sw = (const uint32_t *)((uintptr_t)s0 & ~(uintptr_t)3);
+    uint4 *dv = (uint4 *)(dst + head);
+    for (uint64_t v = tid; v < n_vec; v += nthr) {
+        const uint32_t *w = sw + v * 4;
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+        const uint32_t w4 = sh ? __ldg(w + 4) : 0u;  // unshifted copies never read past the source
+        dv[v] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                           __funnelshift_r(w3, w4, sh));
+    }
+}
+static int copy_bytes(sq_ctx *ctx, uint8_t *dst, const uint8_t *src, uint64_t n) {
+    if (n == 0) return SQ_OK;
+    SQ_LAUNCH(ctx, k_copy_bytes, sq_grid_for(ctx, (n >> 4) + 32, 256, 16), 256, 0, dst, src, n);
+    return SQ_OK;
+}
+
+struct sq_fastq_stream {
+    static constexpr int SLOTS = 3;
+    sq_ctx *ctx = nullptr;
+    const uint8_t *host = nullptr;
+    uint64_t nbytes = 0, window = 0;
+    cudaStream_t copy = nullptr;
+    uint8_t *slot[SLOTS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t filled[SLOTS] = {nullptr, nullptr, nullptr}, drained[SLOTS] = {nullptr, nullptr, nullptr};
+    uint64_t slot_len[SLOTS] = {0, 0, 0};
+    uint64_t issue_pos = 0;            // host offset of the next window to copy
+    uint64_t n_issued = 0, n_taken = 0;
+    uint8_t *tail = nullptr;           // bytes behind the last complete record of the previous array
+    uint64_t tail_len = 0, tail_cap = 0;
+    bool slots_from_ctx = false;
+};
+
+static int stream_issue(sq_fastq_stream *s) {
+    while (s->n_issued - s->n_taken < (uint64_t)sq_fastq_stream::SLOTS && s->issue_pos < s->nbytes) {
+        const int k = (int)(s->n_issued % sq_fastq_stream::SLOTS);
+        const uint64_t len = s->nbytes - s->issue_pos < s->window ? s->nbytes - s->issue_pos : s->window;
+        if (s->n_issued >= (uint64_t)sq_fastq_stream::SLOTS) CUDA_TRY(cudaStreamWaitEvent(s->copy, s->drained[k], 0));
+        CUDA_TRY(cudaMemcpyAsync(s->slot[k], s->host + s->issue_pos, len, cudaMemcpyHostToDevice, s->copy));
+        CUDA_TRY(cudaEventRecord(s->filled[k], s->copy));
+        s->slot_len[k] = len;
+        s->issue_pos += len;
+        s->n_issued++;
+    }
+    return SQ_OK;
+}
+
+extern "C" void sq_fastq_stream_destroy(sq_fastq_stream *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    if (s->copy) cudaStreamSynchronize(s->copy);
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->slots_from_ctx) s->ctx->stage_in_use = false;
+    for (int k = 0; k < sq_fastq_stream::SLOTS; k++) {
+        if (s->slot[k] && !s->slots_from_ctx) cudaFree(s->slot[k]);
+        if (s->filled[k]) cudaEventDestroy(s->filled[k]);
+        if (s->drained[k]) cudaEventDestroy(s->drained[k]);
+    }
+    if (s->tail) cudaFree(s->tail);
+    if (s->copy) cudaStreamDestroy(s->copy);
+    delete s;
+}
+
+extern "C" int sq_fastq_stream_create(sq_ctx *ctx, const uint8_t *host_text, uint64_t nbytes, uint64_t window,
+                                      sq_fastq_stream **out) {
+    *out = nullptr;
+    if (window < 4096 || window >= 0xF0000000ULL) {
+        sq_set_error("window must be between 4 KiB and 3.75 GiB");
+        return SQ_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sq_fastq_stream *s = new sq_fastq_stream();
+    s->ctx = ctx;
+    s->host = host_text;
+    s->nbytes = nbytes;
+    s->window = window;
+    int rc = SQ_OK;
+    auto fail = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == SQ_OK) rc = sq_cuda_fail(e, what, __FILE__, __LINE__);
+    };
+    fail(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking), "copy stream");
+    // the staging ring lives in the context between readers (page-mapping 3 x window per pass is slow)
+    if (!ctx->stage_in_use) {
+        if (ctx->stage_cap < window + 64) {
+            cudaStreamSynchronize(ctx->stream);
+            for (int k = 0; k < 3; k++) {
+                if (ctx->stage_slot[k]) cudaFree(ctx->stage_slot[k]);
+                ctx->stage_slot[k] = nullptr;
+            }
+            ctx->stage_cap = 0;
+            for (int k = 0; k < 3; k++) fail(cudaMalloc(&ctx->stage_slot[k], window + 64), "staging slot");
+            if (rc == SQ_OK) ctx->stage_cap = window + 64;
+        }
+        if (rc == SQ_OK) {
+            for (int k = 0; k < 3; k++) s->slot[k] = (uint8_t *)ctx->stage_slot[k];
+            s->slots_from_ctx = true;
+            ctx->stage_in_use = true;
+        }
+    }
+    for (int k = 0; k < sq_fastq_stream::SLOTS && rc == SQ_OK; k++) {
+        if (!s->slots_from_ctx) fail(cudaMalloc(&s->slot[k], window + 64), "staging slot");
+        fail(cudaEventCreateWithFlags(&s->filled[k], cudaEventDisableTiming), "event");
+        fail(cudaEventCreateWithFlags(&s->drained[k], cudaEventDisableTiming), "event");
+    }
+    if (rc == SQ_OK) rc = stream_issue(s);
+    if (rc != SQ_OK) {
+        sq_fastq_stream_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return SQ_OK;
+}
+
+extern "C" uint64_t sq_fastq_stream_leftover(const sq_fastq_stream *s) { return s->tail_len; }
+
+// The next record array, or *out == NULL at the end of the text (bytes of a
+// trailing partial record: sq_fastq_stream_leftover).  A window that holds no
+// complete record is carried over whole and joined with the next one.
+extern "C" int sq_fastq_stream_next(sq_fastq_stream *s, sq_batch **out, sq_parse_info *info) {
+    *out = nullptr;
+    memset(info, 0, sizeof(*info));
+    sq_ctx *ctx = s->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    while (s->n_taken < s->n_issued) {
+        const int k = (int)(s->n_taken % sq_fastq_stream::SLOTS);
+        const uint64_t len = s->slot_len[k], total = s->tail_len + len;
+        SQ_TRY(check_size(total));
+        sq_batch *b = new sq_batch();
+        b->ctx = ctx;
+        b->nbytes = total;
+        int rc = sq_dalloc(ctx, (void **)&b->text, total + 64, false);
+        if (rc != SQ_OK) {
+            delete b;
+            return rc;
+        }
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->filled[k], 0));
+        SQ_TRY(copy_bytes(ctx, b->text, s->tail, s->tail_len));
+        SQ_TRY(copy_bytes(ctx, b->text + s->tail_len, s->slot[k], len));
+        CUDA_TRY(cudaMemsetAsync(b->text + total, 0, 64, ctx->stream));
+        CUDA_TRY(cudaEventRecord(s->drained[k], ctx->stream));
+        s->n_taken++;
+        SQ_TRY(stream_issue(s));  // the slot refills as soon as the copy above has run
+        rc = parse_device_text(ctx, b, UINT64_MAX, info);
+        if (rc != SQ_OK) {
+            sq_batch_free(b);
+            return rc;
+        }
+        const uint64_t left = total - info->consumed;
+        if (left > s->tail_cap) {
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (s->tail) CUDA_TRY(cudaFree(s->tail));
+            s->tail = nullptr;
+            s->tail_cap = 0;
+            CUDA_TRY(cudaMalloc(&s->tail, left + left / 2 + 4096));
+            s->tail_cap = left + left / 2 + 4096;
+        }
+        SQ_TRY(copy_bytes(ctx, s->tail, b->text + info->consumed, left));
+        s->tail_len = left;
+        if (info->n_records == 0) {  // no complete record yet: join with the next window
+            sq_batch_free(b);
+            continue;
+        }
+        *out = b;
+        return SQ_OK;
+    }
     return SQ_OK;
 }
 

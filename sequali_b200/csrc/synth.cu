@@ -116,8 +116,8 @@ extern "C" int sq_synth_illumina(sq_ctx *ctx, uint8_t *dev_text, uint64_t cap, u
     const uint64_t reads_per_tile = 1ULL << (seed >> 56);
     *nbytes = 0;
     if (n_reads == 0) return SQ_OK;
-    if (n_reads > (1u << 22)) {
-        sq_set_error("generate at most 4 Mi reads per call");
+    if (n_reads > (1u << 23) || n_reads * (2ULL * read_length + 64) >= 0xFFFFFF00ULL) {
+        sq_set_error("generate at most 8 Mi reads / 4 GiB of text per call");
         return SQ_E_ARG;
     }
     CUDA_TRY(cudaSetDevice(ctx->device));

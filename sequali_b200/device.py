@@ -39,7 +39,7 @@ class DeviceFastq:
         """NovaSeq-style reads generated on the device (csrc/synth.cu, recipe C2)."""
         ctx = Context.get()
         self = cls(ctx)
-        chunk_reads = min(chunk_reads, 1 << 22)
+        chunk_reads = min(chunk_reads, 1 << 23)  # 2.9 GB of text: u32 offsets reach 4 GiB
         n_chunks = (n_reads + chunk_reads - 1) // chunk_reads
         stride = (chunk_reads * (2 * read_length + 52) + 255) & ~255
         self._base = ctx.lib.sq_device_alloc(ctx.h, n_chunks * stride)
@@ -132,18 +132,28 @@ class HostFastq:
         return memoryview((C.c_char * self.nbytes).from_address(self.ptr)).cast("B")
 
     def record_arrays(self, window: int = 256 << 20):
+        """Record arrays of ~`window` bytes of text each (sq_fastq_stream_*: the host->device
+        copies run ahead of the parser on their own stream)."""
         ctx = self._ctx
-        pos = 0
-        while pos < self.nbytes:
-            size = min(window, self.nbytes - pos)
-            h, info = C.c_void_p(), _lib.ParseInfo()
-            check(ctx.lib.sq_batch_from_fastq(ctx.h, self.ptr + pos, size, 2 ** 63, C.byref(h), C.byref(info)),
-                  "sq_batch_from_fastq")
-            if info.n_records == 0:
-                ctx.lib.sq_batch_free(h)
-                raise ValueError("window smaller than one record")
-            yield FastqRecordArrayView._from_parser(h, info.n_records, None, size)
-            pos += info.consumed
+        stream = C.c_void_p()
+        check(ctx.lib.sq_fastq_stream_create(ctx.h, self.ptr, self.nbytes, window, C.byref(stream)),
+              "sq_fastq_stream_create")
+        try:
+            while True:
+                h, info = C.c_void_p(), _lib.ParseInfo()
+                rc = ctx.lib.sq_fastq_stream_next(stream, C.byref(h), C.byref(info))
+                if rc == _lib.SQ_E_FORMAT:
+                    raise ValueError(f"malformed FASTQ text: parse error {info.err_code} in record "
+                                     f"{info.err_record} at byte {info.err_pos} of its record array")
+                check(rc, "sq_fastq_stream_next")
+                if not h:
+                    break
+                yield FastqRecordArrayView._from_parser(h, info.n_records, None, ctx.lib.sq_batch_nbytes(h))
+            left = ctx.lib.sq_fastq_stream_leftover(stream)
+            if left:
+                raise EOFError(f"Incomplete record at the end of the text: {left} bytes")
+        finally:
+            ctx.lib.sq_fastq_stream_destroy(stream)
 
     def free(self):
         if self.ptr:

@@ -428,3 +428,54 @@ def test_bench_input_prefix_all_modules(sq):
     assert want["overrep"]["collected_unique_fragments"] == 5_000_000   # the cap was hit
     assert want["dedup"]["modulo_bits"] >= 1                               # at least one escalation
     H.assert_same(got, want)
+
+
+# ----------------------------------------------------------------------------
+# the host reader bench.py's e2e leg uses (sq_fastq_stream_*): windows of pinned
+# host text copied ahead of the parser, leftovers carried on the device
+# ----------------------------------------------------------------------------
+def _host_stream_case(sq, text, window):
+    import ctypes
+    from sequali_b200.device import HostFastq
+    from sequali_b200._lib import Context
+    ctx = Context.get()
+    hq = HostFastq(ctx, len(text))
+    ctypes.memmove(hq.ptr, text, len(text))
+    mods = dict(qc=sq.QCMetrics(), ptq=sq.PerTileQuality(), ov=sq.OverrepresentedSequences(),
+                ns=sq.NanoStats(), ad=sq.AdapterCounter(H.ILLUMINA_ADAPTERS),
+                dd=sq.DedupEstimator(front_sequence_offset=64, back_sequence_offset=0))
+    n, arrays = 0, 0
+    for arr in hq.record_arrays(window):
+        n += len(arr)
+        arrays += 1
+        for key in ("qc", "ptq", "ov", "ns", "ad", "dd"):
+            mods[key].add_record_array(arr)
+    got = dict(qc=H.dump_qc(mods["qc"]), adapters=H.dump_adapters(mods["ad"]), ptq=H.dump_ptq(mods["ptq"]),
+               overrep=H.dump_overrep(mods["ov"]), dedup=H.dump_dedup(mods["dd"]), nano=H.dump_nano(mods["ns"]))
+    hq.free()
+    return got, n, arrays
+
+
+@pytest.mark.parametrize("window", [4096, 65_536, 1 << 26])
+def test_host_stream_windows(sq, window):
+    text = synth.illumina_fastq(3000, length=150, seed=31, n_tiles=9)
+    got, n, arrays = _host_stream_case(sq, text, window)
+    assert n == 3000 and arrays == min(3000, -(-len(text) // window))
+    H.assert_same(got, H.oracle_single_end(text, H.ILLUMINA_ADAPTERS, chunk_records=700))
+
+
+def test_host_stream_record_longer_than_window(sq):
+    # nanopore-sized reads: several windows hold no complete record and are joined with the next
+    text = synth.nanopore_fastq(40, seed=12, mean_length=9000)
+    recs, _ = orc.parse_fastq(text)
+    assert max(int(r["seq_len"]) for r in recs) > 8192
+    got, n, _ = _host_stream_case(sq, text, 4096)
+    assert n == len(recs)
+    want = H.oracle_single_end(text, H.ILLUMINA_ADAPTERS)
+    H.assert_same(got, want)
+
+
+def test_host_stream_partial_tail_raises(sq):
+    text = synth.illumina_fastq(50, length=100, seed=3, n_tiles=2)
+    with pytest.raises(EOFError):
+        _host_stream_case(sq, text[:-7], 4096)
