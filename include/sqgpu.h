@@ -192,6 +192,14 @@ SQ_API int sq_pertile_sync(sq_pertile *p, sq_pertile_info *info);
 SQ_API int sq_pertile_skipped_name(sq_pertile *p, uint8_t *out, uint64_t cap, uint64_t *len);
 /* tiles ascending; errors[t*max_len+j] is the ordered sum, counts[..] = reads longer than j */
 SQ_API int sq_pertile_read(sq_pertile *p, uint64_t *tile_ids, double *errors, uint64_t *counts);
+/* Sharded runs: PerTileQuality's sums (_qcmodule.c:3199-3219) are a chain over the reads of a
+ * tile in read order, so the lowest rank holding a tile owns it.  The other ranks copy their
+ * records r < limit_records whose tile id is in tile_ids[0..n_ids) (host, ascending) whole and
+ * in order to dev_out (DEVICE; NULL = size only); the owner parses that text with
+ * sq_batch_from_device_fastq and adds it behind its own reads. */
+SQ_API int sq_batch_select_tiles(sq_batch *b, const int64_t *tile_ids, uint64_t n_ids,
+                                 uint64_t limit_records, uint8_t *dev_out, uint64_t cap,
+                                 uint64_t *nbytes);
 
 /* ---- OverrepresentedSequences (_qcmodule.c:3543-3568, 3830-3942) --------- */
 typedef struct sq_overrep sq_overrep;
@@ -209,6 +217,22 @@ SQ_API int sq_overrep_add(sq_overrep *o, sq_batch *b);
 SQ_API int sq_overrep_sync(sq_overrep *o, sq_overrep_info *info);
 /* the stored fragments as 2-bit k-mers (wanghash64_inverse applied) + counts */
 SQ_API int sq_overrep_read(sq_overrep *o, uint64_t *kmers, uint32_t *counts, uint64_t *n);
+/* Sharded runs: Sequence_duplication_insert_hash (_qcmodule.c:3543-3568) admits the first
+ * max_unique_fragments distinct hashes in read order.  A deferred collector (ranks behind the
+ * first; `first_record` = global index of its first read, which fixes the sampling phase :3833)
+ * keeps the fragment hashes of its sampled reads; sq_overrep_apply_deferred runs the table
+ * maintenance on them once the table of the ranks before it has been loaded
+ * (sq_overrep_load_table: DEVICE keys[table_size] u64, counts[table_size] u32 or NULL = zero).
+ * sq_overrep_copy_table copies the table out to DEVICE buffers; sq_overrep_set_counters
+ * installs the merged additive counters. */
+SQ_API int sq_overrep_set_deferred(sq_overrep *o, int deferred, uint64_t first_record);
+SQ_API int sq_overrep_apply_deferred(sq_overrep *o);
+SQ_API int sq_overrep_copy_table(sq_overrep *o, uint64_t *dev_keys, uint32_t *dev_counts);
+SQ_API int sq_overrep_load_table(sq_overrep *o, const uint64_t *dev_keys, const uint32_t *dev_counts,
+                                 uint64_t n_unique);
+SQ_API int sq_overrep_set_counters(sq_overrep *o, uint64_t number_of_sequences,
+                                   uint64_t sampled_sequences, uint64_t total_fragments,
+                                   uint64_t warn_records, uint64_t first_warn_record);
 /* only fragments seen at least min_count times (the filter of
  * OverrepresentedSequences_overrepresented_sequences, _qcmodule.c:4100-4180),
  * compacted on the device; *n > cap means "call again with room for *n" */
@@ -229,6 +253,17 @@ SQ_API int sq_dedup_add_pair(sq_dedup *d, sq_batch *b1, sq_batch *b2);
 SQ_API int sq_dedup_sync(sq_dedup *d, sq_dedup_info *info);
 /* counts of the occupied slots in slot order, like duplication_counts() */
 SQ_API int sq_dedup_read(sq_dedup *d, uint64_t *counts, uint64_t *n);
+/* Sharded runs (one process per GPU, contiguous shards of the read stream): the table of
+ * DedupEstimator_add_fingerprint (_qcmodule.c:4426-4460) is order dependent, so the first rank
+ * owns it.  A deferred estimator only hashes (sq_dedup_add / sq_fused_add keep the hashes);
+ * sq_dedup_deferred_compact keeps those passing the mask of `mod_bits` bits (the owner's
+ * _modulo_bits after its own shard -- the mask only grows, :4429-4431) in record order,
+ * sq_dedup_deferred_fetch copies them to a caller-owned DEVICE buffer, and the owner feeds what
+ * it received through sq_dedup_add_hashes, rank by rank. */
+SQ_API int sq_dedup_set_deferred(sq_dedup *d, int deferred);
+SQ_API int sq_dedup_deferred_compact(sq_dedup *d, uint64_t mod_bits, uint64_t *n);
+SQ_API int sq_dedup_deferred_fetch(sq_dedup *d, uint64_t *dev_out);
+SQ_API int sq_dedup_add_hashes(sq_dedup *d, const uint64_t *dev_hashes, uint64_t n);
 
 /* ---- NanoStats (_qcmodule.c:5006-5324) ------------------------------------ */
 typedef struct sq_nanostats sq_nanostats;

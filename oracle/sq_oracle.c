@@ -885,6 +885,30 @@ orc_ov_entries(const orc_ov *o, uint64_t *kmers, uint32_t *counts)
     return w;
 }
 
+/* Table hand-over for the sharded-run protocol tests (tests/test_sharded.py): the
+ * state a rank passes to the next one.  No reference counterpart. */
+ORC_API void
+orc_ov_get_table(const orc_ov *o, uint64_t *keys, uint32_t *counts)
+{
+    memcpy(keys, o->keys, o->table_size * 8);
+    memcpy(counts, o->counts, o->table_size * 4);
+}
+ORC_API void
+orc_ov_set_table(orc_ov *o, const uint64_t *keys, const uint32_t *counts, uint64_t n_unique)
+{
+    memcpy(o->keys, keys, o->table_size * 8);
+    if (counts) memcpy(o->counts, counts, o->table_size * 4);
+    else memset(o->counts, 0, o->table_size * 4);
+    o->n_unique = n_unique;
+}
+ORC_API void
+orc_ov_set_counters(orc_ov *o, uint64_t n_seqs, uint64_t n_sampled, uint64_t total_frags)
+{
+    o->n_seqs = n_seqs;
+    o->n_sampled = n_sampled;
+    o->total_frags = total_frags;
+}
+
 /* ------------------------------------------------------------------ */
 /* DedupEstimator (_qcmodule.c:4383-4517)                              */
 /* ------------------------------------------------------------------ */

@@ -115,6 +115,16 @@ SIGNATURES = {
     "sq_fastq_stream_next": (_int, [_vp, _P(_vp), _P(ParseInfo)]),
     "sq_fastq_stream_leftover": (_u64, [_vp]),
     "sq_fastq_stream_destroy": (None, [_vp]),
+    "sq_dedup_set_deferred": (_int, [_vp, _int]),
+    "sq_dedup_deferred_compact": (_int, [_vp, _u64, _P(_u64)]),
+    "sq_dedup_deferred_fetch": (_int, [_vp, _vp]),
+    "sq_dedup_add_hashes": (_int, [_vp, _vp, _u64]),
+    "sq_overrep_set_deferred": (_int, [_vp, _int, _u64]),
+    "sq_overrep_apply_deferred": (_int, [_vp]),
+    "sq_overrep_copy_table": (_int, [_vp, _vp, _vp]),
+    "sq_overrep_load_table": (_int, [_vp, _vp, _vp, _u64]),
+    "sq_overrep_set_counters": (_int, [_vp, _u64, _u64, _u64, _u64, _u64]),
+    "sq_batch_select_tiles": (_int, [_vp, _vp, _u64, _u64, _vp, _u64, _P(_u64)]),
     "sq_batch_size": (_u64, [_vp]),
     "sq_batch_nbytes": (_u64, [_vp]),
     "sq_batch_max_seq_len": (_u32, [_vp]),

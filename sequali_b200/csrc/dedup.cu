@@ -336,6 +336,8 @@ extern "C" void sq_dedup_destroy(sq_dedup *d) {
     cudaSetDevice(d->ctx->device);
     table_free(d->ctx, &d->tab);
     table_free(d->ctx, &d->spare);
+    for (auto &k : d->kept) sq_dfree(d->ctx, k.hashes);
+    sq_dfree(d->ctx, d->compact);
     sq_dfree(d->ctx, d->cnt);
     sq_dfree(d->ctx, d->stale_fp);
     delete d;
@@ -344,6 +346,11 @@ extern "C" void sq_dedup_destroy(sq_dedup *d) {
 // Process hashes[0..n) in record order.
 int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n) {
     sq_ctx *ctx = d->ctx;
+    if (d->deferred) {
+        d->kept.push_back({(uint64_t *)hashes, n});
+        d->n_records += n;
+        return SQ_OK;
+    }
     const uint64_t tmask = d->table_size - 1;
     const uint64_t prio_base = d->table_size + 1 + d->n_records;  // above every rebuild priority
     uint32_t *cls = nullptr, *flag = nullptr, *rank = nullptr;
@@ -448,7 +455,7 @@ extern "C" int sq_dedup_add(sq_dedup *d, sq_batch *b) {
     SQ_LAUNCH(ctx, k_dd_hash, sq_grid_for(ctx, b->n, DD_TPB, 16), DD_TPB, 0, b->view(), d->front_len,
               d->back_len, d->front_off, d->back_off, hashes);
     int rc = dedup_consume(d, hashes, (uint32_t)b->n);
-    sq_dfree(ctx, hashes);
+    if (!d->deferred) sq_dfree(ctx, hashes);
     return rc;
 }
 
@@ -484,7 +491,7 @@ extern "C" int sq_dedup_add_pair(sq_dedup *d, sq_batch *b1, sq_batch *b2) {
                   d->front_off, d->back_off, hashes, d->stale_fp);
     sq_dfree(ctx, tmp);
     int rc = dedup_consume(d, hashes, n);
-    sq_dfree(ctx, hashes);
+    if (!d->deferred) sq_dfree(ctx, hashes);
     sq_dfree(ctx, short_flag);
     return rc;
 }
@@ -541,5 +548,110 @@ extern "C" int sq_dedup_read(sq_dedup *d, uint64_t *counts, uint64_t *n) {
     sq_dfree(ctx, flag);
     sq_dfree(ctx, rank);
     sq_dfree(ctx, out);
+    return SQ_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// Sharded runs.  The estimator's table is order dependent
+// (escalation point, stale-index quirk), so one rank owns it.  Every other rank
+// only hashes its reads (deferred mode).  A hash that fails the mask of m bits
+// fails every later mask too (:4429-4431 tests the low bits, m only grows), so
+// once the owner has finished its own shard with m0 bits the other ranks can
+// drop everything that fails mask(m0) and hand over the rest in record order:
+// about n / 2^m0 hashes per rank.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(DD_TPB)
+k_dd_pass_flags(const uint64_t *__restrict__ hashes, uint32_t n, uint64_t mask, uint32_t *__restrict__ flag) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        flag[i] = (hashes[i] & mask) == 0;
+}
+__global__ void __launch_bounds__(DD_TPB)
+k_dd_pass_scatter(const uint64_t *__restrict__ hashes, const uint32_t *__restrict__ flag,
+                  const uint32_t *__restrict__ rank, uint32_t n, uint64_t *__restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (flag[i]) out[rank[i]] = hashes[i];
+}
+
+extern "C" int sq_dedup_set_deferred(sq_dedup *d, int deferred) {
+    if (d->n_records != 0 && (deferred != 0) != d->deferred) {
+        sq_set_error("deferred mode must be chosen before the first record array");
+        return SQ_E_ARG;
+    }
+    d->deferred = deferred != 0;
+    return SQ_OK;
+}
+
+// Compacts the kept hashes that pass mask(mod_bits) into one device buffer (record order kept)
+// and releases the per-array buffers.  *n = number of surviving hashes.
+extern "C" int sq_dedup_deferred_compact(sq_dedup *d, uint64_t mod_bits, uint64_t *n) {
+    sq_ctx *ctx = d->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    *n = 0;
+    const uint64_t mask = mod_bits >= 64 ? ~0ULL : (1ULL << mod_bits) - 1;
+    const size_t n_arr = d->kept.size();
+    std::vector<uint32_t *> flags(n_arr, nullptr), ranks(n_arr, nullptr);
+    uint32_t *totals = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&totals, (n_arr + 1) * 4, true));
+    for (size_t a = 0; a < n_arr; a++) {
+        const uint32_t len = d->kept[a].n;
+        SQ_TRY(sq_dalloc(ctx, (void **)&flags[a], (size_t)len * 4, false));
+        SQ_TRY(sq_dalloc(ctx, (void **)&ranks[a], (size_t)len * 4, false));
+        SQ_LAUNCH(ctx, k_dd_pass_flags, sq_grid_for(ctx, len, DD_TPB, 16), DD_TPB, 0, d->kept[a].hashes, len, mask,
+                  flags[a]);
+        SQ_TRY(sq_scan_exclusive_u32(ctx, flags[a], ranks[a], len, totals + a));
+    }
+    std::vector<uint32_t> h_tot(n_arr + 1, 0);
+    if (n_arr) CUDA_TRY(cudaMemcpyAsync(h_tot.data(), totals, n_arr * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint64_t total = 0;
+    for (size_t a = 0; a < n_arr; a++) total += h_tot[a];
+    sq_dfree(ctx, d->compact);
+    d->compact = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&d->compact, (total + 1) * 8, false));
+    uint64_t off = 0;
+    for (size_t a = 0; a < n_arr; a++) {
+        const uint32_t len = d->kept[a].n;
+        SQ_LAUNCH(ctx, k_dd_pass_scatter, sq_grid_for(ctx, len, DD_TPB, 16), DD_TPB, 0, d->kept[a].hashes, flags[a],
+                  ranks[a], len, d->compact + off);
+        off += h_tot[a];
+        sq_dfree(ctx, flags[a]);
+        sq_dfree(ctx, ranks[a]);
+        sq_dfree(ctx, d->kept[a].hashes);
+    }
+    d->kept.clear();
+    sq_dfree(ctx, totals);
+    d->compact_n = total;
+    *n = total;
+    return SQ_OK;
+}
+
+// Copies the compacted hashes to a caller-owned DEVICE buffer of compact_n entries.
+extern "C" int sq_dedup_deferred_fetch(sq_dedup *d, uint64_t *dev_out) {
+    sq_ctx *ctx = d->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (d->compact_n)
+        CUDA_TRY(cudaMemcpyAsync(dev_out, d->compact, d->compact_n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    sq_dfree(ctx, d->compact);
+    d->compact = nullptr;
+    d->compact_n = 0;
+    return SQ_OK;
+}
+
+// DedupEstimator_add_fingerprint (:4426-4460) for n hashes that already sit in device memory,
+// in record order (the hashes another rank handed over).
+extern "C" int sq_dedup_add_hashes(sq_dedup *d, const uint64_t *dev_hashes, uint64_t n) {
+    if (d->deferred) {
+        sq_set_error("a deferred DedupEstimator owns no table");
+        return SQ_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(d->ctx->device));
+    const uint64_t step = 1ULL << 26;
+    for (uint64_t lo = 0; lo < n; lo += step) {
+        const uint64_t len = n - lo < step ? n - lo : step;
+        SQ_TRY(dedup_consume(d, dev_hashes + lo, (uint32_t)len));
+    }
+    CUDA_TRY(cudaStreamSynchronize(d->ctx->stream));
     return SQ_OK;
 }

@@ -909,7 +909,7 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     }
     if (rc == SQ_OK && dd) rc = dedup_consume(dd, hashes, n);
     sq_dfree(ctx, tile);
-    sq_dfree(ctx, hashes);
+    if (!(dd && dd->deferred && rc == SQ_OK)) sq_dfree(ctx, hashes);  // a deferred estimator keeps them
     sq_dfree(ctx, approx);
     sq_dfree(ctx, cta_mixed);
     return rc;

@@ -131,6 +131,13 @@ struct sq_dedup {
     DdTable tab, spare;
     DdCounters *cnt = nullptr;
     uint8_t *stale_fp = nullptr;  // pair path: persistent fingerprint scratch of the reference
+    // sharded runs (rank > 0): keep the fingerprint hashes, the table lives on the first rank
+    bool deferred = false;
+    struct Kept { uint64_t *hashes; uint32_t n; };
+    std::vector<Kept> kept;
+    uint64_t *compact = nullptr;  // hashes that pass the requested mask, in record order
+    uint64_t compact_n = 0;
 };
 
+// Takes `hashes` in record order.  In deferred mode the buffer is KEPT (the caller must not free it).
 int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n);

@@ -39,6 +39,11 @@ struct sq_overrep {
     uint64_t *keys = nullptr;    // wang hash, 0 = empty
     uint32_t *counts = nullptr;
     OvCounters *cnt = nullptr;
+    // sharded runs: fragments of the sampled reads are kept, the table work waits for the
+    // table state of the ranks before this one (sq_overrep_apply_deferred)
+    bool deferred = false;
+    struct Kept { uint64_t *frag_hash; uint32_t *frag_n; uint64_t n_sampled, total; uint32_t fcap; };
+    std::vector<Kept> kept;
 };
 
 // canonical k-mer of s[0..k): 0 ok, 1 holds N/n, 2 holds another non-ACGT letter (:3612-3694)
@@ -262,6 +267,10 @@ extern "C" int sq_overrep_create(sq_ctx *ctx, uint64_t max_unique_fragments, uin
 extern "C" void sq_overrep_destroy(sq_overrep *o) {
     if (!o) return;
     cudaSetDevice(o->ctx->device);
+    for (auto &k : o->kept) {
+        sq_dfree(o->ctx, k.frag_hash);
+        sq_dfree(o->ctx, k.frag_n);
+    }
     sq_dfree(o->ctx, o->keys);
     sq_dfree(o->ctx, o->counts);
     sq_dfree(o->ctx, o->cnt);
@@ -278,47 +287,13 @@ static int ov_refresh_unique(sq_overrep *o) {
     return SQ_OK;
 }
 
-extern "C" int sq_overrep_add(sq_overrep *o, sq_batch *b) {
+static int ov_refresh_unique(sq_overrep *o);
+// Table maintenance for the fragments of one record array (staging layout of k_ov_fragments):
+// Sequence_duplication_insert_hash (:3543-3568) for every staged hash in (read, slot) order.
+static int ov_apply(sq_overrep *o, const uint64_t *frag_hash, const uint32_t *frag_n, uint64_t n_sampled,
+                    uint64_t total, uint32_t fcap) {
     sq_ctx *ctx = o->ctx;
-    if (b->ctx != ctx) {
-        sq_set_error("record array belongs to another context");
-        return SQ_E_ARG;
-    }
-    const uint64_t n = b->n;
-    if (n == 0) return SQ_OK;
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    // reads whose running index is a multiple of sample_every (:3833)
-    const uint64_t se = o->sample_every;
-    const uint64_t first = (se - o->n_seqs % se) % se;
-    const uint64_t n_sampled = first < n ? (n - first + se - 1) / se : 0;
-    const uint64_t record_base = o->n_seqs;
-    o->n_seqs += n;
-    o->n_sampled += n_sampled;
-    if (n_sampled == 0 || b->max_len < o->k) return SQ_OK;
-    // staging capacity needed by the longest read of this array
-    const uint64_t maxf = (b->max_len + o->k - 1) / o->k;
-    const uint64_t nf = std::min(o->frags_front, maxf - maxf / 2), nb = std::min(o->frags_back, maxf / 2);
-    const uint64_t total = nf + nb;
-    if (total == 0) return SQ_OK;
-    uint32_t fcap = 1;
-    while (2 * (uint64_t)fcap < 3 * total) fcap <<= 1;
-    if (fcap > OV_STAGE_MAX) {
-        sq_set_error("more than %d fragments per read are not supported yet (got %llu)",
-                     OV_STAGE_MAX * 2 / 3, (unsigned long long)total);
-        return SQ_E_LIMIT;
-    }
     const uint64_t occ = n_sampled * fcap;
-    if (occ >= 0xFFFFFFFFULL) {
-        sq_set_error("record array too large for the fragment index");
-        return SQ_E_LIMIT;
-    }
-    uint64_t *frag_hash = nullptr;
-    uint32_t *frag_n = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&frag_hash, occ * 8, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&frag_n, n_sampled * 4, false));
-    SQ_LAUNCH(ctx, k_ov_fragments, sq_grid_for(ctx, n_sampled, OV_TPB, 16), OV_TPB, 0, b->view(), (uint32_t)first,
-              (uint32_t)se, (uint32_t)n_sampled, (uint32_t)o->k, o->frags_front, o->frags_back, fcap, frag_hash,
-              frag_n, o->cnt, record_base);
     const uint64_t mask = o->table_size - 1;
     const int grid = sq_grid_for(ctx, occ, 256, 16);
     int rc = SQ_OK;
@@ -367,6 +342,56 @@ extern "C" int sq_overrep_add(sq_overrep *o, sq_batch *b) {
             sq_dfree(ctx, S.first);
         }
     }
+    return rc;
+}
+
+
+extern "C" int sq_overrep_add(sq_overrep *o, sq_batch *b) {
+    sq_ctx *ctx = o->ctx;
+    if (b->ctx != ctx) {
+        sq_set_error("record array belongs to another context");
+        return SQ_E_ARG;
+    }
+    const uint64_t n = b->n;
+    if (n == 0) return SQ_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // reads whose running index is a multiple of sample_every (:3833)
+    const uint64_t se = o->sample_every;
+    const uint64_t first = (se - o->n_seqs % se) % se;
+    const uint64_t n_sampled = first < n ? (n - first + se - 1) / se : 0;
+    const uint64_t record_base = o->n_seqs;
+    o->n_seqs += n;
+    o->n_sampled += n_sampled;
+    if (n_sampled == 0 || b->max_len < o->k) return SQ_OK;
+    // staging capacity needed by the longest read of this array
+    const uint64_t maxf = (b->max_len + o->k - 1) / o->k;
+    const uint64_t nf = std::min(o->frags_front, maxf - maxf / 2), nb = std::min(o->frags_back, maxf / 2);
+    const uint64_t total = nf + nb;
+    if (total == 0) return SQ_OK;
+    uint32_t fcap = 1;
+    while (2 * (uint64_t)fcap < 3 * total) fcap <<= 1;
+    if (fcap > OV_STAGE_MAX) {
+        sq_set_error("more than %d fragments per read are not supported yet (got %llu)",
+                     OV_STAGE_MAX * 2 / 3, (unsigned long long)total);
+        return SQ_E_LIMIT;
+    }
+    const uint64_t occ = n_sampled * fcap;
+    if (occ >= 0xFFFFFFFFULL) {
+        sq_set_error("record array too large for the fragment index");
+        return SQ_E_LIMIT;
+    }
+    uint64_t *frag_hash = nullptr;
+    uint32_t *frag_n = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&frag_hash, occ * 8, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&frag_n, n_sampled * 4, false));
+    SQ_LAUNCH(ctx, k_ov_fragments, sq_grid_for(ctx, n_sampled, OV_TPB, 16), OV_TPB, 0, b->view(), (uint32_t)first,
+              (uint32_t)se, (uint32_t)n_sampled, (uint32_t)o->k, o->frags_front, o->frags_back, fcap, frag_hash,
+              frag_n, o->cnt, record_base);
+    if (o->deferred) {
+        o->kept.push_back({frag_hash, frag_n, n_sampled, total, fcap});
+        return SQ_OK;
+    }
+    int rc = ov_apply(o, frag_hash, frag_n, n_sampled, total, fcap);
     sq_dfree(ctx, frag_hash);
     sq_dfree(ctx, frag_n);
     return rc;
@@ -455,4 +480,88 @@ extern "C" int sq_overrep_read(sq_overrep *o, uint64_t *kmers, uint32_t *counts,
     sq_overrep_info info;
     SQ_TRY(sq_overrep_sync(o, &info));
     return sq_overrep_read_min(o, 0, kmers, counts, info.collected_unique_fragments, n);
+}
+
+
+// ---------------------------------------------------------------------------
+// Sharded runs.  The table is "the first
+// max_unique_fragments distinct hashes in (sampled read, staging slot) order,
+// each with all of its occurrences": order matters only until the table is
+// full.  Ranks behind the first one keep their fragments (deferred mode) and
+//   - while the table is not full, take it over from the rank before them and
+//     apply their fragments to it (the sequential semantics, rank by rank);
+//   - once it is full the key set is frozen: every remaining rank loads the
+//     keys with zero counts, counts its own fragments (lookup only, any order)
+//     and the count arrays are summed.
+// ---------------------------------------------------------------------------
+extern "C" int sq_overrep_set_deferred(sq_overrep *o, int deferred, uint64_t first_record) {
+    if (o->n_seqs != 0 || !o->kept.empty()) {
+        sq_set_error("deferred mode must be chosen before the first record array");
+        return SQ_E_ARG;
+    }
+    o->deferred = deferred != 0;
+    o->n_seqs = first_record;  // global index of the shard's first read: sampling phase (:3833) and warnings
+    return SQ_OK;
+}
+
+extern "C" int sq_overrep_apply_deferred(sq_overrep *o) {
+    sq_ctx *ctx = o->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = SQ_OK;
+    for (auto &k : o->kept) {
+        if (rc == SQ_OK) rc = ov_apply(o, k.frag_hash, k.frag_n, k.n_sampled, k.total, k.fcap);
+        sq_dfree(ctx, k.frag_hash);
+        sq_dfree(ctx, k.frag_n);
+    }
+    o->kept.clear();
+    o->deferred = false;
+    return rc;
+}
+
+// keys[table_size] (u64) and counts[table_size] (u32) into caller-owned DEVICE buffers
+extern "C" int sq_overrep_copy_table(sq_overrep *o, uint64_t *dev_keys, uint32_t *dev_counts) {
+    sq_ctx *ctx = o->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (dev_keys) CUDA_TRY(cudaMemcpyAsync(dev_keys, o->keys, o->table_size * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (dev_counts)
+        CUDA_TRY(cudaMemcpyAsync(dev_counts, o->counts, o->table_size * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SQ_OK;
+}
+
+// Replace the table: keys (nullptr: keep), counts (nullptr: zero) from DEVICE buffers, and the
+// number of stored keys.
+extern "C" int sq_overrep_load_table(sq_overrep *o, const uint64_t *dev_keys, const uint32_t *dev_counts,
+                                     uint64_t n_unique) {
+    sq_ctx *ctx = o->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (dev_keys) CUDA_TRY(cudaMemcpyAsync(o->keys, dev_keys, o->table_size * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (dev_counts)
+        CUDA_TRY(cudaMemcpyAsync(o->counts, dev_counts, o->table_size * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    else CUDA_TRY(cudaMemsetAsync(o->counts, 0, o->table_size * 4, ctx->stream));
+    unsigned int *h = (unsigned int *)((char *)ctx->h_scratch + 1664);
+    *h = (unsigned int)n_unique;
+    CUDA_TRY(cudaMemcpyAsync(&o->cnt->n_unique, h, 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    o->unique_known = o->unique_upper = n_unique;
+    o->full = n_unique >= o->max_unique;
+    return SQ_OK;
+}
+
+// Overwrite the additive counters with merged values (what the members report afterwards).
+extern "C" int sq_overrep_set_counters(sq_overrep *o, uint64_t number_of_sequences, uint64_t sampled_sequences,
+                                       uint64_t total_fragments, uint64_t warn_records, uint64_t first_warn_record) {
+    sq_ctx *ctx = o->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    o->n_seqs = number_of_sequences;
+    o->n_sampled = sampled_sequences;
+    OvCounters *h = (OvCounters *)((char *)ctx->h_scratch + 1536);
+    CUDA_TRY(cudaMemcpyAsync(h, o->cnt, sizeof(OvCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    h->total_frags = total_fragments;
+    h->warn_records = warn_records;
+    h->first_warn = first_warn_record;
+    CUDA_TRY(cudaMemcpyAsync(o->cnt, h, sizeof(OvCounters), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SQ_OK;
 }

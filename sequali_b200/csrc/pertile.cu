@@ -842,3 +842,89 @@ extern "C" int sq_pertile_read(sq_pertile *p, uint64_t *tile_ids, double *errors
     }
     return SQ_OK;
 }
+
+
+// ---------------------------------------------------------------------------
+// Sharded runs.  total_errors[tile][pos] is a chain over the
+// reads of a tile in read order, so one rank must see all reads of a tile: the
+// lowest rank that holds any read of it.  The other ranks copy their records of
+// such tiles, whole and in order, into one FASTQ text (sq_batch_select_tiles)
+// and hand it to the owner, which parses it like any other record array and
+// adds it after its own reads.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT_TPB)
+k_pt_select_sizes(BatchView bv, uint32_t limit, const long long *__restrict__ ids, uint32_t n_ids,
+                  uint32_t *__restrict__ sizes) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < bv.n; r += gridDim.x * blockDim.x) {
+        uint32_t sz = 0;
+        if (r < limit) {
+            const long long t = tile_id_of(bv.text + bv.name_off[r], bv.seq_off[r] - 1 - bv.name_off[r]);
+            uint32_t lo = 0, hi = n_ids;  // ids sorted ascending
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (ids[mid] < t) lo = mid + 1;
+                else hi = mid;
+            }
+            if (t >= 0 && lo < n_ids && ids[lo] == t) sz = bv.name_off[r + 1] - bv.name_off[r];
+        }
+        sizes[r] = sz;
+    }
+}
+__global__ void __launch_bounds__(PT_TPB)
+k_pt_select_copy(BatchView bv, const uint32_t *__restrict__ sizes, const uint32_t *__restrict__ offs,
+                 uint8_t *__restrict__ out) {
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < bv.n; r += warps) {
+        const uint32_t sz = sizes[r];
+        if (!sz) continue;
+        const uint8_t *src = bv.text + bv.name_off[r] - 1;
+        uint8_t *dst = out + offs[r];
+        for (uint32_t i = lane_id(); i < sz; i += 32) dst[i] = src[i];
+    }
+}
+
+// Records r < limit_records of a FASTQ-text record array whose tile id is in tile_ids[0..n_ids)
+// (host array, ascending), copied in order to dev_out (DEVICE, cap bytes).  dev_out == NULL only
+// sizes the output.  *nbytes = bytes needed / written.
+extern "C" int sq_batch_select_tiles(sq_batch *b, const int64_t *tile_ids, uint64_t n_ids, uint64_t limit_records,
+                                     uint8_t *dev_out, uint64_t cap, uint64_t *nbytes) {
+    sq_ctx *ctx = b->ctx;
+    *nbytes = 0;
+    if (b->name_len != nullptr) {
+        sq_set_error("sq_batch_select_tiles needs a FASTQ-text record array");
+        return SQ_E_ARG;
+    }
+    if (b->n == 0 || n_ids == 0 || limit_records == 0) return SQ_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint32_t n = (uint32_t)b->n;
+    long long *ids = nullptr;
+    uint32_t *sizes = nullptr, *offs = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&ids, n_ids * 8, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&sizes, (size_t)n * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&offs, (size_t)n * 4 + 4, false));
+    CUDA_TRY(cudaMemcpyAsync(ids, tile_ids, n_ids * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t limit = limit_records > n ? n : (uint32_t)limit_records;
+    const int grid = sq_grid_for(ctx, n, PT_TPB, 16);
+    SQ_LAUNCH(ctx, k_pt_select_sizes, grid, PT_TPB, 0, b->view(), limit, ids, (uint32_t)n_ids, sizes);
+    SQ_TRY(sq_scan_exclusive_u32(ctx, sizes, offs, n, offs + n));
+    uint32_t *h_total = (uint32_t *)((char *)ctx->h_scratch + 3400);
+    CUDA_TRY(cudaMemcpyAsync(h_total, offs + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // also: the pageable tile_ids have been read
+    *nbytes = *h_total;
+    int rc = SQ_OK;
+    if (dev_out && *h_total) {
+        if (*h_total > cap) {
+            sq_set_error("selected records need %u bytes, buffer has %llu", *h_total, (unsigned long long)cap);
+            rc = SQ_E_ARG;
+        }
+        else {
+            SQ_LAUNCH(ctx, k_pt_select_copy, sq_grid_for(ctx, (uint64_t)n * 32, PT_TPB, 32), PT_TPB, 0, b->view(), sizes,
+                      offs, dev_out);
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    sq_dfree(ctx, ids);
+    sq_dfree(ctx, sizes);
+    sq_dfree(ctx, offs);
+    return rc;
+}

@@ -12,12 +12,22 @@ What merges exactly:
     ``max_length`` (all-reduce(MAX));
   * NanoStats: per-read records concatenated in rank order, min/max times by
     all-reduce;
-  * PerTileQuality: tiles seen by one rank only are taken as they are.  A tile
-    whose reads straddle a shard border has order-dependent double sums: it is
-    reported in ``straddling`` and merged by adding the partial sums (NOT the
-    reference's rounding order) -- shard at tile borders to avoid it.
-DedupEstimator / OverrepresentedSequences tables are order dependent across
-shards (escalation point, table-full admission) and stay per rank for now.
+  * PerTileQuality (``merge_pertile``): the per-(tile, position) double sums are
+    chains in read order, so the lowest rank that holds a tile owns it; the
+    other ranks hand their records of that tile over (whole records, in
+    order) and the owner adds them behind its own reads -- bit-identical to one
+    sequential pass.  With tile-sorted input only the tile at each shard
+    border moves.
+  * DedupEstimator (``merge_dedup``): the first rank owns the table; the
+    others only hash, drop what fails the owner's final sampling mask (the
+    mask only grows) and hand the rest over in read order.
+  * OverrepresentedSequences (``merge_overrep``): the table travels rank by
+    rank while it is not full (order matters); once full the key set is
+    frozen, the remaining ranks count against it independently and the count
+    arrays are summed.
+The merge functions talk to the collectors through small adapters
+(``Gpu*`` below for sequali_b200; the CPU tests plug the oracle in), so the
+protocol itself is covered by world_size-2 gloo tests without a GPU.
 """
 from __future__ import annotations
 
@@ -138,3 +148,402 @@ def merge_tile_counts(tiles) -> tuple[list, list]:
                 me[i] += x
                 mc[i] += y
     return [(t, merged[t][0], merged[t][1]) for t in sorted(merged)], sorted(set(straddling))
+
+
+# ------------------------------------------------------------------------------
+# order-dependent collectors: exact merges
+# ------------------------------------------------------------------------------
+_NO_FAIL = (1 << 62)
+
+
+def _rank_world():
+    torch, dist, dev = _dist()
+    if dist is None:
+        return 0, 1
+    return dist.get_rank(), dist.get_world_size()
+
+
+def _bcast_ints(values, src: int) -> list[int]:
+    torch, dist, dev = _dist()
+    if dist is None:
+        return [int(v) for v in values]
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
+    dist.broadcast(t, src=src)
+    return [int(v) for v in t.cpu().tolist()]
+
+
+def _allgather_obj(obj) -> list:
+    torch, dist, dev = _dist()
+    if dist is None:
+        return [obj]
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, obj)
+    return parts
+
+
+def _bcast_obj(obj, src: int):
+    torch, dist, dev = _dist()
+    if dist is None:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def _comm_sync():
+    """Collectives on device tensors run on torch's streams, the collectors on the library's."""
+    torch, dist, dev = _dist()
+    if dist is not None and dev.type == "cuda":
+        torch.cuda.synchronize()
+
+
+def merge_dedup(dd) -> tuple[np.ndarray, dict]:
+    """DedupEstimator over all shards.  ``dd``: rank 0 a live estimator that has seen its shard,
+    other ranks deferred ones.  Adapter interface: ``modulo_bits()``, ``deferred_hashes(bits) ->
+    int64 tensor`` (record order), ``consume(tensor)``, ``counts() -> np.ndarray``, ``info() ->
+    dict``, ``empty(n) -> tensor``.  Returns (duplication counts in slot order, info) on every rank."""
+    torch, dist, dev = _dist()
+    rank, world = _rank_world()
+    if world > 1:
+        bits = _bcast_ints([dd.modulo_bits() if rank == 0 else 0], 0)[0]
+        mine = dd.deferred_hashes(bits) if rank > 0 else None
+        sizes = _allgather_obj(0 if mine is None else int(mine.numel()))
+        for g in range(1, world):
+            if sizes[g] == 0:
+                continue
+            if rank == g:
+                dist.send(mine, dst=0)
+            elif rank == 0:
+                buf = dd.empty(sizes[g])
+                dist.recv(buf, src=g)
+                _comm_sync()
+                dd.consume(buf)
+        _comm_sync()
+    result = (dd.counts(), dd.info()) if rank == 0 else None
+    return _bcast_obj(result, 0)
+
+
+def merge_overrep(ov) -> None:
+    """OverrepresentedSequences over all shards; afterwards every rank's collector holds the
+    merged table and counters.  Adapter interface: ``state() -> (n_unique, full)``,
+    ``table() -> (keys int64 tensor, counts int32 tensor)``, ``load(keys, counts | None,
+    n_unique)``, ``apply_deferred()``, ``local_counters() -> [n_seqs, n_sampled, total_fragments,
+    warn_records, first_warn]``, ``set_counters(...)``, ``empty_table()``."""
+    torch, dist, dev = _dist()
+    rank, world = _rank_world()
+    if world == 1:
+        return
+    cur = 0
+    while True:
+        n_unique, full = _bcast_ints(ov.state() if rank == cur else (0, 0), cur)
+        if full or cur == world - 1:
+            break
+        if rank == cur:
+            keys, counts = ov.table()
+            dist.send(keys, dst=cur + 1)
+            dist.send(counts, dst=cur + 1)
+        elif rank == cur + 1:
+            keys, counts = ov.empty_table()
+            dist.recv(keys, src=cur)
+            dist.recv(counts, src=cur)
+            _comm_sync()
+            ov.load(keys, counts, n_unique)
+            ov.apply_deferred()
+        cur += 1
+    # `cur` holds the table of everything up to its own shard; behind it the key set is frozen
+    keys, counts = ov.table() if rank == cur else ov.empty_table()
+    dist.broadcast(keys, src=cur)
+    _comm_sync()
+    if rank > cur:
+        ov.load(keys, None, n_unique)
+        ov.apply_deferred()
+        _, counts = ov.table()
+    elif rank < cur:
+        counts.zero_()
+    dist.all_reduce(counts)  # int32 wrap-around = the reference's u32 counter
+    _comm_sync()
+    ov.load(keys, counts, n_unique)
+    local = ov.local_counters()  # reads, sampled reads, fragments, warnings of this shard only
+    sums = allreduce_sum_tables([np.array(local[:4], dtype=np.uint64)])[0]
+    first_warn = -allreduce_max(-(int(local[4]) if local[4] >= 0 else _NO_FAIL))
+    ov.set_counters(int(sums[0]), int(sums[1]), int(sums[2]), int(sums[3]),
+                    -1 if first_warn == _NO_FAIL else first_warn)
+
+
+def merge_pertile(pt, first_record: int) -> dict:
+    """PerTileQuality over all shards -> {"tiles": [(tile, sums, counts)], "number_of_reads",
+    "max_length", "skipped_record"} on every rank.  Adapter interface: ``tile_ids() -> list``,
+    ``fail_index() -> local index of the first unparsable header or None``, ``number_of_reads()``,
+    ``select(sorted tile ids, limit_records) -> list of uint8 tensors (FASTQ text, <= 2 GiB
+    each)``, ``add_text(tensor)``, ``tile_counts()``, ``empty(n) -> uint8 tensor``."""
+    torch, dist, dev = _dist()
+    rank, world = _rank_world()
+    if world == 1:
+        tiles = pt.tile_counts()
+        return dict(tiles=tiles, number_of_reads=pt.number_of_reads(),
+                    max_length=max([len(e) for _, e, _ in tiles], default=0), skipped_record=pt.fail_index())
+    fail = pt.fail_index()
+    fail_global = _NO_FAIL if fail is None else first_record + fail
+    F = -allreduce_max(-fail_global)
+    dropped = first_record >= F            # the whole shard lies behind the first unparsable header
+    my_tiles = [] if dropped else sorted(int(t) for t in pt.tile_ids())
+    my_reads = 0 if dropped else pt.number_of_reads()
+    all_tiles = _allgather_obj(my_tiles)
+    owner = {}
+    for g, ts in enumerate(all_tiles):
+        for t in ts:
+            owner.setdefault(t, g)
+    # what this rank hands over, per owner
+    outgoing = {}
+    for o in range(rank):
+        ids = [t for t in my_tiles if owner[t] == o]
+        if ids:
+            outgoing[o] = pt.select(ids, max(0, min(F - first_record, 1 << 62)))
+    plan = _allgather_obj({o: [int(c.numel()) for c in chunks] for o, chunks in outgoing.items()})
+    for o in range(world):
+        for g in range(o + 1, world):
+            for i, nbytes in enumerate(plan[g].get(o, [])):
+                if nbytes == 0:
+                    continue
+                if rank == g:
+                    dist.send(outgoing[o][i], dst=o)
+                elif rank == o:
+                    buf = pt.empty(nbytes)
+                    dist.recv(buf, src=g)
+                    _comm_sync()
+                    pt.add_text(buf)
+    _comm_sync()
+    mine = [] if dropped else [(int(t), e, c) for t, e, c in pt.tile_counts() if owner.get(int(t)) == rank]
+    parts = _allgather_obj(mine)
+    tiles = sorted((x for part in parts for x in part), key=lambda x: x[0])
+    width = max([len(e) for _, e, _ in tiles], default=0)
+    tiles = [(t, list(e) + [0.0] * (width - len(e)), list(c) + [0] * (width - len(c))) for t, e, c in tiles]
+    total_reads = int(allreduce_sum_tables([np.array([my_reads], dtype=np.uint64)])[0][0])
+    return dict(tiles=tiles, number_of_reads=total_reads, max_length=width,
+                skipped_record=None if F == _NO_FAIL else F)
+
+
+# ------------------------------------------------------------------------------
+# adapters for the sequali_b200 collectors (device tensors, NCCL)
+# ------------------------------------------------------------------------------
+class GpuDedup:
+    def __init__(self, estimator, deferred: bool):
+        from ._lib import check
+        self.dd, self._check = estimator, check
+        if deferred:
+            check(estimator._ctx.lib.sq_dedup_set_deferred(estimator._h, 1), "sq_dedup_set_deferred")
+
+    def empty(self, n):
+        import torch
+        return torch.empty(max(int(n), 1), dtype=torch.int64, device="cuda")[:int(n)]
+
+    def modulo_bits(self):
+        return self.dd._modulo_bits
+
+    def deferred_hashes(self, bits):
+        import ctypes as C
+        self.dd._sync()
+        n = C.c_uint64()
+        lib = self.dd._ctx.lib
+        self._check(lib.sq_dedup_deferred_compact(self.dd._h, bits, C.byref(n)), "sq_dedup_deferred_compact")
+        _comm_sync()
+        out = self.empty(n.value)
+        self._check(lib.sq_dedup_deferred_fetch(self.dd._h, out.data_ptr()), "sq_dedup_deferred_fetch")
+        return out
+
+    def consume(self, t):
+        self.dd._sync()
+        self._check(self.dd._ctx.lib.sq_dedup_add_hashes(self.dd._h, t.data_ptr(), int(t.numel())),
+                    "sq_dedup_add_hashes")
+
+    def counts(self):
+        return np.frombuffer(self.dd.duplication_counts(), dtype=np.uint64).copy()
+
+    def info(self):
+        i = self.dd._sync()
+        return dict(modulo_bits=int(i.modulo_bits), hash_table_size=int(i.hash_table_size),
+                    tracked_sequences=int(i.tracked_sequences))
+
+
+class GpuOverrep:
+    def __init__(self, collector, deferred: bool, first_record: int):
+        from ._lib import check
+        self.ov, self._check, self.first_record = collector, check, first_record
+        check(collector._ctx.lib.sq_overrep_set_deferred(collector._h, 1 if deferred else 0, first_record),
+              "sq_overrep_set_deferred")
+
+    def _lib(self):
+        return self.ov._ctx.lib
+
+    def state(self):
+        i = self.ov._sync()
+        return int(i.collected_unique_fragments), int(i.collected_unique_fragments >= i.max_unique_fragments)
+
+    def empty_table(self):
+        import torch
+        size = int(self.ov._sync().table_size)
+        _comm_sync()
+        return (torch.empty(size, dtype=torch.int64, device="cuda"),
+                torch.empty(size, dtype=torch.int32, device="cuda"))
+
+    def table(self):
+        keys, counts = self.empty_table()
+        self._check(self._lib().sq_overrep_copy_table(self.ov._h, keys.data_ptr(), counts.data_ptr()),
+                    "sq_overrep_copy_table")
+        return keys, counts
+
+    def load(self, keys, counts, n_unique):
+        self.ov._sync()
+        self._check(self._lib().sq_overrep_load_table(self.ov._h, keys.data_ptr(),
+                                                      counts.data_ptr() if counts is not None else None,
+                                                      n_unique), "sq_overrep_load_table")
+
+    def apply_deferred(self):
+        self._check(self._lib().sq_overrep_apply_deferred(self.ov._h), "sq_overrep_apply_deferred")
+        self.ov._ctx.sync()
+
+    def local_counters(self):
+        i = self.ov._sync()
+        first = int(i.first_warn_record) if i.warn_records else -1
+        return [int(i.number_of_sequences) - self.first_record, int(i.sampled_sequences),
+                int(i.total_fragments), int(i.warn_records), first]
+
+    def set_counters(self, n_seqs, n_sampled, total_frags, warn_records, first_warn):
+        self.ov._warned = max(self.ov._warned, warn_records)  # the shard that met it has warned already
+        self._check(self._lib().sq_overrep_set_counters(
+            self.ov._h, n_seqs, n_sampled, total_frags, warn_records,
+            first_warn if first_warn >= 0 else 0xFFFFFFFFFFFFFFFF), "sq_overrep_set_counters")
+
+
+class GpuPerTile:
+    """Keeps the record arrays of the shard alive until the merge: records of tiles owned by a
+    lower rank are copied out of them."""
+
+    def __init__(self, collector):
+        from ._lib import check
+        self.pt, self._check, self.arrays, self._keep = collector, check, [], []
+
+    def add_record_array(self, arr):
+        self.arrays.append(arr)
+        self.pt.add_record_array(arr)
+
+    def empty(self, n):
+        import torch
+        t = torch.empty(int(n) + 64, dtype=torch.uint8, device="cuda")
+        t[int(n):] = 0  # the parser's vector loads may look a few bytes past the text
+        return t[:int(n)]
+
+    def tile_ids(self):
+        return [t for t, _, _ in self.pt.get_tile_counts()]
+
+    def fail_index(self):
+        info = self.pt._sync()
+        return int(info.skipped_record) if info.skipped else None
+
+    def number_of_reads(self):
+        return int(self.pt.number_of_reads)
+
+    def tile_counts(self):
+        return self.pt.get_tile_counts()
+
+    def select(self, ids, limit_records):
+        import ctypes as C
+        lib = self.pt._ctx.lib
+        self.pt._sync()
+        idarr = np.asarray(sorted(ids), dtype=np.int64)
+        idp = idarr.ctypes.data_as(C.c_void_p)
+        sizes, base = [], 0
+        for arr in self.arrays:
+            n = C.c_uint64()
+            lim = max(0, min(len(arr), limit_records - base))
+            if lim:
+                self._check(lib.sq_batch_select_tiles(arr._handle(), idp, len(idarr), lim, None, 0, C.byref(n)),
+                            "sq_batch_select_tiles")
+            sizes.append((lim, n.value))
+            base += len(arr)
+        # chunks of whole arrays' selections, at most 2 GiB each (a record array is < 4 GiB)
+        chunks, cur, cur_bytes = [], [], 0
+        for i, (lim, nb) in enumerate(sizes):
+            if nb == 0:
+                continue
+            if cur and cur_bytes + nb > (1 << 31):
+                chunks.append((cur, cur_bytes))
+                cur, cur_bytes = [], 0
+            cur.append(i)
+            cur_bytes += nb
+        if cur:
+            chunks.append((cur, cur_bytes))
+        out = []
+        _comm_sync()
+        for members, total in chunks:
+            t = self.empty(total)
+            off = 0
+            for i in members:
+                lim, nb = sizes[i]
+                n = C.c_uint64()
+                self._check(lib.sq_batch_select_tiles(self.arrays[i]._handle(), idp, len(idarr), lim,
+                                                      t.data_ptr() + off, nb, C.byref(n)), "sq_batch_select_tiles")
+                assert n.value == nb
+                off += nb
+            out.append(t)
+        return out
+
+    def add_text(self, t):
+        import ctypes as C
+        from . import _lib
+        from ._qc import FastqRecordArrayView
+        ctx = self.pt._ctx
+        h, info = C.c_void_p(), _lib.ParseInfo()
+        self._check(ctx.lib.sq_batch_from_device_fastq(ctx.h, t.data_ptr(), int(t.numel()), 2 ** 63, C.byref(h),
+                                                       C.byref(info)), "sq_batch_from_device_fastq")
+        assert info.consumed == t.numel()
+        arr = FastqRecordArrayView._from_parser(h, info.n_records, None, int(t.numel()))
+        self._keep.append((t, arr))  # the record array borrows the tensor's memory
+        self.pt.add_record_array(arr)
+        self.pt._sync()
+
+
+# ------------------------------------------------------------------------------
+# one rank's collectors for a contiguous shard of the read stream
+# ------------------------------------------------------------------------------
+class ShardedCollectors:
+    """The single-end hot loop (src/sequali/__main__.py:279-306) on one shard, plus the merges.
+
+    ``first_record`` is the global index of the shard's first read (it fixes which reads
+    OverrepresentedSequences samples, _qcmodule.c:3833).  Rank 0 runs every collector as usual;
+    on the other ranks DedupEstimator and OverrepresentedSequences only hash (their tables are
+    order dependent and travel between ranks in ``merge``)."""
+
+    def __init__(self, mod, adapters, first_record: int = 0, dedup_kwargs=None, overrep_kwargs=None):
+        rank, _ = _rank_world()
+        self.first_record = first_record
+        self.qc, self.ns, self.ad = mod.QCMetrics(), mod.NanoStats(), mod.AdapterCounter(adapters)
+        self.pt = GpuPerTile(mod.PerTileQuality())
+        self.ov = GpuOverrep(mod.OverrepresentedSequences(**(overrep_kwargs or {})), rank > 0, first_record)
+        self.dd = GpuDedup(mod.DedupEstimator(**(dedup_kwargs or dict(front_sequence_offset=64,
+                                                                       back_sequence_offset=0))), rank > 0)
+
+    def add_record_array(self, arr) -> None:
+        self.qc.add_record_array(arr)
+        self.pt.add_record_array(arr)
+        self.ov.ov.add_record_array(arr)
+        self.ns.add_record_array(arr)
+        self.ad.add_record_array(arr)
+        self.dd.dd.add_record_array(arr)
+
+    def merge(self) -> dict:
+        """Merged results of all ranks, on every rank."""
+        qc = self.qc
+        out = dict(qc=merge_qc(*[np.frombuffer(x, dtype=np.uint64) for x in (
+            qc.base_count_table(), qc.phred_count_table(), qc.end_anchored_base_count_table(),
+            qc.end_anchored_phred_count_table(), qc.gc_content(), qc.phred_scores())]))
+        out["qc"]["number_of_reads"] = int(allreduce_sum_tables(
+            [np.array([qc.number_of_reads], dtype=np.uint64)])[0][0])
+        out["adapters"] = merge_adapter_counts([(a, np.frombuffer(f, dtype=np.uint64), np.frombuffer(r, dtype=np.uint64))
+                                                for a, f, r in self.ad.get_counts()])
+        out["ptq"] = merge_pertile(self.pt, self.first_record)
+        counts, info = merge_dedup(self.dd)
+        out["dedup"] = dict(counts=counts, **info)
+        merge_overrep(self.ov)
+        out["overrep"] = self.ov.ov  # the merged table answers the usual getters
+        return out

@@ -93,3 +93,97 @@ def test_two_rank_merge_equals_single_process():
         assert a == wa and f.tolist() == wf and r.tolist() == wr
     assert straddling == []
     assert [(t, e, c) for t, e, c in m_pt] == [(t, e, c) for t, e, c in want_pt["tiles"]]
+
+
+# ------------------------------------------------------------------------------
+# order-dependent collectors: the rank-to-rank protocol of sequali_b200.sharded
+# (merge_dedup / merge_overrep / merge_pertile), driven through the oracle
+# ------------------------------------------------------------------------------
+def _exact_worker(rank, world, port, text, cuts, dd_kw, ov_kw, out):
+    import torch.distributed as dist
+    from tests import sharded_adapters as A
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        recs, _ = orc.parse_fastq(text)
+        lo, hi = cuts[rank], cuts[rank + 1]
+        dd = A.OracleDedup(deferred=rank > 0, **dd_kw)
+        ov = A.OracleOverrep(deferred=rank > 0, first_record=lo, **ov_kw)
+        pt = A.OraclePerTile()
+        mid = (lo + hi) // 2
+        for a, b in ((lo, mid), (mid, hi)):  # two record arrays per shard
+            if b > a:
+                dd.add(text, recs[a:b])
+                ov.add(text, recs[a:b])
+                pt.add(text, recs[a:b])
+        counts, info = sharded.merge_dedup(dd)
+        sharded.merge_overrep(ov)
+        ptq = sharded.merge_pertile(pt, lo)
+        got = dict(dd_counts=counts.tolist(), dd_info=info, ov=H.odump_overrep(ov.o), ptq=ptq)
+        if rank == world - 1:  # every rank holds the merged result; take it from the last one
+            out.put(got)
+    finally:
+        dist.destroy_process_group()
+
+
+def _exact_case(text, world, cuts, dd_kw, ov_kw):
+    import torch.multiprocessing as mp
+    recs, _ = orc.parse_fastq(text)
+    dd = orc.DedupEstimator(**dd_kw)
+    ov = orc.OverrepresentedSequences(**ov_kw)
+    pt = orc.PerTileQuality()
+    dd.add(text, recs)
+    ov.add(text, recs)
+    rc = pt.add(text, recs)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exact_worker, args=(r, world, port, text, cuts, dd_kw, ov_kw, out))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    import queue
+    got = None
+    for _ in range(600):
+        try:
+            got = out.get(timeout=0.5)
+            break
+        except queue.Empty:
+            assert all(p.exitcode in (None, 0) for p in procs), "a rank died"
+    assert got is not None
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got["dd_info"]["modulo_bits"] == dd.info()["_modulo_bits"]
+    assert got["dd_info"]["tracked_sequences"] == dd.info()["tracked_sequences"]
+    assert got["dd_counts"] == dd.duplication_counts().tolist()        # slot order included
+    H.assert_same(got["ov"], H.odump_overrep(ov))
+    want_tiles = [(t, H.f64_bits(e), c.tolist()) for t, e, c in pt.get_tile_counts()]
+    got_tiles = [(t, H.f64_bits(np.array(e)), list(c)) for t, e, c in got["ptq"]["tiles"]]
+    assert got_tiles == want_tiles
+    assert got["ptq"]["number_of_reads"] == pt.number_of_reads
+    assert (got["ptq"]["skipped_record"] is not None) == (rc == 1)
+    return dd, ov, got
+
+
+@pytest.mark.parametrize("ov_kw", [dict(max_unique_fragments=400, sample_every=3),     # cap crossed in shard 0
+                                   dict(max_unique_fragments=9000, sample_every=3),    # ... in shard 1
+                                   dict(max_unique_fragments=10 ** 6, sample_every=8)])  # never
+def test_two_rank_order_dependent_merges(ov_kw):
+    # tiles in runs: the cut falls inside a run, so that tile straddles the border
+    text = synth.illumina_fastq(3000, length=100, seed=21, n_tiles=5, variable_length=True)
+    dd_kw = dict(max_stored_fingerprints=300, front_sequence_offset=64, back_sequence_offset=0)
+    dd, ov, _ = _exact_case(text, 2, [0, 1333, 3000], dd_kw, ov_kw)
+    assert dd.info()["_modulo_bits"] >= 2  # escalations happened in both shards
+
+
+def test_three_rank_random_tiles_and_unparsable_header():
+    # every tile on every rank; the module switches itself off inside the second shard
+    text = synth.illumina_fastq(1500, length=60, seed=22, n_tiles=4, tile_runs=False)
+    recs, _ = orc.parse_fastq(text)
+    no = int(recs[900]["name_off"])
+    text = text[:no] + text[no:].replace(b":", b"_", 5)  # record 900 loses its tile field
+    dd_kw = dict(max_stored_fingerprints=200, front_sequence_offset=64, back_sequence_offset=0)
+    _, _, got = _exact_case(text, 3, [0, 501, 1007, 1500], dd_kw,
+                            dict(max_unique_fragments=1500, sample_every=2))
+    assert got["ptq"]["skipped_record"] == 900 and got["ptq"]["number_of_reads"] == 900
