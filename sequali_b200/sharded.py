@@ -26,7 +26,7 @@ What merges exactly:
     frozen, the remaining ranks count against it independently and the count
     arrays are summed.
 The merge functions talk to the collectors through small adapters
-(``Gpu*`` below for sequali_b200; the CPU tests plug the oracle in), so the
+(``Gpu*`` below for sequali_b200; the CPU tests plug a host-side stand-in in), so the
 protocol itself is covered by world_size-2 gloo tests without a GPU.
 """
 from __future__ import annotations
