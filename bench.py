@@ -249,6 +249,8 @@ def run_cuda(args):
     step_resident()
     prof = ctx.profile_report()
     ctx.profile(False)
+    gaps = {k[4:]: v for k, v in prof.items() if k.startswith("gap>")}
+    prof = {k: v for k, v in prof.items() if not k.startswith("gap>")}
     kernel_ms = sum(v[1] for v in prof.values())
     top = max(prof.items(), key=lambda kv: kv[1][1])
     peak, peak_src = measured_peak_gbs()
@@ -265,6 +267,9 @@ def run_cuda(args):
         "all_kernels_gbs": round(text_bytes / (kernel_ms * 1e-3) / 1e9, 1),
         "all_kernels_frac": round(text_bytes / (kernel_ms * 1e-3) / 1e9 / peak, 4),
         "kernels_ms_per_step": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:48]},
+        # stream time between launches (memsets, copies, host syncs), by the kernel that follows
+        "gaps_ms_per_step": {k: round(v[1], 3) for k, v in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:16]},
+        "gaps_ms_total": round(sum(v[1] for v in gaps.values()), 3),
     }
 
     # ---- end to end: host text -> parser -> collectors -> getters --------------

@@ -155,13 +155,22 @@ extern "C" int sq_ctx_profile_report(sq_ctx *ctx, char *buf, size_t cap) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     struct Row { std::string name; uint64_t n; double ms; };
     std::vector<Row> rows;
-    for (auto &e : ctx->prof_events) {
+    auto add = [&rows](const std::string &name, float ms) {
+        for (auto &r : rows)
+            if (r.name == name) { r.n++; r.ms += ms; return; }
+        rows.push_back({name, 1, ms});
+    };
+    for (size_t i = 0; i < ctx->prof_events.size(); i++) {
+        auto &e = ctx->prof_events[i];
         float ms = 0;
         cudaEventElapsedTime(&ms, e.start, e.stop);
-        bool found = false;
-        for (auto &r : rows)
-            if (r.name == e.name) { r.n++; r.ms += ms; found = true; break; }
-        if (!found) rows.push_back({e.name, 1, ms});
+        add(e.name, ms);
+        // idle stream time in front of this launch (host work, syncs, copies, memsets), as "gap>kernel"
+        if (i) {
+            float gap = 0;
+            cudaEventElapsedTime(&gap, ctx->prof_events[i - 1].stop, e.start);
+            add(std::string("gap>") + e.name, gap);
+        }
     }
     for (size_t i = 0; i < rows.size(); i++)
         for (size_t j = i + 1; j < rows.size(); j++)
