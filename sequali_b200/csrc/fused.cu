@@ -354,19 +354,18 @@ k_fused_reads(const FusedArgs A) {
 // Per-position pass ("columns"): a thread owns four read positions and walks
 // the records of a tile that a TMA bulk copy staged in shared memory.
 //
-//   k_fused_columns<false>  QCMetrics base / phred-bin histograms (:2004-2031,
-//                           :2068-2124) with the counters of qc.cu's vertical
-//                           kernel (byte-sliced registers, byte counters in
-//                           shared memory, no atomics in the loop), and, for
-//                           PerTileQuality, the approximate per-(tile of 128
-//                           records, position) error sums that pertile.cu's
-//                           chain needs as binade hints
-//   k_fused_columns<true>   PerTileQuality's exact in-binade integer sums for
-//                           the hinted binades (see pertile.cu)
+//   QCMetrics       base / phred-bin histograms (:2004-2031, :2068-2124) with the
+//                   counters of qc.cu's vertical kernel (byte-sliced registers,
+//                   byte counters in shared memory, no atomics in the loop)
+//   PerTileQuality  for tiles whose records belong to one flow-cell tile: the
+//                   exact in-binade integer sums r_k(e) of the error rates for
+//                   BOTH binades hinted by pertile.cu's k_pt_guess (k, k + 1),
+//                   from rows of the precomputed increment table copied into
+//                   shared memory per tile; the chain kernel picks the one that
+//                   matches the exact state, or replays the tile read by read
 // ===========================================================================
-constexpr int FC_TPB = 128;
 constexpr int FC_BINS = 17;       // 5 base classes + 12 phred bins
-constexpr int FC_LUT_WINDOW = 8;  // binades tabulated per tile in the exact pass
+constexpr int FC_LUT_WINDOW = 8;  // binade pairs tabulated per tile: rows kmin .. kmin + 8
 
 struct ColumnArgs {
     BatchView bv;
@@ -381,42 +380,35 @@ struct ColumnArgs {
     uint8_t *cta_mixed;  // [grid] CTAs that met reads of different lengths
     // PerTileQuality
     int do_pt;
-    const double *err_tab;
-    float *approx;            // [W][n_tiles]  (position-major: a chain reads consecutive tiles)
-    const uint16_t *kguess;   // [W][n_tiles]
-    uint64_t *incr;           // [W][n_tiles]
+    const uint64_t *lut;      // [PT_LUT_NK][94] r_k(10^-(q/10)), k = PT_LUT_KMIN + row
+    const uint16_t *kguess;   // [W][n_tiles]  (position-major: a chain reads consecutive tiles)
+    uint64_t *incr, *incr_hi; // [W][n_tiles] sums for binade kguess / kguess + 1
     const uint8_t *tile_uniform;  // [n_tiles] 1: all records of the tile belong to one flow-cell tile
     PtState *pt_st;
     uint64_t pt_base;
 };
 
-template <bool EXACT>
-__global__ void __launch_bounds__(FC_TPB)
+template <int TPB>
+__global__ void __launch_bounds__(TPB)
 k_fused_columns(const ColumnArgs A) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ float s_errf[128];  // by raw quality byte; 0 outside '!'..'~' (0x7F marks padding)
-    __shared__ double s_errd[94];
     __shared__ uint32_t s_lmin, s_lmax, s_kmin;
     const uint32_t tid = threadIdx.x, R = A.recs_per_tile, W = A.W;
     uint8_t *buf = smem_raw;
     uint32_t *s_qo = (uint32_t *)(smem_raw + A.buf_bytes + 16);
     uint32_t *s_so = s_qo + R;
     uint32_t *s_L = s_so + R;
-    uint32_t *hist = s_L + R;                    // [W][17]            (!EXACT, do_qc)
-    uint32_t *priv = hist + W * FC_BINS;         // [13][FC_TPB] words (!EXACT, do_qc); row 12 = padding
-    float *partf = (float *)(priv + 13 * FC_TPB);  // [RG][W]          (!EXACT, do_pt)
-    uint64_t *s_lut = (uint64_t *)(s_L + R + ((R & 1) ? 1 : 0));  // [WINDOW + 1][128] by raw byte; last row zero
-    uint64_t *parti = s_lut + (FC_LUT_WINDOW + 1) * 128;           // [RG][W]       (EXACT)
+    uint64_t *s_lut = (uint64_t *)(s_L + R + (R & 1));    // [WINDOW + 1][128] by raw byte; zero outside '!'..'~'
+    uint64_t *parti = s_lut + (FC_LUT_WINDOW + 1) * 128;  // [W][2]
+    uint32_t *hist = (uint32_t *)(parti + 2 * W);         // [W][17]
+    uint32_t *priv = hist + W * FC_BINS;                  // [16][TPB] words; row 12 = padding, 13..15 only
+                                                          // reachable through an invalid quality byte
 
-    if (!EXACT) {
-        for (uint32_t i = tid; i < 128; i += FC_TPB) s_errf[i] = (i >= 33 && i < 127) ? (float)A.err_tab[i - 33] : 0.f;
-        if (A.do_qc)
-            for (uint32_t i = tid; i < W * FC_BINS + 13 * FC_TPB; i += FC_TPB) hist[i] = 0;
-    }
-    else {
-        for (uint32_t i = tid; i < 94; i += FC_TPB) s_errd[i] = A.err_tab[i];
-    }
+    if (A.do_qc)
+        for (uint32_t i = tid; i < W * FC_BINS + 16 * TPB; i += TPB) hist[i] = 0;
+    if (A.do_pt)
+        for (uint32_t i = tid; i < (FC_LUT_WINDOW + 1) * 128; i += TPB) s_lut[i] = 0;
     if (tid == 0) {
         s_lmin = 0xFFFFFFFFu;
         s_lmax = 0;
@@ -453,9 +445,9 @@ k_fused_columns(const ColumnArgs A) {
         acc_v = acc_h = acc_g = acc_hg = acc_n = 0;
 #pragma unroll
         for (int b = 0; b < 12; b++) {
-            const uint32_t wv = priv[b * FC_TPB + tid];
+            const uint32_t wv = priv[b * TPB + tid];
             if (wv) {
-                priv[b * FC_TPB + tid] = 0;
+                priv[b * TPB + tid] = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const uint32_t c = (wv >> (8 * j)) & 0xFF;
@@ -469,8 +461,9 @@ k_fused_columns(const ColumnArgs A) {
     uint32_t parity = 0;
     for (uint32_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
         const uint32_t r0 = t * R, r1 = min(r0 + R, bv.n), nrec = r1 - r0;
-        const bool skip = EXACT && !A.tile_uniform[t];  // replayed read by read in the chain kernel
-        if (!skip) {
+        const bool pt_here = A.do_pt && A.tile_uniform[t];  // other tiles are replayed read by read in the chain
+        if (!A.do_qc && !pt_here) continue;
+        {
             const uint64_t start = (uint64_t)bv.name_off[r0] - 1;
             const uint64_t end = r1 < bv.n ? (uint64_t)bv.name_off[r1] - 1 : A.text_end;
             const uint64_t gstart = start & ~15ULL;
@@ -479,9 +472,9 @@ k_fused_columns(const ColumnArgs A) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&bar, bytes);
                 bulk_g2s(buf, bv.text + gstart, bytes, &bar);
-                if (EXACT) s_kmin = 0xFFFFFFFFu;
+                s_kmin = 0xFFFFFFFFu;
             }
-            for (uint32_t i = tid; i < nrec; i += FC_TPB) {
+            for (uint32_t i = tid; i < nrec; i += TPB) {
                 const uint32_t L = bv.seq_len[r0 + i];
                 s_so[i] = bv.seq_off[r0 + i] - (uint32_t)gstart;
                 s_qo[i] = bv.qual_off[r0 + i] - (uint32_t)gstart;
@@ -490,13 +483,11 @@ k_fused_columns(const ColumnArgs A) {
                 lmax = max(lmax, L);
             }
         }
-        __syncthreads();
-        if (skip) continue;
-        // ---- exact pass: this tile's window of binades ----------------------------------------
+        // ---- PerTileQuality: this tile's window of binades -------------------------------------
         uint32_t kg[4] = {0, 0, 0, 0};
-        if (EXACT) {
+        if (pt_here) {
             uint32_t kmin = 0xFFFFFFFFu;
-            if (worker && rg == 0) {
+            if (worker) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     kg[j] = col0 + j < W ? A.kguess[(uint64_t)(col0 + j) * A.n_tiles + t] : 0;
@@ -504,33 +495,29 @@ k_fused_columns(const ColumnArgs A) {
                 }
             }
             kmin = ~warp_max_u32(~kmin);
+            __syncthreads();  // s_kmin is reset, nobody reads the previous tile's table or sums any more
             if (lane_id() == 0 && kmin != 0xFFFFFFFFu) atomicMin(&s_kmin, kmin);
             __syncthreads();
             kmin = s_kmin;
-            for (uint32_t i = tid; i < (FC_LUT_WINDOW + 1) * 128; i += FC_TPB) {
-                const uint32_t row = i >> 7, byte = i & 127;
-                s_lut[i] = (row < FC_LUT_WINDOW && byte >= 33 && byte < 127)
-                               ? pt_increment(kmin + row, (uint64_t)__double_as_longlong(s_errd[byte - 33]))
-                               : 0;
+            for (uint32_t i = tid; i < (FC_LUT_WINDOW + 1) * 94; i += TPB) {
+                const uint32_t row = i / 94, q = i - row * 94;
+                const uint32_t k = kmin + row - (uint32_t)PT_LUT_KMIN;
+                s_lut[row * 128 + 33 + q] = k < (uint32_t)PT_LUT_NK ? A.lut[k * 94 + q] : PT_HARD;
             }
-            if (worker && rg != 0) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) kg[j] = col0 + j < W ? A.kguess[(uint64_t)(col0 + j) * A.n_tiles + t] : 0;
-            }
-            __syncthreads();
+            for (uint32_t i = tid; i < 2 * W; i += TPB) parti[i] = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) kg[j] = (kg[j] && kg[j] - kmin < FC_LUT_WINDOW) ? kg[j] - kmin + 1 : 0;  // 0: no table
         }
+        __syncthreads();
         mbar_wait(&bar, parity);
         parity ^= 1;
-        float fa[4] = {0.f, 0.f, 0.f, 0.f};
-        uint64_t ia[4] = {0, 0, 0, 0};
+        uint64_t ia[4] = {0, 0, 0, 0}, ib[4] = {0, 0, 0, 0};
         if (worker) {
-            // kg[j] == 0 (no table for that column): read the all-zero row, marked PT_HARD below
-            const uint64_t *lrow0 = s_lut + (kg[0] ? kg[0] - 1 : FC_LUT_WINDOW) * 128;
-            const uint64_t *lrow1 = s_lut + (kg[1] ? kg[1] - 1 : FC_LUT_WINDOW) * 128;
-            const uint64_t *lrow2 = s_lut + (kg[2] ? kg[2] - 1 : FC_LUT_WINDOW) * 128;
-            const uint64_t *lrow3 = s_lut + (kg[3] ? kg[3] - 1 : FC_LUT_WINDOW) * 128;
+            // kg[j] == 0 (no table for that column): any row will do, the sums are marked PT_HARD below
+            const uint64_t *lrow0 = s_lut + (kg[0] ? kg[0] - 1 : 0) * 128;
+            const uint64_t *lrow1 = s_lut + (kg[1] ? kg[1] - 1 : 0) * 128;
+            const uint64_t *lrow2 = s_lut + (kg[2] ? kg[2] - 1 : 0) * 128;
+            const uint64_t *lrow3 = s_lut + (kg[3] ? kg[3] - 1 : 0) * 128;
             uint32_t badw = 0;
             for (uint32_t i = rg; i < nrec; i += RG) {
                 const uint32_t L = s_L[i];
@@ -540,48 +527,44 @@ k_fused_columns(const ColumnArgs A) {
                 const uint32_t keep = 0xFFFFFFFFu >> (8 * (4 - nvalid));
                 const uint32_t raw = fh_word(buf, s_qo[i], cg);
                 const uint32_t q = (raw & keep) | (0x7F7F7F7Fu & ~keep);
-                const uint32_t q0 = q & 0xFF, q1 = (q >> 8) & 0xFF, q2 = (q >> 16) & 0xFF, q3 = q >> 24;
-                if (!EXACT) {
-                    if (A.do_qc) {
-                        const uint32_t w = fh_word(buf, s_so[i], cg);
-                        const uint32_t pm = keep & 0x01010101u;
-                        const uint32_t vb = fh_acgt_bytes(w) & pm;
-                        const uint32_t hb = (w >> 1) & vb, gb = (w >> 2) & vb;
-                        acc_v += vb;
-                        acc_h += hb;
-                        acc_g += gb;
-                        acc_hg += hb & gb;
-                        acc_n += pm & ~vb;
-                        // phred bins min(q,47)>>2 as byte counters at bin*FC_TPB*4 + tid*4 + j; the
-                        // padding byte is counted in the spare 13th row that nobody reads
-                        // four bins at once: 4*min(q,47)>>2 per byte (q >= 48 saturates to bin 11,
-                        // padding goes to row 12)
-                        const uint32_t t = q - 0x21212121u;
-                        const uint32_t sat = (((t + 0x50505050u) >> 7) & 0x01010101u) * 0xFFu;
-                        uint32_t bin4 = ((t & 0x3C3C3C3Cu) & ~sat) | (0x2C2C2C2Cu & sat);
-                        bin4 = (bin4 & keep) | (0x30303030u & ~keep);
-                        priv8[(bin4 & 0xFF) * (FC_TPB) + 0] += 1;
-                        priv8[((bin4 >> 8) & 0xFF) * (FC_TPB) + 1] += 1;
-                        priv8[((bin4 >> 16) & 0xFF) * (FC_TPB) + 2] += 1;
-                        priv8[(bin4 >> 24) * (FC_TPB) + 3] += 1;
-                        if (++rows == 255) spill();
-                    }
-                    if (A.do_pt) {
-                        badw |= ((raw - 0x21212121u) | (raw + 0x01010101u)) & keep;
-                        fa[0] += s_errf[q0];
-                        fa[1] += s_errf[q1];
-                        fa[2] += s_errf[q2];
-                        fa[3] += s_errf[q3];
-                    }
+                if (A.do_qc) {
+                    const uint32_t w = fh_word(buf, s_so[i], cg);
+                    const uint32_t pm = keep & 0x01010101u;
+                    const uint32_t vb = fh_acgt_bytes(w) & pm;
+                    const uint32_t hb = (w >> 1) & vb, gb = (w >> 2) & vb;
+                    acc_v += vb;
+                    acc_h += hb;
+                    acc_g += gb;
+                    acc_hg += hb & gb;
+                    acc_n += pm & ~vb;
+                    // phred bins min(q,47)>>2 as byte counters at bin*TPB*4 + tid*4 + j, four bins at
+                    // once: 4*(min(q,47)>>2) per byte (q >= 48 saturates to bin 11, the padding byte is
+                    // counted in the spare 13th row that nobody reads)
+                    const uint32_t t4 = q - 0x21212121u;
+                    const uint32_t sat = (((t4 + 0x50505050u) >> 7) & 0x01010101u) * 0xFFu;
+                    uint32_t bin4 = ((t4 & 0x3C3C3C3Cu) & ~sat) | (0x2C2C2C2Cu & sat);
+                    bin4 = (bin4 & keep) | (0x30303030u & ~keep);
+                    priv8[(bin4 & 0xFF) * TPB + 0] += 1;
+                    priv8[((bin4 >> 8) & 0xFF) * TPB + 1] += 1;
+                    priv8[((bin4 >> 16) & 0xFF) * TPB + 2] += 1;
+                    priv8[(bin4 >> 24) * TPB + 3] += 1;
+                    if (++rows == 255) spill();
                 }
-                else {
-                    ia[0] += lrow0[q0];
-                    ia[1] += lrow1[q1];
-                    ia[2] += lrow2[q2];
-                    ia[3] += lrow3[q3];
+                if (pt_here) {
+                    badw |= ((raw - 0x21212121u) | (raw + 0x01010101u)) & keep;
+                    const uint64_t *e0 = lrow0 + (q & 0xFF), *e1 = lrow1 + ((q >> 8) & 0xFF);
+                    const uint64_t *e2 = lrow2 + ((q >> 16) & 0xFF), *e3 = lrow3 + (q >> 24);
+                    ia[0] += e0[0];
+                    ib[0] += e0[128];
+                    ia[1] += e1[0];
+                    ib[1] += e1[128];
+                    ia[2] += e2[0];
+                    ib[2] += e2[128];
+                    ia[3] += e3[0];
+                    ib[3] += e3[128];
                 }
             }
-            if (!EXACT && A.do_pt && (badw & 0x80808080u)) {
+            if (pt_here && (badw & 0x80808080u)) {
                 // a quality byte outside '!'..'~' (PerTileQuality raises for it, :3213): find it
                 for (uint32_t i = rg; i < nrec; i += RG) {
                     const uint32_t L = s_L[i];
@@ -594,31 +577,28 @@ k_fused_columns(const ColumnArgs A) {
             }
         }
         // ---- per-tile column sums: combine the row groups -------------------------------------
-        if (A.do_pt) {
+        if (pt_here) {
             if (worker) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    if (EXACT) parti[rg * W + col0 + j] = kg[j] ? (ia[j] < PT_HARD ? ia[j] : PT_HARD) : PT_HARD;
-                    else partf[rg * W + col0 + j] = fa[j];
+                    if (col0 + j < W) {
+                        const uint64_t a = kg[j] && ia[j] < PT_HARD ? ia[j] : PT_HARD;
+                        const uint64_t b = kg[j] && ib[j] < PT_HARD ? ib[j] : PT_HARD;
+                        atomicAdd((unsigned long long *)(parti + 2 * (col0 + j)), (unsigned long long)a);
+                        atomicAdd((unsigned long long *)(parti + 2 * (col0 + j) + 1), (unsigned long long)b);
+                    }
                 }
             }
             __syncthreads();
-            for (uint32_t c = tid; c < W; c += FC_TPB) {
-                if (EXACT) {
-                    uint64_t s = 0;
-                    for (uint32_t g = 0; g < RG; g++) s += parti[g * W + c];
-                    A.incr[(uint64_t)c * A.n_tiles + t] = s < PT_HARD ? s : PT_HARD;
-                }
-                else {
-                    float s = 0.f;
-                    for (uint32_t g = 0; g < RG; g++) s += partf[g * W + c];
-                    A.approx[(uint64_t)c * A.n_tiles + t] = s;
-                }
+            for (uint32_t c = tid; c < W; c += TPB) {
+                const uint64_t a = parti[2 * c], b = parti[2 * c + 1];
+                A.incr[(uint64_t)c * A.n_tiles + t] = a < PT_HARD ? a : PT_HARD;
+                A.incr_hi[(uint64_t)c * A.n_tiles + t] = b < PT_HARD ? b : PT_HARD;
             }
         }
-        __syncthreads();  // tile buffer, offsets and partial sums are free again
+        __syncthreads();  // tile buffer, offsets, table and partial sums are free again
     }
-    if (EXACT || !A.do_qc) return;
+    if (!A.do_qc) return;
     if (worker) spill();
     lmax = warp_max_u32(lmax);
     lmin = ~warp_max_u32(~lmin);
@@ -628,7 +608,7 @@ k_fused_columns(const ColumnArgs A) {
     }
     __syncthreads();
     // CTA histogram -> global tables
-    for (uint32_t i = tid; i < W * FC_BINS; i += FC_TPB) {
+    for (uint32_t i = tid; i < W * FC_BINS; i += TPB) {
         const uint32_t c = hist[i];
         if (!c) continue;
         const uint32_t pos = i / FC_BINS, k = i % FC_BINS;
@@ -641,7 +621,7 @@ k_fused_columns(const ColumnArgs A) {
         const uint32_t L0 = s_lmin, ea_n = min(L0, A.ea_len);
         const uint32_t lo = L0 - ea_n, hi = L0;
         const uint32_t span = (hi - lo) * FC_BINS;
-        for (uint32_t i = tid; i < span; i += FC_TPB) {
+        for (uint32_t i = tid; i < span; i += TPB) {
             const uint32_t pos = lo + i / FC_BINS, k = i % FC_BINS;
             const uint32_t c = hist[pos * FC_BINS + k];
             if (!c) continue;
@@ -655,6 +635,7 @@ k_fused_columns(const ColumnArgs A) {
 
 // end-anchored tables for the CTAs of k_fused_columns that met reads of different
 // lengths (:2034-2043, :2115-2124): same tile assignment, one warp per read
+constexpr int FC_TPB = 128;  // block size of the fallback (the columns kernel picks its own)
 __global__ void __launch_bounds__(FC_TPB)
 k_fused_ea_fallback(BatchView bv, uint32_t R, uint32_t n_tiles, const uint8_t *cta_mixed, uint64_t *g_ea_base,
                     uint64_t *g_ea_phred, uint32_t ea_len, int smem_hist) {
@@ -721,10 +702,11 @@ static bool fused_eligible(const sq_batch *b, const sq_adapters *ad) {
     return true;
 }
 
-// shared-memory plan of k_fused_columns: four CTAs per SM
-constexpr uint32_t FC_SMEM = 55 * 1024;
+// shared-memory plan of k_fused_columns.  The block size is the one of 128 / 192 / 256 threads
+// that wastes the fewest lanes for this read length (150 bp: 38 column groups, 5 x 38 = 190 of
+// 192 threads work); 4 / 3 / 2 CTAs share an SM.
 struct ColGeom {
-    uint32_t R, n_tiles, CG, RG, W, buf_bytes, grid;
+    uint32_t R, n_tiles, CG, RG, W, buf_bytes, grid, tpb;
     size_t smem;
     bool ok;
 };
@@ -733,53 +715,43 @@ static ColGeom col_geometry(sq_ctx *ctx, const sq_batch *b) {
     memset(&g, 0, sizeof(g));
     if (b->max_len == 0) return g;
     g.CG = (b->max_len + 3) / 4;
-    if (g.CG > FC_TPB) return g;
-    g.RG = FC_TPB / g.CG;
+    if (g.CG > 256) return g;
     g.W = g.CG * 4;
-    const uint32_t hist = g.W * FC_BINS * 4 + 13 * FC_TPB * 4 + g.RG * g.W * 4;
-    const uint32_t exact = (FC_LUT_WINDOW + 1) * 128 * 8 + g.RG * g.W * 8 + 8;
-    const uint32_t fixed = (hist > exact ? hist : exact) + 64;
-    if (fixed + 8 * (b->max_rec_bytes + 12) > FC_SMEM) return g;
-    g.R = (FC_SMEM - fixed) / (b->max_rec_bytes + 12);
+    uint32_t best_used = 0;
+    for (uint32_t tpb = 128; tpb <= 256; tpb += 64) {
+        if (tpb < g.CG) continue;
+        const uint32_t used = (tpb / g.CG) * g.CG * 1024 / tpb;  // working lanes per 1024
+        if (used > best_used + 16) {
+            best_used = used;
+            g.tpb = tpb;
+        }
+    }
+    g.RG = g.tpb / g.CG;
+    const uint32_t ctas = g.tpb == 128 ? 4 : g.tpb == 192 ? 3 : 2;
+    const uint32_t budget = (228u * 1024u) / ctas - 1024u - 128u;
+    const uint32_t fixed = (FC_LUT_WINDOW + 1) * 128 * 8 + 2 * g.W * 8 + g.W * FC_BINS * 4 + 16 * g.tpb * 4 + 64;
+    if (fixed + 8 * (b->max_rec_bytes + 12) + 64 > budget) return g;
+    g.R = (budget - fixed - 64) / (b->max_rec_bytes + 12);
     if (g.R > 255) g.R = 255;
     g.buf_bytes = (g.R * b->max_rec_bytes + 32 + 15) & ~15u;
     g.smem = (size_t)g.buf_bytes + 16 + (size_t)(3 * g.R + 1) * 4 + fixed;
     g.n_tiles = (uint32_t)((b->n + g.R - 1) / g.R);
-    g.grid = (uint32_t)ctx->num_sms * 4;
+    g.grid = (uint32_t)ctx->num_sms * ctas;
     if (g.grid > g.n_tiles) g.grid = g.n_tiles;
     g.ok = true;
     return g;
 }
 
-static void col_args_common(ColumnArgs &A, sq_ctx *ctx, sq_batch *b, const ColGeom &g) {
-    memset(&A, 0, sizeof(A));
-    A.bv = b->view();
-    A.recs_per_tile = g.R;
-    A.n_tiles = g.n_tiles;
-    A.text_end = b->text_end;
-    A.CG = g.CG;
-    A.RG = g.RG;
-    A.W = g.W;
-    A.buf_bytes = g.buf_bytes;
-    A.err_tab = ctx->d_err_table;
-}
-
-int fused_exact_sums(sq_ctx *ctx, sq_batch *b, uint32_t R, uint32_t n_ftiles, uint32_t W, const uint16_t *kguess,
-                     uint64_t *incr, const uint8_t *tile_uniform) {
-    const ColGeom g = col_geometry(ctx, b);
-    if (!g.ok || g.R != R || g.n_tiles != n_ftiles || g.W != W) {
-        sq_set_error("fused_exact_sums: tile geometry changed between the passes");
-        return SQ_E_ARG;
-    }
-    ColumnArgs A;
-    col_args_common(A, ctx, b, g);
-    A.do_pt = 1;
-    A.kguess = kguess;
-    A.incr = incr;
-    A.tile_uniform = tile_uniform;
-    CUDA_TRY(cudaFuncSetAttribute(k_fused_columns<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-    SQ_LAUNCH(ctx, k_fused_columns<true>, g.grid, FC_TPB, g.smem, A);
+template <int TPB>
+static int launch_columns_t(sq_ctx *ctx, const ColGeom &g, const ColumnArgs &C) {
+    CUDA_TRY(cudaFuncSetAttribute(k_fused_columns<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    SQ_LAUNCH(ctx, k_fused_columns<TPB>, g.grid, TPB, g.smem, C);
     return SQ_OK;
+}
+static int launch_columns(sq_ctx *ctx, const ColGeom &g, const ColumnArgs &C) {
+    if (g.tpb == 128) return launch_columns_t<128>(ctx, g, C);
+    if (g.tpb == 192) return launch_columns_t<192>(ctx, g, C);
+    return launch_columns_t<256>(ctx, g, C);
 }
 
 extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt, sq_overrep *ov,
@@ -815,7 +787,6 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     A.edges = ctx->d_phred_thresholds;
     long long *tile = nullptr;
     uint64_t *hashes = nullptr;
-    float *approx = nullptr;
     uint8_t *cta_mixed = nullptr;
     if (qc) {
         A.do_qc = 1;
@@ -855,11 +826,24 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     else if (b->max_len <= 256) rc = launch_fused<8>(ctx, A);
     else rc = launch_fused<10>(ctx, A);
 
-    // ---- per-position pass: QCMetrics histograms + PerTileQuality hints ----------------------
+    // ---- PerTileQuality: slots, segments and binade hints (needs the tile ids) ---------------
     const ColGeom g = col_geometry(ctx, b);
-    if (rc == SQ_OK && g.ok && (qc || pt)) {
+    PtPlan plan;
+    const uint64_t pt_base = pt ? pt->n_added : 0;
+    if (rc == SQ_OK && pt) rc = pt_prepare(pt, b, tile, g.ok ? g.R : 0, g.n_tiles, g.W, &plan);
+
+    // ---- per-position pass: QCMetrics histograms + PerTileQuality in-binade sums --------------
+    if (rc == SQ_OK && g.ok && (qc || plan.runs)) {
         ColumnArgs C;
-        col_args_common(C, ctx, b, g);
+        memset(&C, 0, sizeof(C));
+        C.bv = b->view();
+        C.recs_per_tile = g.R;
+        C.n_tiles = g.n_tiles;
+        C.text_end = b->text_end;
+        C.CG = g.CG;
+        C.RG = g.RG;
+        C.W = g.W;
+        C.buf_bytes = g.buf_bytes;
         if (qc) {
             rc = qc_grow(qc, b->max_len);
             if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&cta_mixed, g.grid, true);
@@ -871,26 +855,25 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
             C.ea_len = (uint32_t)qc->ea_len;
             C.cta_mixed = cta_mixed;
         }
-        if (pt && rc == SQ_OK) {
-            rc = sq_dalloc(ctx, (void **)&approx, (size_t)g.n_tiles * g.W * 4, false);
+        if (plan.runs) {
             C.do_pt = 1;
-            C.approx = approx;
+            C.lut = pt->lut;
+            C.kguess = plan.kguess;
+            C.incr = plan.incr;
+            C.incr_hi = plan.incr_hi;
+            C.tile_uniform = plan.uniform;
             C.pt_st = pt->st;
-            C.pt_base = pt->n_added;
+            C.pt_base = pt_base;
         }
-        if (rc == SQ_OK) {
-            CUDA_TRY(cudaFuncSetAttribute(k_fused_columns<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)g.smem));
-            SQ_LAUNCH(ctx, k_fused_columns<false>, g.grid, FC_TPB, g.smem, C);
-            if (qc && qc->ea_len) {
-                const size_t ea_smem = (size_t)qc->ea_len * FC_BINS * 4;
-                const int use_smem = ea_smem <= 96 * 1024;
-                if (use_smem)
-                    CUDA_TRY(cudaFuncSetAttribute(k_fused_ea_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  96 * 1024));
-                SQ_LAUNCH(ctx, k_fused_ea_fallback, g.grid, FC_TPB, use_smem ? ea_smem : 0, b->view(), g.R, g.n_tiles,
-                          cta_mixed, qc->ea_base, qc->ea_phred, (uint32_t)qc->ea_len, use_smem);
-            }
+        if (rc == SQ_OK) rc = launch_columns(ctx, g, C);
+        if (rc == SQ_OK && qc && qc->ea_len) {
+            const size_t ea_smem = (size_t)qc->ea_len * FC_BINS * 4;
+            const int use_smem = ea_smem <= 96 * 1024;
+            if (use_smem)
+                CUDA_TRY(cudaFuncSetAttribute(k_fused_ea_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              96 * 1024));
+            SQ_LAUNCH(ctx, k_fused_ea_fallback, g.grid, FC_TPB, use_smem ? ea_smem : 0, b->view(), g.R, g.n_tiles,
+                      cta_mixed, qc->ea_base, qc->ea_phred, (uint32_t)qc->ea_len, use_smem);
         }
     }
     else if (rc == SQ_OK && qc) rc = qc_add_vertical(qc, b);
@@ -900,7 +883,10 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
         b->err_sum_valid = true;
     }
     // ---- table maintenance, in the reference's module order ------------------------------------
-    if (rc == SQ_OK && pt) rc = pt_add_with_tiles(pt, b, tile, approx, g.R, g.n_tiles, g.W);
+    if (pt) {
+        if (rc == SQ_OK) rc = pt_finish(pt, b, &plan);
+        else pt_plan_free(ctx, &plan);
+    }
     if (rc == SQ_OK && ov) rc = sq_overrep_add(ov, b);
     if (rc == SQ_OK && ns) rc = sq_nanostats_add(ns, b);
     if (ad) {
@@ -910,7 +896,6 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     if (rc == SQ_OK && dd) rc = dedup_consume(dd, hashes, n);
     sq_dfree(ctx, tile);
     if (!(dd && dd->deferred && rc == SQ_OK)) sq_dfree(ctx, hashes);  // a deferred estimator keeps them
-    sq_dfree(ctx, approx);
     sq_dfree(ctx, cta_mixed);
     return rc;
 }

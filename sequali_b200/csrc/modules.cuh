@@ -92,15 +92,29 @@ struct PtSeg {  // a run of consecutive reads of one tile: rows [lo, hi) of `ord
 };
 
 
-// Everything after the tile ids are known (tile[r] < 0: unparsable header, already folded
-// into st->fail_idx).  `approx` != nullptr: [n_ftiles][W] approximate error sums of fixed
-// tiles of R records (k_fused_columns<false>), which lets reads that arrive in tile runs
-// skip the sort and the segment passes over the text.
-int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile, const float *approx, uint32_t R,
-                      uint32_t n_ftiles, uint32_t W);
-// exact in-binade integer sums of the uniform tiles (fused.cu)
-int fused_exact_sums(sq_ctx *ctx, sq_batch *b, uint32_t R, uint32_t n_ftiles, uint32_t W,
-                     const uint16_t *kguess, uint64_t *incr, const uint8_t *tile_uniform);
+// One record array's way through PerTileQuality once the tile ids are known (tile[r] < 0:
+// unparsable header, already folded into st->fail_idx):
+//   pt_prepare   tile ids -> slots, table growth, length counts.  R != 0 announces that the
+//                caller runs k_fused_columns over fixed tiles of R records: when the reads arrive
+//                in tile runs the plan then holds the segments, their sampled sums and the two
+//                hinted binades per (tile, position) (plan.runs), and the caller must have
+//                k_fused_columns fill plan.incr / plan.incr_hi
+//   pt_finish    the ordered chains (run path), or the sort-based general path; frees the plan
+struct PtPlan {
+    bool work = false, runs = false;
+    uint32_t R = 0, n_ftiles = 0, W = 0, n_slots = 0, width = 0;
+    unsigned long long fail_idx = ~0ULL;
+    uint32_t *slot = nullptr, *idx = nullptr, *tmpk = nullptr, *tmpv = nullptr, *seg = nullptr;
+    uint32_t *runs_cnt = nullptr, *seg_off = nullptr, *nseg = nullptr;
+    uint8_t *uniform = nullptr;   // [n_ftiles] 1: all records of the fixed tile belong to one flow-cell tile
+    PtSeg *segs = nullptr;
+    uint64_t *incr = nullptr, *incr_hi = nullptr;  // [W][n_ftiles] sums for binade kguess / kguess + 1
+    uint16_t *kguess = nullptr;                    // [W][n_ftiles]
+    float *approx = nullptr;                       // [W][n_ftiles] sampled estimates
+};
+int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t n_ftiles, uint32_t W, PtPlan *pl);
+int pt_finish(sq_pertile *p, sq_batch *b, PtPlan *pl);
+void pt_plan_free(sq_ctx *ctx, PtPlan *pl);
 
 // ---- DedupEstimator (dedup.cu) -------------------------------------------------
 constexpr int DD_TPB = 256;

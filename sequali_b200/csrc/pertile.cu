@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(PT_TPB)
 k_pt_guess(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__restrict__ segs,
            const uint32_t *__restrict__ seg_first, const uint32_t *__restrict__ nseg, uint32_t n_slots,
            uint32_t width, uint32_t stride, const float *__restrict__ approx, const double *__restrict__ errors,
-           uint64_t len_cap, const double *__restrict__ err_tab, uint16_t *__restrict__ kguess) {
+           uint64_t len_cap, const double *__restrict__ err_tab, uint16_t *__restrict__ kguess, int dual) {
     const uint64_t chains = (uint64_t)n_slots * width;
     const uint64_t warps = (uint64_t)gridDim.x * (PT_TPB / 32);
     for (uint64_t c = (uint64_t)blockIdx.x * (PT_TPB / 32) + (threadIdx.x >> 5); c < chains; c += warps) {
@@ -338,8 +338,18 @@ k_pt_guess(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__rest
                 if (lane_id() >= (uint32_t)o) x += y;
             }
             const double start = run + (x - v);
-            if (data != PT_NONE)
-                kguess[(uint64_t)pos * stride + data] = (uint16_t)((uint64_t)__double_as_longlong(start) >> 52);
+            if (data != PT_NONE) {
+                uint32_t kg;
+                if (dual) {
+                    // the sums are estimates from a sample of the reads: tabulate the two binades around
+                    // the middle of the segment, (k-1, k) below sqrt(2) * 2^k and (k, k+1) above
+                    const uint64_t mb = (uint64_t)__double_as_longlong(start + 0.5 * v);
+                    kg = (uint32_t)(mb >> 52);
+                    if ((mb & PT_MANT) < 0x6A09E667F3BCDULL && kg > 1) kg--;
+                }
+                else kg = (uint32_t)((uint64_t)__double_as_longlong(start) >> 52);
+                kguess[(uint64_t)pos * stride + data] = (uint16_t)kg;
+            }
             run += __shfl_sync(0xffffffffu, x, 31);
         }
     }
@@ -413,8 +423,9 @@ __global__ void __launch_bounds__(PT_TPB)
 k_pt_chain(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__restrict__ segs,
            const uint32_t *__restrict__ seg_first, const uint32_t *__restrict__ nseg, uint32_t n_slots,
            uint32_t width, uint32_t stride, const uint16_t *__restrict__ kguess,
-           const uint64_t *__restrict__ incr, double *errors, uint64_t len_cap,
-           const double *__restrict__ err_tab) {
+           const uint64_t *__restrict__ incr, const uint64_t *__restrict__ incr_hi, double *errors,
+           uint64_t len_cap, const double *__restrict__ err_tab) {
+    // incr_hi != nullptr: incr holds the sums for binade kguess, incr_hi those for kguess + 1
     __shared__ double s_err[94];
     for (uint32_t i = threadIdx.x; i < 94; i += PT_TPB) s_err[i] = err_tab[i];
     __syncthreads();
@@ -433,6 +444,7 @@ k_pt_chain(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__rest
             uint64_t inc = 0;
             uint32_t kg = 0, lo = 0, hi = 0;
             bool mine = false;
+            const uint32_t k = (uint32_t)(sbits >> 52);
             if (jj < cnt) {
                 const PtSeg sg = segs[first + jj];
                 if (sg.slot == s) {  // a foreign segment adds nothing
@@ -441,12 +453,15 @@ k_pt_chain(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__rest
                     hi = sg.hi;
                     inc = PT_HARD;
                     if (sg.data != PT_NONE) {
-                        inc = incr[(uint64_t)pos * stride + sg.data];
                         kg = kguess[(uint64_t)pos * stride + sg.data];
+                        if (incr_hi && kg + 1 == k) {
+                            inc = incr_hi[(uint64_t)pos * stride + sg.data];
+                            kg = k;
+                        }
+                        else if (kg == k) inc = incr[(uint64_t)pos * stride + sg.data];
                     }
                 }
             }
-            const uint32_t k = (uint32_t)(sbits >> 52);
             const bool hard = mine && (inc >= PT_HARD || kg != k);
             if (hard) inc = 0;
             const uint64_t incl = warp_incl_scan_u64(inc);
@@ -628,11 +643,12 @@ static int pt_accumulate(sq_pertile *p, sq_batch *b, const uint32_t *order, cons
               ctx->d_err_table, p->lut, kguess, approx, incr, base, p->st);
     const int chain_grid = sq_grid_for(ctx, (uint64_t)n_slots * width * 32, PT_TPB, 32);
     SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, bv, order, segs, seg_first, nseg,
-              n_slots, width, seg_cap, approx, p->errors, p->len_cap, ctx->d_err_table, kguess);
+              n_slots, width, seg_cap, approx, p->errors, p->len_cap, ctx->d_err_table, kguess, 0);
     SQ_LAUNCH(ctx, k_pt_segment_sums<true>, sgrid, PT_TPB, (size_t)PT_LUT_NK * 94 * 8, bv, order, segs, n_segs_dev,
               CG, RG, width4, seg_cap, ctx->d_err_table, p->lut, kguess, approx, incr, base, p->st);
     SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, bv, order, segs, seg_first, nseg,
-              n_slots, width, seg_cap, kguess, incr, p->errors, p->len_cap, ctx->d_err_table);
+              n_slots, width, seg_cap, kguess, incr, (const uint64_t *)nullptr, p->errors, p->len_cap,
+              ctx->d_err_table);
     sq_dfree(ctx, nseg);
     sq_dfree(ctx, seg_first);
     sq_dfree(ctx, n_segs_dev);
@@ -643,49 +659,81 @@ static int pt_accumulate(sq_pertile *p, sq_batch *b, const uint32_t *order, cons
     return SQ_OK;
 }
 
-// Reads that arrive in tile runs (every real Illumina file): no sort, no extra
-// passes for the approximate sums (k_fused_columns<false> produced them per fixed
-// tile of R records), one TMA-staged pass for the exact integer sums.
-static int pt_accumulate_runs(sq_pertile *p, sq_batch *b, const uint32_t *slot, const float *approx, uint32_t R,
-                              uint32_t n_ftiles, uint32_t W, uint32_t n_slots, uint32_t seg_cap, uint32_t width) {
+// Estimated per-(fixed tile of R records, position) error sums from every PT_SAMPLE-th record of
+// the tile, scaled to the tile: the binade hints of the chain only need the prefix sums to within
+// a factor sqrt(2) (k_pt_guess tabulates two binades around the estimate, k_pt_chain verifies
+// every step exactly), so the text is not walked for them.  A thread owns four positions.
+constexpr uint32_t PT_SAMPLE = 8;
+__global__ void __launch_bounds__(PT_TPB)
+k_pt_sample(BatchView bv, uint32_t R, uint32_t n_ftiles, uint32_t CG, const uint8_t *__restrict__ uniform,
+            const double *__restrict__ err_tab, float *__restrict__ approx) {
+    __shared__ float s_errf[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += PT_TPB) s_errf[i] = (i >= 33 && i < 127) ? (float)err_tab[i - 33] : 0.f;
+    __syncthreads();
+    const uint64_t total = (uint64_t)n_ftiles * CG;
+    for (uint64_t w = (uint64_t)blockIdx.x * PT_TPB + threadIdx.x; w < total; w += (uint64_t)gridDim.x * PT_TPB) {
+        const uint32_t t = (uint32_t)(w / CG), cg = (uint32_t)(w - (uint64_t)t * CG), col0 = cg * 4;
+        if (!uniform[t]) continue;
+        const uint32_t r0 = t * R, r1 = min(r0 + R, bv.n);
+        float fa[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t taken = 0;
+        for (uint32_t r = r0 + (PT_SAMPLE / 2 < r1 - r0 ? PT_SAMPLE / 2 : 0); r < r1; r += PT_SAMPLE) {
+            taken++;
+            const uint32_t L = bv.seq_len[r];
+            if (L <= col0) continue;
+            const uint32_t nvalid = min(4u, L - col0);
+            const uint32_t q = load_u32_unaligned(bv.text + bv.qual_off[r] + col0) & (0xFFFFFFFFu >> (8 * (4 - nvalid)));
+            fa[0] += s_errf[q & 0xFF];
+            fa[1] += s_errf[(q >> 8) & 0xFF];
+            fa[2] += s_errf[(q >> 16) & 0xFF];
+            fa[3] += s_errf[q >> 24];
+        }
+        const float scale = taken ? (float)(r1 - r0) / (float)taken : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) approx[(uint64_t)(col0 + j) * n_ftiles + t] = fa[j] * scale;
+    }
+}
+
+void pt_plan_free(sq_ctx *ctx, PtPlan *pl) {
+    void *ptrs[] = {pl->slot, pl->idx, pl->tmpk, pl->tmpv, pl->seg, pl->runs_cnt, pl->seg_off, pl->uniform,
+                    pl->segs, pl->nseg, pl->incr, pl->incr_hi, pl->kguess, pl->approx};
+    for (void *q : ptrs) sq_dfree(ctx, q);
+    *pl = PtPlan();
+}
+
+// Reads that arrive in tile runs (every real Illumina file): no sort and no extra pass over the
+// text.  Fixed tiles of R records (the tiles k_fused_columns walks) whose records belong to one
+// flow-cell tile are the segments; their binade hints come from sampled sums (k_pt_sample) and
+// k_fused_columns produces the exact in-binade integer sums for both hinted binades.
+static int pt_prepare_runs(sq_pertile *p, sq_batch *b, PtPlan *pl, uint32_t seg_cap) {
     sq_ctx *ctx = p->ctx;
-    const uint32_t n = (uint32_t)b->n;
-    uint32_t *runs = nullptr, *seg_off = nullptr, *seg = nullptr, *nseg = nullptr;
-    uint8_t *uniform = nullptr;
-    PtSeg *segs = nullptr;
-    uint64_t *incr = nullptr;
-    uint16_t *kguess = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&runs, (size_t)n_ftiles * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&seg_off, (size_t)n_ftiles * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&uniform, n_ftiles, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&segs, (size_t)seg_cap * sizeof(PtSeg), false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&seg, (size_t)n_slots * 8, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&nseg, (size_t)n_slots * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&incr, (size_t)n_ftiles * W * 8, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&kguess, (size_t)n_ftiles * W * 2, true));
-    uint32_t *seg_lo = seg, *seg_hi = seg + n_slots;
+    const uint32_t n = (uint32_t)b->n, n_ftiles = pl->n_ftiles, W = pl->W, n_slots = pl->n_slots, R = pl->R;
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->runs_cnt, (size_t)n_ftiles * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->seg_off, (size_t)n_ftiles * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->uniform, n_ftiles, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->segs, (size_t)seg_cap * sizeof(PtSeg), false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->seg, (size_t)n_slots * 8, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->nseg, (size_t)n_slots * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->incr, (size_t)n_ftiles * W * 8, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->incr_hi, (size_t)n_ftiles * W * 8, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->kguess, (size_t)n_ftiles * W * 2, true));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->approx, (size_t)n_ftiles * W * 4, false));
+    uint32_t *seg_lo = pl->seg, *seg_hi = pl->seg + n_slots;
     CUDA_TRY(cudaMemsetAsync(seg_lo, 0xFF, (size_t)n_slots * 4, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(seg_hi, 0, (size_t)n_slots * 4, ctx->stream));
     const int tgrid = sq_grid_for(ctx, n_ftiles, PT_TPB, 8);
-    SQ_LAUNCH(ctx, k_pt_ftile_runs, tgrid, PT_TPB, 0, slot, n, R, n_ftiles, runs, uniform);
-    SQ_TRY(sq_scan_exclusive_u32(ctx, runs, seg_off, n_ftiles, nullptr));
-    SQ_LAUNCH(ctx, k_pt_ftile_segs, tgrid, PT_TPB, 0, slot, n, R, n_ftiles, seg_off, uniform, segs, seg_lo, seg_hi);
-    SQ_LAUNCH(ctx, k_pt_seg_counts, sq_grid_for(ctx, n_slots, PT_TPB, 8), PT_TPB, 0, seg_lo, seg_hi, n_slots, 1u, nseg);
+    SQ_LAUNCH(ctx, k_pt_ftile_runs, tgrid, PT_TPB, 0, pl->slot, n, R, n_ftiles, pl->runs_cnt, pl->uniform);
+    SQ_TRY(sq_scan_exclusive_u32(ctx, pl->runs_cnt, pl->seg_off, n_ftiles, nullptr));
+    SQ_LAUNCH(ctx, k_pt_ftile_segs, tgrid, PT_TPB, 0, pl->slot, n, R, n_ftiles, pl->seg_off, pl->uniform, pl->segs,
+              seg_lo, seg_hi);
+    SQ_LAUNCH(ctx, k_pt_seg_counts, sq_grid_for(ctx, n_slots, PT_TPB, 8), PT_TPB, 0, seg_lo, seg_hi, n_slots, 1u,
+              pl->nseg);
     const BatchView bv = b->view();
-    const int chain_grid = sq_grid_for(ctx, (uint64_t)n_slots * width * 32, PT_TPB, 32);
-    SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, bv, (const uint32_t *)nullptr, segs, seg_lo, nseg, n_slots,
-              width, n_ftiles, approx, p->errors, p->len_cap, ctx->d_err_table, kguess);
-    SQ_TRY(fused_exact_sums(ctx, b, R, n_ftiles, W, kguess, incr, uniform));
-    SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, bv, (const uint32_t *)nullptr, segs, seg_lo, nseg, n_slots,
-              width, n_ftiles, kguess, incr, p->errors, p->len_cap, ctx->d_err_table);
-    sq_dfree(ctx, runs);
-    sq_dfree(ctx, seg_off);
-    sq_dfree(ctx, uniform);
-    sq_dfree(ctx, segs);
-    sq_dfree(ctx, seg);
-    sq_dfree(ctx, nseg);
-    sq_dfree(ctx, incr);
-    sq_dfree(ctx, kguess);
+    SQ_LAUNCH(ctx, k_pt_sample, sq_grid_for(ctx, (uint64_t)n_ftiles * (W / 4), PT_TPB, 16), PT_TPB, 0, bv, R, n_ftiles,
+              W / 4, pl->uniform, ctx->d_err_table, pl->approx);
+    const int chain_grid = sq_grid_for(ctx, (uint64_t)n_slots * pl->width * 32, PT_TPB, 32);
+    SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, bv, (const uint32_t *)nullptr, pl->segs, seg_lo, pl->nseg, n_slots,
+              pl->width, n_ftiles, pl->approx, p->errors, p->len_cap, ctx->d_err_table, pl->kguess, 1);
     return SQ_OK;
 }
 
@@ -701,30 +749,35 @@ extern "C" int sq_pertile_add(sq_pertile *p, sq_batch *b) {
     long long *tile = nullptr;
     SQ_TRY(sq_dalloc(ctx, (void **)&tile, (size_t)n * 8, false));
     SQ_LAUNCH(ctx, k_pt_tile, sq_grid_for(ctx, n, PT_TPB, 16), PT_TPB, 0, b->view(), tile, p->n_added, p->st);
-    int rc = pt_add_with_tiles(p, b, tile, nullptr, 0, 0, 0);
+    PtPlan pl;
+    int rc = pt_prepare(p, b, tile, 0, 0, 0, &pl);
+    if (rc == SQ_OK) rc = pt_finish(p, b, &pl);
+    else pt_plan_free(ctx, &pl);
     sq_dfree(ctx, tile);
     return rc;
 }
 
-int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile, const float *approx, uint32_t R,
-                      uint32_t n_ftiles, uint32_t W) {
+// Tile ids -> slots, table growth, length counts; for reads in tile runs (R != 0: the caller
+// will run k_fused_columns over fixed tiles of R records) also the segments and their hints.
+int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t n_ftiles, uint32_t W, PtPlan *pl) {
     sq_ctx *ctx = p->ctx;
     const uint32_t n = (uint32_t)b->n;
     const uint64_t base = p->n_added;
     const int grid = sq_grid_for(ctx, n, PT_TPB, 16);
-    uint32_t *slot = nullptr, *idx = nullptr, *tmpk = nullptr, *tmpv = nullptr, *seg = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&slot, (size_t)n * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&idx, (size_t)n * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&tmpk, (size_t)n * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&tmpv, (size_t)n * 4, false));
+    *pl = PtPlan();
+    pl->R = R;
+    pl->n_ftiles = n_ftiles;
+    pl->W = W;
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->slot, (size_t)n * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->idx, (size_t)n * 4, false));
     SQ_TRY(pt_grow(p, p->n_slots ? p->n_slots : 1, b->max_len ? b->max_len : 1));
     // slot ids of new tiles may exceed slot_cap: slot_tile writes are guarded, and the
     // map is re-read after growing
     CUDA_TRY(cudaMemsetAsync(&p->st->n_changes, 0, 4, ctx->stream));
     SQ_LAUNCH(ctx, k_pt_map_insert, grid, PT_TPB, 0, tile, n, base, p->map_keys, p->map_vals, p->slot_tile,
               p->slot_cap, p->st);
-    SQ_LAUNCH(ctx, k_pt_map_lookup, grid, PT_TPB, 0, b->view(), tile, base, p->map_keys, p->map_vals, slot, idx,
-              p->st);
+    SQ_LAUNCH(ctx, k_pt_map_lookup, grid, PT_TPB, 0, b->view(), tile, base, p->map_keys, p->map_vals, pl->slot,
+              pl->idx, p->st);
     PtState *h = (PtState *)((char *)ctx->h_scratch + 3400);
     CUDA_TRY(cudaMemcpyAsync(h, p->st, sizeof(PtState), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -750,39 +803,59 @@ int pt_add_with_tiles(sq_pertile *p, sq_batch *b, long long *tile, const float *
     if (rc == SQ_OK) rc = pt_grow(p, h->n_slots ? h->n_slots : 1, h->max_len ? h->max_len : 1);
     p->n_slots = h->n_slots;
     p->max_len = h->max_len;
-    if (rc == SQ_OK && h->n_kept && h->n_slots) {
-        uint32_t key_bits = 1;
-        while ((1ull << key_bits) < h->n_slots) key_bits++;
-        // PT_NONE (skipped reads) carries all-ones low bits, so it sorts last within those bits
-        SQ_LAUNCH(ctx, k_pt_lengths, grid, PT_TPB, 0, b->view(), slot, p->lengths, p->len_cap);
+    pl->n_slots = h->n_slots;
+    pl->width = (uint32_t)b->max_len;
+    pl->fail_idx = h->fail_idx;
+    pl->work = rc == SQ_OK && h->n_kept && h->n_slots;
+    if (pl->work) {
+        SQ_LAUNCH(ctx, k_pt_lengths, grid, PT_TPB, 0, b->view(), pl->slot, p->lengths, p->len_cap);
         // reads in tile runs: at most one extra segment per change of tile
         const uint64_t seg_cap = (uint64_t)n_ftiles + h->n_changes + 2;
-        if (approx && b->max_len && seg_cap <= n / 16 + 64) {
-            rc = pt_accumulate_runs(p, b, slot, approx, R, n_ftiles, W, h->n_slots, (uint32_t)seg_cap, b->max_len);
-        }
-        else {
-        rc = sq_radix_sort_pairs(ctx, slot, idx, tmpk, tmpv, n, h->fail_idx != ~0ULL ? 32 : key_bits);
-        if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&seg, (size_t)h->n_slots * 8, true);
-        if (rc == SQ_OK) {
-            uint32_t *seg_lo = seg, *seg_hi = seg + h->n_slots;
-            SQ_LAUNCH(ctx, k_pt_segments, grid, PT_TPB, 0, slot, n, seg_lo, seg_hi);
-            const uint32_t width = b->max_len;
-            if (width) rc = pt_accumulate(p, b, idx, seg_lo, seg_hi, h->n_slots, width, base);
-        }
+        if (R && b->max_len && seg_cap <= n / 16 + 64) {
+            pl->runs = true;
+            rc = pt_prepare_runs(p, b, pl, (uint32_t)seg_cap);
         }
     }
-    if (rc == SQ_OK && h->fail_idx != ~0ULL) {
+    if (rc != SQ_OK) pl->runs = false;
+    return rc;
+}
+
+// After k_fused_columns (run path) or straight after pt_prepare (general path): the ordered sums.
+int pt_finish(sq_pertile *p, sq_batch *b, PtPlan *pl) {
+    sq_ctx *ctx = p->ctx;
+    const uint32_t n = (uint32_t)b->n;
+    const uint64_t base = p->n_added;
+    const int grid = sq_grid_for(ctx, n, PT_TPB, 16);
+    int rc = SQ_OK;
+    if (pl->work && pl->runs) {
+        const int chain_grid = sq_grid_for(ctx, (uint64_t)pl->n_slots * pl->width * 32, PT_TPB, 32);
+        SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, b->view(), (const uint32_t *)nullptr, pl->segs, pl->seg,
+                  pl->nseg, pl->n_slots, pl->width, pl->n_ftiles, pl->kguess, pl->incr, pl->incr_hi, p->errors,
+                  p->len_cap, ctx->d_err_table);
+    }
+    else if (pl->work) {
+        uint32_t key_bits = 1;
+        while ((1ull << key_bits) < pl->n_slots) key_bits++;
+        // PT_NONE (skipped reads) carries all-ones low bits, so it sorts last within those bits
+        rc = sq_dalloc(ctx, (void **)&pl->tmpk, (size_t)n * 4, false);
+        if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&pl->tmpv, (size_t)n * 4, false);
+        if (rc == SQ_OK)
+            rc = sq_radix_sort_pairs(ctx, pl->slot, pl->idx, pl->tmpk, pl->tmpv, n, pl->fail_idx != ~0ULL ? 32 : key_bits);
+        if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&pl->seg, (size_t)pl->n_slots * 8, true);
+        if (rc == SQ_OK) {
+            uint32_t *seg_lo = pl->seg, *seg_hi = pl->seg + pl->n_slots;
+            SQ_LAUNCH(ctx, k_pt_segments, grid, PT_TPB, 0, pl->slot, n, seg_lo, seg_hi);
+            if (pl->width) rc = pt_accumulate(p, b, pl->idx, seg_lo, seg_hi, pl->n_slots, pl->width, base);
+        }
+    }
+    if (rc == SQ_OK && pl->fail_idx != ~0ULL) {
         p->skipped = true;
-        p->skipped_record = h->fail_idx;
-        const uint64_t r = h->fail_idx - base;
+        p->skipped_record = pl->fail_idx;
+        const uint64_t r = pl->fail_idx - base;
         rc = sq_batch_get_name(b, r, p->skipped_name);
     }
     p->n_added += n;
-    sq_dfree(ctx, slot);
-    sq_dfree(ctx, idx);
-    sq_dfree(ctx, tmpk);
-    sq_dfree(ctx, tmpv);
-    sq_dfree(ctx, seg);
+    pt_plan_free(ctx, pl);
     return rc;
 }
 
