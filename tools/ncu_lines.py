@@ -34,15 +34,23 @@ def main(rep, func, skip="0", cubin="/tmp/scratch/libsqgpu.1.sm_100a.cubin", top
     rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[1]
     ii, si = hdr.index("Instructions Executed"), hdr.index("# Samples")
-    body = rows[2:]
+    body = []
+    for r in rows[2:]:  # some ncu versions print the page twice: stop at the second header
+        if r and r[0] == "Kernel Name":
+            break
+        body.append(r)
+    wi = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
     if len(body) != len(lines):
         print(f"warning: {len(body)} ncu rows vs {len(lines)} disassembled instructions", file=sys.stderr)
     agg = collections.Counter()
     samp = collections.Counter()
+    wav = collections.Counter()
     for r, loc in zip(body, lines):
         agg[loc] += float(r[ii] or 0)
         samp[loc] += float(r[si] or 0)
-    tot, stot = sum(agg.values()), sum(samp.values())
+        if wi is not None:
+            wav[loc] += float(r[wi] or 0)
+    tot, stot, wtot = sum(agg.values()), sum(samp.values()), max(sum(wav.values()), 1)
     src = {}
     print(f"total warp instructions {tot:.0f}, samples {stot:.0f}")
     for loc, n in agg.most_common(int(top)):
@@ -55,7 +63,7 @@ def main(rep, func, skip="0", cubin="/tmp/scratch/libsqgpu.1.sm_100a.cubin", top
                     src[loc[0]] = []
             if loc[1] - 1 < len(src[loc[0]]):
                 text = src[loc[0]][loc[1] - 1].strip()
-        print(f"{n / tot * 100:5.1f}% inst {samp[loc] / max(stot, 1) * 100:5.1f}% samples  {loc}  {text[:90]}")
+        print(f"{n / tot * 100:5.1f}% inst {samp[loc] / max(stot, 1) * 100:5.1f}% samples {wav[loc] / wtot * 100:5.1f}% smem-wavefronts  {loc}  {text[:90]}")
 
 
 if __name__ == "__main__":
