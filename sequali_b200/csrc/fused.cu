@@ -129,6 +129,7 @@ k_fused_reads(const FusedArgs A) {
     __syncthreads();
     const BatchView &bv = A.bv;
     uint32_t parity = 0;
+    uint32_t qmn = 0xFFu, qmx = 0;  // quality bytes seen in the sampled words
     for (uint32_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
         const uint32_t r0 = t * A.recs_per_tile, r1 = min(r0 + A.recs_per_tile, bv.n);
         const uint64_t start = (uint64_t)bv.name_off[r0] - 1;
@@ -338,9 +339,38 @@ k_fused_reads(const FusedArgs A) {
                 if (j >= name_len || len < 1 || len > 18 || !ok) v = -1;
                 A.tile[r] = v;
                 if (v < 0) atomicMin(&A.pt_st->fail_idx, (unsigned long long)(A.pt_base + r));
+                // range of the quality values, from two words per read at positions that sweep the read
+                // length over consecutive reads: sizes the per-quality counters of k_fused_columns (a value
+                // the sample misses only costs that kernel its slow path)
+                if (L) {
+                    const uint32_t nw = L >> 2;
+                    uint32_t w0, w1;
+                    if (nw) {
+                        const uint32_t i0 = r % nw, i1 = i0 + (nw >> 1) >= nw ? i0 + (nw >> 1) - nw : i0 + (nw >> 1);
+                        w0 = fh_word(buf, qo, i0);
+                        w1 = fh_word(buf, qo, i1);
+                    }
+                    else {
+                        w0 = fh_word(buf, qo, 0);
+                        const uint32_t b0 = w0 & 0xFF;
+                        w0 = L == 1 ? b0 * 0x01010101u : L == 2 ? (w0 & 0xFFFF) * 0x00010001u : (w0 & 0xFFFFFF) | b0 << 24;
+                        w1 = w0;
+                    }
+                    const uint32_t mn = __vminu4(w0, w1), mx = __vmaxu4(w0, w1);
+                    qmn = min(qmn, min(min(mn & 0xFF, (mn >> 8) & 0xFF), min((mn >> 16) & 0xFF, mn >> 24)));
+                    qmx = max(qmx, max(max(mx & 0xFF, (mx >> 8) & 0xFF), max((mx >> 16) & 0xFF, mx >> 24)));
+                }
             }
         }
         __syncthreads();  // everyone is done with the tile before the next copy lands
+    }
+    if (A.do_pt) {
+        qmx = warp_max_u32(qmx);
+        qmn = ~warp_max_u32(~qmn);
+        if (lane_id() == 0 && qmn <= qmx) {
+            atomicMin(&A.pt_st->qmin, qmn);
+            atomicMax(&A.pt_st->qmax, qmx);
+        }
     }
     if (A.do_qc) {
         for (uint32_t i = tid; i < 101; i += FH_TPB)
@@ -354,22 +384,27 @@ k_fused_reads(const FusedArgs A) {
 // Per-position pass ("columns"): a thread owns four read positions and walks
 // the records of a tile that a TMA bulk copy staged in shared memory.
 //
-//   QCMetrics       base / phred-bin histograms (:2004-2031, :2068-2124) with the
-//                   counters of qc.cu's vertical kernel (byte-sliced registers,
-//                   byte counters in shared memory, no atomics in the loop)
-//   PerTileQuality  for tiles whose records belong to one flow-cell tile: the
-//                   exact in-binade integer sums r_k(e) of the error rates for
-//                   BOTH binades hinted by pertile.cu's k_pt_guess (k, k + 1),
-//                   from rows of the precomputed increment table copied into
-//                   shared memory per tile; the chain kernel picks the one that
-//                   matches the exact state, or replays the tile read by read
+//   QCMetrics       base / phred-bin histograms (:2004-2031, :2068-2124): byte-sliced
+//                   registers for the bases, private byte counters in shared memory
+//                   for the qualities, no atomics in the loop
+//   PerTileQuality  (PT) the private byte counters are indexed by the quality VALUE
+//                   (rows qbase .. qbase + qrows of the range k_fused_reads sampled),
+//                   one set per segment of `tiles_per_seg` text tiles.  At the end of
+//                   a segment the row groups are combined: four consecutive rows are
+//                   one phred bin of QCMetrics, and the per-(position, quality)
+//                   counts leave through a TMA bulk store as the segment's quality
+//                   histogram (PtHistGeom).  k_pt_chain_hist turns a histogram into
+//                   the exact in-binade integer sum of that segment's error rates for
+//                   whatever binade the chain is in -- no table lookups per base here.
+//                   A quality outside the sampled rows takes a slow path (QCMetrics
+//                   counted directly, the segment flagged for a read-by-read replay).
 // ===========================================================================
-constexpr int FC_BINS = 17;       // 5 base classes + 12 phred bins
-constexpr int FC_LUT_WINDOW = 8;  // binade pairs tabulated per tile: rows kmin .. kmin + 8
+constexpr int FC_BINS = 17;  // 5 base classes + 12 phred bins
 
 struct ColumnArgs {
     BatchView bv;
-    uint32_t recs_per_tile, n_tiles;
+    uint32_t recs_per_tile, n_tiles;  // text tiles: one bulk copy each
+    uint32_t tiles_per_seg, n_segs;   // PT: a segment = tiles_per_seg text tiles = one fixed tile of PerTileQuality
     uint64_t text_end;
     uint32_t CG, RG, W;  // column groups (4 positions each), row groups, W = 4*CG >= longest read
     uint32_t buf_bytes;  // shared-memory tile buffer
@@ -379,39 +414,45 @@ struct ColumnArgs {
     uint32_t ea_len;
     uint8_t *cta_mixed;  // [grid] CTAs that met reads of different lengths
     // PerTileQuality
-    int do_pt;
-    const uint64_t *lut;      // [PT_LUT_NK][94] r_k(10^-(q/10)), k = PT_LUT_KMIN + row
-    const uint16_t *kguess;   // [W][n_tiles]  (position-major: a chain reads consecutive tiles)
-    uint64_t *incr, *incr_hi; // [W][n_tiles] sums for binade kguess / kguess + 1
-    const uint8_t *tile_uniform;  // [n_tiles] 1: all records of the tile belong to one flow-cell tile
+    PtHistGeom hg;
+    uint8_t *qh;                 // [n_segs][hg.seg_bytes]
+    const uint8_t *seg_uniform;  // [n_segs] 1: all records of the segment belong to one flow-cell tile
+    uint8_t *seg_oob;            // [n_segs] set to 1 when the histogram misses a read
     PtState *pt_st;
     uint64_t pt_base;
 };
 
-template <int TPB>
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+template <int TPB, bool PT>
 __global__ void __launch_bounds__(TPB)
 k_fused_columns(const ColumnArgs A) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t s_lmin, s_lmax, s_kmin;
+    __shared__ uint32_t s_lmin, s_lmax, s_oob;
     const uint32_t tid = threadIdx.x, R = A.recs_per_tile, W = A.W;
+    const uint32_t prows = PT ? A.hg.qrows + 1 : 16;  // counter rows: PT qualities + trash; else 12 bins + spare
     uint8_t *buf = smem_raw;
     uint32_t *s_qo = (uint32_t *)(smem_raw + A.buf_bytes + 16);
     uint32_t *s_so = s_qo + R;
     uint32_t *s_L = s_so + R;
-    uint64_t *s_lut = (uint64_t *)(s_L + R + (R & 1));    // [WINDOW + 1][128] by raw byte; zero outside '!'..'~'
-    uint64_t *parti = s_lut + (FC_LUT_WINDOW + 1) * 128;  // [W][2]
-    uint32_t *hist = (uint32_t *)(parti + 2 * W);         // [W][17]
-    uint32_t *priv = hist + W * FC_BINS;                  // [16][TPB] words; row 12 = padding, 13..15 only
-                                                          // reachable through an invalid quality byte
+    uint32_t *hist = s_L + R;                  // [W][17]
+    uint32_t *priv = hist + W * FC_BINS;       // [prows][TPB] words = private byte counters of 4 positions
+    uint32_t *stage = priv + prows * TPB;      // PT: [4][CG][QW] words, 16-byte aligned (host pads)
+    stage = (uint32_t *)(((uintptr_t)stage + 15) & ~(uintptr_t)15);
 
-    if (A.do_qc)
-        for (uint32_t i = tid; i < W * FC_BINS + 16 * TPB; i += TPB) hist[i] = 0;
-    if (A.do_pt)
-        for (uint32_t i = tid; i < (FC_LUT_WINDOW + 1) * 128; i += TPB) s_lut[i] = 0;
+    for (uint32_t i = tid; i < W * FC_BINS + prows * TPB; i += TPB) hist[i] = 0;
+    if (PT)
+        for (uint32_t i = tid; i < 4 * A.CG * A.hg.QW; i += TPB) stage[i] = 0;  // padding words stay 0
     if (tid == 0) {
         s_lmin = 0xFFFFFFFFu;
         s_lmax = 0;
+        s_oob = 0;
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -424,8 +465,12 @@ k_fused_columns(const ColumnArgs A) {
     uint8_t *priv8 = (uint8_t *)priv + tid * 4;
     uint32_t acc_v = 0, acc_h = 0, acc_g = 0, acc_hg = 0, acc_n = 0, rows = 0;
     uint32_t lmin = 0xFFFFFFFFu, lmax = 0;
+    // PT: quality byte -> counter row, four at a time
+    const uint32_t base4 = (A.hg.qbase + 33u) * 0x01010101u;
+    const uint32_t hi4 = (0x80u - A.hg.qrows) * 0x01010101u;
+    const uint32_t trash4 = A.hg.qrows * 0x01010101u;
 
-    auto spill = [&]() {
+    auto spill_bases = [&]() {
         // registers -> CTA histogram; per column: A = v-h-g+hg, C = h-hg, G = hg, T = g-hg
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -443,161 +488,180 @@ k_fused_columns(const ColumnArgs A) {
             }
         }
         acc_v = acc_h = acc_g = acc_hg = acc_n = 0;
+        rows = 0;
+    };
+    auto spill = [&]() {
+        spill_bases();
+        if (!PT) {
 #pragma unroll
-        for (int b = 0; b < 12; b++) {
-            const uint32_t wv = priv[b * TPB + tid];
-            if (wv) {
-                priv[b * TPB + tid] = 0;
+            for (int b = 0; b < 12; b++) {
+                const uint32_t wv = priv[b * TPB + tid];
+                if (wv) {
+                    priv[b * TPB + tid] = 0;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t c = (wv >> (8 * j)) & 0xFF;
-                    if (c) atomicAdd(hist + (col0 + j) * FC_BINS + 5 + b, c);
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t c = (wv >> (8 * j)) & 0xFF;
+                        if (c) atomicAdd(hist + (col0 + j) * FC_BINS + 5 + b, c);
+                    }
                 }
             }
         }
-        rows = 0;
     };
 
     uint32_t parity = 0;
-    for (uint32_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
-        const uint32_t r0 = t * R, r1 = min(r0 + R, bv.n), nrec = r1 - r0;
-        const bool pt_here = A.do_pt && A.tile_uniform[t];  // other tiles are replayed read by read in the chain
+    const uint32_t TS = PT ? A.tiles_per_seg : 1, n_segs = PT ? A.n_segs : A.n_tiles;
+    for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
+        const bool pt_here = PT && A.seg_uniform[seg];  // other segments are replayed read by read in the chain
         if (!A.do_qc && !pt_here) continue;
-        {
-            const uint64_t start = (uint64_t)bv.name_off[r0] - 1;
-            const uint64_t end = r1 < bv.n ? (uint64_t)bv.name_off[r1] - 1 : A.text_end;
-            const uint64_t gstart = start & ~15ULL;
-            const uint32_t bytes = (uint32_t)(((end + 15) & ~15ULL) - gstart);
-            if (tid == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&bar, bytes);
-                bulk_g2s(buf, bv.text + gstart, bytes, &bar);
-                s_kmin = 0xFFFFFFFFu;
-            }
-            for (uint32_t i = tid; i < nrec; i += TPB) {
-                const uint32_t L = bv.seq_len[r0 + i];
-                s_so[i] = bv.seq_off[r0 + i] - (uint32_t)gstart;
-                s_qo[i] = bv.qual_off[r0 + i] - (uint32_t)gstart;
-                s_L[i] = L;
-                lmin = min(lmin, L);
-                lmax = max(lmax, L);
-            }
-        }
-        // ---- PerTileQuality: this tile's window of binades -------------------------------------
-        uint32_t kg[4] = {0, 0, 0, 0};
-        if (pt_here) {
-            uint32_t kmin = 0xFFFFFFFFu;
-            if (worker) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    kg[j] = col0 + j < W ? A.kguess[(uint64_t)(col0 + j) * A.n_tiles + t] : 0;
-                    if (kg[j]) kmin = min(kmin, kg[j]);
+        const uint32_t t_end = min((seg + 1) * TS, A.n_tiles);
+        for (uint32_t t = seg * TS; t < t_end; t++) {
+            const uint32_t r0 = t * R, r1 = min(r0 + R, bv.n), nrec = r1 - r0;
+            {
+                const uint64_t start = (uint64_t)bv.name_off[r0] - 1;
+                const uint64_t end = r1 < bv.n ? (uint64_t)bv.name_off[r1] - 1 : A.text_end;
+                const uint64_t gstart = start & ~15ULL;
+                const uint32_t bytes = (uint32_t)(((end + 15) & ~15ULL) - gstart);
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&bar, bytes);
+                    bulk_g2s(buf, bv.text + gstart, bytes, &bar);
+                }
+                for (uint32_t i = tid; i < nrec; i += TPB) {
+                    const uint32_t L = bv.seq_len[r0 + i];
+                    s_so[i] = bv.seq_off[r0 + i] - (uint32_t)gstart;
+                    s_qo[i] = bv.qual_off[r0 + i] - (uint32_t)gstart;
+                    s_L[i] = L;
+                    lmin = min(lmin, L);
+                    lmax = max(lmax, L);
                 }
             }
-            kmin = ~warp_max_u32(~kmin);
-            __syncthreads();  // s_kmin is reset, nobody reads the previous tile's table or sums any more
-            if (lane_id() == 0 && kmin != 0xFFFFFFFFu) atomicMin(&s_kmin, kmin);
             __syncthreads();
-            kmin = s_kmin;
-            for (uint32_t i = tid; i < (FC_LUT_WINDOW + 1) * 94; i += TPB) {
-                const uint32_t row = i / 94, q = i - row * 94;
-                const uint32_t k = kmin + row - (uint32_t)PT_LUT_KMIN;
-                s_lut[row * 128 + 33 + q] = k < (uint32_t)PT_LUT_NK ? A.lut[k * 94 + q] : PT_HARD;
-            }
-            for (uint32_t i = tid; i < 2 * W; i += TPB) parti[i] = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) kg[j] = (kg[j] && kg[j] - kmin < FC_LUT_WINDOW) ? kg[j] - kmin + 1 : 0;  // 0: no table
-        }
-        __syncthreads();
-        mbar_wait(&bar, parity);
-        parity ^= 1;
-        uint64_t ia[4] = {0, 0, 0, 0}, ib[4] = {0, 0, 0, 0};
-        if (worker) {
-            // kg[j] == 0 (no table for that column): any row will do, the sums are marked PT_HARD below
-            const uint64_t *lrow0 = s_lut + (kg[0] ? kg[0] - 1 : 0) * 128;
-            const uint64_t *lrow1 = s_lut + (kg[1] ? kg[1] - 1 : 0) * 128;
-            const uint64_t *lrow2 = s_lut + (kg[2] ? kg[2] - 1 : 0) * 128;
-            const uint64_t *lrow3 = s_lut + (kg[3] ? kg[3] - 1 : 0) * 128;
-            uint32_t badw = 0;
-            for (uint32_t i = rg; i < nrec; i += RG) {
-                const uint32_t L = s_L[i];
-                if (L <= col0) continue;
-                const uint32_t nvalid = min(4u, L - col0);
-                // bytes past the end of the read become 0x7F: zero in every table, own trash bin
-                const uint32_t keep = 0xFFFFFFFFu >> (8 * (4 - nvalid));
-                const uint32_t raw = fh_word(buf, s_qo[i], cg);
-                const uint32_t q = (raw & keep) | (0x7F7F7F7Fu & ~keep);
-                if (A.do_qc) {
-                    const uint32_t w = fh_word(buf, s_so[i], cg);
-                    const uint32_t pm = keep & 0x01010101u;
-                    const uint32_t vb = fh_acgt_bytes(w) & pm;
-                    const uint32_t hb = (w >> 1) & vb, gb = (w >> 2) & vb;
-                    acc_v += vb;
-                    acc_h += hb;
-                    acc_g += gb;
-                    acc_hg += hb & gb;
-                    acc_n += pm & ~vb;
-                    // phred bins min(q,47)>>2 as byte counters at bin*TPB*4 + tid*4 + j, four bins at
-                    // once: 4*(min(q,47)>>2) per byte (q >= 48 saturates to bin 11, the padding byte is
-                    // counted in the spare 13th row that nobody reads)
-                    const uint32_t t4 = q - 0x21212121u;
-                    const uint32_t sat = (((t4 + 0x50505050u) >> 7) & 0x01010101u) * 0xFFu;
-                    uint32_t bin4 = ((t4 & 0x3C3C3C3Cu) & ~sat) | (0x2C2C2C2Cu & sat);
-                    bin4 = (bin4 & keep) | (0x30303030u & ~keep);
-                    priv8[(bin4 & 0xFF) * TPB + 0] += 1;
-                    priv8[((bin4 >> 8) & 0xFF) * TPB + 1] += 1;
-                    priv8[((bin4 >> 16) & 0xFF) * TPB + 2] += 1;
-                    priv8[(bin4 >> 24) * TPB + 3] += 1;
-                    if (++rows == 255) spill();
-                }
-                if (pt_here) {
-                    badw |= ((raw - 0x21212121u) | (raw + 0x01010101u)) & keep;
-                    const uint64_t *e0 = lrow0 + (q & 0xFF), *e1 = lrow1 + ((q >> 8) & 0xFF);
-                    const uint64_t *e2 = lrow2 + ((q >> 16) & 0xFF), *e3 = lrow3 + (q >> 24);
-                    ia[0] += e0[0];
-                    ib[0] += e0[128];
-                    ia[1] += e1[0];
-                    ib[1] += e1[128];
-                    ia[2] += e2[0];
-                    ib[2] += e2[128];
-                    ia[3] += e3[0];
-                    ib[3] += e3[128];
-                }
-            }
-            if (pt_here && (badw & 0x80808080u)) {
-                // a quality byte outside '!'..'~' (PerTileQuality raises for it, :3213): find it
+            mbar_wait(&bar, parity);
+            parity ^= 1;
+            if (worker) {
                 for (uint32_t i = rg; i < nrec; i += RG) {
                     const uint32_t L = s_L[i];
-                    for (uint32_t j = 0; j < 4 && col0 + j < L; j++) {
-                        const uint32_t c = buf[s_qo[i] + col0 + j];
-                        if (c - 33u > 93u)
-                            atomicMin(&A.pt_st->err_key, (unsigned long long)((A.pt_base + r0 + i) << 8 | c));
+                    if (L <= col0) continue;
+                    const uint32_t nvalid = min(4u, L - col0);
+                    const uint32_t keep = 0xFFFFFFFFu >> (8 * (4 - nvalid));
+                    const uint32_t raw = fh_word(buf, s_qo[i], cg);
+                    if (A.do_qc) {
+                        const uint32_t w = fh_word(buf, s_so[i], cg);
+                        const uint32_t pm = keep & 0x01010101u;
+                        const uint32_t vb = fh_acgt_bytes(w) & pm;
+                        const uint32_t hb = (w >> 1) & vb, gb = (w >> 2) & vb;
+                        acc_v += vb;
+                        acc_h += hb;
+                        acc_g += gb;
+                        acc_hg += hb & gb;
+                        acc_n += pm & ~vb;
                     }
-                }
-            }
-        }
-        // ---- per-tile column sums: combine the row groups -------------------------------------
-        if (pt_here) {
-            if (worker) {
+                    uint32_t row4;  // per byte: counter row
+                    if (PT) {
+                        // row = quality - (qbase + 33); bytes past the end of the read and qualities outside
+                        // [qbase, qbase + qrows) go to the trash row, the latter through the slow path
+                        const uint32_t d = (raw | 0x80808080u) - base4;  // bit 7: quality >= first row
+                        const uint32_t idx = d & 0x7F7F7F7Fu;
+                        const uint32_t e = idx + hi4;                     // bit 7: row >= qrows
+                        const uint32_t bad = (~d | e) & 0x80808080u & keep;
+                        row4 = (idx & keep) | (trash4 & ~keep);
+                        if (bad) {
+                            s_oob = 1;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (col0 + j < W) {
-                        const uint64_t a = kg[j] && ia[j] < PT_HARD ? ia[j] : PT_HARD;
-                        const uint64_t b = kg[j] && ib[j] < PT_HARD ? ib[j] : PT_HARD;
-                        atomicAdd((unsigned long long *)(parti + 2 * (col0 + j)), (unsigned long long)a);
-                        atomicAdd((unsigned long long *)(parti + 2 * (col0 + j) + 1), (unsigned long long)b);
+                            for (int j = 0; j < 4; j++) {
+                                if (!((bad >> (8 * j)) & 0x80u)) continue;
+                                const uint32_t c = (raw >> (8 * j)) & 0xFF;
+                                row4 = (row4 & ~(0xFFu << (8 * j))) | (A.hg.qrows << (8 * j));
+                                if (c - 33u > 93u)  // PerTileQuality raises for it (:3213), QCMetrics found it already
+                                    atomicMin(&A.pt_st->err_key,
+                                              (unsigned long long)((A.pt_base + r0 + i) << 8 | c));
+                                else if (A.do_qc)
+                                    atomicAdd(hist + (col0 + j) * FC_BINS + 5 + (min(c - 33u, 47u) >> 2), 1u);
+                            }
+                        }
+                        priv8[(row4 & 0xFF) * (TPB * 4) + 0] += 1;
+                        priv8[((row4 >> 8) & 0xFF) * (TPB * 4) + 1] += 1;
+                        priv8[((row4 >> 16) & 0xFF) * (TPB * 4) + 2] += 1;
+                        priv8[(row4 >> 24) * (TPB * 4) + 3] += 1;
+                        if (A.do_qc && ++rows == 255) spill_bases();
+                    }
+                    else {
+                        // phred bins min(q,47)>>2 as byte counters at bin*TPB*4 + tid*4 + j, four bins at
+                        // once: 4*(min(q,47)>>2) per byte (q >= 48 saturates to bin 11, the padding byte is
+                        // counted in the spare 13th row that nobody reads)
+                        const uint32_t q = (raw & keep) | (0x7F7F7F7Fu & ~keep);
+                        const uint32_t t4 = q - 0x21212121u;
+                        const uint32_t sat = (((t4 + 0x50505050u) >> 7) & 0x01010101u) * 0xFFu;
+                        uint32_t bin4 = ((t4 & 0x3C3C3C3Cu) & ~sat) | (0x2C2C2C2Cu & sat);
+                        bin4 = (bin4 & keep) | (0x30303030u & ~keep);
+                        priv8[(bin4 & 0xFF) * TPB + 0] += 1;
+                        priv8[((bin4 >> 8) & 0xFF) * TPB + 1] += 1;
+                        priv8[((bin4 >> 16) & 0xFF) * TPB + 2] += 1;
+                        priv8[(bin4 >> 24) * TPB + 3] += 1;
+                        if (++rows == 255) spill();
                     }
                 }
             }
-            __syncthreads();
-            for (uint32_t c = tid; c < W; c += TPB) {
-                const uint64_t a = parti[2 * c], b = parti[2 * c + 1];
-                A.incr[(uint64_t)c * A.n_tiles + t] = a < PT_HARD ? a : PT_HARD;
-                A.incr_hi[(uint64_t)c * A.n_tiles + t] = b < PT_HARD ? b : PT_HARD;
-            }
+            if (PT && tid == 0) bulk_wait_read();  // the previous segment's histogram has left `stage`
+            __syncthreads();                       // tile buffer and offsets are free again
         }
-        __syncthreads();  // tile buffer, offsets, table and partial sums are free again
+        if (!PT) continue;
+        // ---- end of a segment: combine the row groups' private counters --------------------------
+        // thread (rg, cg) owns the quads of rows 4m .. 4m+3 with m = rg, rg + RG, ...: one phred bin each
+        if (worker) {
+            const uint32_t nq = A.hg.qrows >> 2, QW = A.hg.QW;
+            for (uint32_t m = rg; m < nq; m += RG) {
+                uint32_t w[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    uint32_t *pr = priv + (4 * m + r) * TPB + cg;
+                    uint32_t acc = 0;
+                    for (uint32_t g = 0; g < RG; g++) {  // counts of a segment fit a byte: packed adds
+                        acc += pr[g * CG];
+                        pr[g * CG] = 0;
+                    }
+                    w[r] = acc;
+                }
+                const uint32_t qsum = w[0] + w[1] + w[2] + w[3];
+                if (qsum == 0) {
+                    if (pt_here) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) stage[(j * CG + cg) * QW + m] = 0;
+                    }
+                    continue;
+                }
+                if (A.do_qc) {
+                    const uint32_t bin = min((A.hg.qbase >> 2) + m, 11u);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t c = (qsum >> (8 * j)) & 0xFF;
+                        if (c) atomicAdd(hist + (col0 + j) * FC_BINS + 5 + bin, c);
+                    }
+                }
+                if (pt_here) {
+                    // 4 x 4 byte transpose: word j = counts of rows 4m .. 4m+3 at position col0 + j
+                    const uint32_t t0 = __byte_perm(w[0], w[1], 0x5140), t1 = __byte_perm(w[2], w[3], 0x5140);
+                    const uint32_t t2 = __byte_perm(w[0], w[1], 0x7362), t3 = __byte_perm(w[2], w[3], 0x7362);
+                    stage[(0 * CG + cg) * QW + m] = __byte_perm(t0, t1, 0x5410);
+                    stage[(1 * CG + cg) * QW + m] = __byte_perm(t0, t1, 0x7632);
+                    stage[(2 * CG + cg) * QW + m] = __byte_perm(t2, t3, 0x5410);
+                    stage[(3 * CG + cg) * QW + m] = __byte_perm(t2, t3, 0x7632);
+                }
+            }
+            // the trash row only ever counts padding and slow-path bytes
+            priv[A.hg.qrows * TPB + tid] = 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (pt_here) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                bulk_s2g(A.qh + (uint64_t)seg * A.hg.seg_bytes, stage, A.hg.seg_bytes);
+                if (s_oob) A.seg_oob[seg] = 1;
+            }
+            s_oob = 0;
+        }
     }
+    if (PT && tid == 0) bulk_wait_read();
     if (!A.do_qc) return;
     if (worker) spill();
     lmax = warp_max_u32(lmax);
@@ -704,15 +768,19 @@ static bool fused_eligible(const sq_batch *b, const sq_adapters *ad) {
 
 // shared-memory plan of k_fused_columns.  The block size is the one of 128 / 192 / 256 threads
 // that wastes the fewest lanes for this read length (150 bp: 38 column groups, 5 x 38 = 190 of
-// 192 threads work); 4 / 3 / 2 CTAs share an SM.
+// 192 threads work); as many CTAs share an SM as leave room for a useful text tile.
 struct ColGeom {
     uint32_t R, n_tiles, CG, RG, W, buf_bytes, grid, tpb;
+    uint32_t TS, n_segs;  // PT: text tiles per segment, segments (R * TS <= 255 records each)
+    PtHistGeom hg;        // PT: qrows != 0
     size_t smem;
     bool ok;
 };
-static ColGeom col_geometry(sq_ctx *ctx, const sq_batch *b) {
+// qmin / qmax: sampled quality byte range for the PerTileQuality histograms, qmin > qmax: QCMetrics only
+static ColGeom col_geometry(sq_ctx *ctx, const sq_batch *b, uint32_t qmin, uint32_t qmax) {
     ColGeom g;
     memset(&g, 0, sizeof(g));
+    g.hg = PtHistGeom();
     if (b->max_len == 0) return g;
     g.CG = (b->max_len + 3) / 4;
     if (g.CG > 256) return g;
@@ -727,31 +795,66 @@ static ColGeom col_geometry(sq_ctx *ctx, const sq_batch *b) {
         }
     }
     g.RG = g.tpb / g.CG;
-    const uint32_t ctas = g.tpb == 128 ? 4 : g.tpb == 192 ? 3 : 2;
-    const uint32_t budget = (228u * 1024u) / ctas - 1024u - 128u;
-    const uint32_t fixed = (FC_LUT_WINDOW + 1) * 128 * 8 + 2 * g.W * 8 + g.W * FC_BINS * 4 + 16 * g.tpb * 4 + 64;
-    if (fixed + 8 * (b->max_rec_bytes + 12) + 64 > budget) return g;
-    g.R = (budget - fixed - 64) / (b->max_rec_bytes + 12);
+    const bool pt = qmin <= qmax;
+    uint32_t prows = 16, stage = 0;
+    if (pt) {
+        const uint32_t lo = (qmin < 33 ? 33 : qmin) - 33, hi = (qmax > 126 ? 126 : qmax) - 33;
+        if (lo > hi) return g;
+        g.hg.qbase = lo & ~3u;
+        g.hg.qrows = (hi - g.hg.qbase + 4) & ~3u;
+        g.hg.QW = (g.hg.qrows / 4) | 1u;  // odd: the transposed stores of a warp hit 32 banks
+        g.hg.CG = g.CG;
+        g.hg.seg_bytes = g.W * g.hg.QW * 4;
+        prows = g.hg.qrows + 1;
+        stage = g.hg.seg_bytes + 16;
+    }
+    const uint32_t fixed = g.W * FC_BINS * 4 + prows * g.tpb * 4 + stage + 64;
+    const uint32_t per_rec = b->max_rec_bytes + 12;
+    uint32_t ctas = g.tpb == 128 ? 4 : g.tpb == 192 ? 3 : 2;
+    uint32_t budget = 0;
+    for (; ctas >= 1; ctas--) {  // fewer CTAs per SM when the counters leave no room for 24 records
+        budget = (228u * 1024u) / ctas - 1024u - 128u;
+        if (budget > 227u * 1024u) budget = 227u * 1024u;
+        if (fixed + (ctas > 1 ? 24 : 8) * per_rec + 64 <= budget) break;
+    }
+    if (ctas == 0) return g;
+    g.R = (budget - fixed - 64) / per_rec;
     if (g.R > 255) g.R = 255;
+    g.TS = pt ? 255 / g.R : 1;
     g.buf_bytes = (g.R * b->max_rec_bytes + 32 + 15) & ~15u;
-    g.smem = (size_t)g.buf_bytes + 16 + (size_t)(3 * g.R + 1) * 4 + fixed;
+    g.smem = (size_t)g.buf_bytes + 16 + (size_t)3 * g.R * 4 + fixed;
     g.n_tiles = (uint32_t)((b->n + g.R - 1) / g.R);
+    g.n_segs = (g.n_tiles + g.TS - 1) / g.TS;
     g.grid = (uint32_t)ctx->num_sms * ctas;
-    if (g.grid > g.n_tiles) g.grid = g.n_tiles;
+    if (g.grid > g.n_segs) g.grid = g.n_segs;
     g.ok = true;
     return g;
 }
 
-template <int TPB>
+template <int TPB, bool PT>
 static int launch_columns_t(sq_ctx *ctx, const ColGeom &g, const ColumnArgs &C) {
-    CUDA_TRY(cudaFuncSetAttribute(k_fused_columns<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-    SQ_LAUNCH(ctx, k_fused_columns<TPB>, g.grid, TPB, g.smem, C);
+    // (named for the profiler: with / without the per-segment quality histograms)
+    if constexpr (PT) {
+        auto k_fused_columns_qhist = k_fused_columns<TPB, true>;
+        CUDA_TRY(cudaFuncSetAttribute(k_fused_columns_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        SQ_LAUNCH(ctx, k_fused_columns_qhist, g.grid, TPB, g.smem, C);
+    }
+    else {
+        auto k_fused_columns_bins = k_fused_columns<TPB, false>;
+        CUDA_TRY(cudaFuncSetAttribute(k_fused_columns_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        SQ_LAUNCH(ctx, k_fused_columns_bins, g.grid, TPB, g.smem, C);
+    }
     return SQ_OK;
 }
 static int launch_columns(sq_ctx *ctx, const ColGeom &g, const ColumnArgs &C) {
-    if (g.tpb == 128) return launch_columns_t<128>(ctx, g, C);
-    if (g.tpb == 192) return launch_columns_t<192>(ctx, g, C);
-    return launch_columns_t<256>(ctx, g, C);
+    if (g.hg.qrows) {
+        if (g.tpb == 128) return launch_columns_t<128, true>(ctx, g, C);
+        if (g.tpb == 192) return launch_columns_t<192, true>(ctx, g, C);
+        return launch_columns_t<256, true>(ctx, g, C);
+    }
+    if (g.tpb == 128) return launch_columns_t<128, false>(ctx, g, C);
+    if (g.tpb == 192) return launch_columns_t<192, false>(ctx, g, C);
+    return launch_columns_t<256, false>(ctx, g, C);
 }
 
 extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt, sq_overrep *ov,
@@ -826,19 +929,32 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     else if (b->max_len <= 256) rc = launch_fused<8>(ctx, A);
     else rc = launch_fused<10>(ctx, A);
 
-    // ---- PerTileQuality: slots, segments and binade hints (needs the tile ids) ---------------
-    const ColGeom g = col_geometry(ctx, b);
+    // ---- PerTileQuality: slots and segments (needs the tile ids) ---------------------------------
+    // two plans for the per-position pass: with per-segment quality histograms (reads in tile runs)
+    // and without (QCMetrics alone, or tiles in random order -> sort-based PerTileQuality)
+    ColGeom g = col_geometry(ctx, b, 1, 0);
     PtPlan plan;
     const uint64_t pt_base = pt ? pt->n_added : 0;
-    if (rc == SQ_OK && pt) rc = pt_prepare(pt, b, tile, g.ok ? g.R : 0, g.n_tiles, g.W, &plan);
+    if (rc == SQ_OK && pt) {
+        uint32_t qmin = 1, qmax = 0;
+        rc = pt_quality_range(pt, &qmin, &qmax);
+        ColGeom gp;
+        memset(&gp, 0, sizeof(gp));
+        if (rc == SQ_OK && qmin <= qmax) gp = col_geometry(ctx, b, qmin, qmax);
+        if (rc == SQ_OK)
+            rc = pt_prepare(pt, b, tile, gp.ok ? gp.R * gp.TS : 0, gp.n_segs, gp.W, gp.hg, &plan);
+        if (rc == SQ_OK && plan.runs) g = gp;
+    }
 
-    // ---- per-position pass: QCMetrics histograms + PerTileQuality in-binade sums --------------
+    // ---- per-position pass: QCMetrics histograms + PerTileQuality quality histograms ----------
     if (rc == SQ_OK && g.ok && (qc || plan.runs)) {
         ColumnArgs C;
         memset(&C, 0, sizeof(C));
         C.bv = b->view();
         C.recs_per_tile = g.R;
         C.n_tiles = g.n_tiles;
+        C.tiles_per_seg = g.TS;
+        C.n_segs = g.n_segs;
         C.text_end = b->text_end;
         C.CG = g.CG;
         C.RG = g.RG;
@@ -856,12 +972,10 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
             C.cta_mixed = cta_mixed;
         }
         if (plan.runs) {
-            C.do_pt = 1;
-            C.lut = pt->lut;
-            C.kguess = plan.kguess;
-            C.incr = plan.incr;
-            C.incr_hi = plan.incr_hi;
-            C.tile_uniform = plan.uniform;
+            C.hg = g.hg;
+            C.qh = plan.qh;
+            C.seg_uniform = plan.uniform;
+            C.seg_oob = plan.oob;
             C.pt_st = pt->st;
             C.pt_base = pt_base;
         }
@@ -872,8 +986,9 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
             if (use_smem)
                 CUDA_TRY(cudaFuncSetAttribute(k_fused_ea_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               96 * 1024));
-            SQ_LAUNCH(ctx, k_fused_ea_fallback, g.grid, FC_TPB, use_smem ? ea_smem : 0, b->view(), g.R, g.n_tiles,
-                      cta_mixed, qc->ea_base, qc->ea_phred, (uint32_t)qc->ea_len, use_smem);
+            // same CTA -> records assignment as k_fused_columns: whole segments
+            SQ_LAUNCH(ctx, k_fused_ea_fallback, g.grid, FC_TPB, use_smem ? ea_smem : 0, b->view(), g.R * g.TS,
+                      g.n_segs, cta_mixed, qc->ea_base, qc->ea_phred, (uint32_t)qc->ea_len, use_smem);
         }
     }
     else if (rc == SQ_OK && qc) rc = qc_add_vertical(qc, b);

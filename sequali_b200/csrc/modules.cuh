@@ -46,6 +46,7 @@ struct PtState {  // device
     unsigned int max_len;          // longest kept read
     unsigned long long n_kept;     // kept reads (before fail_idx)
     unsigned int n_changes;        // this array: reads whose tile differs from the previous read's
+    unsigned int qmin, qmax;       // smallest / largest quality byte among the sampled ones (all arrays so far)
     unsigned int pad;
 };
 
@@ -65,6 +66,7 @@ struct sq_pertile {
     std::vector<uint8_t> skipped_name;
     // host mirror after the last sync
     uint64_t n_slots = 0, max_len = 0;
+    uint32_t qmin = 0xFFFFFFFFu, qmax = 0;  // sampled quality byte range (k_fused_reads), 0xFFFFFFFF: not known yet
 };
 
 constexpr uint64_t PT_HARD = 1ULL << 53;          // no valid in-binade increment reaches this
@@ -88,7 +90,15 @@ __host__ __device__ inline uint64_t pt_increment(uint32_t k, uint64_t ebits) {
 
 struct PtSeg {  // a run of consecutive reads of one tile: rows [lo, hi) of `order` (or of the array)
     uint32_t lo, hi, slot;
-    uint32_t data;  // row of approx / kguess / incr holding this segment's sums, PT_NONE: replay the reads
+    uint32_t data;  // general path: row of approx / kguess / incr holding this segment's sums; run path: the
+                    // fixed tile whose quality histograms cover exactly these reads; PT_NONE: replay the reads
+};
+
+// Layout of the per-(fixed tile, position) quality histograms k_fused_columns writes for the run path:
+// qh[tile][seg_bytes]; position c = 4 * cg + j owns the QW words at word ((j * CG + cg) * QW); byte i of
+// those words = number of the tile's reads with phred qbase + i at that position (0 <= i < qrows).
+struct PtHistGeom {
+    uint32_t qbase = 0, qrows = 0, QW = 0, CG = 0, seg_bytes = 0;
 };
 
 
@@ -96,9 +106,9 @@ struct PtSeg {  // a run of consecutive reads of one tile: rows [lo, hi) of `ord
 // unparsable header, already folded into st->fail_idx):
 //   pt_prepare   tile ids -> slots, table growth, length counts.  R != 0 announces that the
 //                caller runs k_fused_columns over fixed tiles of R records: when the reads arrive
-//                in tile runs the plan then holds the segments, their sampled sums and the two
-//                hinted binades per (tile, position) (plan.runs), and the caller must have
-//                k_fused_columns fill plan.incr / plan.incr_hi
+//                in tile runs the plan then holds the segments (plan.runs) and the caller must
+//                have k_fused_columns fill plan.qh (quality histogram per fixed tile and position)
+//                and plan.oob (tiles that met a quality outside the tabulated rows)
 //   pt_finish    the ordered chains (run path), or the sort-based general path; frees the plan
 struct PtPlan {
     bool work = false, runs = false;
@@ -107,12 +117,15 @@ struct PtPlan {
     uint32_t *slot = nullptr, *idx = nullptr, *tmpk = nullptr, *tmpv = nullptr, *seg = nullptr;
     uint32_t *runs_cnt = nullptr, *seg_off = nullptr, *nseg = nullptr;
     uint8_t *uniform = nullptr;   // [n_ftiles] 1: all records of the fixed tile belong to one flow-cell tile
+    uint8_t *oob = nullptr;       // [n_ftiles] 1: the histogram of the tile is incomplete, replay its reads
     PtSeg *segs = nullptr;
-    uint64_t *incr = nullptr, *incr_hi = nullptr;  // [W][n_ftiles] sums for binade kguess / kguess + 1
-    uint16_t *kguess = nullptr;                    // [W][n_ftiles]
-    float *approx = nullptr;                       // [W][n_ftiles] sampled estimates
+    PtHistGeom hg;
+    uint8_t *qh = nullptr;        // [n_ftiles][hg.seg_bytes]
 };
-int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t n_ftiles, uint32_t W, PtPlan *pl);
+int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t n_ftiles, uint32_t W,
+               const PtHistGeom &hg, PtPlan *pl);
+// sampled quality byte range for the next k_fused_columns launch (syncs once, for the first array)
+int pt_quality_range(sq_pertile *p, uint32_t *qmin, uint32_t *qmax);
 int pt_finish(sq_pertile *p, sq_batch *b, PtPlan *pl);
 void pt_plan_free(sq_ctx *ctx, PtPlan *pl);
 

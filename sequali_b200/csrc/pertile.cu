@@ -482,6 +482,85 @@ k_pt_chain(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__rest
     }
 }
 
+// Run path: the chain over fixed tiles whose per-position quality histograms k_fused_columns
+// wrote (PtHistGeom).  The binade k of the running sum is known exactly at every step, so the
+// integer sum of a tile is the dot product of its histogram with row k of the increment table;
+// 32 tiles are tried per step and accepted up to the first one that leaves the binade, ties,
+// or has no usable histogram -- that one is replayed read by read.
+__global__ void __launch_bounds__(PT_TPB)
+k_pt_chain_hist(BatchView bv, const PtSeg *__restrict__ segs, const uint32_t *__restrict__ seg_first,
+                const uint32_t *__restrict__ nseg, uint32_t n_slots, uint32_t width, const uint8_t *__restrict__ qh,
+                PtHistGeom hg, const uint8_t *__restrict__ oob, const uint64_t *__restrict__ lut, double *errors,
+                uint64_t len_cap, const double *__restrict__ err_tab) {
+    extern __shared__ uint64_t s_lut[];  // [PT_LUT_NK][96]; entries past phred 93 are PT_HARD
+    __shared__ double s_err[94];
+    for (uint32_t i = threadIdx.x; i < 94; i += PT_TPB) s_err[i] = err_tab[i];
+    for (uint32_t i = threadIdx.x; i < PT_LUT_NK * 96; i += PT_TPB) {
+        const uint32_t k = i / 96, q = i - k * 96;
+        s_lut[i] = q < 94 ? lut[k * 94 + q] : PT_HARD;
+    }
+    __syncthreads();
+    const uint64_t chains = (uint64_t)n_slots * width;
+    const uint64_t warps = (uint64_t)gridDim.x * (PT_TPB / 32);
+    const uint32_t nq = hg.qrows / 4;
+    for (uint64_t c = (uint64_t)blockIdx.x * (PT_TPB / 32) + (threadIdx.x >> 5); c < chains; c += warps) {
+        const uint32_t s = (uint32_t)(c / width), pos = (uint32_t)(c % width);
+        const uint32_t cnt = nseg[s];
+        if (cnt == 0) continue;
+        const uint32_t first = seg_first[s];
+        const uint32_t colw = ((pos & 3u) * hg.CG + (pos >> 2)) * hg.QW;
+        double *cell = errors + (uint64_t)s * len_cap + pos;
+        uint64_t sbits = (uint64_t)__double_as_longlong(*cell);
+        uint32_t j = 0;
+        while (j < cnt) {
+            const uint32_t jj = j + lane_id();
+            const uint32_t k = (uint32_t)(sbits >> 52), krow = k - (uint32_t)PT_LUT_KMIN;
+            uint64_t inc = 0;
+            uint32_t lo = 0, hi = 0;
+            bool mine = false, hard = false;
+            if (jj < cnt) {
+                const PtSeg sg = segs[first + jj];
+                if (sg.slot == s) {  // a foreign segment adds nothing
+                    mine = true;
+                    lo = sg.lo;
+                    hi = sg.hi;
+                    if (sg.data == PT_NONE || krow >= (uint32_t)PT_LUT_NK || oob[sg.data]) hard = true;
+                    else {
+                        const uint32_t *h = (const uint32_t *)(qh + (uint64_t)sg.data * hg.seg_bytes) + colw;
+                        const uint64_t *lr = s_lut + krow * 96 + hg.qbase;
+                        for (uint32_t m = 0; m < nq; m++) {
+                            const uint32_t w = h[m];
+                            if (w == 0) continue;
+                            const uint64_t *l4 = lr + 4 * m;
+                            inc += (uint64_t)(w & 0xFF) * l4[0] + (uint64_t)((w >> 8) & 0xFF) * l4[1] +
+                                   (uint64_t)((w >> 16) & 0xFF) * l4[2] + (uint64_t)(w >> 24) * l4[3];
+                        }
+                        // a tabulated PT_HARD (tie, increment that cannot stay in the binade) times a non-zero
+                        // count lifts the sum to >= 2^53; true sums of <= 255 in-binade increments that large
+                        // leave the binade anyway.  (0 * PT_HARD adds nothing: unused rows do not poison.)
+                        hard = inc >= PT_HARD;
+                    }
+                }
+            }
+            if (hard) inc = 0;
+            const uint64_t incl = warp_incl_scan_u64(inc);
+            const bool stays = (uint32_t)((sbits + incl) >> 52) == k;
+            const uint32_t nv = min(32u, cnt - j);
+            const uint32_t bad = __ballot_sync(0xffffffffu, mine && (hard || !stays));
+            const uint32_t f = bad ? (uint32_t)__ffs(bad) - 1 : 32u;
+            const uint32_t nacc = min(f, nv);
+            if (nacc) sbits += __shfl_sync(0xffffffffu, incl, nacc - 1);
+            j += nacc;
+            if (f < nv) {
+                const uint32_t rlo = __shfl_sync(0xffffffffu, lo, f), rhi = __shfl_sync(0xffffffffu, hi, f);
+                sbits = pt_replay_rows(sbits, bv, nullptr, rlo, rhi, pos, s_err);
+                j += 1;
+            }
+        }
+        if (lane_id() == 0) *cell = __longlong_as_double((long long)sbits);
+    }
+}
+
 // ---- segments of the fused path: the record array is cut into fixed tiles of R
 // ---- records (the tiles k_fused_columns sums over); a tile whose records all
 // ---- belong to one flow-cell tile is one segment with precomputed sums, any
@@ -553,6 +632,7 @@ extern "C" int sq_pertile_create(sq_ctx *ctx, sq_pertile **out) {
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         CUDA_TRY(cudaMemsetAsync(p->map_keys, 0xFF, (size_t)PT_MAP_CAP * 8, ctx->stream));
         CUDA_TRY(cudaMemsetAsync(&p->st->fail_idx, 0xFF, 16, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(&p->st->qmin, 0xFF, 4, ctx->stream));
     }
     if (rc != SQ_OK) {
         sq_pertile_destroy(p);
@@ -659,65 +739,28 @@ static int pt_accumulate(sq_pertile *p, sq_batch *b, const uint32_t *order, cons
     return SQ_OK;
 }
 
-// Estimated per-(fixed tile of R records, position) error sums from every PT_SAMPLE-th record of
-// the tile, scaled to the tile: the binade hints of the chain only need the prefix sums to within
-// a factor sqrt(2) (k_pt_guess tabulates two binades around the estimate, k_pt_chain verifies
-// every step exactly), so the text is not walked for them.  A thread owns four positions.
-constexpr uint32_t PT_SAMPLE = 8;
-__global__ void __launch_bounds__(PT_TPB)
-k_pt_sample(BatchView bv, uint32_t R, uint32_t n_ftiles, uint32_t CG, const uint8_t *__restrict__ uniform,
-            const double *__restrict__ err_tab, float *__restrict__ approx) {
-    __shared__ float s_errf[256];
-    for (uint32_t i = threadIdx.x; i < 256; i += PT_TPB) s_errf[i] = (i >= 33 && i < 127) ? (float)err_tab[i - 33] : 0.f;
-    __syncthreads();
-    const uint64_t total = (uint64_t)n_ftiles * CG;
-    for (uint64_t w = (uint64_t)blockIdx.x * PT_TPB + threadIdx.x; w < total; w += (uint64_t)gridDim.x * PT_TPB) {
-        const uint32_t t = (uint32_t)(w / CG), cg = (uint32_t)(w - (uint64_t)t * CG), col0 = cg * 4;
-        if (!uniform[t]) continue;
-        const uint32_t r0 = t * R, r1 = min(r0 + R, bv.n);
-        float fa[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t taken = 0;
-        for (uint32_t r = r0 + (PT_SAMPLE / 2 < r1 - r0 ? PT_SAMPLE / 2 : 0); r < r1; r += PT_SAMPLE) {
-            taken++;
-            const uint32_t L = bv.seq_len[r];
-            if (L <= col0) continue;
-            const uint32_t nvalid = min(4u, L - col0);
-            const uint32_t q = load_u32_unaligned(bv.text + bv.qual_off[r] + col0) & (0xFFFFFFFFu >> (8 * (4 - nvalid)));
-            fa[0] += s_errf[q & 0xFF];
-            fa[1] += s_errf[(q >> 8) & 0xFF];
-            fa[2] += s_errf[(q >> 16) & 0xFF];
-            fa[3] += s_errf[q >> 24];
-        }
-        const float scale = taken ? (float)(r1 - r0) / (float)taken : 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; j++) approx[(uint64_t)(col0 + j) * n_ftiles + t] = fa[j] * scale;
-    }
-}
-
 void pt_plan_free(sq_ctx *ctx, PtPlan *pl) {
     void *ptrs[] = {pl->slot, pl->idx, pl->tmpk, pl->tmpv, pl->seg, pl->runs_cnt, pl->seg_off, pl->uniform,
-                    pl->segs, pl->nseg, pl->incr, pl->incr_hi, pl->kguess, pl->approx};
+                    pl->oob, pl->segs, pl->nseg, pl->qh};
     for (void *q : ptrs) sq_dfree(ctx, q);
     *pl = PtPlan();
 }
 
 // Reads that arrive in tile runs (every real Illumina file): no sort and no extra pass over the
 // text.  Fixed tiles of R records (the tiles k_fused_columns walks) whose records belong to one
-// flow-cell tile are the segments; their binade hints come from sampled sums (k_pt_sample) and
-// k_fused_columns produces the exact in-binade integer sums for both hinted binades.
+// flow-cell tile are the segments; k_fused_columns leaves a quality histogram per (tile, position)
+// and k_pt_chain_hist turns it into the exact in-binade integer sum for the binade the chain is in.
 static int pt_prepare_runs(sq_pertile *p, sq_batch *b, PtPlan *pl, uint32_t seg_cap) {
     sq_ctx *ctx = p->ctx;
-    const uint32_t n = (uint32_t)b->n, n_ftiles = pl->n_ftiles, W = pl->W, n_slots = pl->n_slots, R = pl->R;
+    const uint32_t n = (uint32_t)b->n, n_ftiles = pl->n_ftiles, n_slots = pl->n_slots, R = pl->R;
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->runs_cnt, (size_t)n_ftiles * 4, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->seg_off, (size_t)n_ftiles * 4, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->uniform, n_ftiles, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->oob, n_ftiles, true));
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->segs, (size_t)seg_cap * sizeof(PtSeg), false));
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->seg, (size_t)n_slots * 8, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->nseg, (size_t)n_slots * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&pl->incr, (size_t)n_ftiles * W * 8, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&pl->incr_hi, (size_t)n_ftiles * W * 8, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&pl->kguess, (size_t)n_ftiles * W * 2, true));
-    SQ_TRY(sq_dalloc(ctx, (void **)&pl->approx, (size_t)n_ftiles * W * 4, false));
+    SQ_TRY(sq_dalloc(ctx, (void **)&pl->qh, (size_t)n_ftiles * pl->hg.seg_bytes, false));
     uint32_t *seg_lo = pl->seg, *seg_hi = pl->seg + n_slots;
     CUDA_TRY(cudaMemsetAsync(seg_lo, 0xFF, (size_t)n_slots * 4, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(seg_hi, 0, (size_t)n_slots * 4, ctx->stream));
@@ -728,12 +771,23 @@ static int pt_prepare_runs(sq_pertile *p, sq_batch *b, PtPlan *pl, uint32_t seg_
               seg_lo, seg_hi);
     SQ_LAUNCH(ctx, k_pt_seg_counts, sq_grid_for(ctx, n_slots, PT_TPB, 8), PT_TPB, 0, seg_lo, seg_hi, n_slots, 1u,
               pl->nseg);
-    const BatchView bv = b->view();
-    SQ_LAUNCH(ctx, k_pt_sample, sq_grid_for(ctx, (uint64_t)n_ftiles * (W / 4), PT_TPB, 16), PT_TPB, 0, bv, R, n_ftiles,
-              W / 4, pl->uniform, ctx->d_err_table, pl->approx);
-    const int chain_grid = sq_grid_for(ctx, (uint64_t)n_slots * pl->width * 32, PT_TPB, 32);
-    SQ_LAUNCH(ctx, k_pt_guess, chain_grid, PT_TPB, 0, bv, (const uint32_t *)nullptr, pl->segs, seg_lo, pl->nseg, n_slots,
-              pl->width, n_ftiles, pl->approx, p->errors, p->len_cap, ctx->d_err_table, pl->kguess, 1);
+    return SQ_OK;
+}
+
+// Quality byte range sampled by k_fused_reads over the arrays seen so far (this one included: the
+// kernel is already queued).  Known from the second array on without a sync: a stale range only
+// sends the odd read through k_fused_columns' slow path.
+int pt_quality_range(sq_pertile *p, uint32_t *qmin, uint32_t *qmax) {
+    sq_ctx *ctx = p->ctx;
+    if (p->qmin == 0xFFFFFFFFu) {
+        PtState *h = (PtState *)((char *)ctx->h_scratch + 3400);
+        CUDA_TRY(cudaMemcpyAsync(h, p->st, sizeof(PtState), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        p->qmin = h->qmin;
+        p->qmax = h->qmax;
+    }
+    *qmin = p->qmin;
+    *qmax = p->qmax;
     return SQ_OK;
 }
 
@@ -750,7 +804,7 @@ extern "C" int sq_pertile_add(sq_pertile *p, sq_batch *b) {
     SQ_TRY(sq_dalloc(ctx, (void **)&tile, (size_t)n * 8, false));
     SQ_LAUNCH(ctx, k_pt_tile, sq_grid_for(ctx, n, PT_TPB, 16), PT_TPB, 0, b->view(), tile, p->n_added, p->st);
     PtPlan pl;
-    int rc = pt_prepare(p, b, tile, 0, 0, 0, &pl);
+    int rc = pt_prepare(p, b, tile, 0, 0, 0, PtHistGeom(), &pl);
     if (rc == SQ_OK) rc = pt_finish(p, b, &pl);
     else pt_plan_free(ctx, &pl);
     sq_dfree(ctx, tile);
@@ -759,7 +813,8 @@ extern "C" int sq_pertile_add(sq_pertile *p, sq_batch *b) {
 
 // Tile ids -> slots, table growth, length counts; for reads in tile runs (R != 0: the caller
 // will run k_fused_columns over fixed tiles of R records) also the segments and their hints.
-int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t n_ftiles, uint32_t W, PtPlan *pl) {
+int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t n_ftiles, uint32_t W,
+               const PtHistGeom &hg, PtPlan *pl) {
     sq_ctx *ctx = p->ctx;
     const uint32_t n = (uint32_t)b->n;
     const uint64_t base = p->n_added;
@@ -768,6 +823,7 @@ int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t
     pl->R = R;
     pl->n_ftiles = n_ftiles;
     pl->W = W;
+    pl->hg = hg;
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->slot, (size_t)n * 4, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->idx, (size_t)n * 4, false));
     SQ_TRY(pt_grow(p, p->n_slots ? p->n_slots : 1, b->max_len ? b->max_len : 1));
@@ -803,6 +859,10 @@ int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t
     if (rc == SQ_OK) rc = pt_grow(p, h->n_slots ? h->n_slots : 1, h->max_len ? h->max_len : 1);
     p->n_slots = h->n_slots;
     p->max_len = h->max_len;
+    if (h->qmin <= h->qmax) {
+        p->qmin = h->qmin;
+        p->qmax = h->qmax;
+    }
     pl->n_slots = h->n_slots;
     pl->width = (uint32_t)b->max_len;
     pl->fail_idx = h->fail_idx;
@@ -811,7 +871,7 @@ int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t
         SQ_LAUNCH(ctx, k_pt_lengths, grid, PT_TPB, 0, b->view(), pl->slot, p->lengths, p->len_cap);
         // reads in tile runs: at most one extra segment per change of tile
         const uint64_t seg_cap = (uint64_t)n_ftiles + h->n_changes + 2;
-        if (R && b->max_len && seg_cap <= n / 16 + 64) {
+        if (R && hg.qrows && b->max_len && seg_cap <= n / 16 + 64) {
             pl->runs = true;
             rc = pt_prepare_runs(p, b, pl, (uint32_t)seg_cap);
         }
@@ -828,10 +888,11 @@ int pt_finish(sq_pertile *p, sq_batch *b, PtPlan *pl) {
     const int grid = sq_grid_for(ctx, n, PT_TPB, 16);
     int rc = SQ_OK;
     if (pl->work && pl->runs) {
-        const int chain_grid = sq_grid_for(ctx, (uint64_t)pl->n_slots * pl->width * 32, PT_TPB, 32);
-        SQ_LAUNCH(ctx, k_pt_chain, chain_grid, PT_TPB, 0, b->view(), (const uint32_t *)nullptr, pl->segs, pl->seg,
-                  pl->nseg, pl->n_slots, pl->width, pl->n_ftiles, pl->kguess, pl->incr, pl->incr_hi, p->errors,
-                  p->len_cap, ctx->d_err_table);
+        const int chain_grid = sq_grid_for(ctx, (uint64_t)pl->n_slots * pl->width * 32, PT_TPB, 5);
+        const size_t lut_smem = (size_t)PT_LUT_NK * 96 * 8;
+        CUDA_TRY(cudaFuncSetAttribute(k_pt_chain_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_smem));
+        SQ_LAUNCH(ctx, k_pt_chain_hist, chain_grid, PT_TPB, lut_smem, b->view(), pl->segs, pl->seg, pl->nseg,
+                  pl->n_slots, pl->width, pl->qh, pl->hg, pl->oob, p->lut, p->errors, p->len_cap, ctx->d_err_table);
     }
     else if (pl->work) {
         uint32_t key_bits = 1;

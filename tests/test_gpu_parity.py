@@ -319,6 +319,33 @@ def test_pertile_long_chains(sq, qlo, qhi, bufsize):
     _pertile_case(sq, _tile_fastq(120_000, 24, 3, qlo, qhi, seed=qlo * 100 + qhi), bufsize)
 
 
+def _outlier_fastq(n, length, seed, n_out):
+    """Qualities 30..37 everywhere except n_out single bases with phred 0 / 93 / 12 / 60: values the
+    range sample of k_fused_reads will mostly miss (slow path of k_fused_columns, tiles replayed)."""
+    rng = np.random.default_rng(seed)
+    tiles = synth.novaseq_tiles()[:4]
+    t = np.sort(rng.integers(0, 4, size=n))
+    qual = (rng.integers(30, 38, size=(n, length)) + 33).astype(np.uint8)
+    for k in range(n_out):
+        qual[int(rng.integers(0, n)), int(rng.integers(0, length))] = 33 + (0, 93, 12, 60)[k % 4]
+    seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=(n, length))]
+    out = io.BytesIO()
+    for i in range(n):
+        out.write(b"@SIM:1:FCX:1:%d:%d:%d 1:N:0:ATCACG\n" % (tiles[t[i]], i, i))
+        out.write(seq[i].tobytes() + b"\n+\n" + qual[i].tobytes() + b"\n")
+    return out.getvalue()
+
+
+@pytest.mark.parametrize("bufsize", [1 << 27, 2_000_000])
+@pytest.mark.parametrize("n_out", [1, 40])
+def test_quality_outliers_beside_sampled_range(sq, n_out, bufsize):
+    text = _outlier_fastq(40_000, 75, seed=n_out, n_out=n_out)
+    got = H.api_single_end(sq, text, H.ILLUMINA_ADAPTERS, buffersize=bufsize)
+    want = H.oracle_single_end(text, H.ILLUMINA_ADAPTERS)
+    H.assert_same(got, want)
+    _pertile_case(sq, text, bufsize)  # PerTileQuality alone (no QCMetrics on the array)
+
+
 def test_pertile_random_tiles_variable_length(sq):
     _pertile_case(sq, _tile_fastq(60_000, 37, 11, 2, 41, seed=7, runs=False, variable=True), 1_000_000)
 
