@@ -958,10 +958,15 @@ class DedupEstimator(_Collector):
 
     def duplication_counts(self):
         info = self._sync()
-        out = np.zeros(info.tracked_sequences, "<u8")
+        # the counts land straight in the array the caller gets (no numpy detour: this getter
+        # returns ~10^6 entries and its host time is part of every run)
+        out = array.array("Q", bytes(8 * info.tracked_sequences))
         n = _C.c_uint64()
-        check(self._ctx.lib.sq_dedup_read(self._h, _void(out), _C.byref(n)), "sq_dedup_read")
-        return _u64_array(out[:n.value])
+        check(self._ctx.lib.sq_dedup_read(self._h, _C.c_void_p(out.buffer_info()[0]), _C.byref(n)),
+              "sq_dedup_read")
+        if n.value < len(out):
+            del out[n.value:]
+        return out
 
 
 class NanoporeReadInfo:

@@ -46,6 +46,10 @@ struct sq_ctx {
     double *d_phred_thresholds = nullptr;  // [94] bucket edges derived from host log10
     void *parse_masks = nullptr;        // newline bit masks of the record array being parsed (grow-only)
     size_t parse_masks_cap = 0;
+    void *parse_fields = nullptr;       // one-pass parser: descriptor fields before the record count is known
+    size_t parse_fields_cap = 0;
+    void *parse_status = nullptr;       // one-pass parser: look-back status words + ticket counter
+    size_t parse_status_cap = 0;
     // staging ring of the host reader (sq_fastq_stream), kept between readers
     void *stage_slot[3] = {nullptr, nullptr, nullptr};
     size_t stage_cap = 0;

@@ -123,6 +123,8 @@ extern "C" void sq_ctx_destroy(sq_ctx *ctx) {
     cudaFree(ctx->d_phred_thresholds);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->parse_masks);
+    cudaFree(ctx->parse_fields);
+    cudaFree(ctx->parse_status);
     for (int k = 0; k < 3; k++) cudaFree(ctx->stage_slot[k]);
     cudaFreeHost(ctx->h_scratch);
     cudaStreamDestroy(ctx->stream);
@@ -380,19 +382,182 @@ k_scatter_fields(const uint8_t *__restrict__ text, uint64_t nbytes, const uint16
     }
 }
 
+// ---------------------------------------------------------------------------
+// One-pass variant: count, rank and scatter in a single walk over the text.
+// A CTA takes the next 16 KiB tile (ticket from an atomic counter, so every
+// predecessor is already running), counts its newlines, publishes the count and
+// finds its global rank offset by decoupled look-back over the predecessors'
+// published counts (status word = flag << 62 | value; flag 1: tile count, flag 2:
+// inclusive prefix).  Newline positions are then compacted per warp so that the
+// lanes turn consecutive ranks into descriptor fields: four consecutive ranks are
+// the four fields of one record, and a warp's stores fall into full sectors of the
+// four arrays.  The '+' / '@' probes read bytes this CTA has just pulled through
+// L1.  Fields go to a scratch of `cap` slots per array (the number of records is
+// not known yet); k_finish_records moves them into the record array's own block.
+// ---------------------------------------------------------------------------
+constexpr int OP_ROUND = 128;  // compacted newline positions per warp and round
+constexpr unsigned long long OP_FLAG_COUNT = 1ULL << 62, OP_FLAG_PREFIX = 2ULL << 62, OP_VALUE = (1ULL << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// bits 7/15/23/31 of m -> bits 28..31 of the product (every partial product lands on its own bit)
+__device__ __forceinline__ uint32_t msb_nibble(uint32_t m) { return (m * 0x00204081u) >> 28; }
+
+constexpr int OP_SUB = 4;                                  // 16 KiB sub-tiles per ticket: fewer, longer tiles keep
+constexpr int OP_TILE_BYTES = OP_SUB * PARSE_CTA_BYTES;    // the look-back short (64 KiB per CTA)
+constexpr int OP_WARPS = PARSE_THREADS / 32;
+static_assert(OP_SUB * OP_WARPS == 32, "one warp scans the per-(sub-tile, warp) counts");
+
+__global__ void __launch_bounds__(PARSE_THREADS)
+k_parse_onepass(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t n_tiles, uint64_t max_records,
+                uint32_t cap, unsigned long long *status, unsigned int *ticket,
+                uint32_t *__restrict__ fields /* [4][cap]: seq_off, seq_end, qual_off, name_off */, ParseState *st) {
+    __shared__ __align__(8) uint16_t s_nl[OP_TILE_BYTES / 16];
+    __shared__ uint16_t s_pos[OP_WARPS][OP_ROUND];
+    __shared__ uint32_t part_tot[OP_SUB * OP_WARPS], part_excl[OP_SUB * OP_WARPS];  // [sub-tile][warp]
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile, warp = threadIdx.x >> 5, lane = lane_id();
+    const uint64_t cta_base = (uint64_t)tile * OP_TILE_BYTES;
+#pragma unroll
+    for (int sub = 0; sub < OP_SUB; sub++) {
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int it = 0; it < PARSE_ITERS; it++) {
+            const uint32_t vi = sub * (PARSE_CTA_BYTES / 16) + warp * (PARSE_WARP_BYTES / 16) + it * 32 + lane;
+            const uint64_t off = cta_base + (uint64_t)vi * 16;
+            uint32_t bits = 0;
+            if (off < nbytes) {
+                const uint4 v = load_vec16(text, nbytes, off >> 4);
+                bits = msb_nibble(newline_mask(v.x)) | msb_nibble(newline_mask(v.y)) << 4 |
+                       msb_nibble(newline_mask(v.z)) << 8 | msb_nibble(newline_mask(v.w)) << 12;
+                if ((v.x | v.y | v.z | v.w) & 0x80808080u) {  // rare: first byte >= 0x80 (reference :1056-1061)
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    for (int j = 0; j < 16; j++)
+                        if ((w[j >> 2] >> (8 * (j & 3))) & 0x80u) {
+                            atomicMin(&st->first_non_ascii, (unsigned long long)(off + j));
+                            break;
+                        }
+                }
+            }
+            s_nl[vi] = (uint16_t)bits;
+            cnt += __popc(bits);
+        }
+        cnt = warp_sum_u32(cnt);
+        if (lane == 0) part_tot[sub * OP_WARPS + warp] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t total;
+        const uint32_t ex = warp_excl_scan_u32(part_tot[lane], &total);
+        part_excl[lane] = ex;
+        if (lane == 0) st_status(status + tile, (tile == 0 ? OP_FLAG_PREFIX : OP_FLAG_COUNT) | total);
+        unsigned long long excl = 0;
+        if (tile > 0) {
+            long long j = (long long)tile - 1 - lane;
+            while (true) {
+                unsigned long long v = j >= 0 ? ld_status(status + j) : OP_FLAG_PREFIX;
+                while (__any_sync(0xffffffffu, (v >> 62) == 0)) {
+                    if ((v >> 62) == 0) v = ld_status(status + j);
+                }
+                const uint32_t pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                const uint32_t first = pm ? (uint32_t)__ffs(pm) - 1 : 31u;  // nearest predecessor with a prefix
+                unsigned long long add = lane <= first ? (v & OP_VALUE) : 0ULL;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+                excl += add;
+                if (pm) break;
+                j -= 32;
+            }
+            if (lane == 0) st_status(status + tile, OP_FLAG_PREFIX | (excl + total));
+        }
+        if (lane == 0) {
+            s_prefix = excl;
+            if (tile == n_tiles - 1) st->n_newlines = excl + total;
+            if (tile == 0) fields[3 * (size_t)cap] = 1;  // name_off[0]: the first record starts at byte 0
+        }
+    }
+    __syncthreads();
+    const uint64_t prefix = s_prefix;
+    for (int sub = 0; sub < OP_SUB; sub++) {
+        const uint32_t wsum = part_tot[sub * OP_WARPS + warp];
+        if (wsum == 0) continue;
+        const uint64_t warp_base = cta_base + (uint64_t)sub * PARSE_CTA_BYTES + (uint64_t)warp * PARSE_WARP_BYTES;
+        const uint64_t kbase = prefix + part_excl[sub * OP_WARPS + warp];
+        // this lane's 64 consecutive bytes
+        uint64_t mask = *(const uint64_t *)(s_nl + sub * (PARSE_CTA_BYTES / 16) + warp * (PARSE_WARP_BYTES / 16) + lane * 4);
+        uint32_t unused;
+        uint32_t myrank = warp_excl_scan_u32(__popcll(mask), &unused);  // warp-local rank of this lane's next newline
+        for (uint32_t base = 0; base < wsum; base += OP_ROUND) {
+            while (mask && myrank < base + OP_ROUND) {
+                s_pos[warp][myrank - base] = (uint16_t)(lane * 64 + (uint32_t)(__ffsll((long long)mask) - 1));
+                mask &= mask - 1;
+                myrank++;
+            }
+            __syncwarp();
+            const uint32_t n_here = min((uint32_t)OP_ROUND, wsum - base);
+            for (uint32_t i = lane; i < n_here; i += 32) {
+                const uint64_t p = warp_base + s_pos[warp][i];
+                const uint64_t k = kbase + base + i;
+                const uint64_t rec = k >> 2;
+                const uint32_t line = (uint32_t)k & 3;
+                if (rec >= max_records) continue;
+                const uint32_t l3 = line == 3, l1 = line == 1;
+                const uint64_t slot = rec + l3;
+                if (slot < cap) fields[(size_t)line * cap + slot] = (uint32_t)p + 1 + l3 - l1;
+                if (line & 1) {
+                    // line 1: the byte behind the sequence's newline must be '+' (:1119-1127)
+                    // line 3: the record that starts behind this newline must start with '@' (:1097):
+                    //         complete, or the partial tail when it has at least 3 bytes
+                    const bool look = l1 ? p + 1 < nbytes : (rec + 1 < max_records && p + 3 < nbytes);
+                    if (look && __ldg(text + p + 1) != (l1 ? '+' : '@'))
+                        atomicMin(&st->err_key,
+                                  (unsigned long long)((rec + l3) << 3 | (l1 ? SQ_PARSE_NO_PLUS : SQ_PARSE_NO_AT)));
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // One thread per record: sequence length, the equal-length check (:1140), longest
 // sequence / record.  Thread 0 also looks at the very first byte of the text.
 __global__ void __launch_bounds__(256)
 k_finish_records(const uint8_t *__restrict__ text, uint64_t nbytes, uint64_t n_rec, int check_partial,
-                 const uint32_t *__restrict__ name_off, const uint32_t *__restrict__ seq_off,
-                 uint32_t *__restrict__ seq_len, const uint32_t *__restrict__ qual_off, ParseState *st) {
+                 const uint32_t *s_name_off, const uint32_t *s_seq_off, const uint32_t *s_seq_end,
+                 const uint32_t *s_qual_off,  // where the scatter left the fields (may be the arrays below)
+                 uint32_t *name_off, uint32_t *seq_off, uint32_t *seq_len, uint32_t *qual_off, ParseState *st) {
     uint32_t local_max = 0, local_rec = 0;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec;
+    const bool move = s_name_off != name_off;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n_rec;
          r += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t start = name_off[r] - 1, so = seq_off[r], se = seq_len[r], qo = qual_off[r];
-        const uint32_t e4 = name_off[r + 1] - 2;
+        const uint32_t no = s_name_off[r], so = s_seq_off[r], se = s_seq_end[r], qo = s_qual_off[r];
+        if (r == n_rec) {  // slot n_rec: consumed offset, and what a partial tail left (error wording only)
+            if (move) {
+                name_off[r] = no;
+                seq_off[r] = so;
+                seq_len[r] = se;
+                qual_off[r] = qo;
+            }
+            break;
+        }
+        const uint32_t start = no - 1;
+        const uint32_t e4 = s_name_off[r + 1] - 2;
         const uint32_t L = se - so;
         if (L != e4 - qo) atomicMin(&st->err_key, (unsigned long long)(r << 3 | SQ_PARSE_LEN));
+        if (move) {
+            name_off[r] = no;
+            seq_off[r] = so;
+            qual_off[r] = qo;
+        }
         seq_len[r] = L;
         local_max = max(local_max, L);
         local_rec = max(local_rec, e4 + 1 - start);
@@ -422,13 +587,24 @@ static int alloc_fastq_metas(sq_batch *b, uint64_t n) {
     return SQ_OK;
 }
 
+// grow-only scratch of the context
+static int ensure_scratch(sq_ctx *ctx, void **ptr, size_t *cap, size_t need) {
+    if (need <= *cap) return SQ_OK;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (*ptr) CUDA_TRY(cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    need += need / 8;
+    CUDA_TRY(cudaMalloc(ptr, need));
+    *cap = need;
+    return SQ_OK;
+}
+
 static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_parse_info *info) {
     memset(info, 0, sizeof(*info));
     uint64_t nbytes = b->nbytes;
     if (nbytes == 0) return SQ_OK;
     uint32_t n_cta = (uint32_t)((nbytes + PARSE_CTA_BYTES - 1) / PARSE_CTA_BYTES);
-    uint32_t *cta_counts = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&cta_counts, (size_t)n_cta * 4, false));
     ParseState *st = (ParseState *)ctx->d_scratch;
     ParseState init;
     init.n_newlines = 0;
@@ -438,28 +614,47 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
     init.max_rec_bytes = 0;
     memcpy(ctx->h_scratch, &init, sizeof(init));
     CUDA_TRY(cudaMemcpyAsync(st, ctx->h_scratch, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    // one bit per text byte; a grow-only scratch of the context (a fresh 100+ MB stream-ordered
-    // allocation per record array makes the pool re-map memory every time)
-    const size_t mask_bytes = (size_t)(((nbytes + 15) >> 4) + 4) * 2;
-    if (mask_bytes > ctx->parse_masks_cap) {
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        if (ctx->parse_masks) CUDA_TRY(cudaFree(ctx->parse_masks));
-        ctx->parse_masks = nullptr;
-        ctx->parse_masks_cap = 0;
-        CUDA_TRY(cudaMalloc(&ctx->parse_masks, mask_bytes + mask_bytes / 8));
-        ctx->parse_masks_cap = mask_bytes + mask_bytes / 8;
-    }
-    uint16_t *vec_masks = (uint16_t *)ctx->parse_masks;
-    SQ_LAUNCH(ctx, k_count_newlines, n_cta, PARSE_THREADS, 0, b->text, nbytes, cta_counts, vec_masks, st);
-    // exclusive scan of the per-CTA counts (in place); the total is the number of newlines
-    uint32_t *d_total = (uint32_t *)((char *)ctx->d_scratch + 128);
-    uint32_t *h_total = (uint32_t *)((char *)ctx->h_scratch + 128);
-    SQ_TRY(sq_scan_exclusive_u32(ctx, cta_counts, cta_counts, n_cta, d_total));
     ParseState *hst = (ParseState *)ctx->h_scratch;
-    CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    uint64_t n_newlines = *h_total;
+
+    // ---- one pass: count + rank (decoupled look-back) + scatter into a scratch of `cap` slots ----
+    // (records shorter than 32 bytes on average do not fit the scratch and take the two-pass path)
+    static const bool force_two_pass = getenv("SQ_PARSE_TWO_PASS") != nullptr;
+    const uint32_t cap = (uint32_t)(nbytes / 32 + 1024);
+    uint32_t *fields = nullptr;
+    if (!force_two_pass) {
+        SQ_TRY(ensure_scratch(ctx, &ctx->parse_fields, &ctx->parse_fields_cap, (size_t)cap * 16));
+        SQ_TRY(ensure_scratch(ctx, &ctx->parse_status, &ctx->parse_status_cap, ((size_t)n_cta + 1) * 8));
+        fields = (uint32_t *)ctx->parse_fields;
+        unsigned long long *status = (unsigned long long *)ctx->parse_status;
+        const uint32_t n_op = (uint32_t)((nbytes + OP_TILE_BYTES - 1) / OP_TILE_BYTES);
+        CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)n_op + 1) * 8, ctx->stream));
+        SQ_LAUNCH(ctx, k_parse_onepass, n_op, PARSE_THREADS, 0, b->text, nbytes, n_op, max_records, cap, status,
+                  (unsigned int *)(status + n_op), fields, st);
+        CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    // ---- two passes: count (+ bit masks), device-wide scan of the per-CTA counts, scatter ----------
+    uint32_t *cta_counts = nullptr;
+    uint16_t *vec_masks = nullptr;
+    auto count_pass = [&]() -> int {
+        SQ_TRY(sq_dalloc(ctx, (void **)&cta_counts, (size_t)n_cta * 4, false));
+        // one bit per text byte; a grow-only scratch of the context (a fresh 100+ MB stream-ordered
+        // allocation per record array makes the pool re-map memory every time)
+        SQ_TRY(ensure_scratch(ctx, &ctx->parse_masks, &ctx->parse_masks_cap, (size_t)(((nbytes + 15) >> 4) + 4) * 2));
+        vec_masks = (uint16_t *)ctx->parse_masks;
+        SQ_LAUNCH(ctx, k_count_newlines, n_cta, PARSE_THREADS, 0, b->text, nbytes, cta_counts, vec_masks, st);
+        // exclusive scan of the per-CTA counts (in place); the total is the number of newlines
+        uint32_t *d_total = (uint32_t *)((char *)ctx->d_scratch + 128);
+        uint32_t *h_total = (uint32_t *)((char *)ctx->h_scratch + 128);
+        SQ_TRY(sq_scan_exclusive_u32(ctx, cta_counts, cta_counts, n_cta, d_total));
+        CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        hst->n_newlines = *h_total;
+        return SQ_OK;
+    };
+    if (force_two_pass) SQ_TRY(count_pass());
+    uint64_t n_newlines = hst->n_newlines;
     info->n_newlines = n_newlines;
     if (hst->first_non_ascii != ~0ULL) {  // checked before any record is looked at (:1055)
         info->err_code = SQ_PARSE_ASCII;
@@ -474,17 +669,25 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
         check_partial = 0;
     }
     SQ_TRY(alloc_fastq_metas(b, n_rec));
-    // name_off[0]: the first record starts at byte 0; slot n_rec of the other arrays is only
-    // written when a partial record follows (and only read to word an error message)
-    uint32_t *h_one = (uint32_t *)((char *)ctx->h_scratch + 256);
-    *h_one = 1;
-    CUDA_TRY(cudaMemcpyAsync(b->name_off, h_one, 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (n_newlines)
-        SQ_LAUNCH(ctx, k_scatter_fields, n_cta, PARSE_THREADS, 0, b->text, nbytes, vec_masks, cta_counts, n_rec, check_partial,
-                  b->name_off, b->seq_off, b->seq_len, b->qual_off, st);
     int grid = sq_grid_for(ctx, n_rec + 1, 256);
-    SQ_LAUNCH(ctx, k_finish_records, grid, 256, 0, b->text, nbytes, n_rec, check_partial, b->name_off, b->seq_off,
-              b->seq_len, b->qual_off, st);
+    if (fields && n_rec + 1 <= cap) {
+        SQ_LAUNCH(ctx, k_finish_records, grid, 256, 0, b->text, nbytes, n_rec, check_partial, fields + 3 * (size_t)cap,
+                  fields, fields + (size_t)cap, fields + 2 * (size_t)cap, b->name_off, b->seq_off, b->seq_len,
+                  b->qual_off, st);
+    }
+    else {
+        if (!cta_counts) SQ_TRY(count_pass());
+        // name_off[0]: the first record starts at byte 0; slot n_rec of the other arrays is only
+        // written when a partial record follows (and only read to word an error message)
+        uint32_t *h_one = (uint32_t *)((char *)ctx->h_scratch + 256);
+        *h_one = 1;
+        CUDA_TRY(cudaMemcpyAsync(b->name_off, h_one, 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (n_newlines)
+            SQ_LAUNCH(ctx, k_scatter_fields, n_cta, PARSE_THREADS, 0, b->text, nbytes, vec_masks, cta_counts, n_rec,
+                      check_partial, b->name_off, b->seq_off, b->seq_len, b->qual_off, st);
+        SQ_LAUNCH(ctx, k_finish_records, grid, 256, 0, b->text, nbytes, n_rec, check_partial, b->name_off, b->seq_off,
+                  b->seq_len, b->qual_off, b->name_off, b->seq_off, b->seq_len, b->qual_off, st);
+    }
     // the consumed offset is the byte after the last record's 4th newline = name_off[n_rec] - 1
     uint32_t *h_last = (uint32_t *)((char *)ctx->h_scratch + 260);
     *h_last = 1;

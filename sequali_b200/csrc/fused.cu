@@ -26,7 +26,8 @@
 // module order.
 #include "modules.cuh"
 
-constexpr int FH_TPB = 128;
+constexpr int FH_RECS = 128;          // records per text tile, one per thread of a role
+constexpr int FH_TPB = 2 * FH_RECS;   // two roles (warp specialised): sequence side, quality / header side
 constexpr int FH_BUF = 48 * 1024;     // text tile in shared memory
 constexpr int FH_MAX_ADAPTERS = 64;   // patterns kept in shared memory
 constexpr int FH_MAX_PAT = 32;        // longest adapter the plane matcher shifts by
@@ -101,7 +102,7 @@ __device__ __forceinline__ uint32_t fh_word(const uint8_t *buf, uint32_t off, ui
 }
 
 template <int NW>
-__global__ void __launch_bounds__(FH_TPB)
+__global__ void __launch_bounds__(FH_TPB, NW <= 5 ? 4 : 3)
 k_fused_reads(const FusedArgs A) {
     extern __shared__ __align__(128) uint8_t buf[];  // FH_BUF + 16
     __shared__ __align__(8) uint64_t bar;
@@ -141,7 +142,11 @@ k_fused_reads(const FusedArgs A) {
             mbar_expect_tx(&bar, bytes);
             bulk_g2s(buf, bv.text + gstart, bytes, &bar);
         }
-        const uint32_t r = r0 + tid;
+        // warps 0-3 take the sequence side of a record (planes, GC, adapters), warps 4-7 its quality
+        // string and header (error sum, fingerprint hash, tile id): twice the warps per tile, and
+        // neither half carries the other's registers
+        const uint32_t role = tid / FH_RECS;
+        const uint32_t r = r0 + (tid - role * FH_RECS);
         const bool active = r < r1;
         uint32_t so = 0, qo = 0, no = 0, L = 0, name_len = 0;
         if (active) {
@@ -154,7 +159,7 @@ k_fused_reads(const FusedArgs A) {
         }
         mbar_wait(&bar, parity);
         parity ^= 1;
-        if (active) {
+        if (active && role == 0) {
             // ---- sequence planes ------------------------------------------------------------------
             uint32_t V[NW], H[NW], G[NW];
             if (A.do_qc | A.do_ad) {
@@ -253,6 +258,8 @@ k_fused_reads(const FusedArgs A) {
                     atomic_add_u64(fwd + A.ad_cap_len + (L - 1 - p), 1);
                 }
             }
+        }
+        else if (active) {
             // ---- ordered error sum, mean-phred bucket (:2059-2137) -----------------------------------
             if (A.do_qc) {
                 const uint32_t nit = L >= 5 ? (L - 1) / 4 : 0;
@@ -539,14 +546,24 @@ k_fused_columns(const ColumnArgs A) {
             mbar_wait(&bar, parity);
             parity ^= 1;
             if (worker) {
+                // software pipeline: the words of the next record are on their way while this one is counted
+                uint32_t nL = 0, nraw = 0, nw = 0;
+                if (rg < nrec) {
+                    nL = s_L[rg];
+                    nraw = fh_word(buf, s_qo[rg], cg);
+                    if (A.do_qc) nw = fh_word(buf, s_so[rg], cg);
+                }
                 for (uint32_t i = rg; i < nrec; i += RG) {
-                    const uint32_t L = s_L[i];
+                    const uint32_t L = nL, raw = nraw, w = nw;
+                    if (i + RG < nrec) {
+                        nL = s_L[i + RG];
+                        nraw = fh_word(buf, s_qo[i + RG], cg);
+                        if (A.do_qc) nw = fh_word(buf, s_so[i + RG], cg);
+                    }
                     if (L <= col0) continue;
                     const uint32_t nvalid = min(4u, L - col0);
                     const uint32_t keep = 0xFFFFFFFFu >> (8 * (4 - nvalid));
-                    const uint32_t raw = fh_word(buf, s_qo[i], cg);
                     if (A.do_qc) {
-                        const uint32_t w = fh_word(buf, s_so[i], cg);
                         const uint32_t pm = keep & 0x01010101u;
                         const uint32_t vb = fh_acgt_bytes(w) & pm;
                         const uint32_t hb = (w >> 1) & vb, gb = (w >> 2) & vb;
@@ -579,10 +596,19 @@ k_fused_columns(const ColumnArgs A) {
                                     atomicAdd(hist + (col0 + j) * FC_BINS + 5 + (min(c - 33u, 47u) >> 2), 1u);
                             }
                         }
-                        priv8[(row4 & 0xFF) * (TPB * 4) + 0] += 1;
-                        priv8[((row4 >> 8) & 0xFF) * (TPB * 4) + 1] += 1;
-                        priv8[((row4 >> 16) & 0xFF) * (TPB * 4) + 2] += 1;
-                        priv8[(row4 >> 24) * (TPB * 4) + 3] += 1;
+                        {
+                            // the four counters are different bytes (byte lane j): load all, then store all,
+                            // one shared-memory round trip instead of four in a row
+                            uint8_t *p0 = priv8 + (row4 & 0xFF) * (TPB * 4) + 0;
+                            uint8_t *p1 = priv8 + ((row4 >> 8) & 0xFF) * (TPB * 4) + 1;
+                            uint8_t *p2 = priv8 + ((row4 >> 16) & 0xFF) * (TPB * 4) + 2;
+                            uint8_t *p3 = priv8 + (row4 >> 24) * (TPB * 4) + 3;
+                            const uint32_t c0 = *p0, c1 = *p1, c2 = *p2, c3 = *p3;
+                            *p0 = (uint8_t)(c0 + 1);
+                            *p1 = (uint8_t)(c1 + 1);
+                            *p2 = (uint8_t)(c2 + 1);
+                            *p3 = (uint8_t)(c3 + 1);
+                        }
                         if (A.do_qc && ++rows == 255) spill_bases();
                     }
                     else {
@@ -594,10 +620,17 @@ k_fused_columns(const ColumnArgs A) {
                         const uint32_t sat = (((t4 + 0x50505050u) >> 7) & 0x01010101u) * 0xFFu;
                         uint32_t bin4 = ((t4 & 0x3C3C3C3Cu) & ~sat) | (0x2C2C2C2Cu & sat);
                         bin4 = (bin4 & keep) | (0x30303030u & ~keep);
-                        priv8[(bin4 & 0xFF) * TPB + 0] += 1;
-                        priv8[((bin4 >> 8) & 0xFF) * TPB + 1] += 1;
-                        priv8[((bin4 >> 16) & 0xFF) * TPB + 2] += 1;
-                        priv8[(bin4 >> 24) * TPB + 3] += 1;
+                        {
+                            uint8_t *p0 = priv8 + (bin4 & 0xFF) * TPB + 0;
+                            uint8_t *p1 = priv8 + ((bin4 >> 8) & 0xFF) * TPB + 1;
+                            uint8_t *p2 = priv8 + ((bin4 >> 16) & 0xFF) * TPB + 2;
+                            uint8_t *p3 = priv8 + (bin4 >> 24) * TPB + 3;
+                            const uint32_t c0 = *p0, c1 = *p1, c2 = *p2, c3 = *p3;
+                            *p0 = (uint8_t)(c0 + 1);
+                            *p1 = (uint8_t)(c1 + 1);
+                            *p2 = (uint8_t)(c2 + 1);
+                            *p3 = (uint8_t)(c3 + 1);
+                        }
                         if (++rows == 255) spill();
                     }
                 }
@@ -882,7 +915,7 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     memset(&A, 0, sizeof(A));
     A.bv = b->view();
     uint32_t rpt = (FH_BUF - 32) / b->max_rec_bytes;
-    if (rpt > FH_TPB) rpt = FH_TPB;
+    if (rpt > FH_RECS) rpt = FH_RECS;
     A.recs_per_tile = rpt;
     A.n_tiles = (n + rpt - 1) / rpt;
     A.text_end = b->text_end;

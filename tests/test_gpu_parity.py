@@ -58,6 +58,91 @@ def test_fastq_parse_small_buffers(sq, bufsize):
     assert total == len(recs)
 
 
+def _tiny_records(n, seed):
+    """Records of 0..3 bases: far below 32 bytes each, the one-pass parser's scratch overflows
+    and the two-pass path takes over."""
+    rng = np.random.default_rng(seed)
+    out = bytearray()
+    for i in range(n):
+        L = int(rng.integers(0, 4))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), L))
+        qual = bytes(rng.integers(33, 74, L, dtype=np.uint8))
+        out += b"@" + (b"r%d" % i if i % 3 else b"") + b"\n" + seq + b"\n+\n" + qual + b"\n"
+    return bytes(out)
+
+
+@pytest.mark.parametrize("n", [1, 700, 5000, 60000])
+def test_fastq_parse_tiny_records_both_paths(sq, n):
+    text = _tiny_records(n, n)
+    recs, _ = orc.parse_fastq(text)
+    arrays = list(sq.FastqParser(io.BytesIO(text), 1 << 26))
+    assert sum(len(a) for a in arrays) == n
+    _metas_equal(arrays[0], recs[:len(arrays[0])])
+
+
+def test_fastq_parse_newline_runs(sq):
+    # long runs of empty lines inside otherwise valid records: many newlines per 64-byte window
+    rec = b"@x\n\n+\n\n"
+    text = rec * 40000
+    recs, _ = orc.parse_fastq(text)
+    arr = next(iter(sq.FastqParser(io.BytesIO(text), 1 << 26)))
+    assert len(arr) == 40000
+    _metas_equal(arr, recs)
+
+
+def test_fastq_parse_read_n_clips(sq):
+    text = synth.illumina_fastq(3000, length=150, seed=3, n_tiles=5)
+    recs, _ = orc.parse_fastq(text)
+    parser = sq.FastqParser(io.BytesIO(text), 1 << 26)
+    a = parser.read(1000)
+    b = parser.read(1999)
+    c = parser.read(5)
+    assert (len(a), len(b), len(c)) == (1000, 1999, 1)
+    assert a[999].name() == bytes(text[int(recs[999]["name_off"]):][:int(recs[999]["name_len"])]).decode()
+    assert c[0].sequence() == bytes(text[int(recs[2999]["seq_off"]):][:150]).decode()
+
+
+def _parser_outcome(mod, text, bufsize):
+    """(number of records, None) or (None, (exception type, message))."""
+    try:
+        return sum(len(a) for a in mod.FastqParser(io.BytesIO(text), bufsize)), None
+    except Exception as e:  # noqa: BLE001
+        return None, (type(e), str(e))
+
+
+@pytest.mark.parametrize("where", [0, 1, 777, 2999])
+@pytest.mark.parametrize("kind", ["no_at", "no_plus", "length", "ascii", "partial", "partial_short"])
+def test_fastq_parse_errors_like_reference(sq, kind, where):
+    """Every parser error of the reference (_qcmodule.c:1055-1143), at the first, an inner and the
+    last record of a multi-CTA text; message and exception type equal to the reference's."""
+    ref = H.import_reference()
+    text = bytearray(synth.illumina_fastq(3000, length=150, seed=11, n_tiles=5))
+    recs, _ = orc.parse_fastq(bytes(text))
+    r = recs[where]
+    start = int(r["name_off"]) - 1
+    if kind == "no_at":
+        text[start] = ord("A")
+    elif kind == "no_plus":
+        text[int(r["seq_off"]) + 151] = ord("-")
+    elif kind == "length":
+        del text[int(r["qual_off"]) + 10]
+    elif kind == "ascii":
+        text[int(r["seq_off"]) + 3] = 0xC3
+    elif kind == "partial":
+        del text[len(text) - 40:]
+    else:
+        del text[int(recs[2999]["name_off"]) + 1:]  # "@x": a tail too short to be looked at
+    text = bytes(text)
+    got = _parser_outcome(sq, text, 1 << 26)
+    if ref is not None:
+        want = _parser_outcome(ref, text, 1 << 26)
+        assert got == want
+    else:
+        pat = dict(no_at="does not start with @", no_plus="start with +", length="equal length",
+                   ascii="ASCII", partial="ncomplete record", partial_short="ncomplete record")[kind]
+        assert got[0] is None and pat in got[1][1]
+
+
 def _qc_case(sq, text, bufsize=1 << 26, chunk=None):
     recs, _ = orc.parse_fastq(text)
     oq = orc.QCMetrics()
