@@ -427,32 +427,55 @@ k_parse_onepass(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t n_ti
     __syncthreads();
     const uint32_t tile = s_tile, warp = threadIdx.x >> 5, lane = lane_id();
     const uint64_t cta_base = (uint64_t)tile * OP_TILE_BYTES;
+    const bool full_tile = cta_base + OP_TILE_BYTES <= nbytes;  // no bounds checks, loads issued back to back
 #pragma unroll
     for (int sub = 0; sub < OP_SUB; sub++) {
         uint32_t cnt = 0;
+        const uint32_t v0 = sub * (PARSE_CTA_BYTES / 16) + warp * (PARSE_WARP_BYTES / 16) + lane;
+        uint4 v[PARSE_ITERS];
+        if (full_tile) {
+#pragma unroll
+            for (int it = 0; it < PARSE_ITERS; it++)
+                v[it] = __ldg((const uint4 *)(text + cta_base) + v0 + it * 32);
+        }
+        else {
+#pragma unroll
+            for (int it = 0; it < PARSE_ITERS; it++) {
+                const uint64_t off = cta_base + (uint64_t)(v0 + it * 32) * 16;
+                v[it] = off < nbytes ? load_vec16(text, nbytes, off >> 4) : make_uint4(0, 0, 0, 0);
+            }
+        }
 #pragma unroll
         for (int it = 0; it < PARSE_ITERS; it++) {
-            const uint32_t vi = sub * (PARSE_CTA_BYTES / 16) + warp * (PARSE_WARP_BYTES / 16) + it * 32 + lane;
-            const uint64_t off = cta_base + (uint64_t)vi * 16;
-            uint32_t bits = 0;
-            if (off < nbytes) {
-                const uint4 v = load_vec16(text, nbytes, off >> 4);
-                bits = msb_nibble(newline_mask(v.x)) | msb_nibble(newline_mask(v.y)) << 4 |
-                       msb_nibble(newline_mask(v.z)) << 8 | msb_nibble(newline_mask(v.w)) << 12;
-                if ((v.x | v.y | v.z | v.w) & 0x80808080u) {  // rare: first byte >= 0x80 (reference :1056-1061)
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                    for (int j = 0; j < 16; j++)
-                        if ((w[j >> 2] >> (8 * (j & 3))) & 0x80u) {
-                            atomicMin(&st->first_non_ascii, (unsigned long long)(off + j));
-                            break;
-                        }
-                }
+            const uint32_t vi = v0 + it * 32;
+            const uint32_t bits = msb_nibble(newline_mask(v[it].x)) | msb_nibble(newline_mask(v[it].y)) << 4 |
+                                  msb_nibble(newline_mask(v[it].z)) << 8 | msb_nibble(newline_mask(v[it].w)) << 12;
+            if ((v[it].x | v[it].y | v[it].z | v[it].w) & 0x80808080u) {  // rare: first byte >= 0x80 (:1056-1061)
+                const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+                for (int j = 0; j < 16; j++)
+                    if ((w[j >> 2] >> (8 * (j & 3))) & 0x80u) {
+                        atomicMin(&st->first_non_ascii, (unsigned long long)(cta_base + (uint64_t)vi * 16 + j));
+                        break;
+                    }
             }
             s_nl[vi] = (uint16_t)bits;
             cnt += __popc(bits);
         }
         cnt = warp_sum_u32(cnt);
         if (lane == 0) part_tot[sub * OP_WARPS + warp] = cnt;
+    }
+    // before the prefix is known: this lane's 64 consecutive bytes per sub-tile and its rank inside the warp
+    // (the warp wrote these masks itself)
+    __syncwarp();
+    uint64_t lmask[OP_SUB];
+    uint32_t lrank[OP_SUB];
+    if (warp != 0) {
+#pragma unroll
+        for (int sub = 0; sub < OP_SUB; sub++) {
+            uint32_t unused;
+            lmask[sub] = *(const uint64_t *)(s_nl + sub * (PARSE_CTA_BYTES / 16) + warp * (PARSE_WARP_BYTES / 16) + lane * 4);
+            lrank[sub] = warp_excl_scan_u32(__popcll(lmask[sub]), &unused);
+        }
     }
     __syncthreads();
     if (warp == 0) {
@@ -484,18 +507,23 @@ k_parse_onepass(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t n_ti
             if (tile == n_tiles - 1) st->n_newlines = excl + total;
             if (tile == 0) fields[3 * (size_t)cap] = 1;  // name_off[0]: the first record starts at byte 0
         }
+#pragma unroll
+        for (int sub = 0; sub < OP_SUB; sub++) {  // warp 0's own share of the preparation, off the look-back's path
+            uint32_t unused;
+            lmask[sub] = *(const uint64_t *)(s_nl + sub * (PARSE_CTA_BYTES / 16) + lane * 4);
+            lrank[sub] = warp_excl_scan_u32(__popcll(lmask[sub]), &unused);
+        }
     }
     __syncthreads();
     const uint64_t prefix = s_prefix;
+#pragma unroll
     for (int sub = 0; sub < OP_SUB; sub++) {
         const uint32_t wsum = part_tot[sub * OP_WARPS + warp];
         if (wsum == 0) continue;
         const uint64_t warp_base = cta_base + (uint64_t)sub * PARSE_CTA_BYTES + (uint64_t)warp * PARSE_WARP_BYTES;
         const uint64_t kbase = prefix + part_excl[sub * OP_WARPS + warp];
-        // this lane's 64 consecutive bytes
-        uint64_t mask = *(const uint64_t *)(s_nl + sub * (PARSE_CTA_BYTES / 16) + warp * (PARSE_WARP_BYTES / 16) + lane * 4);
-        uint32_t unused;
-        uint32_t myrank = warp_excl_scan_u32(__popcll(mask), &unused);  // warp-local rank of this lane's next newline
+        uint64_t mask = lmask[sub];
+        uint32_t myrank = lrank[sub];  // warp-local rank of this lane's next newline
         for (uint32_t base = 0; base < wsum; base += OP_ROUND) {
             while (mask && myrank < base + OP_ROUND) {
                 s_pos[warp][myrank - base] = (uint16_t)(lane * 64 + (uint32_t)(__ffsll((long long)mask) - 1));
