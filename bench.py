@@ -468,6 +468,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly one JSON line: anything a native library writes to fd 1 meanwhile
+    # (NCCL prints its version there when NCCL_DEBUG is set) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:

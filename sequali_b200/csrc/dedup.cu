@@ -343,6 +343,20 @@ extern "C" void sq_dedup_destroy(sq_dedup *d) {
     delete d;
 }
 
+__global__ void __launch_bounds__(DD_TPB)
+k_dd_pass_flags(const uint64_t *__restrict__ hashes, uint32_t n, uint64_t mask, uint32_t *__restrict__ flag) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        flag[i] = (hashes[i] & mask) == 0;
+}
+__global__ void __launch_bounds__(DD_TPB)
+k_dd_pass_scatter(const uint64_t *__restrict__ hashes, const uint32_t *__restrict__ flag,
+                  const uint32_t *__restrict__ rank, uint32_t n, uint64_t *__restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (flag[i]) out[rank[i]] = hashes[i];
+}
+
+static int dedup_consume_range(sq_dedup *d, const uint64_t *hashes, uint32_t n);
+
 // Process hashes[0..n) in record order.
 int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n) {
     sq_ctx *ctx = d->ctx;
@@ -351,6 +365,36 @@ int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n) {
         d->n_records += n;
         return SQ_OK;
     }
+    // A hash that fails the mask of m bits fails every later mask (:4429-4431 tests the low bits and m
+    // only grows), so once m > 0 only n / 2^m hashes can touch the table: keep those, in record order,
+    // and run the table kernels over the short list (their order-dependent steps only compare positions).
+    int rc;
+    if (d->mod_bits >= 2 && n >= 4096) {
+        uint32_t *flag = nullptr, *rank = nullptr;
+        uint64_t *kept = nullptr;
+        SQ_TRY(sq_dalloc(ctx, (void **)&flag, (size_t)n * 4, false));
+        SQ_TRY(sq_dalloc(ctx, (void **)&rank, (size_t)n * 4 + 4, false));
+        const int grid = sq_grid_for(ctx, n, DD_TPB, 16);
+        SQ_LAUNCH(ctx, k_dd_pass_flags, grid, DD_TPB, 0, hashes, n, (1ULL << d->mod_bits) - 1, flag);
+        SQ_TRY(sq_scan_exclusive_u32(ctx, flag, rank, n, rank + n));
+        uint32_t *h_total = (uint32_t *)((char *)ctx->h_scratch + 3088);
+        CUDA_TRY(cudaMemcpyAsync(h_total, rank + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        const uint32_t n_kept = *h_total;
+        SQ_TRY(sq_dalloc(ctx, (void **)&kept, ((size_t)n_kept + 1) * 8, false));
+        SQ_LAUNCH(ctx, k_dd_pass_scatter, grid, DD_TPB, 0, hashes, flag, rank, n, kept);
+        rc = n_kept ? dedup_consume_range(d, kept, n_kept) : SQ_OK;
+        sq_dfree(ctx, flag);
+        sq_dfree(ctx, rank);
+        sq_dfree(ctx, kept);
+    }
+    else rc = dedup_consume_range(d, hashes, n);
+    d->n_records += n;
+    return rc;
+}
+
+static int dedup_consume_range(sq_dedup *d, const uint64_t *hashes, uint32_t n) {
+    sq_ctx *ctx = d->ctx;
     const uint64_t tmask = d->table_size - 1;
     const uint64_t prio_base = d->table_size + 1 + d->n_records;  // above every rebuild priority
     uint32_t *cls = nullptr, *flag = nullptr, *rank = nullptr;
@@ -438,7 +482,6 @@ int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n) {
     sq_dfree(ctx, S.key);
     sq_dfree(ctx, S.first);
     sq_dfree(ctx, S.cnt);
-    d->n_records += n;
     return rc;
 }
 
@@ -561,18 +604,6 @@ extern "C" int sq_dedup_read(sq_dedup *d, uint64_t *counts, uint64_t *n) {
 // drop everything that fails mask(m0) and hand over the rest in record order:
 // about n / 2^m0 hashes per rank.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(DD_TPB)
-k_dd_pass_flags(const uint64_t *__restrict__ hashes, uint32_t n, uint64_t mask, uint32_t *__restrict__ flag) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        flag[i] = (hashes[i] & mask) == 0;
-}
-__global__ void __launch_bounds__(DD_TPB)
-k_dd_pass_scatter(const uint64_t *__restrict__ hashes, const uint32_t *__restrict__ flag,
-                  const uint32_t *__restrict__ rank, uint32_t n, uint64_t *__restrict__ out) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        if (flag[i]) out[rank[i]] = hashes[i];
-}
-
 extern "C" int sq_dedup_set_deferred(sq_dedup *d, int deferred) {
     if (d->n_records != 0 && (deferred != 0) != d->deferred) {
         sq_set_error("deferred mode must be chosen before the first record array");

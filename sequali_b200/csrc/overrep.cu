@@ -46,19 +46,35 @@ struct sq_overrep {
     std::vector<Kept> kept;
 };
 
-// canonical k-mer of s[0..k): 0 ok, 1 holds N/n, 2 holds another non-ACGT letter (:3612-3694)
+// canonical k-mer of s[0..k): 0 ok, 1 holds N/n, 2 holds another non-ACGT letter (:3612-3694).
+// The k <= 31 letters come in with aligned word loads issued together (the text has 64 readable
+// bytes of padding), not one dependent byte load per letter.
 __device__ __forceinline__ int canonical_kmer(const uint8_t *s, uint32_t k, uint64_t *out) {
+    const uint32_t *wp = (const uint32_t *)((uintptr_t)s & ~(uintptr_t)3);
+    const uint32_t sh = ((uint32_t)(uintptr_t)s & 3u) * 8;
+    const uint32_t nw = (k + 3) / 4;  // words after alignment; one more is read for the shift
+    uint32_t W[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) W[j] = (uint32_t)j <= nw ? __ldg(wp + j) : 0u;
     uint64_t fw = 0, rc = 0;
     uint32_t flags = 0;
-    for (uint32_t i = 0; i < k; i++) {
-        uint32_t ch = s[i] | 0x20u;
-        uint32_t c = ch == 'a' ? 0u : ch == 'c' ? 1u : ch == 'g' ? 2u : ch == 't' ? 3u : 4u;
-        if (c == 4) {
-            flags |= ch == 'n' ? 1u : 2u;
-            c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t a = __funnelshift_r(W[j], W[j + 1], sh);
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t i = j * 4 + b;
+            if (i < k) {
+                const uint32_t ch = ((a >> (8 * b)) & 0xFFu) | 0x20u;
+                uint32_t c = ch == 'a' ? 0u : ch == 'c' ? 1u : ch == 'g' ? 2u : ch == 't' ? 3u : 4u;
+                if (c == 4) {
+                    flags |= ch == 'n' ? 1u : 2u;
+                    c = 0;
+                }
+                fw = (fw << 2) | c;
+                rc |= (uint64_t)(3 - c) << (2 * i);
+            }
         }
-        fw = (fw << 2) | c;
-        rc |= (uint64_t)(3 - c) << (2 * i);
     }
     if (flags & 2) return 2;
     if (flags & 1) return 1;
@@ -66,10 +82,41 @@ __device__ __forceinline__ int canonical_kmer(const uint8_t *s, uint32_t k, uint
     return 0;
 }
 
+// per-read staging set of fragment hashes (open addressing, read out in slot order: the order the
+// reference's own staging table is walked in)
+template <typename Stage>
+__device__ __forceinline__ uint32_t ov_stage_read(Stage stage, uint32_t ssize, const uint8_t *seq, uint64_t L, uint32_t k,
+                                                  uint64_t nf, uint64_t nb, uint64_t *__restrict__ out, bool *warn,
+                                                  uint32_t *valid) {
+    const uint32_t total = (uint32_t)(nf + nb);
+    for (uint32_t i = 0; i < ssize; i++) stage(i) = 0;
+    for (uint32_t f = 0; f < total; f++) {
+        const uint64_t off = f < nf ? (uint64_t)f * k : L - (nb - (f - nf)) * k;
+        uint64_t kmer;
+        int rc = canonical_kmer(seq + off, k, &kmer);
+        if (rc) {
+            *warn |= rc == 2;
+            continue;
+        }
+        (*valid)++;
+        const uint64_t h = wang64(kmer);
+        uint32_t i = (uint32_t)h & (ssize - 1);
+        while (stage(i) != 0 && stage(i) != h) i = (i + 1) & (ssize - 1);
+        stage(i) = h;
+    }
+    uint32_t emitted = 0;
+    for (uint32_t i = 0; i < ssize; i++)
+        if (stage(i)) out[emitted++] = stage(i);
+    return emitted;
+}
+
+constexpr int OV_STAGE_SMEM = 16;  // staging sets up to this size live in shared memory (short reads)
+
 __global__ void __launch_bounds__(OV_TPB)
 k_ov_fragments(BatchView bv, uint32_t first_sampled, uint32_t sample_every, uint32_t n_sampled, uint32_t k,
                uint64_t frags_front, uint64_t frags_back, uint32_t fcap, uint64_t *__restrict__ frag_hash,
                uint32_t *__restrict__ frag_n, OvCounters *cnt, uint64_t record_base) {
+    __shared__ uint64_t s_stage[OV_STAGE_SMEM][OV_TPB];
     unsigned long long valid_total = 0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_sampled; s += gridDim.x * blockDim.x) {
         const uint32_t r = first_sampled + s * sample_every;
@@ -83,26 +130,19 @@ k_ov_fragments(BatchView bv, uint32_t first_sampled, uint32_t sample_every, uint
             if (total) {
                 uint32_t ssize = 1;  // 2^ceil(log2(1.5*total)); 3*total is never a power of two
                 while (2 * ssize < 3 * total) ssize <<= 1;
-                uint64_t stage[OV_STAGE_MAX];
-                for (uint32_t i = 0; i < ssize; i++) stage[i] = 0;
                 bool warn = false;
                 uint32_t valid = 0;
-                for (uint32_t f = 0; f < total; f++) {
-                    const uint64_t off = f < nf ? (uint64_t)f * k : L - (nb - (f - nf)) * k;
-                    uint64_t kmer;
-                    int rc = canonical_kmer(seq + off, k, &kmer);
-                    if (rc) {
-                        warn |= rc == 2;
-                        continue;
-                    }
-                    valid++;
-                    const uint64_t h = wang64(kmer);
-                    uint32_t i = (uint32_t)h & (ssize - 1);
-                    while (stage[i] != 0 && stage[i] != h) i = (i + 1) & (ssize - 1);
-                    stage[i] = h;
+                uint64_t *out = frag_hash + (size_t)s * fcap;
+                if (ssize <= OV_STAGE_SMEM) {
+                    const uint32_t tid = threadIdx.x;
+                    emitted = ov_stage_read([&](uint32_t i) -> uint64_t & { return s_stage[i][tid]; }, ssize, seq, L, k,
+                                            nf, nb, out, &warn, &valid);
                 }
-                for (uint32_t i = 0; i < ssize; i++)
-                    if (stage[i]) frag_hash[(size_t)s * fcap + emitted++] = stage[i];
+                else {
+                    uint64_t stage[OV_STAGE_MAX];
+                    emitted = ov_stage_read([&](uint32_t i) -> uint64_t & { return stage[i]; }, ssize, seq, L, k, nf, nb,
+                                            out, &warn, &valid);
+                }
                 valid_total += valid;
                 if (warn) {
                     atomicAdd(&cnt->warn_records, 1ULL);

@@ -259,6 +259,14 @@ def test_dedup_escalations(sq, bufsize):
     _run_modules(sq, text, [], bufsize, {"dedup"}, dedup_kwargs=dict(max_stored_fingerprints=200))
 
 
+@pytest.mark.parametrize("slots", [200, 3000])
+def test_dedup_escalations_over_compacted_arrays(sq, slots):
+    # record arrays of ~5700 reads: from the second array on only the hashes that pass the current
+    # mask reach the table kernels (dedup_consume's compaction), and escalations keep happening inside
+    text = synth.illumina_fastq(80000, seed=24, n_tiles=5, dup_frac=0.3)
+    _run_modules(sq, text, [], 2_000_000, {"dedup"}, dedup_kwargs=dict(max_stored_fingerprints=slots))
+
+
 def test_dedup_short_and_odd_fingerprints(sq):
     text = synth.illumina_fastq(5000, length=40, seed=23, n_tiles=5, variable_length=True, dup_frac=0.3)
     for kw in (dict(max_stored_fingerprints=150, front_sequence_length=3, back_sequence_length=5,
