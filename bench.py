@@ -178,7 +178,27 @@ def run_cuda(args):
         from sequali_b200 import sharded
         return sharded.allreduce_sum_tables([tables])[0]
 
+    def step_sharded(record_arrays, first_record):
+        """N > 1: every rank runs the hot loop on its contiguous shard; the merge then makes every
+        table what one sequential pass over all shards gives (sequali_b200.sharded: all-reduce of
+        the additive tables, border-tile records forwarded to the tile's owner, dedup hashes handed
+        to the table's owner, the overrepresented table travelling until full, then frozen-key counts)."""
+        from sequali_b200 import sharded
+        coll = sharded.ShardedCollectors(sq, ILLUMINA_ADAPTERS, first_record=first_record)
+        for arr in record_arrays:
+            coll.add_record_array(arr)
+        out = coll.merge()
+        ov = out["overrep"].overrepresented_sequences(threshold_fraction=0.001, min_threshold=100)
+        width = out["ptq"]["max_length"]
+        nbytes = (sum(v.nbytes for v in out["qc"].values() if isinstance(v, np.ndarray)) +
+                  sum(f.nbytes + r.nbytes for _, f, r in out["adapters"]) +
+                  len(out["dedup"]["counts"]) * 8 + len(out["ptq"]["tiles"]) * 16 * max(width, 1))
+        return nbytes, dict(tiles=len(out["ptq"]["tiles"]), dups=len(out["dedup"]["counts"]), overrep=len(ov),
+                            reads=out["qc"]["number_of_reads"])
+
     def step_resident():
+        if world > 1:
+            return step_sharded(data.record_arrays(), rank * n_reads)
         mods = make_modules(sq)
         for arr in data.record_arrays():
             feed(mods, arr)
@@ -299,6 +319,8 @@ def run_cuda(args):
         # (1) the C-ABI with HOST buffers: pinned host text -> sq_fastq_stream_next (windows copied H2D on a
         #     copy stream ahead of the parser, inside the timed region) -> sq_fused_add -> getters (D2H)
         def step_e2e():
+            if world > 1:
+                return step_sharded(hostq.record_arrays(args.e2e_window), rank * e2e_reads)[0]
             mods = make_modules(sq)
             for arr in hostq.record_arrays(args.e2e_window):
                 feed(mods, arr)
@@ -320,6 +342,8 @@ def run_cuda(args):
         host = np.frombuffer(hostq.view(), dtype=np.uint8)
 
         def step_fileobj():
+            if world > 1:
+                return step_sharded(sq.FastqParser(HostText(host), args.buffersize), rank * e2e_reads)[0]
             mods = make_modules(sq)
             for arr in sq.FastqParser(HostText(host), args.buffersize):
                 feed(mods, arr)
@@ -352,7 +376,9 @@ def run_cuda(args):
                        "reads_per_gpu": n_reads, "read_length": READ_LENGTH,
                        "text_bytes_per_gpu": int(text_bytes), "record_arrays_per_step": n_chunks,
                        "l2": "inputs larger than L2" if text_bytes > 200e6 else "input smaller than L2",
-                       "parallelism": f"{world} x contiguous read shards, NCCL all-reduce of count tables"},
+                       "parallelism": f"{world} x contiguous read shards" + (
+                           "" if world == 1 else ", exact merges over NCCL (all-reduce of the additive tables; border-tile "
+                           "records, dedup hashes and the overrepresented table exchanged between ranks)")},
             "reads_per_s": round(world * n_reads / (ms_per_step * 1e-3), 1),
             "wall_ms_per_step": round(wall * 1e3 / args.steps, 3),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,

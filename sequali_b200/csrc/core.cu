@@ -408,6 +408,11 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
 }
 // bits 7/15/23/31 of m -> bits 28..31 of the product (every partial product lands on its own bit)
 __device__ __forceinline__ uint32_t msb_nibble(uint32_t m) { return (m * 0x00204081u) >> 28; }
+// 0x80 in every byte of w that is a newline, for ASCII text (bytes < 0x80: the addition cannot carry
+// into the next byte).  A text with a byte >= 0x80 fails with the ASCII error before any field is used.
+__device__ __forceinline__ uint32_t newline_mask_ascii(uint32_t w) {
+    return ~((w ^ 0x0A0A0A0Au) + 0x7F7F7F7Fu) & 0x80808080u;
+}
 
 constexpr int OP_SUB = 4;                                  // 16 KiB sub-tiles per ticket: fewer, longer tiles keep
 constexpr int OP_TILE_BYTES = OP_SUB * PARSE_CTA_BYTES;    // the look-back short (64 KiB per CTA)
@@ -448,8 +453,9 @@ k_parse_onepass(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t n_ti
 #pragma unroll
         for (int it = 0; it < PARSE_ITERS; it++) {
             const uint32_t vi = v0 + it * 32;
-            const uint32_t bits = msb_nibble(newline_mask(v[it].x)) | msb_nibble(newline_mask(v[it].y)) << 4 |
-                                  msb_nibble(newline_mask(v[it].z)) << 8 | msb_nibble(newline_mask(v[it].w)) << 12;
+            const uint32_t bits = msb_nibble(newline_mask_ascii(v[it].x)) | msb_nibble(newline_mask_ascii(v[it].y)) << 4 |
+                                  msb_nibble(newline_mask_ascii(v[it].z)) << 8 |
+                                  msb_nibble(newline_mask_ascii(v[it].w)) << 12;
             if ((v[it].x | v[it].y | v[it].z | v[it].w) & 0x80808080u) {  // rare: first byte >= 0x80 (:1056-1061)
                 const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
                 for (int j = 0; j < 16; j++)
@@ -515,13 +521,15 @@ k_parse_onepass(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t n_ti
         }
     }
     __syncthreads();
-    const uint64_t prefix = s_prefix;
+    // a record array is < 4 GiB (check_size): byte offsets, newline ranks and record numbers fit 32 bits
+    const uint32_t prefix = (uint32_t)s_prefix, nb32 = (uint32_t)nbytes;
+    const uint32_t max_rec = (uint32_t)min(max_records, (uint64_t)0xFFFFFFFEu);
 #pragma unroll
     for (int sub = 0; sub < OP_SUB; sub++) {
         const uint32_t wsum = part_tot[sub * OP_WARPS + warp];
         if (wsum == 0) continue;
-        const uint64_t warp_base = cta_base + (uint64_t)sub * PARSE_CTA_BYTES + (uint64_t)warp * PARSE_WARP_BYTES;
-        const uint64_t kbase = prefix + part_excl[sub * OP_WARPS + warp];
+        const uint32_t warp_base = (uint32_t)cta_base + sub * PARSE_CTA_BYTES + warp * PARSE_WARP_BYTES;
+        const uint32_t kbase = prefix + part_excl[sub * OP_WARPS + warp];
         uint64_t mask = lmask[sub];
         uint32_t myrank = lrank[sub];  // warp-local rank of this lane's next newline
         for (uint32_t base = 0; base < wsum; base += OP_ROUND) {
@@ -533,22 +541,21 @@ k_parse_onepass(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t n_ti
             __syncwarp();
             const uint32_t n_here = min((uint32_t)OP_ROUND, wsum - base);
             for (uint32_t i = lane; i < n_here; i += 32) {
-                const uint64_t p = warp_base + s_pos[warp][i];
-                const uint64_t k = kbase + base + i;
-                const uint64_t rec = k >> 2;
-                const uint32_t line = (uint32_t)k & 3;
-                if (rec >= max_records) continue;
+                const uint32_t p = warp_base + s_pos[warp][i];
+                const uint32_t k = kbase + base + i;
+                const uint32_t rec = k >> 2, line = k & 3;
+                if (rec >= max_rec) continue;
                 const uint32_t l3 = line == 3, l1 = line == 1;
-                const uint64_t slot = rec + l3;
-                if (slot < cap) fields[(size_t)line * cap + slot] = (uint32_t)p + 1 + l3 - l1;
+                const uint32_t slot = rec + l3;
+                if (slot < cap) fields[(size_t)line * cap + slot] = p + 1 + l3 - l1;
                 if (line & 1) {
                     // line 1: the byte behind the sequence's newline must be '+' (:1119-1127)
                     // line 3: the record that starts behind this newline must start with '@' (:1097):
                     //         complete, or the partial tail when it has at least 3 bytes
-                    const bool look = l1 ? p + 1 < nbytes : (rec + 1 < max_records && p + 3 < nbytes);
+                    const bool look = l1 ? p + 1 < nb32 : (rec + 1 < max_rec && (uint64_t)p + 3 < nbytes);
                     if (look && __ldg(text + p + 1) != (l1 ? '+' : '@'))
-                        atomicMin(&st->err_key,
-                                  (unsigned long long)((rec + l3) << 3 | (l1 ? SQ_PARSE_NO_PLUS : SQ_PARSE_NO_AT)));
+                        atomicMin(&st->err_key, (unsigned long long)((uint64_t)(rec + l3) << 3 |
+                                                                     (l1 ? SQ_PARSE_NO_PLUS : SQ_PARSE_NO_AT)));
                 }
             }
             __syncwarp();

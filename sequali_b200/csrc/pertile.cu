@@ -573,47 +573,75 @@ k_pt_chain_hist(BatchView bv, const PtSeg *__restrict__ segs, const uint32_t *__
 // ---- records (the tiles k_fused_columns sums over); a tile whose records all
 // ---- belong to one flow-cell tile is one segment with precomputed sums, any
 // ---- other tile is split into runs that the chain replays read by read.
+// One warp per fixed tile: the lanes read the tile's slots together; a tile whose records all carry
+// one slot (nearly all of them when reads arrive in tile runs) is settled by a vote, any other tile
+// is walked by lane 0.
+__device__ __forceinline__ bool pt_ftile_uniform(const uint32_t *__restrict__ slot, uint32_t r0, uint32_t r1) {
+    const uint32_t s0 = slot[r0];
+    bool same = s0 != PT_NONE;
+    for (uint32_t r = r0 + lane_id(); r < r1; r += 32) same &= slot[r] == s0;
+    return __all_sync(0xffffffffu, same);
+}
 __global__ void __launch_bounds__(PT_TPB)
 k_pt_ftile_runs(const uint32_t *__restrict__ slot, uint32_t n, uint32_t R, uint32_t n_ftiles,
                 uint32_t *__restrict__ runs, uint8_t *__restrict__ uniform) {
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_ftiles; t += gridDim.x * blockDim.x) {
+    const uint32_t warps = gridDim.x * (PT_TPB / 32);
+    for (uint32_t t = blockIdx.x * (PT_TPB / 32) + (threadIdx.x >> 5); t < n_ftiles; t += warps) {
         const uint32_t r0 = t * R, r1 = min(n, r0 + R);
-        uint32_t cnt = 0, prev = PT_NONE;
-        for (uint32_t r = r0; r < r1; r++) {
-            const uint32_t s = slot[r];
-            if (s != prev && s != PT_NONE) cnt++;
-            prev = s;
+        const bool uni = pt_ftile_uniform(slot, r0, r1);
+        if (lane_id() != 0) continue;
+        uint32_t cnt = 1;
+        if (!uni) {
+            cnt = 0;
+            uint32_t prev = PT_NONE;
+            for (uint32_t r = r0; r < r1; r++) {
+                const uint32_t s = slot[r];
+                if (s != prev && s != PT_NONE) cnt++;
+                prev = s;
+            }
         }
         runs[t] = cnt;
-        uniform[t] = cnt == 1 && slot[r0] != PT_NONE && slot[r1 - 1] == slot[r0];
+        uniform[t] = uni;
     }
 }
 __global__ void __launch_bounds__(PT_TPB)
 k_pt_ftile_segs(const uint32_t *__restrict__ slot, uint32_t n, uint32_t R, uint32_t n_ftiles,
                 const uint32_t *__restrict__ seg_off, const uint8_t *__restrict__ uniform,
                 PtSeg *__restrict__ segs, uint32_t *__restrict__ seg_lo, uint32_t *__restrict__ seg_hi) {
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_ftiles; t += gridDim.x * blockDim.x) {
-        const uint32_t r0 = t * R, r1 = min(n, r0 + R);
-        uint32_t w = seg_off[t], prev = PT_NONE, lo = r0;
-        for (uint32_t r = r0; r <= r1; r++) {
-            const uint32_t s = r < r1 ? slot[r] : PT_NONE;
-            if (s != prev || r == r1) {
-                if (prev != PT_NONE) {
-                    PtSeg g;
-                    g.lo = lo;
-                    g.hi = r;
-                    g.slot = prev;
-                    g.data = uniform[t] ? t : PT_NONE;
-                    segs[w] = g;
-                    // segments are numbered in read order: a tile's run is [min, max] of its numbers
-                    atomicMin(seg_lo + prev, w);
-                    atomicMax(seg_hi + prev, w + 1);
-                    w++;
-                }
-                lo = r;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // a thread per tile: uniform tiles are one store
+    if (t >= n_ftiles) return;
+    const uint32_t r0 = t * R, r1 = min(n, r0 + R);
+    uint32_t w = seg_off[t];
+    if (uniform[t]) {
+        PtSeg g;
+        g.lo = r0;
+        g.hi = r1;
+        g.slot = slot[r0];
+        g.data = t;
+        segs[w] = g;
+        atomicMin(seg_lo + g.slot, w);
+        atomicMax(seg_hi + g.slot, w + 1);
+        return;
+    }
+    uint32_t prev = PT_NONE, lo = r0;
+    for (uint32_t r = r0; r <= r1; r++) {
+        const uint32_t s = r < r1 ? slot[r] : PT_NONE;
+        if (s != prev || r == r1) {
+            if (prev != PT_NONE) {
+                PtSeg g;
+                g.lo = lo;
+                g.hi = r;
+                g.slot = prev;
+                g.data = PT_NONE;
+                segs[w] = g;
+                // segments are numbered in read order: a tile's run is [min, max] of its numbers
+                atomicMin(seg_lo + prev, w);
+                atomicMax(seg_hi + prev, w + 1);
+                w++;
             }
-            prev = s;
+            lo = r;
         }
+        prev = s;
     }
 }
 
@@ -772,11 +800,11 @@ static int pt_prepare_runs(sq_pertile *p, sq_batch *b, PtPlan *pl, uint32_t seg_
     uint32_t *seg_lo = pl->seg, *seg_hi = pl->seg + n_slots;
     CUDA_TRY(cudaMemsetAsync(seg_lo, 0xFF, (size_t)n_slots * 4, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(seg_hi, 0, (size_t)n_slots * 4, ctx->stream));
-    const int tgrid = sq_grid_for(ctx, n_ftiles, PT_TPB, 8);
-    SQ_LAUNCH(ctx, k_pt_ftile_runs, tgrid, PT_TPB, 0, pl->slot, n, R, n_ftiles, pl->runs_cnt, pl->uniform);
+    const int wgrid = sq_grid_for(ctx, (uint64_t)n_ftiles * 32, PT_TPB, 8);
+    SQ_LAUNCH(ctx, k_pt_ftile_runs, wgrid, PT_TPB, 0, pl->slot, n, R, n_ftiles, pl->runs_cnt, pl->uniform);
     SQ_TRY(sq_scan_exclusive_u32(ctx, pl->runs_cnt, pl->seg_off, n_ftiles, nullptr));
-    SQ_LAUNCH(ctx, k_pt_ftile_segs, tgrid, PT_TPB, 0, pl->slot, n, R, n_ftiles, pl->seg_off, pl->uniform, pl->segs,
-              seg_lo, seg_hi);
+    SQ_LAUNCH(ctx, k_pt_ftile_segs, (n_ftiles + PT_TPB - 1) / PT_TPB, PT_TPB, 0, pl->slot, n, R, n_ftiles, pl->seg_off,
+              pl->uniform, pl->segs, seg_lo, seg_hi);
     SQ_LAUNCH(ctx, k_pt_seg_counts, sq_grid_for(ctx, n_slots, PT_TPB, 8), PT_TPB, 0, seg_lo, seg_hi, n_slots, 1u,
               pl->nseg);
     return SQ_OK;
