@@ -317,10 +317,12 @@ SQ_API int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt, sq_
                         sq_nanostats *ns, sq_adapters *ad, sq_dedup *dd);
 
 /* ---- synthetic input (bench / tests; SURVEY.md 8d recipe C2) -------------- */
-/* Fill dev_text with `n_reads` NovaSeq-style records generated on the device;
- * returns the number of bytes written (<= cap) in *nbytes. */
+/* Fill dev_text with records `first_read .. first_read + n_reads` of a NovaSeq-style stream generated on
+ * the device: read g belongs to tile number (g / reads_per_tile) % 936 of the flow cell (tiles in runs,
+ * as in real files).  Returns the number of bytes written (<= cap) in *nbytes. */
 SQ_API int sq_synth_illumina(sq_ctx *ctx, uint8_t *dev_text, uint64_t cap, uint64_t n_reads,
-                             uint32_t read_length, uint64_t seed, uint64_t *nbytes);
+                             uint32_t read_length, uint64_t seed, uint64_t first_read,
+                             uint64_t reads_per_tile, uint64_t *nbytes);
 
 #ifdef __cplusplus
 }

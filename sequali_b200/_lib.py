@@ -173,7 +173,7 @@ SIGNATURES = {
     "sq_insert_read_sizes": (_int, [_vp, _vp]),
     "sq_insert_read_adapters": (_int, [_vp, _int, _vp, _vp, _P(_u64)]),
     "sq_fused_add": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "sq_synth_illumina": (_int, [_vp, _vp, _u64, _u64, _u32, _u64, _P(_u64)]),
+    "sq_synth_illumina": (_int, [_vp, _vp, _u64, _u64, _u32, _u64, _u64, _u64, _P(_u64)]),
 }
 
 _lib = None

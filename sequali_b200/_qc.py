@@ -756,18 +756,23 @@ class PerTileQuality(_Collector):
         if len(arr):
             _defer("pt", self, arr)
 
-    def get_tile_counts(self):
+    def _tile_arrays(self):
+        """(tile ids u64[nt], sums f64[nt, max_length], counts u64[nt, max_length]) as numpy arrays."""
         info = self._sync()
         nt, ml = info.n_tiles, info.max_length
         ids, err, cnt = np.zeros(nt, "<u8"), np.zeros(nt * ml, "<f8"), np.zeros(nt * ml, "<u8")
         if nt:
             check(self._ctx.lib.sq_pertile_read(self._h, _void(ids), _void(err), _void(cnt)),
                   "sq_pertile_read")
-        if nt == 0:
+        return ids, err.reshape(nt, ml), cnt.reshape(nt, ml)
+
+    def get_tile_counts(self):
+        ids, err, cnt = self._tile_arrays()
+        if len(ids) == 0:
             return []
-        if ml == 0:
+        if err.shape[1] == 0:
             return [(t, [], []) for t in ids.tolist()]
-        return list(zip(ids.tolist(), err.reshape(nt, ml).tolist(), cnt.reshape(nt, ml).tolist()))
+        return list(zip(ids.tolist(), err.tolist(), cnt.tolist()))
 
 
 def _kmer_to_sequence(kmer: int, k: int) -> str:

@@ -88,6 +88,9 @@ struct sq_batch {
     void *meta_block = nullptr;  // single allocation behind the arrays above
     uint64_t meta_stride = 0;    // elements per array inside meta_block (0: (n + 3) & ~3)
     bool err_sum_valid = false;  // QCMetrics ran on this array
+    // tile ids PerTileQuality met in this array (sq_batch_select_tiles skips arrays that cannot hold a tile)
+    bool tile_range_valid = false;
+    uint64_t tile_lo = 0, tile_hi = 0;
 
     BatchView view() const {
         BatchView v;

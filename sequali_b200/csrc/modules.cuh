@@ -48,6 +48,7 @@ struct PtState {  // device
     unsigned int n_changes;        // this array: reads whose tile differs from the previous read's
     unsigned int qmin, qmax;       // smallest / largest quality byte among the sampled ones (all arrays so far)
     unsigned int pad;
+    unsigned long long tile_lo, tile_hi;  // this array: smallest / largest tile id among the kept reads
 };
 
 struct sq_pertile {

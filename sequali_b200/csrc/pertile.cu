@@ -84,6 +84,7 @@ k_pt_map_lookup(BatchView bv, const long long *__restrict__ tile, uint64_t base,
                 const uint32_t *map_vals, uint32_t *__restrict__ slot, uint32_t *__restrict__ idx, PtState *st) {
     const unsigned long long fail = st->fail_idx;
     uint32_t lmax = 0, kept = 0, changes = 0;
+    unsigned long long tlo = ~0ULL, thi = 0;
     const uint32_t n_round = (bv.n + 31) & ~31u;  // whole warps stay in the loop for the match below
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_round; r += gridDim.x * blockDim.x) {
         const bool in = r < bv.n;
@@ -105,7 +106,18 @@ k_pt_map_lookup(BatchView bv, const long long *__restrict__ tile, uint64_t base,
             changes += r == 0 || tile[r - 1] != tile[r];
             lmax = max(lmax, bv.seq_len[r]);
             kept++;
+            tlo = min(tlo, (unsigned long long)t);
+            thi = max(thi, (unsigned long long)t);
         }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tlo = min(tlo, __shfl_xor_sync(0xffffffffu, tlo, o));
+        thi = max(thi, __shfl_xor_sync(0xffffffffu, thi, o));
+    }
+    if (lane_id() == 0 && tlo <= thi) {
+        atomicMin(&st->tile_lo, tlo);
+        atomicMax(&st->tile_hi, thi);
     }
     lmax = warp_max_u32(lmax);
     kept = warp_sum_u32(kept);
@@ -866,6 +878,8 @@ int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t
     // slot ids of new tiles may exceed slot_cap: slot_tile writes are guarded, and the
     // map is re-read after growing
     CUDA_TRY(cudaMemsetAsync(&p->st->n_changes, 0, 4, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(&p->st->tile_lo, 0xFF, 8, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(&p->st->tile_hi, 0, 8, ctx->stream));
     SQ_LAUNCH(ctx, k_pt_map_insert, grid, PT_TPB, 0, tile, n, base, p->map_keys, p->map_vals, p->slot_tile,
               p->slot_cap, p->st);
     SQ_LAUNCH(ctx, k_pt_map_lookup, grid, PT_TPB, 0, b->view(), tile, base, p->map_keys, p->map_vals, pl->slot,
@@ -899,6 +913,9 @@ int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t
         p->qmin = h->qmin;
         p->qmax = h->qmax;
     }
+    b->tile_range_valid = true;  // tile_lo > tile_hi: no read of this array was kept
+    b->tile_lo = h->tile_lo;
+    b->tile_hi = h->tile_hi;
     pl->n_slots = h->n_slots;
     pl->width = (uint32_t)b->max_len;
     pl->fail_idx = h->fail_idx;
@@ -1065,6 +1082,12 @@ extern "C" int sq_batch_select_tiles(sq_batch *b, const int64_t *tile_ids, uint6
         return SQ_E_ARG;
     }
     if (b->n == 0 || n_ids == 0 || limit_records == 0) return SQ_OK;
+    if (b->tile_range_valid) {  // PerTileQuality has seen this array: none of the tiles may lie in its range
+        bool any = false;
+        for (uint64_t i = 0; i < n_ids && !any; i++)
+            any = tile_ids[i] >= 0 && (uint64_t)tile_ids[i] >= b->tile_lo && (uint64_t)tile_ids[i] <= b->tile_hi;
+        if (!any) return SQ_OK;
+    }
     CUDA_TRY(cudaSetDevice(ctx->device));
     const uint32_t n = (uint32_t)b->n;
     long long *ids = nullptr;

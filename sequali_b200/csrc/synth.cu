@@ -109,11 +109,10 @@ k_synth_write(uint64_t seed, uint64_t first, uint32_t n, uint32_t L, uint64_t re
 
 // Writes n_reads records starting at global index `first_read` to dev_text.
 extern "C" int sq_synth_illumina(sq_ctx *ctx, uint8_t *dev_text, uint64_t cap, uint64_t n_reads,
-                                 uint32_t read_length, uint64_t seed, uint64_t *nbytes) {
-    // seed carries (seed, first_read, reads_per_tile) packed by the caller-side helper:
-    // low 16 bits = seed, next 40 bits = first read, top 8 bits = log2(reads_per_tile)
-    const uint64_t s = seed & 0xFFFF, first = (seed >> 16) & 0xFFFFFFFFFFULL;
-    const uint64_t reads_per_tile = 1ULL << (seed >> 56);
+                                 uint32_t read_length, uint64_t seed, uint64_t first_read,
+                                 uint64_t reads_per_tile, uint64_t *nbytes) {
+    const uint64_t s = seed & 0xFFFF, first = first_read;
+    if (reads_per_tile == 0) reads_per_tile = 1;
     *nbytes = 0;
     if (n_reads == 0) return SQ_OK;
     if (n_reads > (1u << 23) || n_reads * (2ULL * read_length + 64) >= 0xFFFFFF00ULL) {

@@ -45,14 +45,16 @@ class DeviceFastq:
         self._base = ctx.lib.sq_device_alloc(ctx.h, n_chunks * stride)
         if not self._base:
             raise MemoryError(_lib.last_error())
+        # one run of reads per tile over the whole stream (all ranks' shards together), as in a
+        # flow-cell-ordered file: a shard border cuts at most one tile
         total = total_reads or n_reads
-        log_rpt = max(0, int(math.log2(max(total // 936, 1))))
+        reads_per_tile = max(1, -(-total // 936))
         for c in range(n_chunks):
             n = min(chunk_reads, n_reads - c * chunk_reads)
-            packed = (seed & 0xFFFF) | ((first_read + c * chunk_reads) << 16) | (log_rpt << 56)
             got = C.c_uint64()
             ptr = self._base + c * stride
-            check(ctx.lib.sq_synth_illumina(ctx.h, ptr, stride, n, read_length, packed,
+            check(ctx.lib.sq_synth_illumina(ctx.h, ptr, stride, n, read_length, seed & 0xFFFF,
+                                            first_read + c * chunk_reads, reads_per_tile,
                                             C.byref(got)), "sq_synth_illumina")
             self.chunks.append((ptr, got.value, n))
         ctx.sync()

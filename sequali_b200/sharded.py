@@ -270,12 +270,29 @@ def merge_overrep(ov) -> None:
                     -1 if first_warn == _NO_FAIL else first_warn)
 
 
+def _tile_table(pt):
+    """(ids int64[nt], sums float64[nt, w], counts uint64[nt, w]) of a collector: through its
+    ``tile_table()`` when it has one (no Python lists on the way), else from ``tile_counts()``."""
+    if hasattr(pt, "tile_table"):
+        return pt.tile_table()
+    tiles = pt.tile_counts()
+    w = max([len(e) for _, e, _ in tiles], default=0)
+    ids = np.array([int(t) for t, _, _ in tiles], dtype=np.int64)
+    sums, counts = np.zeros((len(tiles), w), np.float64), np.zeros((len(tiles), w), np.uint64)
+    for i, (_, e, c) in enumerate(tiles):
+        sums[i, :len(e)] = e
+        counts[i, :len(c)] = c
+    return ids, sums, counts
+
+
 def merge_pertile(pt, first_record: int) -> dict:
     """PerTileQuality over all shards -> {"tiles": [(tile, sums, counts)], "number_of_reads",
     "max_length", "skipped_record"} on every rank.  Adapter interface: ``tile_ids() -> list``,
     ``fail_index() -> local index of the first unparsable header or None``, ``number_of_reads()``,
     ``select(sorted tile ids, limit_records) -> list of uint8 tensors (FASTQ text, <= 2 GiB
-    each)``, ``add_text(tensor)``, ``tile_counts()``, ``empty(n) -> uint8 tensor``."""
+    each)``, ``add_text(tensor)``, ``tile_counts()`` (optionally ``tile_table()``, see
+    ``_tile_table``), ``empty(n) -> uint8 tensor``.  Tables travel as numpy arrays; the Python
+    lists of the result are built once at the end."""
     torch, dist, dev = _dist()
     rank, world = _rank_world()
     if world == 1:
@@ -288,37 +305,56 @@ def merge_pertile(pt, first_record: int) -> dict:
     dropped = first_record >= F            # the whole shard lies behind the first unparsable header
     my_tiles = [] if dropped else sorted(int(t) for t in pt.tile_ids())
     my_reads = 0 if dropped else pt.number_of_reads()
-    all_tiles = _allgather_obj(my_tiles)
+    gathered = _allgather_obj((np.asarray(my_tiles, dtype=np.int64), my_reads))
+    all_tiles = [g[0].tolist() for g in gathered]
+    total_reads = int(sum(g[1] for g in gathered))
     owner = {}
+    shared = False
     for g, ts in enumerate(all_tiles):
         for t in ts:
-            owner.setdefault(t, g)
-    # what this rank hands over, per owner
-    outgoing = {}
-    for o in range(rank):
-        ids = [t for t in my_tiles if owner[t] == o]
-        if ids:
-            outgoing[o] = pt.select(ids, max(0, min(F - first_record, 1 << 62)))
-    plan = _allgather_obj({o: [int(c.numel()) for c in chunks] for o, chunks in outgoing.items()})
-    for o in range(world):
-        for g in range(o + 1, world):
-            for i, nbytes in enumerate(plan[g].get(o, [])):
-                if nbytes == 0:
-                    continue
-                if rank == g:
-                    dist.send(outgoing[o][i], dst=o)
-                elif rank == o:
-                    buf = pt.empty(nbytes)
-                    dist.recv(buf, src=g)
-                    _comm_sync()
-                    pt.add_text(buf)
-    _comm_sync()
-    mine = [] if dropped else [(int(t), e, c) for t, e, c in pt.tile_counts() if owner.get(int(t)) == rank]
+            if owner.setdefault(t, g) != g:
+                shared = True
+    if shared:  # some tile lives on two ranks: its records move to the owner, in read order
+        outgoing = {}
+        for o in range(rank):
+            ids = [t for t in my_tiles if owner[t] == o]
+            if ids:
+                outgoing[o] = pt.select(ids, max(0, min(F - first_record, 1 << 62)))
+        plan = _allgather_obj({o: [int(c.numel()) for c in chunks] for o, chunks in outgoing.items()})
+        for o in range(world):
+            for g in range(o + 1, world):
+                for i, nbytes in enumerate(plan[g].get(o, [])):
+                    if nbytes == 0:
+                        continue
+                    if rank == g:
+                        dist.send(outgoing[o][i], dst=o)
+                    elif rank == o:
+                        buf = pt.empty(nbytes)
+                        dist.recv(buf, src=g)
+                        _comm_sync()
+                        pt.add_text(buf)
+        _comm_sync()
+    if dropped:
+        mine = (np.zeros(0, np.int64), np.zeros((0, 0), np.float64), np.zeros((0, 0), np.uint64))
+    else:
+        ids, sums, counts = _tile_table(pt)
+        keep = np.array([owner.get(int(t)) == rank for t in ids], dtype=bool)
+        mine = (ids[keep], sums[keep], counts[keep])
     parts = _allgather_obj(mine)
-    tiles = sorted((x for part in parts for x in part), key=lambda x: x[0])
-    width = max([len(e) for _, e, _ in tiles], default=0)
-    tiles = [(t, list(e) + [0.0] * (width - len(e)), list(c) + [0] * (width - len(c))) for t, e, c in tiles]
-    total_reads = int(allreduce_sum_tables([np.array([my_reads], dtype=np.uint64)])[0][0])
+    width = max([p[1].shape[1] for p in parts if len(p[0])], default=0)
+    n_all = sum(len(p[0]) for p in parts)
+    ids = np.zeros(n_all, np.int64)
+    sums, counts = np.zeros((n_all, width), np.float64), np.zeros((n_all, width), np.uint64)
+    at = 0
+    for p_ids, p_sums, p_counts in parts:
+        n = len(p_ids)
+        if n:
+            ids[at:at + n] = p_ids
+            sums[at:at + n, :p_sums.shape[1]] = p_sums
+            counts[at:at + n, :p_counts.shape[1]] = p_counts
+            at += n
+    order = np.argsort(ids, kind="stable")
+    tiles = list(zip(ids[order].tolist(), sums[order].tolist(), counts[order].tolist()))
     return dict(tiles=tiles, number_of_reads=total_reads, max_length=width,
                 skipped_record=None if F == _NO_FAIL else F)
 
@@ -434,7 +470,11 @@ class GpuPerTile:
         return t[:int(n)]
 
     def tile_ids(self):
-        return [t for t, _, _ in self.pt.get_tile_counts()]
+        return self.pt._tile_arrays()[0].tolist()
+
+    def tile_table(self):
+        ids, err, cnt = self.pt._tile_arrays()
+        return ids.astype(np.int64), err, cnt
 
     def fail_index(self):
         info = self.pt._sync()
