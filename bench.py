@@ -144,6 +144,24 @@ class HostText(io.RawIOBase):
         return True
 
 
+def ncu_traffic(kernel: str, chunk_reads: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the newest committed
+    `ncu --set full` capture (profiles/*_traffic.json; captured on record arrays of 4 Mi reads, the
+    default array size here).  (None, reason) when there is no capture for this kernel / array size."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files or chunk_reads != 1 << 22:
+        return None, "no ncu capture for this record-array size"
+    doc = json.load(open(files[-1]))
+    alias = {"k_fused_columns_qhist": "k_fused_columns<", "k_fused_columns_bins": "k_fused_columns<",
+             "k_fused_reads<NW>": "k_fused_reads<"}
+    want = alias.get(kernel, kernel)
+    for name, rec in doc["kernels"].items():
+        if name.startswith(want):
+            return int(rec["dram_bytes_per_launch"]), os.path.basename(files[-1]) + ": " + name
+    return None, "kernel not in " + os.path.basename(files[-1])
+
+
 # ----------------------------------------------------------------------------
 def run_cuda(args):
     import sequali_b200 as sq
@@ -278,9 +296,11 @@ def run_cuda(args):
     top_launch_bytes = text_bytes / n_chunks  # one launch per chunk reads that chunk's text once
     top_ms_per_launch = top[1][1] / top[1][0]
     achieved = top_launch_bytes / (top_ms_per_launch * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(top[0], args.chunk_reads)
     roofline = {
         "bound": "hbm", "kernel": top[0], "achieved": round(achieved, 1), "peak": peak,
-        "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+        "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": peak_src,
         "algorithmic_bytes_per_launch": int(top_launch_bytes),
         "launches_per_step": top[1][0], "ms_per_launch": round(top_ms_per_launch, 4),
         "share_of_kernel_time": round(top[1][1] / kernel_ms, 3),

@@ -545,20 +545,28 @@ k_fused_columns(const ColumnArgs A) {
             __syncthreads();
             mbar_wait(&bar, parity);
             parity ^= 1;
-            if (worker) {
-                // software pipeline: the words of the next record are on their way while this one is counted
-                uint32_t nL = 0, nraw = 0, nw = 0;
-                if (rg < nrec) {
-                    nL = s_L[rg];
-                    nraw = fh_word(buf, s_qo[rg], cg);
-                    if (A.do_qc) nw = fh_word(buf, s_so[rg], cg);
+            if (worker && rg < nrec) {
+                // the byte counters (registers and shared memory) hold 255 rows: settle that once per text
+                // tile, not once per row
+                const uint32_t my_rows = (nrec - rg + RG - 1) / RG;
+                if (rows + my_rows > 255) {
+                    if (PT) {
+                        if (A.do_qc) spill_bases();
+                    }
+                    else spill();
                 }
+                rows += my_rows;
+                // software pipeline: the words of the next record are on their way while this one is counted
+                // (the last row prefetches itself again: no branch)
+                uint32_t nL = s_L[rg], nraw = fh_word(buf, s_qo[rg], cg), nw = 0;
+                if (A.do_qc) nw = fh_word(buf, s_so[rg], cg);
                 for (uint32_t i = rg; i < nrec; i += RG) {
                     const uint32_t L = nL, raw = nraw, w = nw;
-                    if (i + RG < nrec) {
-                        nL = s_L[i + RG];
-                        nraw = fh_word(buf, s_qo[i + RG], cg);
-                        if (A.do_qc) nw = fh_word(buf, s_so[i + RG], cg);
+                    {
+                        const uint32_t ip = min(i + RG, nrec - 1);
+                        nL = s_L[ip];
+                        nraw = fh_word(buf, s_qo[ip], cg);
+                        if (A.do_qc) nw = fh_word(buf, s_so[ip], cg);
                     }
                     if (L <= col0) continue;
                     const uint32_t nvalid = min(4u, L - col0);
@@ -609,7 +617,6 @@ k_fused_columns(const ColumnArgs A) {
                             *p2 = (uint8_t)(c2 + 1);
                             *p3 = (uint8_t)(c3 + 1);
                         }
-                        if (A.do_qc && ++rows == 255) spill_bases();
                     }
                     else {
                         // phred bins min(q,47)>>2 as byte counters at bin*TPB*4 + tid*4 + j, four bins at
@@ -631,7 +638,6 @@ k_fused_columns(const ColumnArgs A) {
                             *p2 = (uint8_t)(c2 + 1);
                             *p3 = (uint8_t)(c3 + 1);
                         }
-                        if (++rows == 255) spill();
                     }
                 }
             }
