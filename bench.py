@@ -196,17 +196,24 @@ def run_cuda(args):
         from sequali_b200 import sharded
         return sharded.allreduce_sum_tables([tables])[0]
 
+    sharded_ms = {}  # rank 0's host view of the last sharded step
+
     def step_sharded(record_arrays, first_record):
         """N > 1: every rank runs the hot loop on its contiguous shard; the merge then makes every
         table what one sequential pass over all shards gives (sequali_b200.sharded: all-reduce of
         the additive tables, border-tile records forwarded to the tile's owner, dedup hashes handed
         to the table's owner, the overrepresented table travelling until full, then frozen-key counts)."""
         from sequali_b200 import sharded
+        t_begin = time.perf_counter()
         coll = sharded.ShardedCollectors(sq, ILLUMINA_ADAPTERS, first_record=first_record)
         for arr in record_arrays:
             coll.add_record_array(arr)
+        t_feed = time.perf_counter()
         out = coll.merge()
         ov = out["overrep"].overrepresented_sequences(threshold_fraction=0.001, min_threshold=100)
+        sharded_ms.clear()
+        sharded_ms.update({"feed (host, kernels still running)": round((t_feed - t_begin) * 1e3, 2), **coll.merge_ms,
+                           "total": round((time.perf_counter() - t_begin) * 1e3, 2)})
         width = out["ptq"]["max_length"]
         nbytes = (sum(v.nbytes for v in out["qc"].values() if isinstance(v, np.ndarray)) +
                   sum(f.nbytes + r.nbytes for _, f, r in out["adapters"]) +
@@ -238,6 +245,7 @@ def run_cuda(args):
     barrier()
     ms = ctx.timer_stop()
     wall = time.perf_counter() - t0
+    sharded_resident = dict(sharded_ms)
     clocks = sampler.finish()
     launches = ctx.launch_count - launches0
     if dist is not None:
@@ -402,6 +410,7 @@ def run_cuda(args):
             "reads_per_s": round(world * n_reads / (ms_per_step * 1e-3), 1),
             "wall_ms_per_step": round(wall * 1e3 / args.steps, 3),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            **({"sharded_ms_last_step_rank0": sharded_resident} if world > 1 else {}),
             "result_summary": summary, "host_ms_one_step": host_ms,
         }
         if e2e:

@@ -419,7 +419,7 @@ constexpr int OP_TILE_BYTES = OP_SUB * PARSE_CTA_BYTES;    // the look-back shor
 constexpr int OP_WARPS = PARSE_THREADS / 32;
 static_assert(OP_SUB * OP_WARPS == 32, "one warp scans the per-(sub-tile, warp) counts");
 
-__global__ void __launch_bounds__(PARSE_THREADS)
+__global__ void __launch_bounds__(PARSE_THREADS, 6)
 k_parse_onepass(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t n_tiles, uint64_t max_records,
                 uint32_t cap, unsigned long long *status, unsigned int *ticket,
                 uint32_t *__restrict__ fields /* [4][cap]: seq_off, seq_end, qual_off, name_off */, ParseState *st) {

@@ -190,6 +190,45 @@ def _bcast_obj(obj, src: int):
     return box[0]
 
 
+def _allgather_u64_rows(block: np.ndarray) -> list[np.ndarray]:
+    """All-gather of one 2-D uint64 block per rank (shapes may differ) as tensors: two collectives,
+    no pickling.  Returns the blocks of all ranks in rank order."""
+    torch, dist, dev = _dist()
+    block = np.ascontiguousarray(block, dtype=np.uint64)
+    if dist is None:
+        return [block]
+    world = dist.get_world_size()
+    shape = torch.tensor(list(block.shape), dtype=torch.int64, device=dev)
+    shapes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(shapes, shape)
+    shapes = [tuple(int(v) for v in t.cpu().tolist()) for t in shapes]
+    rows, cols = max(r for r, _ in shapes), max(c for _, c in shapes)
+    if rows == 0 or cols == 0:
+        return [np.zeros(sh, np.uint64) for sh in shapes]
+    padded = np.zeros((rows, cols), np.uint64)
+    padded[:block.shape[0], :block.shape[1]] = block
+    mine = torch.from_numpy(padded.view(np.int64)).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return [t.cpu().numpy().view(np.uint64)[:r, :c].copy() for t, (r, c) in zip(parts, shapes)]
+
+
+def _bcast_u64(arr, src: int) -> np.ndarray:
+    """Broadcast of a 1-D uint64 array from `src` as a tensor (length first)."""
+    torch, dist, dev = _dist()
+    rank, _ = _rank_world()
+    if dist is None:
+        return np.asarray(arr, dtype=np.uint64)
+    n = _bcast_ints([len(arr) if rank == src else 0], src)[0]
+    if rank == src:
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.uint64).view(np.int64)).to(dev)
+    else:
+        t = torch.empty(n, dtype=torch.int64, device=dev)
+    if n:
+        dist.broadcast(t, src=src)
+    return t.cpu().numpy().view(np.uint64).copy()
+
+
 def _comm_sync():
     """Collectives on device tensors run on torch's streams, the collectors on the library's."""
     torch, dist, dev = _dist()
@@ -219,8 +258,13 @@ def merge_dedup(dd) -> tuple[np.ndarray, dict]:
                 _comm_sync()
                 dd.consume(buf)
         _comm_sync()
-    result = (dd.counts(), dd.info()) if rank == 0 else None
-    return _bcast_obj(result, 0)
+    if world == 1:
+        return dd.counts(), dd.info()
+    info = dd.info() if rank == 0 else None
+    keys = ("modulo_bits", "hash_table_size", "tracked_sequences")
+    vals = _bcast_ints([info[k] for k in keys] if rank == 0 else [0] * len(keys), 0)
+    counts = _bcast_u64(dd.counts() if rank == 0 else None, 0)
+    return counts, dict(zip(keys, vals))
 
 
 def merge_overrep(ov) -> None:
@@ -334,25 +378,29 @@ def merge_pertile(pt, first_record: int) -> dict:
                         _comm_sync()
                         pt.add_text(buf)
         _comm_sync()
+    # one uint64 block per rank: [tile id | sums (bit patterns) | counts] per owned tile
     if dropped:
-        mine = (np.zeros(0, np.int64), np.zeros((0, 0), np.float64), np.zeros((0, 0), np.uint64))
+        block = np.zeros((0, 1), np.uint64)
     else:
         ids, sums, counts = _tile_table(pt)
         keep = np.array([owner.get(int(t)) == rank for t in ids], dtype=bool)
-        mine = (ids[keep], sums[keep], counts[keep])
-    parts = _allgather_obj(mine)
-    width = max([p[1].shape[1] for p in parts if len(p[0])], default=0)
-    n_all = sum(len(p[0]) for p in parts)
+        w = sums.shape[1]
+        block = np.zeros((int(keep.sum()), 1 + 2 * w), np.uint64)
+        block[:, 0] = ids[keep].astype(np.uint64)
+        block[:, 1:1 + w] = np.ascontiguousarray(sums[keep], dtype=np.float64).view(np.uint64)
+        block[:, 1 + w:] = counts[keep]
+    parts = [p for p in _allgather_u64_rows(block) if p.shape[0]]
+    width = max([(p.shape[1] - 1) // 2 for p in parts], default=0)
+    n_all = sum(p.shape[0] for p in parts)
     ids = np.zeros(n_all, np.int64)
     sums, counts = np.zeros((n_all, width), np.float64), np.zeros((n_all, width), np.uint64)
     at = 0
-    for p_ids, p_sums, p_counts in parts:
-        n = len(p_ids)
-        if n:
-            ids[at:at + n] = p_ids
-            sums[at:at + n, :p_sums.shape[1]] = p_sums
-            counts[at:at + n, :p_counts.shape[1]] = p_counts
-            at += n
+    for p in parts:
+        n, w = p.shape[0], (p.shape[1] - 1) // 2
+        ids[at:at + n] = p[:, 0].astype(np.int64)
+        sums[at:at + n, :w] = np.ascontiguousarray(p[:, 1:1 + w]).view(np.float64)
+        counts[at:at + n, :w] = p[:, 1 + w:]
+        at += n
     order = np.argsort(ids, kind="stable")
     tiles = list(zip(ids[order].tolist(), sums[order].tolist(), counts[order].tolist()))
     return dict(tiles=tiles, number_of_reads=total_reads, max_length=width,
@@ -572,7 +620,16 @@ class ShardedCollectors:
         self.dd.dd.add_record_array(arr)
 
     def merge(self) -> dict:
-        """Merged results of all ranks, on every rank."""
+        """Merged results of all ranks, on every rank.  ``self.merge_ms`` afterwards: host wall time
+        of each merge on this rank (waiting for slower ranks included)."""
+        import time
+        t = [time.perf_counter()]
+        self.merge_ms = {}
+
+        def lap(name):
+            t.append(time.perf_counter())
+            self.merge_ms[name] = round((t[-1] - t[-2]) * 1e3, 2)
+
         qc = self.qc
         out = dict(qc=merge_qc(*[np.frombuffer(x, dtype=np.uint64) for x in (
             qc.base_count_table(), qc.phred_count_table(), qc.end_anchored_base_count_table(),
@@ -581,9 +638,13 @@ class ShardedCollectors:
             [np.array([qc.number_of_reads], dtype=np.uint64)])[0][0])
         out["adapters"] = merge_adapter_counts([(a, np.frombuffer(f, dtype=np.uint64), np.frombuffer(r, dtype=np.uint64))
                                                 for a, f, r in self.ad.get_counts()])
+        lap("qc+adapters (first getter: waits for the shard's kernels)")
         out["ptq"] = merge_pertile(self.pt, self.first_record)
+        lap("pertile")
         counts, info = merge_dedup(self.dd)
         out["dedup"] = dict(counts=counts, **info)
+        lap("dedup")
         merge_overrep(self.ov)
         out["overrep"] = self.ov.ov  # the merged table answers the usual getters
+        lap("overrep")
         return out
