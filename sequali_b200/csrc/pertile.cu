@@ -85,6 +85,7 @@ k_pt_map_lookup(BatchView bv, const long long *__restrict__ tile, uint64_t base,
     const unsigned long long fail = st->fail_idx;
     uint32_t lmax = 0, kept = 0, changes = 0;
     unsigned long long tlo = ~0ULL, thi = 0;
+    uint64_t tprev = ~0ULL;
     const uint32_t n_round = (bv.n + 31) & ~31u;  // whole warps stay in the loop for the match below
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_round; r += gridDim.x * blockDim.x) {
         const bool in = r < bv.n;
@@ -106,8 +107,11 @@ k_pt_map_lookup(BatchView bv, const long long *__restrict__ tile, uint64_t base,
             changes += r == 0 || tile[r - 1] != tile[r];
             lmax = max(lmax, bv.seq_len[r]);
             kept++;
-            tlo = min(tlo, (unsigned long long)t);
-            thi = max(thi, (unsigned long long)t);
+            if (t != tprev) {  // reads come in tile runs: rarely taken
+                tlo = min(tlo, (unsigned long long)t);
+                thi = max(thi, (unsigned long long)t);
+                tprev = t;
+            }
         }
     }
 #pragma unroll
@@ -372,43 +376,42 @@ k_pt_guess(BatchView bv, const uint32_t *__restrict__ order, const PtSeg *__rest
 // block of 32 rows the in-binade integer rule is applied to as many rows as stay
 // in the binade, the row that does not gets a real addition, and the block is
 // resumed behind it.
+template <int NB = 4>  // blocks of 32 rows gathered together (8: a whole segment of the run path in one go)
 __device__ uint64_t pt_replay_rows(uint64_t sbits, const BatchView &bv, const uint32_t *__restrict__ order,
                                    uint32_t lo, uint32_t hi, uint32_t pos, const double *s_err) {
-    for (uint32_t c0 = lo; c0 < hi; c0 += 128) {
-        uint64_t eb[4];
-        uint32_t rr[4], off[4];
-        bool ok[4];
+    for (uint32_t c0 = lo; c0 < hi; c0 += NB * 32) {
+        uint32_t qv[NB];  // phred of this lane's row in block b; >= 94: the row adds nothing
+        {
+            uint32_t rr[NB], off[NB];
+            bool ok[NB];
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const uint32_t ii = c0 + b * 32 + lane_id();
-            ok[b] = ii < hi;
-            rr[b] = ok[b] ? (order ? order[ii] : ii) : 0;
-        }
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            if (ok[b]) {
-                ok[b] = pos < bv.seq_len[rr[b]];
-                off[b] = bv.qual_off[rr[b]];
+            for (int b = 0; b < NB; b++) {
+                const uint32_t ii = c0 + b * 32 + lane_id();
+                ok[b] = ii < hi;
+                rr[b] = ok[b] ? (order ? order[ii] : ii) : 0;
             }
-        }
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            eb[b] = 0;
-            if (ok[b]) {
-                const uint32_t q = (uint8_t)(bv.text[off[b] + pos] - 33);
-                if (q <= 93) eb[b] = (uint64_t)__double_as_longlong(s_err[q]);
+            for (int b = 0; b < NB; b++) {
+                off[b] = 0;
+                if (ok[b]) {
+                    ok[b] = pos < bv.seq_len[rr[b]];
+                    off[b] = bv.qual_off[rr[b]];
+                }
             }
+#pragma unroll
+            for (int b = 0; b < NB; b++) qv[b] = ok[b] ? (uint32_t)(uint8_t)(bv.text[off[b] + pos] - 33) : 0xFFu;
         }
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
+        for (int b = 0; b < NB; b++) {
             const uint32_t base = c0 + b * 32;
             if (base >= hi) break;
             const uint32_t nv = min(32u, hi - base);
+            const uint64_t eb = qv[b] <= 93 ? (uint64_t)__double_as_longlong(s_err[qv[b]]) : 0ULL;
             uint32_t s0 = 0;  // rows of this block already applied
             while (s0 < nv) {
                 const uint32_t k = (uint32_t)(sbits >> 52);
-                const bool mine = lane_id() >= s0 && lane_id() < nv && eb[b] != 0;
-                uint64_t inc = mine ? pt_increment(k, eb[b]) : 0;
+                const bool mine = lane_id() >= s0 && lane_id() < nv && eb != 0;
+                uint64_t inc = mine ? pt_increment(k, eb) : 0;
                 const bool hard = inc >= PT_HARD;
                 if (hard) inc = 0;
                 const uint64_t incl = warp_incl_scan_u64(inc);
@@ -421,7 +424,7 @@ __device__ uint64_t pt_replay_rows(uint64_t sbits, const BatchView &bv, const ui
                 }
                 if (f > 0) sbits += __shfl_sync(0xffffffffu, incl, f - 1);
                 // a real, ordered addition: crosses a power of two, ties, or starts from 0.0
-                const uint64_t e = __shfl_sync(0xffffffffu, eb[b], f);
+                const uint64_t e = __shfl_sync(0xffffffffu, eb, f);
                 const double sum = __longlong_as_double((long long)sbits) + __longlong_as_double((long long)e);
                 sbits = (uint64_t)__double_as_longlong(sum);
                 s0 = f + 1;
@@ -523,43 +526,65 @@ k_pt_chain_hist(BatchView bv, const PtSeg *__restrict__ segs, const uint32_t *__
         const uint32_t colw = ((pos & 3u) * hg.CG + (pos >> 2)) * hg.QW;
         double *cell = errors + (uint64_t)s * len_cap + pos;
         uint64_t sbits = (uint64_t)__double_as_longlong(*cell);
-        uint32_t j = 0;
-        while (j < cnt) {
-            const uint32_t jj = j + lane_id();
-            const uint32_t k = (uint32_t)(sbits >> 52), krow = k - (uint32_t)PT_LUT_KMIN;
-            uint64_t inc = 0;
-            uint32_t lo = 0, hi = 0;
-            bool mine = false, hard = false;
+        // A window = 32 consecutive segments, one per lane.  Its loads (segment descriptor, then the
+        // segment's histogram words) do not depend on the running sum, so the next window is fetched
+        // before the current one's replay: the chain is a string of dependent memory round trips,
+        // this takes most of them off the critical path.
+        constexpr int HW = 12;  // histogram words held in registers (48 quality values); more are read in the loop
+        uint32_t lo = 0, hi = 0, hw[HW];
+        bool mine = false, nodata = true;
+        const uint32_t *hrow = nullptr;
+        auto load_window = [&](uint32_t j0) {
+            const uint32_t jj = j0 + lane_id();
+            mine = false;
+            nodata = true;
+            hrow = nullptr;
+#pragma unroll
+            for (int u = 0; u < HW; u++) hw[u] = 0;
             if (jj < cnt) {
                 const PtSeg sg = segs[first + jj];
                 if (sg.slot == s) {  // a foreign segment adds nothing
                     mine = true;
                     lo = sg.lo;
                     hi = sg.hi;
-                    if (sg.data == PT_NONE || krow >= (uint32_t)PT_LUT_NK || oob[sg.data]) hard = true;
-                    else {
-                        const uint32_t *h = (const uint32_t *)(qh + (uint64_t)sg.data * hg.seg_bytes) + colw;
-                        const uint64_t *lr = s_lut + krow * 96 + hg.qbase;
-                        // eight histogram words in flight at a time (the chain is latency bound, not
-                        // instruction bound: one dependent load per word was most of its time)
-                        for (uint32_t m0 = 0; m0 < nq; m0 += 8) {
-                            uint32_t hw[8];
+                    if (sg.data != PT_NONE && !oob[sg.data]) {
+                        nodata = false;
+                        hrow = (const uint32_t *)(qh + (uint64_t)sg.data * hg.seg_bytes) + colw;
 #pragma unroll
-                            for (int u = 0; u < 8; u++) hw[u] = m0 + u < nq ? __ldg(h + m0 + u) : 0u;
-#pragma unroll
-                            for (int u = 0; u < 8; u++) {
-                                const uint32_t w = hw[u];
-                                if (w == 0) continue;
-                                const uint64_t *l4 = lr + 4 * (m0 + u);
-                                inc += (uint64_t)(w & 0xFF) * l4[0] + (uint64_t)((w >> 8) & 0xFF) * l4[1] +
-                                       (uint64_t)((w >> 16) & 0xFF) * l4[2] + (uint64_t)(w >> 24) * l4[3];
-                            }
-                        }
-                        // a tabulated PT_HARD (tie, increment that cannot stay in the binade) times a non-zero
-                        // count lifts the sum to >= 2^53; true sums of <= 255 in-binade increments that large
-                        // leave the binade anyway.  (0 * PT_HARD adds nothing: unused rows do not poison.)
-                        hard = inc >= PT_HARD;
+                        for (int u = 0; u < HW; u++) hw[u] = (uint32_t)u < nq ? __ldg(hrow + u) : 0u;
                     }
+                }
+            }
+        };
+        uint32_t j = 0;
+        load_window(0);
+        while (j < cnt) {
+            const uint32_t k = (uint32_t)(sbits >> 52), krow = k - (uint32_t)PT_LUT_KMIN;
+            uint64_t inc = 0;
+            bool hard = false;
+            if (mine) {
+                if (nodata || krow >= (uint32_t)PT_LUT_NK) hard = true;
+                else {
+                    const uint64_t *lr = s_lut + krow * 96 + hg.qbase;
+#pragma unroll
+                    for (int u = 0; u < HW; u++) {
+                        const uint32_t w = hw[u];
+                        if (w == 0) continue;
+                        const uint64_t *l4 = lr + 4 * u;
+                        inc += (uint64_t)(w & 0xFF) * l4[0] + (uint64_t)((w >> 8) & 0xFF) * l4[1] +
+                               (uint64_t)((w >> 16) & 0xFF) * l4[2] + (uint64_t)(w >> 24) * l4[3];
+                    }
+                    for (uint32_t m = HW; m < nq; m++) {  // wide quality ranges only
+                        const uint32_t w = __ldg(hrow + m);
+                        if (w == 0) continue;
+                        const uint64_t *l4 = lr + 4 * m;
+                        inc += (uint64_t)(w & 0xFF) * l4[0] + (uint64_t)((w >> 8) & 0xFF) * l4[1] +
+                               (uint64_t)((w >> 16) & 0xFF) * l4[2] + (uint64_t)(w >> 24) * l4[3];
+                    }
+                    // a tabulated PT_HARD (tie, increment that cannot stay in the binade) times a non-zero
+                    // count lifts the sum to >= 2^53; true sums of <= 255 in-binade increments that large
+                    // leave the binade anyway.  (0 * PT_HARD adds nothing: unused rows do not poison.)
+                    hard = inc >= PT_HARD;
                 }
             }
             if (hard) inc = 0;
@@ -570,12 +595,11 @@ k_pt_chain_hist(BatchView bv, const PtSeg *__restrict__ segs, const uint32_t *__
             const uint32_t f = bad ? (uint32_t)__ffs(bad) - 1 : 32u;
             const uint32_t nacc = min(f, nv);
             if (nacc) sbits += __shfl_sync(0xffffffffu, incl, nacc - 1);
-            j += nacc;
-            if (f < nv) {
-                const uint32_t rlo = __shfl_sync(0xffffffffu, lo, f), rhi = __shfl_sync(0xffffffffu, hi, f);
-                sbits = pt_replay_rows(sbits, bv, nullptr, rlo, rhi, pos, s_err);
-                j += 1;
-            }
+            const bool replay = f < nv;
+            const uint32_t rlo = __shfl_sync(0xffffffffu, lo, f & 31), rhi = __shfl_sync(0xffffffffu, hi, f & 31);
+            j += nacc + (replay ? 1u : 0u);
+            if (j < cnt) load_window(j);  // in flight while the failed segment is replayed
+            if (replay) sbits = pt_replay_rows<8>(sbits, bv, nullptr, rlo, rhi, pos, s_err);
         }
         if (lane_id() == 0) *cell = __longlong_as_double((long long)sbits);
     }
@@ -941,7 +965,8 @@ int pt_finish(sq_pertile *p, sq_batch *b, PtPlan *pl) {
     const int grid = sq_grid_for(ctx, n, PT_TPB, 16);
     int rc = SQ_OK;
     if (pl->work && pl->runs) {
-        const int chain_grid = sq_grid_for(ctx, (uint64_t)pl->n_slots * pl->width * 32, PT_TPB, 5);
+        // 4 CTAs fit an SM next to the increment table: one wave
+        const int chain_grid = sq_grid_for(ctx, (uint64_t)pl->n_slots * pl->width * 32, PT_TPB, 4);
         const size_t lut_smem = (size_t)PT_LUT_NK * 96 * 8;
         CUDA_TRY(cudaFuncSetAttribute(k_pt_chain_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_smem));
         SQ_LAUNCH(ctx, k_pt_chain_hist, chain_grid, PT_TPB, lut_smem, b->view(), pl->segs, pl->seg, pl->nseg,
