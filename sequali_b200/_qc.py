@@ -770,9 +770,15 @@ class PerTileQuality(_Collector):
         ids, err, cnt = self._tile_arrays()
         if len(ids) == 0:
             return []
-        if err.shape[1] == 0:
+        ml = err.shape[1]
+        if ml == 0:
             return [(t, [], []) for t in ids.tolist()]
-        return list(zip(ids.tolist(), err.tolist(), cnt.tolist()))
+        # counts[j] = reads of the tile longer than j: one number repeated for reads of one length,
+        # so such a row is built from a single int object instead of max_length of them
+        flat = (cnt == cnt[:, :1]).all(axis=1).tolist()
+        first = cnt[:, 0].tolist()
+        counts = [[first[i]] * ml if flat[i] else cnt[i].tolist() for i in range(len(first))]
+        return list(zip(ids.tolist(), err.tolist(), counts))
 
 
 def _kmer_to_sequence(kmer: int, k: int) -> str:

@@ -92,8 +92,9 @@ k_pt_map_lookup(BatchView bv, const long long *__restrict__ tile, uint64_t base,
         const bool keep = in && base + r < fail;
         if (in) idx[r] = r;
         const uint64_t t = keep ? (uint64_t)tile[r] : ~0ULL;
-        // one probe per distinct tile in the warp
-        const uint32_t peers = __match_any_sync(0xffffffffu, t);
+        // one probe per distinct tile in the warp (reads in tile runs: usually one tile, settled by a vote)
+        const uint64_t t0 = __shfl_sync(0xffffffffu, t, 0);
+        const uint32_t peers = __all_sync(0xffffffffu, t == t0) ? 0xffffffffu : __match_any_sync(0xffffffffu, t);
         const uint32_t leader = (uint32_t)__ffs(peers) - 1;
         uint32_t sl = PT_NONE;
         if (keep && lane_id() == leader) {
