@@ -384,8 +384,8 @@ k_scatter_fields(const uint8_t *__restrict__ text, uint64_t nbytes, const uint16
 
 // ---------------------------------------------------------------------------
 // One-pass variant: count, rank and scatter in a single walk over the text.
-// A CTA takes the next 16 KiB tile (ticket from an atomic counter, so every
-// predecessor is already running), counts its newlines, publishes the count and
+// A CTA takes the 64 KiB tile of its block index (blocks are handed out in index order, so
+// every predecessor is already running), counts its newlines, publishes the count and
 // finds its global rank offset by decoupled look-back over the predecessors'
 // published counts (status word = flag << 62 | value; flag 1: tile count, flag 2:
 // inclusive prefix).  Newline positions are then compacted per warp so that the
@@ -414,23 +414,22 @@ __device__ __forceinline__ uint32_t newline_mask_ascii(uint32_t w) {
     return ~((w ^ 0x0A0A0A0Au) + 0x7F7F7F7Fu) & 0x80808080u;
 }
 
-constexpr int OP_SUB = 4;                                  // 16 KiB sub-tiles per ticket: fewer, longer tiles keep
+constexpr int OP_SUB = 4;                                  // 16 KiB sub-tiles per CTA: fewer, longer tiles keep
 constexpr int OP_TILE_BYTES = OP_SUB * PARSE_CTA_BYTES;    // the look-back short (64 KiB per CTA)
 constexpr int OP_WARPS = PARSE_THREADS / 32;
 static_assert(OP_SUB * OP_WARPS == 32, "one warp scans the per-(sub-tile, warp) counts");
 
 __global__ void __launch_bounds__(PARSE_THREADS, 6)
 k_parse_onepass(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t n_tiles, uint64_t max_records,
-                uint32_t cap, unsigned long long *status, unsigned int *ticket,
+                uint32_t cap, unsigned long long *status,
                 uint32_t *__restrict__ fields /* [4][cap]: seq_off, seq_end, qual_off, name_off */, ParseState *st) {
     __shared__ __align__(8) uint16_t s_nl[OP_TILE_BYTES / 16];
     __shared__ uint16_t s_pos[OP_WARPS][OP_ROUND];
     __shared__ uint32_t part_tot[OP_SUB * OP_WARPS], part_excl[OP_SUB * OP_WARPS];  // [sub-tile][warp]
-    __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_prefix;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile, warp = threadIdx.x >> 5, lane = lane_id();
+    // tiles in block-index order: the hardware hands out blocks in that order, so every predecessor
+    // of a running block is running or done (what CUB's decoupled look-back relies on as well)
+    const uint32_t tile = blockIdx.x, warp = threadIdx.x >> 5, lane = lane_id();
     const uint64_t cta_base = (uint64_t)tile * OP_TILE_BYTES;
     const bool full_tile = cta_base + OP_TILE_BYTES <= nbytes;  // no bounds checks, loads issued back to back
 #pragma unroll
@@ -664,7 +663,7 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
         const uint32_t n_op = (uint32_t)((nbytes + OP_TILE_BYTES - 1) / OP_TILE_BYTES);
         CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)n_op + 1) * 8, ctx->stream));
         SQ_LAUNCH(ctx, k_parse_onepass, n_op, PARSE_THREADS, 0, b->text, nbytes, n_op, max_records, cap, status,
-                  (unsigned int *)(status + n_op), fields, st);
+                  fields, st);
         CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
