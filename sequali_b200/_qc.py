@@ -971,7 +971,8 @@ class DedupEstimator(_Collector):
         info = self._sync()
         # the counts land straight in the array the caller gets (no numpy detour: this getter
         # returns ~10^6 entries and its host time is part of every run)
-        out = array.array("Q", bytes(8 * info.tracked_sequences))
+        out = array.array("Q")
+        out.frombytes(bytes(8 * info.tracked_sequences))  # (the constructor walks a bytes initialiser item by item)
         n = _C.c_uint64()
         check(self._ctx.lib.sq_dedup_read(self._h, _C.c_void_p(out.buffer_info()[0]), _C.byref(n)),
               "sq_dedup_read")

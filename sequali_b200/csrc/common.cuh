@@ -48,8 +48,10 @@ struct sq_ctx {
     size_t parse_masks_cap = 0;
     void *parse_fields = nullptr;       // one-pass parser: descriptor fields before the record count is known
     size_t parse_fields_cap = 0;
-    void *parse_status = nullptr;       // one-pass parser: look-back status words + ticket counter
+    void *parse_status = nullptr;       // one-pass parser: look-back status words
     size_t parse_status_cap = 0;
+    void *h_bounce = nullptr;           // pinned bounce buffer for large read-outs into pageable caller memory
+    size_t h_bounce_cap = 0;
     // staging ring of the host reader (sq_fastq_stream), kept between readers
     void *stage_slot[3] = {nullptr, nullptr, nullptr};
     size_t stage_cap = 0;
@@ -102,6 +104,10 @@ struct sq_batch {
         return v;
     }
 };
+
+// device -> pageable host memory through the context's pinned bounce buffer (DMA at full speed,
+// then a plain memcpy), synchronous
+int sq_d2h_bounced(sq_ctx *ctx, void *dst, const void *dev_src, size_t nbytes);
 
 // name bytes of record r of a record array (host copy; rare paths only)
 int sq_batch_get_name(sq_batch *b, uint64_t r, std::vector<uint8_t> &out);

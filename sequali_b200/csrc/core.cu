@@ -125,6 +125,7 @@ extern "C" void sq_ctx_destroy(sq_ctx *ctx) {
     cudaFree(ctx->parse_masks);
     cudaFree(ctx->parse_fields);
     cudaFree(ctx->parse_status);
+    if (ctx->h_bounce) cudaFreeHost(ctx->h_bounce);
     for (int k = 0; k < 3; k++) cudaFree(ctx->stage_slot[k]);
     cudaFreeHost(ctx->h_scratch);
     cudaStreamDestroy(ctx->stream);
@@ -619,6 +620,46 @@ static int alloc_fastq_metas(sq_batch *b, uint64_t n) {
     b->err_sum = (double *)(p + 4 * n4);
     CUDA_TRY(cudaMemsetAsync(b->err_sum, 0, n4 * 8, b->ctx->stream));
     return SQ_OK;
+}
+
+int sq_d2h_bounced(sq_ctx *ctx, void *dst, const void *dev_src, size_t nbytes) {
+    const size_t chunk = (size_t)8 << 20;
+    if (!ctx->h_bounce) {
+        CUDA_TRY(cudaMallocHost(&ctx->h_bounce, 2 * chunk));
+        ctx->h_bounce_cap = 2 * chunk;
+    }
+    // two halves: the copy of chunk i + 1 runs while chunk i is moved to the caller's memory
+    size_t done = 0, issued = 0;
+    int slot = 0;
+    cudaEvent_t ev[2];
+    CUDA_TRY(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    size_t len[2] = {0, 0};
+    auto issue = [&](int sl) -> int {
+        len[sl] = std::min(chunk, nbytes - issued);
+        CUDA_TRY(cudaMemcpyAsync((char *)ctx->h_bounce + sl * chunk, (const char *)dev_src + issued, len[sl],
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaEventRecord(ev[sl], ctx->stream));
+        issued += len[sl];
+        return SQ_OK;
+    };
+    int rc = SQ_OK;
+    if (nbytes) rc = issue(0);
+    while (rc == SQ_OK && done < nbytes) {
+        if (issued < nbytes) rc = issue(slot ^ 1);
+        if (rc != SQ_OK) break;
+        if (cudaEventSynchronize(ev[slot]) != cudaSuccess) {
+            sq_set_error("cudaEventSynchronize failed in sq_d2h_bounced");
+            rc = SQ_E_CUDA;
+            break;
+        }
+        memcpy((char *)dst + done, (char *)ctx->h_bounce + slot * chunk, len[slot]);
+        done += len[slot];
+        slot ^= 1;
+    }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    return rc;
 }
 
 // grow-only scratch of the context

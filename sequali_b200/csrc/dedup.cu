@@ -585,8 +585,7 @@ extern "C" int sq_dedup_read(sq_dedup *d, uint64_t *counts, uint64_t *n) {
                      (unsigned long long)d->stored);
         return SQ_E_CUDA;
     }
-    if (got) CUDA_TRY(cudaMemcpyAsync(counts, out, got * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (got) SQ_TRY(sq_d2h_bounced(ctx, counts, out, got * 8));
     *n = got;
     sq_dfree(ctx, flag);
     sq_dfree(ctx, rank);

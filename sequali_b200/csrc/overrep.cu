@@ -39,6 +39,11 @@ struct sq_overrep {
     uint64_t *keys = nullptr;    // wang hash, 0 = empty
     uint32_t *counts = nullptr;
     OvCounters *cnt = nullptr;
+    // Once the table is full its key set is frozen (:3553): a presence bitmap (one bit per value of
+    // 27 hash bits the table index does not use, 16 MiB: stays in L2) answers most lookups of unknown
+    // hashes without touching the table in HBM.
+    uint32_t *filter = nullptr;
+    bool filter_valid = false;
     // sharded runs: fragments of the sampled reads are kept, the table work waits for the
     // table state of the ranks before this one (sq_overrep_apply_deferred)
     bool deferred = false;
@@ -183,14 +188,37 @@ __device__ __forceinline__ void ov_insert_or_count(uint64_t *keys, uint32_t *cou
     }
 }
 
+constexpr uint32_t OV_FILTER_BITS = 27, OV_FILTER_SHIFT = 23;  // table index = low bits of the hash
+__device__ __forceinline__ uint32_t ov_filter_slot(uint64_t h) {
+    return (uint32_t)(h >> OV_FILTER_SHIFT) & ((1u << OV_FILTER_BITS) - 1);
+}
+__global__ void __launch_bounds__(256)
+k_ov_filter_build(const uint64_t *__restrict__ keys, uint64_t table_size, uint32_t *__restrict__ filter) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < table_size;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = keys[i];
+        if (h) {
+            const uint32_t b = ov_filter_slot(h);
+            atomicOr(filter + (b >> 5), 1u << (b & 31));
+        }
+    }
+}
+
+// filter != nullptr: the table is full (lookup only) and `filter` holds a bit for every stored key
 __global__ void __launch_bounds__(256)
 k_ov_count(const uint64_t *__restrict__ frag_hash, const uint32_t *__restrict__ frag_n, uint32_t n_sampled,
-           uint32_t fcap, uint64_t *keys, uint32_t *counts, uint64_t mask, int may_insert, OvCounters *cnt) {
+           uint32_t fcap, uint64_t *keys, uint32_t *counts, uint64_t mask, int may_insert, OvCounters *cnt,
+           const uint32_t *__restrict__ filter) {
     const uint64_t total = (uint64_t)n_sampled * fcap;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t s = (uint32_t)(t / fcap), i = (uint32_t)(t % fcap);
         if (i >= frag_n[s]) continue;
-        ov_insert_or_count(keys, counts, mask, frag_hash[t], may_insert != 0, &cnt->n_unique);
+        const uint64_t h = frag_hash[t];
+        if (filter) {
+            const uint32_t b = ov_filter_slot(h);
+            if (!((filter[b >> 5] >> (b & 31)) & 1u)) continue;  // not a stored key: dropped (:3553)
+        }
+        ov_insert_or_count(keys, counts, mask, h, may_insert != 0, &cnt->n_unique);
     }
 }
 
@@ -314,6 +342,7 @@ extern "C" void sq_overrep_destroy(sq_overrep *o) {
     sq_dfree(o->ctx, o->keys);
     sq_dfree(o->ctx, o->counts);
     sq_dfree(o->ctx, o->cnt);
+    sq_dfree(o->ctx, o->filter);
     delete o;
 }
 
@@ -340,12 +369,20 @@ static int ov_apply(sq_overrep *o, const uint64_t *frag_hash, const uint32_t *fr
     if (!o->full && o->unique_upper + n_sampled * total > o->max_unique) rc = ov_refresh_unique(o);
     if (rc == SQ_OK) {
         if (o->full) {
+            if (!o->filter_valid) {
+                const size_t fbytes = (size_t)1 << (OV_FILTER_BITS - 3);
+                if (!o->filter) SQ_TRY(sq_dalloc(ctx, (void **)&o->filter, fbytes, false));
+                CUDA_TRY(cudaMemsetAsync(o->filter, 0, fbytes, ctx->stream));
+                SQ_LAUNCH(ctx, k_ov_filter_build, sq_grid_for(ctx, o->table_size, 256, 16), 256, 0, o->keys,
+                          o->table_size, o->filter);
+                o->filter_valid = true;
+            }
             SQ_LAUNCH(ctx, k_ov_count, grid, 256, 0, frag_hash, frag_n, (uint32_t)n_sampled, fcap, o->keys,
-                      o->counts, mask, 0, o->cnt);
+                      o->counts, mask, 0, o->cnt, o->filter_valid ? o->filter : nullptr);
         }
         else if (o->unique_upper + n_sampled * total <= o->max_unique) {
             SQ_LAUNCH(ctx, k_ov_count, grid, 256, 0, frag_hash, frag_n, (uint32_t)n_sampled, fcap, o->keys,
-                      o->counts, mask, 1, o->cnt);
+                      o->counts, mask, 1, o->cnt, (const uint32_t *)nullptr);
             o->unique_upper += n_sampled * total;
         }
         else {
@@ -585,6 +622,7 @@ extern "C" int sq_overrep_load_table(sq_overrep *o, const uint64_t *dev_keys, co
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     o->unique_known = o->unique_upper = n_unique;
     o->full = n_unique >= o->max_unique;
+    o->filter_valid = false;  // another key set
     return SQ_OK;
 }
 
