@@ -101,6 +101,14 @@ __device__ __forceinline__ uint32_t fh_word(const uint8_t *buf, uint32_t off, ui
     return __funnelshift_r(w[0], w[1], (off & 3u) * 8);
 }
 
+// the same for an offset packed as (off >> 2) << 5 | (off & 3) * 8: the funnel shift takes the low five
+// bits as they are, the word index is one shift away (k_fused_columns packs once per record and tile)
+__device__ __forceinline__ uint32_t fh_pack_off(uint32_t off) { return (off >> 2) << 5 | (off & 3u) * 8; }
+__device__ __forceinline__ uint32_t fh_word_packed(const uint8_t *buf, uint32_t packed, uint32_t k) {
+    const uint32_t *w = (const uint32_t *)buf + (packed >> 5) + k;
+    return __funnelshift_r(w[0], w[1], packed);
+}
+
 template <int NW>
 __global__ void __launch_bounds__(FH_TPB, NW <= 5 ? 4 : 3)
 k_fused_reads(const FusedArgs A) {
@@ -535,8 +543,8 @@ k_fused_columns(const ColumnArgs A) {
                 }
                 for (uint32_t i = tid; i < nrec; i += TPB) {
                     const uint32_t L = bv.seq_len[r0 + i];
-                    s_so[i] = bv.seq_off[r0 + i] - (uint32_t)gstart;
-                    s_qo[i] = bv.qual_off[r0 + i] - (uint32_t)gstart;
+                    s_so[i] = fh_pack_off(bv.seq_off[r0 + i] - (uint32_t)gstart);
+                    s_qo[i] = fh_pack_off(bv.qual_off[r0 + i] - (uint32_t)gstart);
                     s_L[i] = L;
                     lmin = min(lmin, L);
                     lmax = max(lmax, L);
@@ -558,15 +566,15 @@ k_fused_columns(const ColumnArgs A) {
                 rows += my_rows;
                 // software pipeline: the words of the next record are on their way while this one is counted
                 // (the last row prefetches itself again: no branch)
-                uint32_t nL = s_L[rg], nraw = fh_word(buf, s_qo[rg], cg), nw = 0;
-                if (A.do_qc) nw = fh_word(buf, s_so[rg], cg);
+                uint32_t nL = s_L[rg], nraw = fh_word_packed(buf, s_qo[rg], cg), nw = 0;
+                if (A.do_qc) nw = fh_word_packed(buf, s_so[rg], cg);
                 for (uint32_t i = rg; i < nrec; i += RG) {
                     const uint32_t L = nL, raw = nraw, w = nw;
                     {
                         const uint32_t ip = min(i + RG, nrec - 1);
                         nL = s_L[ip];
-                        nraw = fh_word(buf, s_qo[ip], cg);
-                        if (A.do_qc) nw = fh_word(buf, s_so[ip], cg);
+                        nraw = fh_word_packed(buf, s_qo[ip], cg);
+                        if (A.do_qc) nw = fh_word_packed(buf, s_so[ip], cg);
                     }
                     if (L <= col0) continue;
                     const uint32_t nvalid = min(4u, L - col0);
