@@ -42,6 +42,7 @@ struct FusedArgs {
     uint64_t *gc, *mean_phred;
     unsigned long long *qc_err_key;
     uint64_t qc_base;
+    uint8_t *all_acgt;  // [n] 1: every base of the read is ACGTacgt (k_fused_columns skips the letter test)
     // AdapterCounter
     int do_ad;
     const uint8_t *pat;
@@ -207,6 +208,7 @@ k_fused_reads(const FusedArgs A) {
                     const double pct = (double)gc * 100.0 / (double)valid;
                     atomicAdd(&s_gc[(uint32_t)round(pct)], 1u);
                 }
+                A.all_acgt[r] = valid == L;
             }
             // ---- adapters: first occurrence per adapter (:2786-2823) ---------------------------------
             if (A.do_ad) {
@@ -428,6 +430,7 @@ struct ColumnArgs {
     uint64_t *base, *phred, *ea_base, *ea_phred;
     uint32_t ea_len;
     uint8_t *cta_mixed;  // [grid] CTAs that met reads of different lengths
+    const uint8_t *all_acgt;  // [n] from k_fused_reads
     // PerTileQuality
     PtHistGeom hg;
     uint8_t *qh;                 // [n_segs][hg.seg_bytes]
@@ -545,7 +548,8 @@ k_fused_columns(const ColumnArgs A) {
                     const uint32_t L = bv.seq_len[r0 + i];
                     s_so[i] = fh_pack_off(bv.seq_off[r0 + i] - (uint32_t)gstart);
                     s_qo[i] = fh_pack_off(bv.qual_off[r0 + i] - (uint32_t)gstart);
-                    s_L[i] = L;
+                    // bit 31: the read holds nothing but ACGT (k_fused_reads looked at every base already)
+                    s_L[i] = L | (A.do_qc && A.all_acgt[r0 + i] ? 0x80000000u : 0u);
                     lmin = min(lmin, L);
                     lmax = max(lmax, L);
                 }
@@ -569,7 +573,8 @@ k_fused_columns(const ColumnArgs A) {
                 uint32_t nL = s_L[rg], nraw = fh_word_packed(buf, s_qo[rg], cg), nw = 0;
                 if (A.do_qc) nw = fh_word_packed(buf, s_so[rg], cg);
                 for (uint32_t i = rg; i < nrec; i += RG) {
-                    const uint32_t L = nL, raw = nraw, w = nw;
+                    const uint32_t L = nL & 0x7FFFFFFFu, raw = nraw, w = nw;
+                    const bool acgt_only = nL >> 31;
                     {
                         const uint32_t ip = min(i + RG, nrec - 1);
                         nL = s_L[ip];
@@ -581,13 +586,16 @@ k_fused_columns(const ColumnArgs A) {
                     const uint32_t keep = 0xFFFFFFFFu >> (8 * (4 - nvalid));
                     if (A.do_qc) {
                         const uint32_t pm = keep & 0x01010101u;
-                        const uint32_t vb = fh_acgt_bytes(w) & pm;
+                        uint32_t vb = pm;
+                        if (!acgt_only) {  // (a warp mostly walks one record: the branch is nearly uniform)
+                            vb = fh_acgt_bytes(w) & pm;
+                            acc_n += pm & ~vb;
+                        }
                         const uint32_t hb = (w >> 1) & vb, gb = (w >> 2) & vb;
                         acc_v += vb;
                         acc_h += hb;
                         acc_g += gb;
                         acc_hg += hb & gb;
-                        acc_n += pm & ~vb;
                     }
                     uint32_t row4;  // per byte: counter row
                     if (PT) {
@@ -937,8 +945,10 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     A.edges = ctx->d_phred_thresholds;
     long long *tile = nullptr;
     uint64_t *hashes = nullptr;
-    uint8_t *cta_mixed = nullptr;
+    uint8_t *cta_mixed = nullptr, *all_acgt = nullptr;
     if (qc) {
+        SQ_TRY(sq_dalloc(ctx, (void **)&all_acgt, n, false));
+        A.all_acgt = all_acgt;
         A.do_qc = 1;
         A.gc = qc->gc;
         A.mean_phred = qc->mean_phred;
@@ -1017,6 +1027,7 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
             C.ea_phred = qc->ea_phred;
             C.ea_len = (uint32_t)qc->ea_len;
             C.cta_mixed = cta_mixed;
+            C.all_acgt = all_acgt;
         }
         if (plan.runs) {
             C.hg = g.hg;
@@ -1059,5 +1070,6 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     sq_dfree(ctx, tile);
     if (!(dd && dd->deferred && rc == SQ_OK)) sq_dfree(ctx, hashes);  // a deferred estimator keeps them
     sq_dfree(ctx, cta_mixed);
+    sq_dfree(ctx, all_acgt);
     return rc;
 }
