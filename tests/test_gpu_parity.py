@@ -143,6 +143,46 @@ def test_fastq_parse_errors_like_reference(sq, kind, where):
         assert got[0] is None and pat in got[1][1]
 
 
+@pytest.mark.parametrize("bufsize", [1, 2, 7, 100])
+def test_fastq_parser_tiny_initial_buffersize(sq, bufsize):
+    """The argument is a minimum read step (reference tests/test_fastq_parser.py:141-145): any value >= 1
+    parses, and the arrays' `obj` concatenate to the text (:148-174)."""
+    text = synth.illumina_fastq(40, length=60, seed=9, n_tiles=3)
+    recs, _ = orc.parse_fastq(text)
+    arrays = list(sq.FastqParser(io.BytesIO(text), bufsize))
+    assert sum(len(a) for a in arrays) == len(recs)
+    names = [a[i].name() for a in arrays for i in range(len(a))]
+    assert names[0] == bytes(text[1:text.index(b"\n")]).decode() and len(set(names)) == len(recs)
+    # obj = leftover + what was read for this array (the partial next record included), as in the reference
+    assert all(a.obj.startswith(b"@") for a in arrays)
+    ref = H.import_reference()
+    if ref is not None:
+        ref_arrays = list(ref.FastqParser(io.BytesIO(text), bufsize))
+        assert [len(a) for a in arrays] == [len(a) for a in ref_arrays]
+        assert [a.obj for a in arrays] == [a.obj for a in ref_arrays]
+
+
+def test_fastq_parser_empty_input_and_read_exactly_n(sq):
+    assert list(sq.FastqParser(io.BytesIO(b""), 1024)) == []
+    text = synth.illumina_fastq(25, length=50, seed=10, n_tiles=2)
+    parser = sq.FastqParser(io.BytesIO(text), 64)
+    sizes = [len(parser.read(n)) for n in (1, 7, 10, 100, 5)]
+    assert sizes == [1, 7, 10, 7, 0]
+    assert parser.read(1).obj == b""
+
+
+@pytest.mark.parametrize("bufsize", [4, 40, 1000])
+def test_bam_parser_tiny_initial_buffersize(sq, bufsize):
+    bam = synth.nanopore_ubam(12, mean_length=300, max_length=2000, seed=12)
+    stream = bam[len(synth.bam_header()):]
+    packed, recs, consumed, skipped = orc.decode_bam(stream)
+    n, got = 0, b""
+    for arr in sq.BamParser(io.BytesIO(bam), bufsize):
+        n += len(arr)
+        got += arr.obj
+    assert n == len(recs) and got == packed.tobytes()
+
+
 def _qc_case(sq, text, bufsize=1 << 26, chunk=None):
     recs, _ = orc.parse_fastq(text)
     oq = orc.QCMetrics()
