@@ -415,12 +415,16 @@ __device__ __forceinline__ uint32_t newline_mask_ascii(uint32_t w) {
     return ~((w ^ 0x0A0A0A0Au) + 0x7F7F7F7Fu) & 0x80808080u;
 }
 
-constexpr int OP_SUB = 4;                                  // 16 KiB sub-tiles per CTA: fewer, longer tiles keep
+#ifndef SQ_OP_SUB
+#define SQ_OP_SUB 4
+#endif
+constexpr int OP_SUB = SQ_OP_SUB;                          // 16 KiB sub-tiles per CTA: fewer, longer tiles keep
 constexpr int OP_TILE_BYTES = OP_SUB * PARSE_CTA_BYTES;    // the look-back short (64 KiB per CTA)
 constexpr int OP_WARPS = PARSE_THREADS / 32;
-static_assert(OP_SUB * OP_WARPS == 32, "one warp scans the per-(sub-tile, warp) counts");
+constexpr int OP_PARTS = OP_SUB * OP_WARPS;  // (sub-tile, warp) counts, scanned by one warp
+static_assert(OP_PARTS == 32 || OP_PARTS == 64, "one or two parts per lane of the scanning warp");
 
-__global__ void __launch_bounds__(PARSE_THREADS, 6)
+__global__ void __launch_bounds__(PARSE_THREADS, OP_SUB <= 4 ? 6 : 4)
 k_parse_onepass(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t n_tiles, uint64_t max_records,
                 uint32_t cap, unsigned long long *status,
                 uint32_t *__restrict__ fields /* [4][cap]: seq_off, seq_end, qual_off, name_off */, ParseState *st) {
@@ -486,8 +490,16 @@ k_parse_onepass(const uint8_t *__restrict__ text, uint64_t nbytes, uint32_t n_ti
     __syncthreads();
     if (warp == 0) {
         uint32_t total;
-        const uint32_t ex = warp_excl_scan_u32(part_tot[lane], &total);
-        part_excl[lane] = ex;
+        if (OP_PARTS == 32) {
+            const uint32_t ex = warp_excl_scan_u32(part_tot[lane], &total);
+            part_excl[lane] = ex;
+        }
+        else {
+            const uint32_t x0 = part_tot[(2 * lane) % OP_PARTS], x1 = part_tot[(2 * lane + 1) % OP_PARTS];
+            const uint32_t ex = warp_excl_scan_u32(x0 + x1, &total);
+            part_excl[(2 * lane) % OP_PARTS] = ex;
+            part_excl[(2 * lane + 1) % OP_PARTS] = ex + x0;
+        }
         if (lane == 0) st_status(status + tile, (tile == 0 ? OP_FLAG_PREFIX : OP_FLAG_COUNT) | total);
         unsigned long long excl = 0;
         if (tile > 0) {
