@@ -51,9 +51,22 @@ struct sq_overrep {
     std::vector<Kept> kept;
 };
 
+// 0x01 per byte that is ACGTacgt (same construction as qc.cu / fused.cu)
+__device__ __forceinline__ uint32_t ov_acgt_bytes(uint32_t w) {
+    uint32_t sel = w & 0x07070707u;
+    uint32_t t = sel | (sel >> 4);
+    uint32_t nib = __byte_perm(t, 0, 0x4420);
+    uint32_t expect = __byte_perm(0x40FF40FFu, 0x40FFFF50u, nib);
+    return zero_bytes80((w & 0xD8D8D8D8u) ^ expect) >> 7;
+}
+
 // canonical k-mer of s[0..k): 0 ok, 1 holds N/n, 2 holds another non-ACGT letter (:3612-3694).
 // The k <= 31 letters come in with aligned word loads issued together (the text has 64 readable
-// bytes of padding), not one dependent byte load per letter.
+// bytes of padding) and are encoded four at a time: the 2-bit code A=0 C=1 G=2 T=3 is
+// ((c >> 1) & 3) ^ ((c >> 2) & 1) for either case, one multiplication gathers four codes into a
+// byte, and the reverse complement is the complemented forward k-mer with its 2-bit groups in
+// reverse order (bit reversal + a swap inside the pairs).  A fragment with any other letter takes
+// the letter-by-letter path (it only has to tell N from the rest).
 __device__ __forceinline__ int canonical_kmer(const uint8_t *s, uint32_t k, uint64_t *out) {
     const uint32_t *wp = (const uint32_t *)((uintptr_t)s & ~(uintptr_t)3);
     const uint32_t sh = ((uint32_t)(uintptr_t)s & 3u) * 8;
@@ -61,28 +74,31 @@ __device__ __forceinline__ int canonical_kmer(const uint8_t *s, uint32_t k, uint
     uint32_t W[9];
 #pragma unroll
     for (int j = 0; j < 9; j++) W[j] = (uint32_t)j <= nw ? __ldg(wp + j) : 0u;
-    uint64_t fw = 0, rc = 0;
-    uint32_t flags = 0;
+    uint64_t fw = 0;
+    uint32_t bad = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const uint32_t a = __funnelshift_r(W[j], W[j + 1], sh);
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const uint32_t i = j * 4 + b;
-            if (i < k) {
-                const uint32_t ch = ((a >> (8 * b)) & 0xFFu) | 0x20u;
-                uint32_t c = ch == 'a' ? 0u : ch == 'c' ? 1u : ch == 'g' ? 2u : ch == 't' ? 3u : 4u;
-                if (c == 4) {
-                    flags |= ch == 'n' ? 1u : 2u;
-                    c = 0;
-                }
-                fw = (fw << 2) | c;
-                rc |= (uint64_t)(3 - c) << (2 * i);
-            }
+        if ((uint32_t)j < nw) {
+            const uint32_t a = __funnelshift_r(W[j], W[j + 1], sh);
+            const uint32_t left = k - 4 * j;  // letters of the fragment in this word (>= 1)
+            const uint32_t pm = left >= 4 ? 0x01010101u : 0x01010101u >> (8 * (4 - left));
+            bad |= pm & ~ov_acgt_bytes(a);
+            const uint32_t code = (((a >> 1) & 0x03030303u) ^ ((a >> 2) & 0x01010101u)) & (pm * 3u);
+            fw = (fw << 8) | ((code * 0x40100401u) >> 24);  // first letter in the top two bits
         }
     }
-    if (flags & 2) return 2;
-    if (flags & 1) return 1;
+    if (bad) {  // rare: which kind of letter is it
+        uint32_t flags = 0;
+        for (uint32_t i = 0; i < k; i++) {
+            const uint32_t ch = s[i] | 0x20u;
+            if (ch != 'a' && ch != 'c' && ch != 'g' && ch != 't') flags |= ch == 'n' ? 1u : 2u;
+        }
+        return flags & 2 ? 2 : 1;
+    }
+    fw >>= 2 * (4 * nw - k);  // the padding letters of the last word were encoded as zeros
+    uint64_t r = __brevll(~fw);  // complement, then reverse the order of the 2-bit groups
+    r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+    const uint64_t rc = r >> (64 - 2 * k);
     *out = rc < fw ? rc : fw;
     return 0;
 }
