@@ -19,7 +19,7 @@ def _n_gpus():
         return 0
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_merges_match_the_oracle(world):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
