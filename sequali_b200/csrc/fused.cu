@@ -93,6 +93,14 @@ __device__ __forceinline__ uint32_t fh_acgt_bytes(uint32_t w) {
     uint32_t expect = __byte_perm(0x40FF40FFu, 0x40FFFF50u, nib);
     return zero_bytes80((w & 0xD8D8D8D8u) ^ expect) >> 7;
 }
+// the same test with the flag left in bit 7 of each byte
+__device__ __forceinline__ uint32_t fh_acgt_bytes80(uint32_t w) {
+    uint32_t sel = w & 0x07070707u;
+    uint32_t t = sel | (sel >> 4);
+    uint32_t nib = __byte_perm(t, 0, 0x4420);
+    uint32_t expect = __byte_perm(0x40FF40FFu, 0x40FFFF50u, nib);
+    return zero_bytes80((w & 0xD8D8D8D8u) ^ expect);
+}
 // bit i of the result = bit 0 of byte i of x (x has only bit 0 of each byte set)
 __device__ __forceinline__ uint32_t fh_pack4(uint32_t x) { return (x * 0x00204081u) >> 21 & 0xFu; }
 
@@ -180,14 +188,18 @@ k_fused_reads(const FusedArgs A) {
                         for (int k = 0; k < 8; k++) {
                             const uint32_t pos = pw * 32 + k * 4;
                             if (pos < L) {
+                                // flags live in bit 7 of their byte: one multiplication lands the four of a
+                                // word in bits 28..31 (every partial product on its own bit), one shift and one
+                                // masked OR put them at positions 4k .. 4k+3 of the plane
                                 const uint32_t w = fh_word(buf, so, pos >> 2);
                                 const uint32_t nvalid = min(4u, L - pos);
-                                const uint32_t pm = 0x01010101u >> (8 * (4 - nvalid));
-                                const uint32_t vb = fh_acgt_bytes(w) & pm;
-                                const uint32_t hb = (w >> 1) & vb, gb = (w >> 2) & vb;
-                                v |= fh_pack4(vb) << (k * 4);
-                                h |= fh_pack4(hb) << (k * 4);
-                                g |= fh_pack4(gb) << (k * 4);
+                                const uint32_t pm = 0x80808080u >> (8 * (4 - nvalid));
+                                const uint32_t vb = fh_acgt_bytes80(w) & pm;
+                                const uint32_t hb = (w << 6) & vb, gb = (w << 5) & vb;  // bit 1 / bit 2 of the letter
+                                const uint32_t nib = 0xFu << (k * 4);
+                                v |= ((vb * 0x00204081u) >> (28 - k * 4)) & nib;
+                                h |= ((hb * 0x00204081u) >> (28 - k * 4)) & nib;
+                                g |= ((gb * 0x00204081u) >> (28 - k * 4)) & nib;
                             }
                         }
                     }
@@ -223,7 +235,7 @@ k_fused_reads(const FusedArgs A) {
 #pragma unroll
                     for (int pw = 0; pw < NW; pw++) M[pw] = 0xFFFFFFFFu;
                     bool alive = true;
-                    for (uint32_t j = 0; j < m && alive; j++) {
+                    auto letter = [&](uint32_t j) {
                         const uint32_t c = s_pat[a * FH_MAX_PAT + j];
                         uint32_t X[NW + 1];
                         X[NW] = 0;
@@ -250,13 +262,26 @@ k_fused_reads(const FusedArgs A) {
                             for (int pw = 0; pw < NW; pw++) X[pw] = ~V[pw] & P[pw];
                             break;
                         }
+#pragma unroll
+                        for (int pw = 0; pw < NW; pw++) M[pw] &= __funnelshift_r(X[pw], X[pw + 1], j);
+                    };
+                    auto any_left = [&]() {
                         uint32_t any = 0;
 #pragma unroll
-                        for (int pw = 0; pw < NW; pw++) {
-                            M[pw] &= __funnelshift_r(X[pw], X[pw + 1], j);
-                            any |= M[pw];
-                        }
-                        alive = any != 0;
+                        for (int pw = 0; pw < NW; pw++) any |= M[pw];
+                        return any != 0;
+                    };
+                    // two letters per look at the candidates (a letter too many now and then costs less
+                    // than testing after every one)
+                    uint32_t j = 0;
+                    for (; j + 1 < m && alive; j += 2) {
+                        letter(j);
+                        letter(j + 1);
+                        alive = any_left();
+                    }
+                    if (alive && j < m) {
+                        letter(j);
+                        alive = any_left();
                     }
                     if (!alive) continue;
                     uint32_t p = 0xFFFFFFFFu;
