@@ -58,7 +58,8 @@ k_dd_hash(BatchView bv, uint64_t front_len, uint64_t back_len, uint64_t front_of
 // such pairs are rare enough to be handled by one thread in record order.
 __global__ void __launch_bounds__(DD_TPB)
 k_dd_hash_pair(BatchView b1, BatchView b2, uint64_t front_len, uint64_t back_len, uint64_t front_off,
-               uint64_t back_off, uint64_t *__restrict__ hashes, uint32_t *__restrict__ short_flag) {
+               uint64_t back_off, uint64_t *__restrict__ hashes, uint32_t *__restrict__ short_flag,
+               uint32_t *range) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < b1.n; r += gridDim.x * blockDim.x) {
         const uint8_t *s1 = b1.text + b1.seq_off[r], *s2 = b2.text + b2.seq_off[r];
         const uint64_t L1 = b1.seq_len[r], L2 = b2.seq_len[r], fl = front_len + back_len;
@@ -66,6 +67,8 @@ k_dd_hash_pair(BatchView b1, BatchView b2, uint64_t front_len, uint64_t back_len
         if (f + b < fl) {  // would read stale scratch bytes: defer to the ordered kernel
             short_flag[r] = 1;
             hashes[r] = 0;
+            atomicMin(range, r);
+            atomicMax(range + 1, r);
             continue;
         }
         short_flag[r] = 0;
@@ -75,21 +78,62 @@ k_dd_hash_pair(BatchView b1, BatchView b2, uint64_t front_len, uint64_t back_len
     }
 }
 
-// one thread walks the batch in order, maintaining the scratch buffer exactly
-// as the reference does; only launched when a short pair exists
-__global__ void k_dd_hash_pair_ordered(BatchView b1, BatchView b2, uint64_t front_len, uint64_t back_len,
-                                       uint64_t front_off, uint64_t back_off, uint64_t *hashes,
-                                       uint8_t *stale) {
-    if (blockIdx.x || threadIdx.x) return;
+// The scratch buffer of the reference (fingerprint_store, :4500-4516) as it stands after record r: a pair
+// that is long enough overwrites all of it, a short pair only its first f and the b bytes behind them.
+__device__ __forceinline__ void dd_pair_into_stale(const BatchView &b1, const BatchView &b2, uint32_t r,
+                                                   uint64_t front_len, uint64_t back_len, uint64_t front_off,
+                                                   uint64_t back_off, uint8_t *stale, uint64_t *f_out) {
+    const uint8_t *s1 = b1.text + b1.seq_off[r], *s2 = b2.text + b2.seq_off[r];
+    const uint64_t L1 = b1.seq_len[r], L2 = b2.seq_len[r];
+    const uint64_t f = min(front_len, L1), b = min(back_len, L2);
+    const uint64_t fo = min(front_off, L1 - f), bo = min(back_off, L2 - b);
+    for (uint64_t i = 0; i < f; i++) stale[i] = s1[fo + i];
+    for (uint64_t i = 0; i < b; i++) stale[f + i] = s2[bo + i];
+    *f_out = f;
+}
+
+// One CTA walks the short-pair flags between the first and the last flagged record (`range`, kept by
+// k_dd_hash_pair), 1024 records per step; thread 0 re-hashes the flagged pairs in record order with the
+// scratch buffer exactly as the reference leaves it: the record in front of a short pair (or the last
+// pair of an earlier batch, kept in `stale`) supplies the bytes the short pair does not overwrite.
+// The last pair of the batch is left in `stale` for the next batch.
+__global__ void __launch_bounds__(1024)
+k_dd_hash_pair_ordered(BatchView b1, BatchView b2, uint64_t front_len, uint64_t back_len, uint64_t front_off,
+                       uint64_t back_off, uint64_t *hashes, const uint32_t *__restrict__ short_flag,
+                       uint32_t *range, uint8_t *stale) {
+    __shared__ uint32_t s_flag[1024];
     const uint64_t fl = front_len + back_len;
-    for (uint32_t r = 0; r < b1.n; r++) {
-        const uint8_t *s1 = b1.text + b1.seq_off[r], *s2 = b2.text + b2.seq_off[r];
-        const uint64_t L1 = b1.seq_len[r], L2 = b2.seq_len[r];
-        const uint64_t f = min(front_len, L1), b = min(back_len, L2);
-        const uint64_t fo = min(front_off, L1 - f), bo = min(back_off, L2 - b);
-        for (uint64_t i = 0; i < f; i++) stale[i] = s1[fo + i];
-        for (uint64_t i = 0; i < b; i++) stale[f + i] = s2[bo + i];
-        hashes[r] = murmur3_h2([&](uint64_t i) { return stale[i]; }, fl, (L1 + L2) >> 6);
+    const uint32_t n = b1.n, tid = threadIdx.x;
+    const uint32_t lo = range[0], hi = range[1];
+    uint32_t applied = 0xFFFFFFFFu;  // thread 0: last record whose bytes are in `stale`
+    if (lo <= hi) {
+        for (uint32_t base = lo & ~1023u; base <= hi; base += 1024) {
+            const uint32_t r = base + tid;
+            const uint32_t fl_here = r < n ? short_flag[r] : 0u;
+            s_flag[tid] = fl_here;
+            if (__syncthreads_or((int)fl_here) && tid == 0) {
+                for (uint32_t i = 0; i < 1024; i++) {
+                    if (!s_flag[i]) continue;
+                    const uint32_t rr = base + i;
+                    uint64_t f;
+                    if (rr > 0 && applied != rr - 1)
+                        dd_pair_into_stale(b1, b2, rr - 1, front_len, back_len, front_off, back_off, stale, &f);
+                    dd_pair_into_stale(b1, b2, rr, front_len, back_len, front_off, back_off, stale, &f);
+                    applied = rr;
+                    hashes[rr] = murmur3_h2([&](uint64_t k) { return stale[k]; }, fl,
+                                            ((uint64_t)b1.seq_len[rr] + b2.seq_len[rr]) >> 6);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        if (n && applied != n - 1) {
+            uint64_t f;
+            dd_pair_into_stale(b1, b2, n - 1, front_len, back_len, front_off, back_off, stale, &f);
+        }
+        range[0] = 0xFFFFFFFFu;  // ready for the next batch
+        range[1] = 0;
     }
 }
 
@@ -323,6 +367,8 @@ extern "C" int sq_dedup_create(sq_ctx *ctx, uint64_t max_stored_fingerprints, ui
     if (rc == SQ_OK) rc = table_alloc(ctx, &d->spare, d->table_size);
     if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&d->cnt, sizeof(DdCounters), true);
     if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&d->stale_fp, front_len + back_len + 16, true);
+    if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&d->pair_range, 8, true);
+    if (rc == SQ_OK) rc = cudaMemsetAsync(d->pair_range, 0xFF, 4, ctx->stream) == cudaSuccess ? SQ_OK : SQ_E_CUDA;
     if (rc != SQ_OK) {
         sq_dedup_destroy(d);
         return rc;
@@ -340,6 +386,7 @@ extern "C" void sq_dedup_destroy(sq_dedup *d) {
     sq_dfree(d->ctx, d->compact);
     sq_dfree(d->ctx, d->cnt);
     sq_dfree(d->ctx, d->stale_fp);
+    sq_dfree(d->ctx, d->pair_range);
     delete d;
 }
 
@@ -516,23 +563,18 @@ extern "C" int sq_dedup_add_pair(sq_dedup *d, sq_batch *b1, sq_batch *b2) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     const uint32_t n = (uint32_t)b1->n;
     uint64_t *hashes = nullptr;
-    uint32_t *short_flag = nullptr, *short_total = nullptr;
+    uint32_t *short_flag = nullptr;
     SQ_TRY(sq_dalloc(ctx, (void **)&hashes, (size_t)n * 8, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&short_flag, (size_t)n * 4 + 4, false));
-    short_total = short_flag + n;
+    if (int rc = sq_dalloc(ctx, (void **)&short_flag, (size_t)n * 4, false)) {
+        sq_dfree(ctx, hashes);
+        return rc;
+    }
     SQ_LAUNCH(ctx, k_dd_hash_pair, sq_grid_for(ctx, n, DD_TPB, 16), DD_TPB, 0, b1->view(), b2->view(),
-              d->front_len, d->back_len, d->front_off, d->back_off, hashes, short_flag);
-    // any pair shorter than the fingerprint?  (needs the reference's stale-buffer semantics)
-    uint32_t *tmp = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&tmp, (size_t)n * 4, false));
-    SQ_TRY(sq_scan_exclusive_u32(ctx, short_flag, tmp, n, short_total));
-    uint32_t *h_total = (uint32_t *)((char *)ctx->h_scratch + 3072);
-    CUDA_TRY(cudaMemcpyAsync(h_total, short_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (*h_total)
-        SQ_LAUNCH(ctx, k_dd_hash_pair_ordered, 1, 32, 0, b1->view(), b2->view(), d->front_len, d->back_len,
-                  d->front_off, d->back_off, hashes, d->stale_fp);
-    sq_dfree(ctx, tmp);
+              d->front_len, d->back_len, d->front_off, d->back_off, hashes, short_flag, d->pair_range);
+    // short pairs hash what the previous pair left in the reference's scratch buffer (:4503-4516): one warp
+    // re-hashes them in record order and leaves the batch's last pair in stale_fp for the next batch
+    SQ_LAUNCH(ctx, k_dd_hash_pair_ordered, 1, 1024, 0, b1->view(), b2->view(), d->front_len, d->back_len,
+              d->front_off, d->back_off, hashes, short_flag, d->pair_range, d->stale_fp);
     int rc = dedup_consume(d, hashes, n);
     if (!d->deferred) sq_dfree(ctx, hashes);
     sq_dfree(ctx, short_flag);

@@ -159,6 +159,7 @@ struct sq_dedup {
     DdTable tab, spare;
     DdCounters *cnt = nullptr;
     uint8_t *stale_fp = nullptr;  // pair path: persistent fingerprint scratch of the reference
+    uint32_t *pair_range = nullptr;  // pair path: {first, last} short pair of the batch being hashed
     // sharded runs (rank > 0): keep the fingerprint hashes, the table lives on the first rank
     bool deferred = false;
     struct Kept { uint64_t *hashes; uint32_t n; };

@@ -159,9 +159,16 @@ k_ov_fragments(BatchView bv, uint32_t first_sampled, uint32_t sample_every, uint
                     emitted = ov_stage_read([&](uint32_t i) -> uint64_t & { return s_stage[i][tid]; }, ssize, seq, L, k,
                                             nf, nb, out, &warn, &valid);
                 }
-                else {
+                else if (ssize <= OV_STAGE_MAX) {
                     uint64_t stage[OV_STAGE_MAX];
                     emitted = ov_stage_read([&](uint32_t i) -> uint64_t & { return stage[i]; }, ssize, seq, L, k, nf, nb,
+                                            out, &warn, &valid);
+                }
+                else {
+                    // whole-read fragment sets of long reads (bases_from_start / bases_from_end < 0 or large,
+                    // :3499-3504): the read's own row of frag_hash (fcap >= ssize slots) is the staging table,
+                    // compacted in place in slot order afterwards (the write index never passes the read index)
+                    emitted = ov_stage_read([&](uint32_t i) -> uint64_t & { return out[i]; }, ssize, seq, L, k, nf, nb,
                                             out, &warn, &valid);
                 }
                 valid_total += valid;
@@ -463,11 +470,6 @@ extern "C" int sq_overrep_add(sq_overrep *o, sq_batch *b) {
     if (total == 0) return SQ_OK;
     uint32_t fcap = 1;
     while (2 * (uint64_t)fcap < 3 * total) fcap <<= 1;
-    if (fcap > OV_STAGE_MAX) {
-        sq_set_error("more than %d fragments per read are not supported yet (got %llu)",
-                     OV_STAGE_MAX * 2 / 3, (unsigned long long)total);
-        return SQ_E_LIMIT;
-    }
     const uint64_t occ = n_sampled * fcap;
     if (occ >= 0xFFFFFFFFULL) {
         sq_set_error("record array too large for the fragment index");

@@ -1,0 +1,117 @@
+"""-m gpu: BamParser edge cases on the CUDA path (reference tests/test_bam_parser.py:95-147 and
+_qcmodule.c:1623-1694): missing qualities (0xff block -> '!'), secondary / supplementary records
+skipped, every truncation point of header and records, tiny read steps -- the unmodified reference
+extension (oracle/_ref) and sequali_b200 side by side on the same bytes."""
+import gzip
+import io
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from sequali_b200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+REF = H.import_reference()
+if REF is None:  # pragma: no cover
+    pytest.skip("oracle/_ref is not built", allow_module_level=True)
+
+REF_DATA = os.path.join(H.ROOT, "oracle", "_ref", "tests", "tests", "data")
+
+
+@pytest.fixture(scope="module")
+def sq():
+    import sequali_b200
+    return sequali_b200
+
+
+def make_bam(rng, n, flags=(4,), missing_every=0, lengths=(0, 1, 2, 7, 8, 33, 150, 151, 1000)):
+    out = io.BytesIO()
+    out.write(synth.bam_header())
+    letters = np.frombuffer(b"=ACMGRSVTWYHKDBN", dtype=np.uint8)
+    for i in range(n):
+        ln = int(lengths[i % len(lengths)])
+        seq = letters[rng.integers(0, 16, size=ln)]
+        qual = (rng.integers(0, 94, size=ln).astype(np.uint8) + 33)
+        tags = b"chS" + struct.pack("<H", i % 2048 + 1) + b"stZ2023-01-0%dT10:00:00Z\0" % (i % 9 + 1) + \
+            b"duf" + struct.pack("<f", 1.5 + i)
+        rec = synth.bam_record(b"read%d" % i, seq, qual, tags, flag=int(flags[i % len(flags)]))
+        if missing_every and i % missing_every == 0 and ln:
+            # qualities absent: the block is 0xff bytes (SAM spec 4.2.3; _qcmodule.c:1658-1663)
+            body = bytearray(rec)
+            qoff = 4 + 32 + len(b"read%d" % i) + 1 + (ln + 1) // 2
+            body[qoff:qoff + ln] = b"\xff" * ln
+            rec = bytes(body)
+        out.write(rec)
+    return out.getvalue()
+
+
+def records(mod, raw, bufsize=None):
+    """Every record a BamParser yields, as plain tuples."""
+    parser = mod.BamParser(io.BytesIO(raw)) if bufsize is None else mod.BamParser(io.BytesIO(raw), bufsize)
+    out = []
+    for arr in parser:
+        for i in range(len(arr)):
+            r = arr[i]
+            out.append((r.name(), r.sequence(), r.qualities(), r.tags()))
+    return parser.header, out
+
+
+def outcome(fn):
+    try:
+        return fn()
+    except Exception as e:  # noqa: BLE001
+        return ("raised", type(e).__name__)
+
+
+def test_missing_qualities_and_skipped_flags(sq):
+    rng = np.random.default_rng(31)
+    raw = make_bam(rng, 120, flags=(4, 0x100, 4, 0x800, 0x904, 77, 141), missing_every=3)
+    want, got = records(REF, raw), records(sq, raw)
+    assert got == want
+    assert any(set(q) == {"!"} for _, s, q, _ in want if s)      # the 0xff branch was taken
+    assert len(want[1]) < 120                                     # records were skipped
+    H.assert_same(H.api_single_end(sq, b"", H.NANOPORE_ADAPTERS, fileobj=io.BytesIO(raw), bam=True),
+                  H.api_single_end(REF, b"", H.NANOPORE_ADAPTERS, fileobj=io.BytesIO(raw), bam=True))
+
+
+def test_only_skipped_records(sq):
+    raw = make_bam(np.random.default_rng(32), 9, flags=(0x100, 0x800))
+    assert records(sq, raw) == records(REF, raw) and records(REF, raw)[1] == []
+
+
+@pytest.mark.parametrize("bufsize", [4, 8, 10, 20, 40, 333, 4096])
+def test_small_read_steps(sq, bufsize):
+    raw = make_bam(np.random.default_rng(33), 40, flags=(4, 4, 0x100), missing_every=5)
+    assert records(sq, raw, bufsize) == records(REF, raw, bufsize)
+
+
+def test_every_truncation_point(sq):
+    """tests/test_bam_parser.py:95-120: cut the stream anywhere in the header or in a record."""
+    raw = make_bam(np.random.default_rng(34), 3, lengths=(7, 8, 5))
+    header_len = len(synth.bam_header())
+    for end in range(len(raw)):
+        a = outcome(lambda: records(REF, raw[:end]))
+        b = outcome(lambda: records(sq, raw[:end]))
+        assert a == b, (end, header_len, a, b)
+    with pytest.raises(EOFError, match="ncomplete record"):
+        records(sq, raw[:header_len + 9])
+    with pytest.raises(EOFError, match="runcated BAM"):
+        records(sq, raw[:header_len - 3])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DATA), reason="reference fixtures not staged")
+@pytest.mark.parametrize("name", ["missing_quals.bam", "test_skip.bam", "secondary_alignment.bam",
+                                  "simple.unaligned.bam", "simple.raw.bam", "dorado_nanopore_100reads.bam",
+                                  "project.NIST_NIST7035_H7AP8ADXX_TAAGGCGA_1_NA12878.bwa.markDuplicates.bam"])
+def test_reference_fixture_files(sq, name):
+    with open(os.path.join(REF_DATA, name), "rb") as f:
+        raw = f.read()
+    if raw[:2] == b"\x1f\x8b":
+        raw = gzip.decompress(raw)
+    assert records(sq, raw) == records(REF, raw)
+    H.assert_same(H.api_single_end(sq, b"", H.NANOPORE_ADAPTERS, fileobj=io.BytesIO(raw), bam=True),
+                  H.api_single_end(REF, b"", H.NANOPORE_ADAPTERS, fileobj=io.BytesIO(raw), bam=True))
