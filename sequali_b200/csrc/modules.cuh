@@ -123,8 +123,10 @@ struct PtPlan {
     PtHistGeom hg;
     uint8_t *qh = nullptr;        // [n_ftiles][hg.seg_bytes]
 };
+// qh / oob != nullptr: the histograms were already written (k_onewalk computes the tile ids and the
+// histograms in the same pass); the plan owns and frees them either way
 int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t n_ftiles, uint32_t W,
-               const PtHistGeom &hg, PtPlan *pl);
+               const PtHistGeom &hg, PtPlan *pl, uint8_t *qh, uint8_t *oob);
 // sampled quality byte range for the next k_fused_columns launch (syncs once, for the first array)
 int pt_quality_range(sq_pertile *p, uint32_t *qmin, uint32_t *qmax);
 int pt_finish(sq_pertile *p, sq_batch *b, PtPlan *pl);

@@ -829,11 +829,11 @@ static int pt_prepare_runs(sq_pertile *p, sq_batch *b, PtPlan *pl, uint32_t seg_
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->runs_cnt, (size_t)n_ftiles * 4, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->seg_off, (size_t)n_ftiles * 4, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->uniform, n_ftiles, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&pl->oob, n_ftiles, true));
+    if (!pl->oob) SQ_TRY(sq_dalloc(ctx, (void **)&pl->oob, n_ftiles, true));
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->segs, (size_t)seg_cap * sizeof(PtSeg), false));
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->seg, (size_t)n_slots * 8, false));
     SQ_TRY(sq_dalloc(ctx, (void **)&pl->nseg, (size_t)n_slots * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&pl->qh, (size_t)n_ftiles * pl->hg.seg_bytes, false));
+    if (!pl->qh) SQ_TRY(sq_dalloc(ctx, (void **)&pl->qh, (size_t)n_ftiles * pl->hg.seg_bytes, false));
     uint32_t *seg_lo = pl->seg, *seg_hi = pl->seg + n_slots;
     CUDA_TRY(cudaMemsetAsync(seg_lo, 0xFF, (size_t)n_slots * 4, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(seg_hi, 0, (size_t)n_slots * 4, ctx->stream));
@@ -877,7 +877,7 @@ extern "C" int sq_pertile_add(sq_pertile *p, sq_batch *b) {
     SQ_TRY(sq_dalloc(ctx, (void **)&tile, (size_t)n * 8, false));
     SQ_LAUNCH(ctx, k_pt_tile, sq_grid_for(ctx, n, PT_TPB, 16), PT_TPB, 0, b->view(), tile, p->n_added, p->st);
     PtPlan pl;
-    int rc = pt_prepare(p, b, tile, 0, 0, 0, PtHistGeom(), &pl);
+    int rc = pt_prepare(p, b, tile, 0, 0, 0, PtHistGeom(), &pl, nullptr, nullptr);
     if (rc == SQ_OK) rc = pt_finish(p, b, &pl);
     else pt_plan_free(ctx, &pl);
     sq_dfree(ctx, tile);
@@ -887,12 +887,14 @@ extern "C" int sq_pertile_add(sq_pertile *p, sq_batch *b) {
 // Tile ids -> slots, table growth, length counts; for reads in tile runs (R != 0: the caller
 // will run k_fused_columns over fixed tiles of R records) also the segments and their hints.
 int pt_prepare(sq_pertile *p, sq_batch *b, long long *tile, uint32_t R, uint32_t n_ftiles, uint32_t W,
-               const PtHistGeom &hg, PtPlan *pl) {
+               const PtHistGeom &hg, PtPlan *pl, uint8_t *qh, uint8_t *oob) {
     sq_ctx *ctx = p->ctx;
     const uint32_t n = (uint32_t)b->n;
     const uint64_t base = p->n_added;
     const int grid = sq_grid_for(ctx, n, PT_TPB, 16);
     *pl = PtPlan();
+    pl->qh = qh;
+    pl->oob = oob;
     pl->R = R;
     pl->n_ftiles = n_ftiles;
     pl->W = W;

@@ -72,7 +72,7 @@ def test_missing_qualities_and_skipped_flags(sq):
     raw = make_bam(rng, 120, flags=(4, 0x100, 4, 0x800, 0x904, 77, 141), missing_every=3)
     want, got = records(REF, raw), records(sq, raw)
     assert got == want
-    assert any(set(q) == {"!"} for _, s, q, _ in want if s)      # the 0xff branch was taken
+    assert any(set(q) == {"!"} for _, s, q, _ in want[1] if s)      # the 0xff branch was taken
     assert len(want[1]) < 120                                     # records were skipped
     H.assert_same(H.api_single_end(sq, b"", H.NANOPORE_ADAPTERS, fileobj=io.BytesIO(raw), bam=True),
                   H.api_single_end(REF, b"", H.NANOPORE_ADAPTERS, fileobj=io.BytesIO(raw), bam=True))

@@ -13,7 +13,6 @@ TESTS="tests/test_gpu_parity.py -k 'tiny_records or outliers or odd_content or e
 for tool in memcheck racecheck initcheck synccheck; do
     extra=""
     [ "$tool" = memcheck ] && extra="--leak-check no"
-    [ "$tool" = initcheck ] && extra="--track-unused-memory no"
     timeout 1500 $SAN --tool $tool $extra --error-exitcode 9 --print-limit 20 \
         python -c "$SMOKE" > "$OUT/sanitize_${tool}_smoke.log" 2>&1
     rc1=$?
