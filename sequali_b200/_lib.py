@@ -217,6 +217,58 @@ def check(rc: int, what: str = ""):
     raise SqGpuError(f"{what} failed (code {rc}): {msg}")
 
 
+def prefetched(gen, depth: int = 1):
+    """Advance the generator `gen` on a helper thread, `depth` items ahead of the consumer.
+
+    The parsers' entry points of libsqgpu put their device work on the context's parser stream, so
+    the record-boundary scan (and the host->device copy) of the NEXT record array overlaps with the
+    collectors' kernels of the current one -- the read-ahead the reference gets from xopen's
+    decompression threads (src/sequali/util.py:108-123).  Exceptions of `gen` surface at the item
+    they belong to.  SEQUALI_B200_NO_PREFETCH=1 switches the helper thread off."""
+    if os.environ.get("SEQUALI_B200_NO_PREFETCH"):
+        yield from gen
+        return
+    import queue
+    q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
+    stop = threading.Event()
+
+    def put(msg) -> bool:
+        while not stop.is_set():
+            try:
+                q.put(msg, timeout=0.05)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def work():
+        try:
+            for item in gen:
+                if not put(("item", item)):
+                    return
+            put(("done", None))
+        except BaseException as e:  # noqa: BLE001 -- handed to the consumer
+            put(("error", e))
+
+    t = threading.Thread(target=work, name="sequali-b200-parser", daemon=True)
+    t.start()
+    try:
+        while True:
+            kind, val = q.get()
+            if kind == "item":
+                yield val
+            elif kind == "error":
+                raise val
+            else:
+                return
+    finally:
+        stop.set()
+        t.join()
+        while not q.empty():
+            q.get_nowait()
+        gen.close()
+
+
 class Context:
     """One device context per process (device = $SEQUALI_B200_DEVICE, else
     $LOCAL_RANK, else 0)."""

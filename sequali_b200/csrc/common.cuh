@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -38,7 +40,13 @@ struct sq_ctx {
     int device = 0;
     int num_sms = SQ_NUM_SMS_HINT;
     cudaStream_t stream = nullptr;
-    uint64_t launches = 0;
+    // The record-boundary scan of the NEXT record array may run on a helper thread while this thread
+    // feeds the collectors with the current one: parser entry points put their work on `pstream`
+    // (SqParserScope below), so their host synchronisations do not wait for the collectors' kernels.
+    // One collector thread + one parser thread per context is the supported concurrency.
+    cudaStream_t pstream = nullptr;
+    std::atomic<uint64_t> launches{0};
+    std::mutex prof_mutex;
     // pinned scratch for small device->host result structs
     void *h_scratch = nullptr;  // 4 KiB pinned
     void *d_scratch = nullptr;  // 4 KiB device
@@ -65,6 +73,17 @@ struct sq_ctx {
 };
 void sq_prof_begin(sq_ctx *ctx, const char *name);
 void sq_prof_end(sq_ctx *ctx);
+
+// stream of the calling thread's work: the context's launch stream, or the parser stream inside a
+// parser entry point
+extern thread_local cudaStream_t sq_tls_stream;
+inline cudaStream_t sq_cur_stream(const sq_ctx *ctx) { return sq_tls_stream ? sq_tls_stream : ctx->stream; }
+struct SqParserScope {
+    cudaStream_t prev;
+    // (while per-kernel profiling is on everything stays on the launch stream: its events are ordered)
+    explicit SqParserScope(const sq_ctx *ctx) : prev(sq_tls_stream) { sq_tls_stream = ctx->profile ? nullptr : ctx->pstream; }
+    ~SqParserScope() { sq_tls_stream = prev; }
+};
 
 // Device-side view of a record array.  Offsets index `text`.
 struct BatchView {
@@ -133,9 +152,16 @@ inline int sq_grid_for(sq_ctx *ctx, uint64_t work_items, int per_block, int max_
 
 #define SQ_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
     do {                                                                       \
-        if ((ctx)->profile) sq_prof_begin((ctx), #kernel);                     \
-        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);       \
-        if ((ctx)->profile) sq_prof_end((ctx));                                \
+        const bool _prof = (ctx)->profile;                                     \
+        if (_prof) {                                                           \
+            (ctx)->prof_mutex.lock();                                          \
+            sq_prof_begin((ctx), #kernel);                                     \
+        }                                                                      \
+        kernel<<<(grid), (block), (smem), sq_cur_stream(ctx)>>>(__VA_ARGS__);  \
+        if (_prof) {                                                           \
+            sq_prof_end((ctx));                                                \
+            (ctx)->prof_mutex.unlock();                                        \
+        }                                                                      \
         (ctx)->launches++;                                                     \
         CUDA_TRY(cudaGetLastError());                                          \
     } while (0)

@@ -20,6 +20,7 @@
 // errors
 // ---------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
+thread_local cudaStream_t sq_tls_stream = nullptr;
 
 void sq_set_error(const char *fmt, ...) {
     va_list ap;
@@ -49,12 +50,12 @@ extern "C" int sq_device_count(void) {
 int sq_dalloc(sq_ctx *ctx, void **p, size_t nbytes, bool zero) {
     *p = nullptr;
     if (nbytes == 0) nbytes = 16;
-    CUDA_TRY(cudaMallocAsync(p, nbytes, ctx->stream));
-    if (zero) CUDA_TRY(cudaMemsetAsync(*p, 0, nbytes, ctx->stream));
+    CUDA_TRY(cudaMallocAsync(p, nbytes, sq_cur_stream(ctx)));
+    if (zero) CUDA_TRY(cudaMemsetAsync(*p, 0, nbytes, sq_cur_stream(ctx)));
     return SQ_OK;
 }
 void sq_dfree(sq_ctx *ctx, void *p) {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    if (p) cudaFreeAsync(p, sq_cur_stream(ctx));
 }
 
 // Largest x with floor(-10*log10(x)) >= k, found on the bit pattern of the
@@ -96,6 +97,7 @@ extern "C" int sq_ctx_create(int device, sq_ctx **out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->pstream, cudaStreamNonBlocking));
     // keep freed blocks in the pool: record arrays come and go every batch
     cudaMemPool_t pool;
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -118,6 +120,7 @@ extern "C" int sq_ctx_create(int device, sq_ctx **out) {
 extern "C" void sq_ctx_destroy(sq_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->pstream);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_err_table);
     cudaFree(ctx->d_phred_thresholds);
@@ -128,6 +131,7 @@ extern "C" void sq_ctx_destroy(sq_ctx *ctx) {
     if (ctx->h_bounce) cudaFreeHost(ctx->h_bounce);
     for (int k = 0; k < 3; k++) cudaFree(ctx->stage_slot[k]);
     cudaFreeHost(ctx->h_scratch);
+    cudaStreamDestroy(ctx->pstream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -138,10 +142,10 @@ void sq_prof_begin(sq_ctx *ctx, const char *name) {
     e.name = name;
     cudaEventCreate(&e.start);
     cudaEventCreate(&e.stop);
-    cudaEventRecord(e.start, ctx->stream);
+    cudaEventRecord(e.start, sq_cur_stream(ctx));
     ctx->prof_events.push_back(e);
 }
-void sq_prof_end(sq_ctx *ctx) { cudaEventRecord(ctx->prof_events.back().stop, ctx->stream); }
+void sq_prof_end(sq_ctx *ctx) { cudaEventRecord(ctx->prof_events.back().stop, sq_cur_stream(ctx)); }
 
 extern "C" int sq_ctx_profile(sq_ctx *ctx, int enable) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -211,11 +215,12 @@ extern "C" int sq_timer_stop(sq_ctx *ctx, double *ms) {
 }
 
 extern "C" int sq_ctx_sync(sq_ctx *ctx) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->pstream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return SQ_OK;
 }
 extern "C" void *sq_ctx_stream(sq_ctx *ctx) { return (void *)ctx->stream; }
-extern "C" uint64_t sq_ctx_launch_count(sq_ctx *ctx) { return ctx->launches; }
+extern "C" uint64_t sq_ctx_launch_count(sq_ctx *ctx) { return ctx->launches.load(); }
 
 extern "C" void *sq_pinned_alloc(sq_ctx *ctx, size_t nbytes) {
     void *p = nullptr;
@@ -239,22 +244,22 @@ extern "C" void *sq_device_alloc(sq_ctx *ctx, size_t nbytes) {
         sq_set_error("cudaMalloc(%zu) failed", nbytes);
         return nullptr;
     }
-    cudaMemsetAsync((uint8_t *)p + nbytes, 0, 64, ctx->stream);
+    cudaMemsetAsync((uint8_t *)p + nbytes, 0, 64, sq_cur_stream(ctx));
     return p;
 }
 extern "C" void sq_device_free(sq_ctx *ctx, void *p) {
     if (!p) return;
-    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(sq_cur_stream(ctx));
     cudaFree(p);
 }
 extern "C" int sq_memcpy_h2d(sq_ctx *ctx, void *dst, const void *src, size_t n) {
-    CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     return SQ_OK;
 }
 extern "C" int sq_memcpy_d2h(sq_ctx *ctx, void *dst, const void *src, size_t n) {
-    CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     return SQ_OK;
 }
 
@@ -630,7 +635,7 @@ static int alloc_fastq_metas(sq_batch *b, uint64_t n) {
     b->seq_len = p + 2 * n4;
     b->qual_off = p + 3 * n4;
     b->err_sum = (double *)(p + 4 * n4);
-    CUDA_TRY(cudaMemsetAsync(b->err_sum, 0, n4 * 8, b->ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(b->err_sum, 0, n4 * 8, sq_cur_stream(b->ctx)));
     return SQ_OK;
 }
 
@@ -650,8 +655,8 @@ int sq_d2h_bounced(sq_ctx *ctx, void *dst, const void *dev_src, size_t nbytes) {
     auto issue = [&](int sl) -> int {
         len[sl] = std::min(chunk, nbytes - issued);
         CUDA_TRY(cudaMemcpyAsync((char *)ctx->h_bounce + sl * chunk, (const char *)dev_src + issued, len[sl],
-                                 cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaEventRecord(ev[sl], ctx->stream));
+                                 cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaEventRecord(ev[sl], sq_cur_stream(ctx)));
         issued += len[sl];
         return SQ_OK;
     };
@@ -677,7 +682,7 @@ int sq_d2h_bounced(sq_ctx *ctx, void *dst, const void *dev_src, size_t nbytes) {
 // grow-only scratch of the context
 static int ensure_scratch(sq_ctx *ctx, void **ptr, size_t *cap, size_t need) {
     if (need <= *cap) return SQ_OK;
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     if (*ptr) CUDA_TRY(cudaFree(*ptr));
     *ptr = nullptr;
     *cap = 0;
@@ -700,7 +705,7 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
     init.max_seq_len = 0;
     init.max_rec_bytes = 0;
     memcpy(ctx->h_scratch, &init, sizeof(init));
-    CUDA_TRY(cudaMemcpyAsync(st, ctx->h_scratch, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(st, ctx->h_scratch, sizeof(init), cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
     ParseState *hst = (ParseState *)ctx->h_scratch;
 
     // ---- one pass: count + rank (decoupled look-back) + scatter into a scratch of `cap` slots ----
@@ -714,11 +719,11 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
         fields = (uint32_t *)ctx->parse_fields;
         unsigned long long *status = (unsigned long long *)ctx->parse_status;
         const uint32_t n_op = (uint32_t)((nbytes + OP_TILE_BYTES - 1) / OP_TILE_BYTES);
-        CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)n_op + 1) * 8, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)n_op + 1) * 8, sq_cur_stream(ctx)));
         SQ_LAUNCH(ctx, k_parse_onepass, n_op, PARSE_THREADS, 0, b->text, nbytes, n_op, max_records, cap, status,
                   fields, st);
-        CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     }
     // ---- two passes: count (+ bit masks), device-wide scan of the per-CTA counts, scatter ----------
     uint32_t *cta_counts = nullptr;
@@ -734,9 +739,9 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
         uint32_t *d_total = (uint32_t *)((char *)ctx->d_scratch + 128);
         uint32_t *h_total = (uint32_t *)((char *)ctx->h_scratch + 128);
         SQ_TRY(sq_scan_exclusive_u32(ctx, cta_counts, cta_counts, n_cta, d_total));
-        CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
         hst->n_newlines = *h_total;
         return SQ_OK;
     };
@@ -768,7 +773,7 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
         // written when a partial record follows (and only read to word an error message)
         uint32_t *h_one = (uint32_t *)((char *)ctx->h_scratch + 256);
         *h_one = 1;
-        CUDA_TRY(cudaMemcpyAsync(b->name_off, h_one, 4, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->name_off, h_one, 4, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
         if (n_newlines)
             SQ_LAUNCH(ctx, k_scatter_fields, n_cta, PARSE_THREADS, 0, b->text, nbytes, vec_masks, cta_counts, n_rec,
                       check_partial, b->name_off, b->seq_off, b->seq_len, b->qual_off, st);
@@ -778,9 +783,9 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
     // the consumed offset is the byte after the last record's 4th newline = name_off[n_rec] - 1
     uint32_t *h_last = (uint32_t *)((char *)ctx->h_scratch + 260);
     *h_last = 1;
-    if (n_rec) CUDA_TRY(cudaMemcpyAsync(h_last, b->name_off + n_rec, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (n_rec) CUDA_TRY(cudaMemcpyAsync(h_last, b->name_off + n_rec, 4, cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaMemcpyAsync(hst, st, sizeof(ParseState), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     info->n_records = n_rec;
     info->consumed = n_rec ? (uint64_t)*h_last - 1 : 0;
     info->max_seq_len = hst->max_seq_len;
@@ -832,14 +837,15 @@ extern "C" int sq_batch_from_fastq(sq_ctx *ctx, const uint8_t *text, uint64_t nb
     *out = nullptr;
     SQ_TRY(check_size(nbytes));
     CUDA_TRY(cudaSetDevice(ctx->device));
+    SqParserScope on_parser_stream(ctx);
     sq_batch *b = new sq_batch();
     b->ctx = ctx;
     b->nbytes = nbytes;
     int rc = sq_dalloc(ctx, (void **)&b->text, nbytes + 64, false);
     if (rc == SQ_OK && nbytes)
-        rc = cudaMemcpyAsync(b->text, text, nbytes, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess
+        rc = cudaMemcpyAsync(b->text, text, nbytes, cudaMemcpyHostToDevice, sq_cur_stream(ctx)) == cudaSuccess
                  ? SQ_OK : sq_cuda_fail(cudaGetLastError(), "H2D text", __FILE__, __LINE__);
-    if (rc == SQ_OK) cudaMemsetAsync(b->text + nbytes, 0, 64, ctx->stream);
+    if (rc == SQ_OK) cudaMemsetAsync(b->text + nbytes, 0, 64, sq_cur_stream(ctx));
     if (rc == SQ_OK) rc = parse_device_text(ctx, b, max_records, info);
     if (rc != SQ_OK) {
         sq_batch_free(b);
@@ -858,6 +864,7 @@ extern "C" int sq_batch_from_device_fastq(sq_ctx *ctx, const uint8_t *dev_text, 
         return SQ_E_ARG;
     }
     CUDA_TRY(cudaSetDevice(ctx->device));
+    SqParserScope on_parser_stream(ctx);
     sq_batch *b = new sq_batch();
     b->ctx = ctx;
     b->nbytes = nbytes;
@@ -912,11 +919,11 @@ extern "C" int sq_batch_from_packed(sq_ctx *ctx, const uint8_t *buf, uint64_t nb
         return rc;
     }
     // pageable sources: cudaMemcpyAsync stages them before returning
-    if (nbytes) CUDA_TRY(cudaMemcpyAsync(b->text, buf, nbytes, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(b->text + nbytes, 0, 64, ctx->stream));
+    if (nbytes) CUDA_TRY(cudaMemcpyAsync(b->text, buf, nbytes, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaMemsetAsync(b->text + nbytes, 0, 64, sq_cur_stream(ctx)));
     if (meta_bytes)
-        CUDA_TRY(cudaMemcpyAsync(b->meta_block, host.data(), meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->meta_block, host.data(), meta_bytes, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     uint32_t *d = (uint32_t *)b->meta_block;
     b->name_off = d;
     b->seq_off = d + n4;
@@ -1002,6 +1009,7 @@ extern "C" void sq_fastq_stream_destroy(sq_fastq_stream *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     if (s->copy) cudaStreamSynchronize(s->copy);
+    cudaStreamSynchronize(s->ctx->pstream);
     cudaStreamSynchronize(s->ctx->stream);
     if (s->slots_from_ctx) s->ctx->stage_in_use = false;
     for (int k = 0; k < sq_fastq_stream::SLOTS; k++) {
@@ -1035,6 +1043,7 @@ extern "C" int sq_fastq_stream_create(sq_ctx *ctx, const uint8_t *host_text, uin
     // the staging ring lives in the context between readers (page-mapping 3 x window per pass is slow)
     if (!ctx->stage_in_use) {
         if (ctx->stage_cap < window + 64) {
+            cudaStreamSynchronize(ctx->pstream);
             cudaStreamSynchronize(ctx->stream);
             for (int k = 0; k < 3; k++) {
                 if (ctx->stage_slot[k]) cudaFree(ctx->stage_slot[k]);
@@ -1074,6 +1083,7 @@ extern "C" int sq_fastq_stream_next(sq_fastq_stream *s, sq_batch **out, sq_parse
     memset(info, 0, sizeof(*info));
     sq_ctx *ctx = s->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    SqParserScope on_parser_stream(ctx);
     while (s->n_taken < s->n_issued) {
         const int k = (int)(s->n_taken % sq_fastq_stream::SLOTS);
         const uint64_t len = s->slot_len[k], total = s->tail_len + len;
@@ -1086,11 +1096,11 @@ extern "C" int sq_fastq_stream_next(sq_fastq_stream *s, sq_batch **out, sq_parse
             delete b;
             return rc;
         }
-        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->filled[k], 0));
+        CUDA_TRY(cudaStreamWaitEvent(sq_cur_stream(ctx), s->filled[k], 0));
         SQ_TRY(copy_bytes(ctx, b->text, s->tail, s->tail_len));
         SQ_TRY(copy_bytes(ctx, b->text + s->tail_len, s->slot[k], len));
-        CUDA_TRY(cudaMemsetAsync(b->text + total, 0, 64, ctx->stream));
-        CUDA_TRY(cudaEventRecord(s->drained[k], ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(b->text + total, 0, 64, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaEventRecord(s->drained[k], sq_cur_stream(ctx)));
         s->n_taken++;
         SQ_TRY(stream_issue(s));  // the slot refills as soon as the copy above has run
         rc = parse_device_text(ctx, b, UINT64_MAX, info);
@@ -1100,7 +1110,7 @@ extern "C" int sq_fastq_stream_next(sq_fastq_stream *s, sq_batch **out, sq_parse
         }
         const uint64_t left = total - info->consumed;
         if (left > s->tail_cap) {
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
             if (s->tail) CUDA_TRY(cudaFree(s->tail));
             s->tail = nullptr;
             s->tail_cap = 0;
@@ -1125,8 +1135,8 @@ extern "C" uint32_t sq_batch_max_seq_len(const sq_batch *b) { return b->max_len;
 
 extern "C" int sq_batch_get_bytes(sq_batch *b, uint8_t *out) {
     CUDA_TRY(cudaSetDevice(b->ctx->device));
-    if (b->nbytes) CUDA_TRY(cudaMemcpyAsync(out, b->text, b->nbytes, cudaMemcpyDeviceToHost, b->ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+    if (b->nbytes) CUDA_TRY(cudaMemcpyAsync(out, b->text, b->nbytes, cudaMemcpyDeviceToHost, sq_cur_stream(b->ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(b->ctx)));
     return SQ_OK;
 }
 
@@ -1138,8 +1148,8 @@ extern "C" int sq_batch_get_metas(sq_batch *b, sq_meta *out) {
     bool aux = b->name_len != nullptr;
     size_t bytes = n4 * 4 * (aux ? 7 : 4) + n4 * 8;
     std::vector<uint8_t> host(bytes);
-    CUDA_TRY(cudaMemcpyAsync(host.data(), b->meta_block, bytes, cudaMemcpyDeviceToHost, b->ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(host.data(), b->meta_block, bytes, cudaMemcpyDeviceToHost, sq_cur_stream(b->ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(b->ctx)));
     const uint32_t *p = (const uint32_t *)host.data();
     const double *es = (const double *)(p + (aux ? 7 : 4) * n4);
     for (uint64_t i = 0; i < n; i++) {
@@ -1219,10 +1229,10 @@ extern "C" int sq_batch_is_mate(sq_batch *a, sq_batch *b, uint64_t *first_mismat
     unsigned long long *d = (unsigned long long *)((char *)ctx->d_scratch + 512);
     unsigned long long *h = (unsigned long long *)((char *)ctx->h_scratch + 512);
     *h = a->n;
-    CUDA_TRY(cudaMemcpyAsync(d, h, 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d, h, 8, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
     SQ_LAUNCH(ctx, k_is_mate, sq_grid_for(ctx, a->n, 256), 256, 0, a->view(), b->view(), d);
-    CUDA_TRY(cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     *first_mismatch = *h;
     return SQ_OK;
 }

@@ -1708,8 +1708,12 @@ static int launch_onewalk(sq_ctx *ctx, const WalkGeom &g, const WalkArgs &A) {
 static int fused_add_onewalk(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt, sq_overrep *ov, sq_nanostats *ns,
                              sq_adapters *ad, sq_dedup *dd, bool *done) {
     *done = false;
-    static const bool disabled = getenv("SQ_NO_ONEWALK") != nullptr;
-    if (disabled) return SQ_OK;
+    // Opt-in (SQ_ONEWALK=1).  Measured on B200 (profiles/r2d_onewalk_*): 258 warp instructions per read
+    // against 306 for the two kernels, but its shared-memory footprint (text tile + staging + private
+    // counters) leaves 12 warps per SM and the issue slots 42 % busy: 2.23 ms per 4 Mi reads against
+    // 0.90 + 0.86 ms.  Kept as the starting point for a version with the counters split off.
+    static const bool enabled = getenv("SQ_ONEWALK") != nullptr;
+    if (!enabled) return SQ_OK;
     const uint32_t n = (uint32_t)b->n;
     // quality range for PerTileQuality's counter rows: sampled by the kernels over the arrays seen so
     // far; the first array is sampled on its own (one host synchronisation per collector)

@@ -86,7 +86,7 @@ k_scan_apply(const uint32_t *__restrict__ in, uint32_t n, const uint32_t *__rest
 // out[i] = sum(in[0..i)); *total_dev (device, optional) = sum of all.  in != out allowed to alias.
 int sq_scan_exclusive_u32(sq_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total_dev) {
     if (n == 0) {
-        if (total_dev) CUDA_TRY(cudaMemsetAsync(total_dev, 0, 4, ctx->stream));
+        if (total_dev) CUDA_TRY(cudaMemsetAsync(total_dev, 0, 4, sq_cur_stream(ctx)));
         return SQ_OK;
     }
     uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;

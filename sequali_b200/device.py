@@ -61,7 +61,11 @@ class DeviceFastq:
         return self
 
     def record_arrays(self):
-        """One FastqRecordArrayView per chunk; boundaries are found on the device."""
+        """One FastqRecordArrayView per chunk; boundaries are found on the device, one chunk ahead of
+        the consumer (parser stream + helper thread, see _lib.prefetched)."""
+        return _lib.prefetched(self._record_arrays())
+
+    def _record_arrays(self):
         ctx = self._ctx
         for ptr, nbytes, n in self.chunks:
             h, info = C.c_void_p(), _lib.ParseInfo()
@@ -135,7 +139,11 @@ class HostFastq:
 
     def record_arrays(self, window: int = 256 << 20):
         """Record arrays of ~`window` bytes of text each (sq_fastq_stream_*: the host->device
-        copies run ahead of the parser on their own stream)."""
+        copies run ahead of the parser on their own stream, the parser one array ahead of the
+        collectors)."""
+        return _lib.prefetched(self._record_arrays(window))
+
+    def _record_arrays(self, window: int):
         ctx = self._ctx
         stream = C.c_void_p()
         check(ctx.lib.sq_fastq_stream_create(ctx.h, self.ptr, self.nbytes, window, C.byref(stream)),
