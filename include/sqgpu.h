@@ -114,6 +114,12 @@ SQ_API int sq_batch_from_device_fastq(sq_ctx *ctx, const uint8_t *dev_text, uint
  * 610-687): a packed name|seq|qual|tags buffer with host-built descriptors. */
 SQ_API int sq_batch_from_packed(sq_ctx *ctx, const uint8_t *buf, uint64_t nbytes,
                                 const sq_meta *metas, uint64_t n, sq_batch **out);
+/* BamParser__next__ record walk (_qcmodule.c:1623-1637) on the HOST bytes read so far: rec_off[0..*n_kept)
+ * = offsets of the complete records to keep (cap slots; nbytes / 36 + 1 always suffices for well
+ * formed records), *n_skipped = complete records dropped for flag & (0x100 | 0x800) (:1633),
+ * *consumed = bytes covered by complete records (the rest is the caller's leftover). */
+SQ_API int sq_bam_walk(const uint8_t *bam, uint64_t nbytes, uint64_t *rec_off, uint64_t cap, uint64_t *n_kept,
+                       uint64_t *n_skipped, uint64_t *consumed);
 /* BamParser__next__ record decode (_qcmodule.c:1623-1694): `bam` holds
  * alignment records; rec_off[i] is the offset of the i-th record to keep (the
  * host walks the block_size chain and drops secondary/supplementary records).

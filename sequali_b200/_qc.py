@@ -533,27 +533,21 @@ class BamParser:
             if got == 0:
                 raise EOFError(f"Incomplete record at the end of file {bytes(data)!r}")
             data += chunk[:got]
-            # walk the record chain (:1623-1637)
-            mv = memoryview(data)
+            # walk the record chain (:1623-1637): sq_bam_walk, on the bytes read so far
             n = len(data)
-            pos, offsets, skipped = 0, [], 0
-            while pos + 4 < n:
-                end = pos + 4 + int.from_bytes(mv[pos:pos + 4], "little")
-                if end > n:
-                    break
-                if int.from_bytes(mv[pos + 18:pos + 20], "little") & (0x100 | 0x800):
-                    skipped += 1
-                else:
-                    offsets.append(pos)
-                pos = end
-            mv.release()
-            if offsets or skipped:
+            raw = np.frombuffer(data, dtype=np.uint8)
+            offs = np.empty(n // 36 + 1, dtype=np.uint64)
+            kept, skipped, used = _C.c_uint64(), _C.c_uint64(), _C.c_uint64()
+            check(lib.sq_bam_walk(_void(raw), n, _void(offs), len(offs), _C.byref(kept), _C.byref(skipped),
+                                  _C.byref(used)), "sq_bam_walk")
+            pos = used.value
+            if kept.value or skipped.value:
                 break
+            del raw
         self._leftover = bytes(data[pos:])
-        if not offsets:
+        if not kept.value:
             return FastqRecordArrayView._empty()
-        offs = np.asarray(offsets, dtype=np.uint64)
-        raw = np.frombuffer(data, dtype=np.uint8, count=pos)
+        offs = offs[:kept.value]
         h, plen = _C.c_void_p(), _C.c_uint64()
         check(lib.sq_batch_from_bam(ctx.h, _void(raw), pos, _void(offs), len(offs),
                                     _C.byref(h), _C.byref(plen)), "sq_batch_from_bam")

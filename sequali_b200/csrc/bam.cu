@@ -75,6 +75,36 @@ k_bam_decode(const uint8_t *__restrict__ bam, const uint64_t *__restrict__ rec_o
     }
 }
 
+// The block_size chain of BamParser__next__ (_qcmodule.c:1623-1637) over the bytes the caller has read so
+// far: offsets of the complete records to keep, how many were dropped for being secondary or
+// supplementary alignments (flag & 0x900, :1633), and how many bytes the complete records cover.
+extern "C" int sq_bam_walk(const uint8_t *bam, uint64_t nbytes, uint64_t *rec_off, uint64_t cap, uint64_t *n_kept,
+                           uint64_t *n_skipped, uint64_t *consumed) {
+    uint64_t pos = 0, kept = 0, skipped = 0;
+    while (pos + 4 < nbytes) {
+        const uint64_t block = (uint64_t)bam[pos] | (uint64_t)bam[pos + 1] << 8 | (uint64_t)bam[pos + 2] << 16 |
+                               (uint64_t)bam[pos + 3] << 24;
+        const uint64_t end = pos + 4 + block;
+        if (end > nbytes) break;
+        uint32_t flag = 0;
+        if (pos + 18 < nbytes) flag = bam[pos + 18];
+        if (pos + 19 < nbytes) flag |= (uint32_t)bam[pos + 19] << 8;
+        if (flag & (0x100u | 0x800u)) skipped++;
+        else {
+            if (kept == cap) {
+                sq_set_error("BAM records smaller than their fixed fields");
+                return SQ_E_FORMAT;
+            }
+            rec_off[kept++] = pos;
+        }
+        pos = end;
+    }
+    *n_kept = kept;
+    *n_skipped = skipped;
+    *consumed = pos;
+    return SQ_OK;
+}
+
 extern "C" int sq_batch_from_bam(sq_ctx *ctx, const uint8_t *bam, uint64_t nbytes, const uint64_t *rec_off,
                                  uint64_t n, sq_batch **out, uint64_t *packed_len) {
     *out = nullptr;

@@ -16,8 +16,12 @@ if REF is None:  # pragma: no cover
     pytest.skip("oracle/_ref is not built", allow_module_level=True)
 
 
-@pytest.fixture(scope="module")
-def sq():
+@pytest.fixture(scope="module", params=["ctypes", "extension"])
+def sq(request):
+    """The B200 build behind its two host layers: the ctypes mirror and the CPython extension."""
+    if request.param == "extension":
+        import sequali_b200.ext
+        return sequali_b200.ext
     import sequali_b200
     return sequali_b200
 

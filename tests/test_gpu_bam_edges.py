@@ -22,8 +22,12 @@ if REF is None:  # pragma: no cover
 REF_DATA = os.path.join(H.ROOT, "oracle", "_ref", "tests", "tests", "data")
 
 
-@pytest.fixture(scope="module")
-def sq():
+@pytest.fixture(scope="module", params=["ctypes", "extension"])
+def sq(request):
+    """The B200 build behind its two host layers: the ctypes mirror and the CPython extension."""
+    if request.param == "extension":
+        import sequali_b200.ext
+        return sequali_b200.ext
     import sequali_b200
     return sequali_b200
 

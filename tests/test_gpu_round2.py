@@ -66,3 +66,51 @@ def test_dedup_pair_stale_bytes_across_batches(sq):
             dd.add_record_array_pair(a, p2.read(len(a)))
         return H.dump_dedup(dd)
     H.assert_same(run(sq), run(REF))
+
+
+# ---- the CPython extension (sequali_b200/ext/qc_ext.cpp) on whole runs --------------------------------
+@pytest.fixture(scope="module")
+def ext():
+    import sequali_b200.ext
+    return sequali_b200.ext
+
+
+def test_extension_single_end_illumina(ext):
+    text = synth.illumina_fastq(30_000, length=150, seed=21, n_tiles=24)
+    for bufsize in (100_000, 4 << 20):
+        H.assert_same(H.api_single_end(ext, text, H.ILLUMINA_ADAPTERS, buffersize=bufsize),
+                      H.oracle_single_end(text, H.ILLUMINA_ADAPTERS, chunk_records=777))
+
+
+def test_extension_paired(ext):
+    t1, t2 = synth.paired_fastq(6000, seed=22)
+    H.assert_same(H.api_paired(ext, t1, t2, buffersize=300_000), H.oracle_paired(t1, t2))
+
+
+def test_extension_nanopore_fastq_and_bam(ext, sq):
+    text = synth.nanopore_fastq(200, mean_length=4000, max_length=60_000, seed=23)
+    H.assert_same(H.api_single_end(ext, text, H.NANOPORE_ADAPTERS, buffersize=1 << 20),
+                  H.oracle_single_end(text, H.NANOPORE_ADAPTERS, chunk_records=50))
+    bam = synth.nanopore_ubam(200, mean_length=3000, max_length=50_000, seed=24)
+    H.assert_same(H.api_single_end(ext, b"", H.NANOPORE_ADAPTERS, buffersize=1 << 20, fileobj=io.BytesIO(bam), bam=True),
+                  H.api_single_end(sq, b"", H.NANOPORE_ADAPTERS, buffersize=1 << 20, fileobj=io.BytesIO(bam), bam=True))
+
+
+def test_extension_parser_errors_and_record_access(ext, sq):
+    text = synth.illumina_fastq(50, length=40, seed=25, n_tiles=3)
+    for bad in (text.replace(b"\n+\n", b"\n-\n", 1), b"x" + text, text[:-7], text.replace(b"A", b"\xc3", 1),
+                text[:200] + text[203:]):
+        outs = []
+        for mod in (ext, sq):
+            try:
+                outs.append([len(a) for a in mod.FastqParser(io.BytesIO(bad), 997)])
+            except Exception as e:  # noqa: BLE001
+                outs.append((type(e).__name__, str(e)))
+        assert outs[0] == outs[1], outs
+    arrs = [list(m.FastqParser(io.BytesIO(text), 1500)) for m in (ext, sq)]
+    assert [len(a) for a in arrs[0]] == [len(a) for a in arrs[1]]
+    for a, b in zip(*arrs):
+        assert a.obj == b.obj
+        for i in (0, len(a) - 1):
+            assert (a[i].name(), a[i].sequence(), a[i].qualities(), a[i].tags()) == \
+                   (b[i].name(), b[i].sequence(), b[i].qualities(), b[i].tags())
