@@ -23,9 +23,17 @@ DedupEstimator) over the full input with fresh collectors.
   cpu_baseline  the unmodified reference (oracle/_ref) on one host core over a
             bounded prefix of the same input
 
+  configs   the other workloads BASELINE.json names (C1 1 M reads, C3 paired end,
+            C4 ultra-long nanopore FASTQ, C5 the same reads as unaligned BAM) at bounded
+            sizes: Gbases/s through the reference-shaped API on host bytes, the unmodified
+            reference on the identical bytes (1 thread), and the step-level roofline fraction
+
 Multi-GPU: reads shard across ranks (each rank owns an equal, contiguous slice
-of the record stream: weak scaling), no data-path collective; the additive
-count tables are merged with one NCCL all-reduce inside the timed region.
+of the record stream: weak scaling), no data-path collective; the tables are
+merged exactly inside the timed region over NCCL (sq_comm_* of libsqgpu: no
+torch in this process -- torchrun only launches the ranks).  Before timing, a
+2 M-read sharded pass is compared with a single-rank pass over the same text
+("parity_checked").
 """
 from __future__ import annotations
 
@@ -162,23 +170,198 @@ def ncu_traffic(kernel: str, chunk_reads: int):
     return None, "kernel not in " + os.path.basename(files[-1])
 
 
+NANOPORE_ADAPTERS = ["TTACGTATTGCT", "GCAATACGTAAC", "CTTGCGGGCGGC", "GGTAGTAGGTTC", "GAGGCGAGCGGT", "CAAGATACGCAC",
+                     "GTGACTTGCCTG", "ATCGCCTACCGT", "TCTATCTTCTTT", "TCTTCAGAGGAG", "GATATTGCTGGG", "TGATATTGCTTT",
+                     "GTACGTATTGCT", "ACGTAACTGAAC"]  # src/sequali/adapters/adapter_list.tsv:44-57
+
+
+def loop_single_end(mod, fileobj, adapters, bam=False, buffersize=None):
+    """src/sequali/__main__.py:214-306 (single end) + the getters the report calls; returns bases."""
+    mods = dict(qc=mod.QCMetrics(), ptq=mod.PerTileQuality(), ov=mod.OverrepresentedSequences(), ns=mod.NanoStats(),
+                ad=mod.AdapterCounter(adapters), dd=mod.DedupEstimator(front_sequence_offset=64, back_sequence_offset=0))
+    kw = {} if buffersize is None else dict(initial_buffersize=buffersize)
+    parser = (mod.BamParser if bam else mod.FastqParser)(fileobj, **kw)
+    for arr in parser:
+        feed(mods, arr)
+    bases = int(np.frombuffer(mods["qc"].base_count_table(), dtype=np.uint64).sum())
+    mods["qc"].phred_count_table()
+    mods["ad"].get_counts()
+    mods["ptq"].get_tile_counts()
+    mods["dd"].duplication_counts()
+    mods["ov"].overrepresented_sequences(threshold_fraction=0.001, min_threshold=100)
+    sum(1 for _ in mods["ns"].nano_info_iterator())
+    return bases
+
+
+def loop_paired(mod, f1, f2, buffersize=None):
+    """src/sequali/__main__.py:284-303 (paired end) + getters; returns bases."""
+    kw = {} if buffersize is None else dict(initial_buffersize=buffersize)
+    qc1, qc2, p1, p2 = mod.QCMetrics(), mod.QCMetrics(), mod.PerTileQuality(), mod.PerTileQuality()
+    o1, o2 = mod.OverrepresentedSequences(), mod.OverrepresentedSequences()
+    dd = mod.DedupEstimator(front_sequence_offset=0, back_sequence_offset=0)
+    ins = mod.InsertSizeMetrics()
+    rd1, rd2 = mod.FastqParser(f1, **kw), mod.FastqParser(f2, **kw)
+    for a in rd1:
+        qc1.add_record_array(a)
+        p1.add_record_array(a)
+        o1.add_record_array(a)
+        b = rd2.read(len(a))
+        if len(a) != len(b) or not a.is_mate(b):
+            raise RuntimeError("mates out of step")
+        dd.add_record_array_pair(a, b)
+        ins.add_record_array_pair(a, b)
+        qc2.add_record_array(b)
+        p2.add_record_array(b)
+        o2.add_record_array(b)
+    bases = int(np.frombuffer(qc1.base_count_table(), dtype=np.uint64).sum() +
+                np.frombuffer(qc2.base_count_table(), dtype=np.uint64).sum())
+    for m in (p1, p2):
+        m.get_tile_counts()
+    for m in (o1, o2):
+        m.overrepresented_sequences(threshold_fraction=0.001, min_threshold=100)
+    dd.duplication_counts()
+    ins.insert_sizes(), ins.adapters_read1(), ins.adapters_read2()
+    return bases
+
+
+def run_configs(gpu_mod, peak_gbs):
+    """C1 / C3 / C4 / C5 of BASELINE.json at bounded sizes: the B200 build through the reference-shaped
+    API on host bytes (device copies inside the timed region), the unmodified reference on the identical
+    bytes with one thread, and text bytes / time / HBM peak for the B200 run."""
+    from sequali_b200 import synth
+    ref, _ = import_cpu_impl()
+    big = 64 << 20
+
+    def timed(fn, repeat):
+        best, bases = None, 0
+        for _ in range(repeat):
+            t0 = time.perf_counter()
+            bases = fn()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return best, bases
+
+    def entry(workload, nbytes, gpu_fn, cpu_fn):
+        gpu_fn()  # warm-up (allocations, table growth)
+        dt, bases = timed(gpu_fn, 2)
+        row = {"workload": workload, "bases": bases, "text_bytes": int(nbytes),
+               "value": round(bases / dt / 1e9, 3), "unit": "Gbases/s", "ms": round(dt * 1e3, 2),
+               "path": "sequali._qc extension on host bytes (H2D inside the timed region)",
+               "roofline": {"bound": "hbm", "frac_step": round(nbytes / dt / 1e9 / peak_gbs, 5),
+                            "step_gbs": round(nbytes / dt / 1e9, 2), "peak": peak_gbs}}
+        if ref is not None:
+            cdt, cbases = timed(cpu_fn, 1)
+            assert cbases == bases, (workload, cbases, bases)
+            row["cpu_reference"] = {"value": round(cbases / cdt / 1e9, 4), "unit": "Gbases/s", "cores": 1,
+                                    "kind": "reference", "sample": "the identical bytes, whole"}
+            row["speedup_vs_1_core"] = round(cdt / dt, 1)
+        return row
+
+    out = {}
+    text = synth.illumina_fastq(1_000_000, READ_LENGTH, seed=1, n_tiles=192)
+    out["C1"] = entry("1M synthetic Illumina 150 bp single-end reads, all default modules", len(text),
+                      lambda: loop_single_end(gpu_mod, io.BytesIO(text), ILLUMINA_ADAPTERS, buffersize=big),
+                      lambda: loop_single_end(ref, io.BytesIO(text), ILLUMINA_ADAPTERS))
+    t1, t2 = synth.paired_fastq(400_000, seed=3)
+    out["C3"] = entry("paired-end 2x150 bp, 400k pairs (BASELINE: 50M pairs; scaled 1/125): adapter overlap "
+                      "detection and InsertSizeMetrics", len(t1) + len(t2),
+                      lambda: loop_paired(gpu_mod, io.BytesIO(t1), io.BytesIO(t2), buffersize=big),
+                      lambda: loop_paired(ref, io.BytesIO(t1), io.BytesIO(t2)))
+    del t1, t2
+    text = synth.nanopore_fastq(20_000, mean_length=20_000, max_length=1_000_000, seed=4)
+    out["C4"] = entry("synthetic ultra-long Nanopore reads (mean 20 kb, max 1 Mb), 20k reads (BASELINE: 10 Gbases; "
+                      "scaled ~1/25) with guppy headers: NanoStats, 14 adapters, 21-mer overrepresentation", len(text),
+                      lambda: loop_single_end(gpu_mod, io.BytesIO(text), NANOPORE_ADAPTERS, buffersize=big),
+                      lambda: loop_single_end(ref, io.BytesIO(text), NANOPORE_ADAPTERS))
+    bam = synth.nanopore_ubam(20_000, mean_length=20_000, max_length=1_000_000, seed=5)
+    out["C5"] = entry("dorado-style unaligned BAM, 20k reads (BASELINE: 10 Gbases; scaled ~1/25) with channel / "
+                      "duration tags via BamParser", len(bam),
+                      lambda: loop_single_end(gpu_mod, io.BytesIO(bam), NANOPORE_ADAPTERS, bam=True, buffersize=big),
+                      lambda: loop_single_end(ref, io.BytesIO(bam), NANOPORE_ADAPTERS, bam=True))
+    return out
+
+
+def sharded_parity_check(sq, sharded, DeviceFastq, comm, rank, world, total_reads):
+    """Every rank runs its shard of a `total_reads` stream through ShardedCollectors + merge(), then the
+    whole stream alone with plain collectors; every table must be equal (doubles by bit pattern, the
+    dedup counts in slot order).  Returns True, or raises with the first table that differs."""
+    per = max(total_reads // world, 1)
+    total = per * world
+    shard = DeviceFastq.synth_illumina(per, READ_LENGTH, seed=2, chunk_reads=1 << 20, first_read=rank * per,
+                                       total_reads=total)
+    coll = sharded.ShardedCollectors(sq, ILLUMINA_ADAPTERS, first_record=rank * per)
+    for arr in shard.record_arrays():
+        coll.add_record_array(arr)
+    got = coll.merge()
+    got_ov = got["overrep"]
+    merged = {
+        **{"qc." + k: np.asarray(v).tolist() for k, v in got["qc"].items()},
+        "adapters": [(a, f.tolist(), r.tolist()) for a, f, r in got["adapters"]],
+        "ptq.tiles": [(int(t), np.asarray(e, dtype=np.float64).view(np.uint64).tolist(), [int(x) for x in c])
+                      for t, e, c in got["ptq"]["tiles"]],
+        "ptq.number_of_reads": int(got["ptq"]["number_of_reads"]),
+        "dedup.counts": np.asarray(got["dedup"]["counts"]).tolist(),
+        "dedup.info": (int(got["dedup"]["modulo_bits"]), int(got["dedup"]["tracked_sequences"])),
+        "overrep.counts": dict(got_ov.sequence_counts()),
+        "overrep.counters": (got_ov.number_of_sequences, got_ov.sampled_sequences, got_ov.collected_unique_fragments,
+                             got_ov.total_fragments),
+    }
+    del coll, got, got_ov
+    shard.free()
+    whole = DeviceFastq.synth_illumina(total, READ_LENGTH, seed=2, chunk_reads=1 << 20, first_read=0, total_reads=total)
+    sharded.use_comm(None)  # a plain single-rank pass
+    try:
+        mods = make_modules(sq)
+        for arr in whole.record_arrays():
+            feed(mods, arr)
+        qc = mods["qc"]
+        single = {
+            **{"qc." + k: list(getattr(qc, k)()) for k in (
+                "base_count_table", "phred_count_table", "end_anchored_base_count_table",
+                "end_anchored_phred_count_table", "gc_content", "phred_scores")},
+            "qc.number_of_reads": qc.number_of_reads, "qc.max_length": qc.max_length,
+            "adapters": [(a, list(f), list(r)) for a, f, r in mods["ad"].get_counts()],
+            "ptq.tiles": [(int(t), np.asarray(e, dtype=np.float64).view(np.uint64).tolist(), [int(x) for x in c])
+                          for t, e, c in mods["ptq"].get_tile_counts()],
+            "ptq.number_of_reads": mods["ptq"].number_of_reads,
+            "dedup.counts": list(mods["dd"].duplication_counts()),
+            "dedup.info": (mods["dd"]._modulo_bits, mods["dd"].tracked_sequences),
+            "overrep.counts": dict(mods["ov"].sequence_counts()),
+            "overrep.counters": (mods["ov"].number_of_sequences, mods["ov"].sampled_sequences,
+                                 mods["ov"].collected_unique_fragments, mods["ov"].total_fragments),
+        }
+        del mods
+    finally:
+        sharded.use_comm(comm)
+        whole.free()
+    bad = [k for k in single if single[k] != merged.get(k)]
+    n_bad = int(comm.allreduce_host_u64([len(bad)], "sum")[0])
+    if n_bad:
+        raise AssertionError(f"rank {rank}: sharded pass differs from the single-rank pass in {bad}")
+    return True
+
+
 # ----------------------------------------------------------------------------
 def run_cuda(args):
     import sequali_b200 as sq
     from sequali_b200 import _lib
     from sequali_b200.device import DeviceFastq
 
+    from sequali_b200 import sharded
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     os.environ.setdefault("SEQUALI_B200_DEVICE", str(local))
     ctx = _lib.Context.get()
+    comm = sharded.NcclComm.from_env(ctx)  # NCCL inside libsqgpu; None for a single rank
+    sharded.use_comm(comm)
+
+    def max_over_ranks(x: float) -> float:
+        if comm is None:
+            return x
+        bits = np.array([x], dtype=np.float64).view(np.uint64)  # positive doubles order like their bit patterns
+        return float(comm.allreduce_host_u64(bits, "max").view(np.float64)[0])
 
     n_reads = args.reads  # per GPU (weak scaling)
     data = DeviceFastq.synth_illumina(n_reads, READ_LENGTH, seed=2, chunk_reads=args.chunk_reads,
@@ -188,13 +371,11 @@ def run_cuda(args):
 
     def barrier():
         ctx.sync()
-        if dist is not None:
-            dist.barrier()
+        if comm is not None:
+            comm.barrier()
 
     def merge(tables: np.ndarray):
-        # additive count tables of all ranks: one all-reduce (NCCL over NVLink when world > 1)
-        from sequali_b200 import sharded
-        return sharded.allreduce_sum_tables([tables])[0]
+        return tables  # single rank: nothing to merge (N > 1 goes through step_sharded)
 
     sharded_ms = {}  # rank 0's host view of the last sharded step
 
@@ -203,7 +384,6 @@ def run_cuda(args):
         table what one sequential pass over all shards gives (sequali_b200.sharded: all-reduce of
         the additive tables, border-tile records forwarded to the tile's owner, dedup hashes handed
         to the table's owner, the overrepresented table travelling until full, then frozen-key counts)."""
-        from sequali_b200 import sharded
         t_begin = time.perf_counter()
         coll = sharded.ShardedCollectors(sq, ILLUMINA_ADAPTERS, first_record=first_record)
         for arr in record_arrays:
@@ -231,6 +411,11 @@ def run_cuda(args):
         merge(tables)
         return nbytes, summary
 
+    # ---- N > 1: the sharded pass equals a single-rank pass over the same text ---------------
+    parity_checked = None
+    if world > 1:
+        parity_checked = sharded_parity_check(sq, sharded, DeviceFastq, comm, rank, world, args.parity_reads)
+
     # ---- HBM-resident timing -------------------------------------------------
     for _ in range(args.warmup):
         step_resident()
@@ -248,11 +433,7 @@ def run_cuda(args):
     sharded_resident = dict(sharded_ms)
     clocks = sampler.finish()
     launches = ctx.launch_count - launches0
-    if dist is not None:
-        import torch
-        tm = torch.tensor([ms], dtype=torch.float64).cuda()
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ms = float(tm.item())
+    ms = max_over_ranks(ms)
     ms_per_step = ms / args.steps
     value = world * bases / (ms_per_step * 1e-3) / 1e9
 
@@ -305,7 +486,10 @@ def run_cuda(args):
     top_ms_per_launch = top[1][1] / top[1][0]
     achieved = top_launch_bytes / (top_ms_per_launch * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(top[0], args.chunk_reads)
+    step_gbs = text_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = {
+        # the number that answers north_star: text bytes of the whole step (read once) / step time / peak
+        "frac_step": round(step_gbs / peak, 4), "step_gbs": round(step_gbs, 1),
         "bound": "hbm", "kernel": top[0], "achieved": round(achieved, 1), "peak": peak,
         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peak_src,
@@ -326,14 +510,6 @@ def run_cuda(args):
         from sequali_b200.device import HostFastq
         e2e_reads = min(n_reads, args.e2e_reads)
         hostq, e2e_reads = HostFastq.from_device(data, e2e_reads)
-
-        def max_over_ranks(dt):
-            if dist is None:
-                return dt
-            import torch
-            tm = torch.tensor([dt], dtype=torch.float64).cuda()
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            return float(tm.item())
 
         def timed(step_fn, steps):
             step_fn()
@@ -369,21 +545,22 @@ def run_cuda(args):
         #     one extra host copy by the Python file object, as with the reference's xopen stream)
         host = np.frombuffer(hostq.view(), dtype=np.uint8)
 
+        import sequali_b200.ext as sqx  # the CPython extension `_qc`: what `import sequali` gives a user
+
         def step_fileobj():
             if world > 1:
                 return step_sharded(sq.FastqParser(HostText(host), args.buffersize), rank * e2e_reads)[0]
-            mods = make_modules(sq)
-            for arr in sq.FastqParser(HostText(host), args.buffersize):
+            mods = make_modules(sqx)
+            for arr in sqx.FastqParser(HostText(host), args.buffersize):
                 feed(mods, arr)
             tables, nbytes, _ = read_results(mods)
-            merge(tables)
             return nbytes
 
         dt2, _ = timed(step_fileobj, 1)
         e2e["fileobj_api"] = {"value": round(world * e2e_reads * READ_LENGTH / dt2 / 1e9, 4), "unit": "Gbases/s",
                               "buffersize": args.buffersize,
-                              "path": "FastqParser(host file object).readinto -> pinned staging -> H2D -> kernels "
-                                      "-> getters"}
+                              "path": "sequali._qc extension: FastqParser(host file object).readinto (one host memcpy "
+                                      "per byte, single thread) -> pinned staging -> H2D -> kernels -> getters"}
         del host
         hostq.free()
 
@@ -391,6 +568,13 @@ def run_cuda(args):
     cpu = None
     if rank == 0 and not args.no_cpu:
         cpu = cpu_baseline(data, args.cpu_reads)
+
+    # ---- the other configurations BASELINE.json names (bounded sizes, single GPU) -------------
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        import sequali_b200.ext as sqx
+        data.free()  # the 100 M reads leave HBM first
+        configs = run_configs(sqx, measured_peak_gbs()[0])
 
     if rank == 0:
         line = {
@@ -405,11 +589,13 @@ def run_cuda(args):
                        "text_bytes_per_gpu": int(text_bytes), "record_arrays_per_step": n_chunks,
                        "l2": "inputs larger than L2" if text_bytes > 200e6 else "input smaller than L2",
                        "parallelism": f"{world} x contiguous read shards" + (
-                           "" if world == 1 else ", exact merges over NCCL (all-reduce of the additive tables; border-tile "
-                           "records, dedup hashes and the overrepresented table exchanged between ranks)")},
+                           "" if world == 1 else ", exact merges over NCCL inside libsqgpu (all-reduce of the additive "
+                           "tables on the device; border-tile records, dedup hashes and the overrepresented table "
+                           "exchanged between ranks)")},
             "reads_per_s": round(world * n_reads / (ms_per_step * 1e-3), 1),
             "wall_ms_per_step": round(wall * 1e3 / args.steps, 3),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            **({"parity_checked": parity_checked} if parity_checked is not None else {}),
             **({"sharded_ms_last_step_rank0": sharded_resident} if world > 1 else {}),
             "result_summary": summary, "host_ms_one_step": host_ms,
         }
@@ -417,10 +603,12 @@ def run_cuda(args):
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if configs:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if comm is not None:
+        comm.barrier()
+        comm.close()
 
 
 # ----------------------------------------------------------------------------
@@ -465,41 +653,89 @@ def cpu_baseline(data, reads: int):
 
 
 def _ref_worker(args):
-    seed, n, steps = args
-    from sequali_b200 import synth
-    text = synth.illumina_fastq(n, READ_LENGTH, seed=seed, n_tiles=936)
+    path, seed, n, steps = args
+    if path is not None:
+        with open(path, "rb") as f:
+            text = f.read()
+    else:
+        from sequali_b200 import synth
+        text = synth.illumina_fastq(n, READ_LENGTH, seed=seed, n_tiles=936)
     return [cpu_all_modules(text) for _ in range(steps)]
+
+
+_GEN_SAMPLE = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+from sequali_b200.device import DeviceFastq
+import numpy as np
+shards, n, total, out = {shards}, {n}, {total}, {out!r}
+data = DeviceFastq.synth_illumina(shards * n, {length}, seed=2, chunk_reads=n, first_read=0, total_reads=total)
+host, reads = data.to_host()
+assert reads == shards * n
+off = 0
+for i, (_, nbytes, k) in enumerate(data.chunks):
+    host[off:off + nbytes].tofile(os.path.join(out, "shard_%d.fastq" % i))
+    off += nbytes
+"""
+
+
+def reference_sample_files(cores: int, n: int, total_reads: int):
+    """The first cores x n reads of the SAME synthetic stream the CUDA arm measures (csrc/synth.cu, seed 2,
+    tile runs of a `total_reads` stream), written by a helper process as one file per worker under
+    /dev/shm: the processes that are timed load nothing but the reference.  None without a GPU."""
+    import tempfile
+    out = tempfile.mkdtemp(prefix="sq_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    code = _GEN_SAMPLE.format(root=ROOT, shards=cores, n=n, total=total_reads, out=out, length=READ_LENGTH)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    files = [os.path.join(out, f"shard_{i}.fastq") for i in range(cores)]
+    if p.returncode != 0 or not all(os.path.exists(f) for f in files):
+        return None, out
+    return files, out
 
 
 def run_reference(args):
     """The reference's CPU path on all host cores: one independent process per
     core over its own shard (the usage README.rst:160-166 recommends), each step
-    a bounded sample of the workload."""
+    a bounded sample of the workload: the first cores x ref_reads reads of the
+    same device-generated stream the CUDA arm runs on."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    import shutil
     cores = os.cpu_count() or 1
     n = args.ref_reads
     _, kind = import_cpu_impl()
-    with mp.get_context("spawn").Pool(cores) as pool:
-        t0 = time.perf_counter()
-        times = pool.map(_ref_worker, [(1000 + i, n, args.warmup + args.steps) for i in range(cores)])
-        total_wall = time.perf_counter() - t0
+    files, tmpdir = reference_sample_files(cores, n, args.reads)
+    same_stream = files is not None
+    jobs = [(files[i] if same_stream else None, 1000 + i, n, args.warmup + args.steps) for i in range(cores)]
+    try:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            t0 = time.perf_counter()
+            times = pool.map(_ref_worker, jobs)
+            total_wall = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
     per_step = [max(t[args.warmup + s] for t in times) for s in range(args.steps)]
     dt = float(np.mean(per_step))
     value = cores * n * READ_LENGTH / dt / 1e9
+    sample = (f"the first {cores} x {n} reads of the same synthetic stream as the CUDA arm (csrc/synth.cu, seed 2), "
+              f"one contiguous shard per process" if same_stream else
+              f"{cores} x {n} reads of the Python generator of the same recipe (no GPU for the device generator)")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": "Gbases/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u64 (+f64 ordered sums)", "data": "synthetic",
-        "config": {"workload": f"bounded sample: {cores} processes x {n} synthetic NovaSeq {READ_LENGTH} bp "
-                               "reads per step, all default modules"},
+        "config": {"workload": f"{args.reads} synthetic NovaSeq {READ_LENGTH} bp single-end reads per GPU, "
+                               "936 tiles in runs, all default modules (QCMetrics, PerTileQuality, "
+                               "OverrepresentedSequences, NanoStats, AdapterCounter, DedupEstimator)",
+                   "reads_per_gpu": args.reads, "read_length": READ_LENGTH,
+                   "sample": sample, "same_stream_as_cuda_arm": same_stream},
         "reads_per_s": round(cores * n / dt, 1),
         "cpu_baseline": {"value": round(value, 5), "unit": "Gbases/s", "cores": cores, "kind": kind,
-                         "sample": f"{cores} independent single-threaded processes x {n} reads per step "
-                                   f"(the reference's QC loop has no internal threading); total wall {total_wall:.1f}s"},
+                         "sample": f"{sample}; {cores} independent single-threaded processes (the reference's QC loop "
+                                   f"has no internal threading); total wall {total_wall:.1f}s"},
         "e2e": {"value": round(value, 5), "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -518,6 +754,8 @@ def main():
     ap.add_argument("--e2e-window", type=int, default=512 << 20, help="bytes of host text per record array (e2e)")
     ap.add_argument("--cpu-reads", type=int, default=8_000_000)
     ap.add_argument("--ref-reads", type=int, default=500_000)
+    ap.add_argument("--parity-reads", type=int, default=2_000_000, help="N > 1: reads of the sharded-vs-single check")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 / C5 leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

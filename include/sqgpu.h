@@ -322,6 +322,43 @@ SQ_API int sq_insert_read_adapters(sq_insert *m, int which, uint8_t *seqs, uint6
 SQ_API int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt, sq_overrep *ov,
                         sq_nanostats *ns, sq_adapters *ad, sq_dedup *dd);
 
+/* ---- sharded runs: one process per GPU, NCCL over NVLink ---- */
+/* The reference is single process; these entry points have no counterpart in it.  Every rank owns a
+ * contiguous shard of the read stream; after the pass the tables are merged so that they equal one
+ * sequential pass over all shards (protocol: sequali_b200/sharded.py).  All collectives run on the
+ * context's launch stream, behind the collectors' kernels.  NCCL is dlopen'ed on first use. */
+typedef struct sq_comm sq_comm;
+SQ_API int sq_comm_unique_id(uint8_t *out128); /* rank 0 makes it, the other ranks get it out of band */
+SQ_API int sq_comm_create(sq_ctx *ctx, const uint8_t *id128, int rank, int world, sq_comm **out);
+SQ_API void sq_comm_destroy(sq_comm *c);
+SQ_API int sq_comm_rank(const sq_comm *c);
+SQ_API int sq_comm_world(const sq_comm *c);
+/* device buffers; op: 0 sum, 1 max, 2 min */
+SQ_API int sq_comm_allreduce_u64(sq_comm *c, uint64_t *dev, uint64_t n, int op);
+SQ_API int sq_comm_allreduce_u32(sq_comm *c, uint32_t *dev, uint64_t n, int op);
+SQ_API int sq_comm_bcast(sq_comm *c, void *dev, uint64_t nbytes, int root);
+SQ_API int sq_comm_send(sq_comm *c, const void *dev, uint64_t nbytes, int dst);
+SQ_API int sq_comm_recv(sq_comm *c, void *dev, uint64_t nbytes, int src);
+SQ_API int sq_comm_group_start(sq_comm *c);
+SQ_API int sq_comm_group_end(sq_comm *c);
+/* small host payloads, staged through pinned memory; these synchronise */
+SQ_API int sq_comm_allreduce_host_u64(sq_comm *c, uint64_t *host, uint64_t n, int op);
+SQ_API int sq_comm_bcast_host(sq_comm *c, void *host, uint64_t nbytes, int root);
+SQ_API int sq_comm_allgather_host(sq_comm *c, const void *host_in, void *host_out, uint64_t nbytes);
+SQ_API int sq_comm_barrier(sq_comm *c);
+/* additive tables (QCMetrics _qcmodule.c:1786-1803, AdapterCounter :2912-2914): ncclAllReduce(sum, u64) in
+ * place on the device tables, max_length by all-reduce(max); afterwards every rank's collector answers
+ * its getters with the merged tables */
+SQ_API int sq_qc_allreduce(sq_qc *m, sq_comm *c);
+SQ_API int sq_adapters_allreduce(sq_adapters *a, sq_comm *c);
+/* NanoStats (:5314-5322): per-read records of all ranks in rank (= read) order, cut at the first header
+ * of any rank that cannot be parsed; first_record = global index of this rank's first read */
+SQ_API int sq_nanostats_allgather(sq_nanostats *s, sq_comm *c, uint64_t first_record);
+/* stream-ordered device memory for exchange buffers (hash lists, table copies, border-tile text) */
+SQ_API void *sq_stream_alloc(sq_ctx *ctx, uint64_t nbytes);
+SQ_API void sq_stream_free(sq_ctx *ctx, void *p);
+SQ_API int sq_stream_memset(sq_ctx *ctx, void *p, int value, uint64_t nbytes);
+
 /* ---- synthetic input (bench / tests; SURVEY.md 8d recipe C2) -------------- */
 /* Fill dev_text with records `first_read .. first_read + n_reads` of a NovaSeq-style stream generated on
  * the device: read g belongs to tile number (g / reads_per_tile) % 936 of the flow cell (tiles in runs,

@@ -174,6 +174,28 @@ SIGNATURES = {
     "sq_insert_read_sizes": (_int, [_vp, _vp]),
     "sq_insert_read_adapters": (_int, [_vp, _int, _vp, _vp, _P(_u64)]),
     "sq_fused_add": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sq_comm_unique_id": (_int, [_vp]),
+    "sq_comm_create": (_int, [_vp, _vp, _int, _int, _P(_vp)]),
+    "sq_comm_destroy": (None, [_vp]),
+    "sq_comm_rank": (_int, [_vp]),
+    "sq_comm_world": (_int, [_vp]),
+    "sq_comm_allreduce_u64": (_int, [_vp, _vp, _u64, _int]),
+    "sq_comm_allreduce_u32": (_int, [_vp, _vp, _u64, _int]),
+    "sq_comm_bcast": (_int, [_vp, _vp, _u64, _int]),
+    "sq_comm_send": (_int, [_vp, _vp, _u64, _int]),
+    "sq_comm_recv": (_int, [_vp, _vp, _u64, _int]),
+    "sq_comm_group_start": (_int, [_vp]),
+    "sq_comm_group_end": (_int, [_vp]),
+    "sq_comm_allreduce_host_u64": (_int, [_vp, _vp, _u64, _int]),
+    "sq_comm_bcast_host": (_int, [_vp, _vp, _u64, _int]),
+    "sq_comm_allgather_host": (_int, [_vp, _vp, _vp, _u64]),
+    "sq_comm_barrier": (_int, [_vp]),
+    "sq_qc_allreduce": (_int, [_vp, _vp]),
+    "sq_adapters_allreduce": (_int, [_vp, _vp]),
+    "sq_nanostats_allgather": (_int, [_vp, _vp, _u64]),
+    "sq_stream_alloc": (_vp, [_vp, _u64]),
+    "sq_stream_free": (None, [_vp, _vp]),
+    "sq_stream_memset": (_int, [_vp, _vp, _int, _u64]),
     "sq_synth_illumina": (_int, [_vp, _vp, _u64, _u64, _u32, _u64, _u64, _u64, _P(_u64)]),
 }
 

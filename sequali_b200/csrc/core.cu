@@ -252,6 +252,18 @@ extern "C" void sq_device_free(sq_ctx *ctx, void *p) {
     cudaStreamSynchronize(sq_cur_stream(ctx));
     cudaFree(p);
 }
+extern "C" void *sq_stream_alloc(sq_ctx *ctx, uint64_t nbytes) {
+    void *p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (sq_dalloc(ctx, &p, nbytes + 64, false) != SQ_OK) return nullptr;
+    cudaMemsetAsync((uint8_t *)p + nbytes, 0, 64, sq_cur_stream(ctx));  // readable tail for vector loads
+    return p;
+}
+extern "C" void sq_stream_free(sq_ctx *ctx, void *p) { sq_dfree(ctx, p); }
+extern "C" int sq_stream_memset(sq_ctx *ctx, void *p, int value, uint64_t nbytes) {
+    if (nbytes) CUDA_TRY(cudaMemsetAsync(p, value, nbytes, sq_cur_stream(ctx)));
+    return SQ_OK;
+}
 extern "C" int sq_memcpy_h2d(sq_ctx *ctx, void *dst, const void *src, size_t n) {
     CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
     CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));

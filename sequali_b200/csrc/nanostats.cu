@@ -386,3 +386,68 @@ extern "C" int sq_nanostats_read(sq_nanostats *s, sq_nanoinfo *out) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return SQ_OK;
 }
+
+// Sharded runs: NanoStats_add_meta appends one record per read, in read order (:5314-5322), and the first
+// header that cannot be parsed switches the module off for everything behind it (:5302-5313).  Rank g
+// holds the reads [first_record, first_record + n_added) of the stream: the reads in front of the first
+// failing header of ANY rank are kept, and their records are gathered on every rank in rank (= read)
+// order; sq_nanostats_sync recomputes the time range over the merged array.
+extern "C" int sq_nanostats_allgather(sq_nanostats *s, sq_comm *c, uint64_t first_record) {
+    sq_ctx *ctx = s->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const int rank = sq_comm_rank(c), world = sq_comm_world(c);
+    const uint64_t NONE = 1ULL << 62;
+    uint64_t fail = s->skipped ? first_record + s->skipped_record : NONE;
+    uint64_t F = fail;
+    SQ_TRY(sq_comm_allreduce_host_u64(c, &F, 1, 2));  // min
+    uint64_t kept = s->skipped ? s->skipped_record : s->n_added;
+    if (F < first_record) kept = 0;
+    else if (F - first_record < kept) kept = F - first_record;
+    std::vector<uint64_t> counts((size_t)world);
+    SQ_TRY(sq_comm_allgather_host(c, &kept, counts.data(), 8));
+    uint64_t total = 0, my_off = 0;
+    for (int g = 0; g < world; g++) {
+        if (g == rank) my_off = total;
+        total += counts[g];
+    }
+    sq_nanoinfo *merged = nullptr;
+    SQ_TRY(sq_dalloc(ctx, (void **)&merged, (total ? total : 1) * sizeof(sq_nanoinfo), false));
+    if (kept)
+        CUDA_TRY(cudaMemcpyAsync(merged + my_off, s->infos, kept * sizeof(sq_nanoinfo), cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+    uint64_t off = 0;
+    SQ_TRY(sq_comm_group_start(c));
+    for (int g = 0; g < world; g++) {
+        SQ_TRY(sq_comm_bcast(c, merged + off, counts[g] * sizeof(sq_nanoinfo), g));
+        off += counts[g];
+    }
+    SQ_TRY(sq_comm_group_end(c));
+    // the header that switched the module off travels from the rank that met it
+    uint64_t owner = fail == F && F != NONE ? (uint64_t)rank : NONE;
+    SQ_TRY(sq_comm_allreduce_host_u64(c, &owner, 1, 2));
+    if (F != NONE) {
+        uint64_t len = s->skipped_name.size();
+        SQ_TRY(sq_comm_bcast_host(c, &len, 8, (int)owner));
+        s->skipped_name.resize(len);
+        SQ_TRY(sq_comm_bcast_host(c, s->skipped_name.data(), len, (int)owner));
+    }
+    // pi warnings / tag errors: counters of all ranks
+    NsState *h = (NsState *)((char *)ctx->h_scratch + 2560);
+    CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint64_t pi = h->pi_warnings, tag_err = h->tag_err_idx == ~0ULL ? NONE : first_record + h->tag_err_idx;
+    SQ_TRY(sq_comm_allreduce_host_u64(c, &pi, 1, 0));
+    SQ_TRY(sq_comm_allreduce_host_u64(c, &tag_err, 1, 2));
+    h->pi_warnings = pi;
+    h->tag_err_idx = tag_err == NONE ? ~0ULL : tag_err;
+    CUDA_TRY(cudaMemcpyAsync(&s->st->tag_err_idx, &h->tag_err_idx, 16, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    sq_dfree(ctx, s->infos);
+    s->infos = merged;
+    s->cap = total ? total : 1;
+    s->n_added = total;
+    s->skipped = F != NONE;
+    s->skipped_record = total;  // every merged record lies in front of the failing header
+    return SQ_OK;
+}

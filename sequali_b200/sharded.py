@@ -2,9 +2,9 @@
 
 The record stream is cut into contiguous shards (rank g owns global record
 indices [lo_g, hi_g)); every rank runs the whole hot loop on its shard with its
-own collectors; afterwards the tables are merged with ``torch.distributed``
-(NCCL over NVLink on the GPU box, gloo in the CPU tests).  No collective sits
-on the data path.
+own collectors; afterwards the tables are merged through a communicator (NCCL over
+NVLink inside libsqgpu on the GPU box -- ``NcclComm``, no torch; a gloo stand-in in
+the CPU tests).  No collective sits on the data path.
 
 What merges exactly:
   * additive count tables -- QCMetrics, AdapterCounter, InsertSizeMetrics
@@ -31,6 +31,9 @@ protocol itself is covered by world_size-2 gloo tests without a GPU.
 """
 from __future__ import annotations
 
+import os
+import pickle
+
 import numpy as np
 
 
@@ -41,35 +44,218 @@ def shard_bounds(n_records: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def _dist():
-    import torch
-    import torch.distributed as dist
-    if not dist.is_initialized():
-        return None, None, None
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" \
-        else torch.device("cpu")
-    return torch, dist, dev
+# ------------------------------------------------------------------------------
+# the communicator the merges talk through
+# ------------------------------------------------------------------------------
+# Product: NcclComm (libsqgpu's sq_comm_*: NCCL on the context's launch stream, device buffers are
+# DevBuf objects).  The CPU tests install a torch.distributed/gloo communicator of their own
+# (tests/sharded_adapters.TorchComm) whose buffers are CPU tensors: the protocol below only uses
+# `numel()`, `data_ptr()` and `zero_()` of a buffer, and hands buffers back to the communicator and
+# to the collector adapter they came from.
+class SoloComm:
+    """world size 1: every collective is the identity."""
+    rank, world = 0, 1
+
+    def allreduce_host_u64(self, arr, op="sum"):
+        return np.asarray(arr, dtype=np.uint64).copy()
+
+    def bcast_bytes(self, data, src):
+        return data
+
+    def allgather_bytes(self, data):
+        return [data]
+
+    def barrier(self):
+        pass
+
+    def sync(self):
+        pass
+
+
+_COMM = SoloComm()
+
+
+def use_comm(comm) -> None:
+    """Install the communicator of this process (None: single rank)."""
+    global _COMM
+    _COMM = comm if comm is not None else SoloComm()
+
+
+def comm():
+    return _COMM
+
+
+class DevBuf:
+    """Stream-ordered device memory (sq_stream_alloc) with the three tensor methods the protocol uses."""
+
+    def __init__(self, ctx, nbytes: int, itemsize: int = 1):
+        self._ctx, self.nbytes, self.itemsize = ctx, int(nbytes), itemsize
+        self.ptr = ctx.lib.sq_stream_alloc(ctx.h, max(self.nbytes, 16))
+        if not self.ptr:
+            from . import _lib
+            raise MemoryError(_lib.last_error())
+
+    def numel(self) -> int:
+        return self.nbytes // self.itemsize
+
+    def data_ptr(self) -> int:
+        return self.ptr
+
+    def zero_(self):
+        self._ctx.lib.sq_stream_memset(self._ctx.h, self.ptr, 0, self.nbytes)
+        return self
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr:
+            try:
+                self._ctx.lib.sq_stream_free(self._ctx.h, ptr)
+            except Exception:
+                pass
+
+
+class NcclComm:
+    """One process per GPU over NCCL, without torch: libsqgpu's sq_comm_* on the context's stream.
+
+    The ncclUniqueId goes from rank 0 to the others through a file in /tmp named after the launcher
+    (the parent process all local ranks share) and MASTER_PORT: ranks of one launch find each
+    other, launches do not collide.  Single node, as the rest of the sharded path."""
+
+    _serial = 0
+
+    def __init__(self, rank: int, world: int, ctx=None, key: str | None = None):
+        import ctypes as C
+        import time
+        from . import _lib
+        self._ctx = ctx or _lib.Context.get()
+        lib = self._ctx.lib
+        self.rank, self.world = rank, world
+        NcclComm._serial += 1
+        key = key or f"{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}_{NcclComm._serial}"
+        path = os.path.join(os.environ.get("SQ_COMM_DIR", "/tmp"), f"sqgpu_nccl_{key}.id")
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            _lib.check(lib.sq_comm_unique_id(ident), "sq_comm_unique_id")
+            with open(path + ".tmp", "wb") as f:
+                f.write(bytes(ident))
+            os.replace(path + ".tmp", path)
+        else:
+            deadline = time.time() + 120
+            while not os.path.exists(path):
+                if time.time() > deadline:
+                    raise TimeoutError(f"rank 0 did not publish {path}")
+                time.sleep(0.01)
+            with open(path, "rb") as f:
+                data = f.read()
+            ident = (C.c_uint8 * 128).from_buffer_copy(data)
+        h = C.c_void_p()
+        _lib.check(lib.sq_comm_create(self._ctx.h, ident, rank, world, C.byref(h)), "sq_comm_create")
+        self.h, self._path = h, path
+        self.barrier()
+        if rank == 0:
+            try:
+                os.remove(path)
+            except OSError:
+                pass
+
+    @classmethod
+    def from_env(cls, ctx=None):
+        """RANK / WORLD_SIZE as torchrun (or any launcher) exports them; None for a single rank."""
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world <= 1:
+            return None
+        return cls(int(os.environ["RANK"]), world, ctx)
+
+    def _check(self, rc, what):
+        from . import _lib
+        _lib.check(rc, what)
+
+    # -- small host payloads ----------------------------------------------------------------------
+    def allreduce_host_u64(self, arr, op="sum"):
+        a = np.ascontiguousarray(arr, dtype=np.uint64).copy()
+        code = {"sum": 0, "max": 1, "min": 2}[op]
+        self._check(self._ctx.lib.sq_comm_allreduce_host_u64(self.h, a.ctypes.data, a.size, code),
+                    "sq_comm_allreduce_host_u64")
+        return a
+
+    def bcast_bytes(self, data, src):
+        n = self.allreduce_host_u64([len(data) if self.rank == src else 0], "max")[0]
+        buf = np.zeros(max(int(n), 1), np.uint8)
+        if self.rank == src:
+            buf[:n] = np.frombuffer(data, np.uint8)
+        self._check(self._ctx.lib.sq_comm_bcast_host(self.h, buf.ctypes.data, int(n), src), "sq_comm_bcast_host")
+        return buf[:n].tobytes()
+
+    def allgather_bytes(self, data):
+        sizes = np.zeros(self.world, np.uint64)
+        mine = np.array([len(data)], np.uint64)
+        self._check(self._ctx.lib.sq_comm_allgather_host(self.h, mine.ctypes.data, sizes.ctypes.data, 8),
+                    "sq_comm_allgather_host")
+        width = int(sizes.max())
+        if width == 0:
+            return [b""] * self.world
+        src = np.zeros(width, np.uint8)
+        src[:len(data)] = np.frombuffer(data, np.uint8)
+        out = np.zeros(width * self.world, np.uint8)
+        self._check(self._ctx.lib.sq_comm_allgather_host(self.h, src.ctypes.data, out.ctypes.data, width),
+                    "sq_comm_allgather_host")
+        return [out[g * width:g * width + int(sizes[g])].tobytes() for g in range(self.world)]
+
+    def barrier(self):
+        self._check(self._ctx.lib.sq_comm_barrier(self.h), "sq_comm_barrier")
+
+    def sync(self):
+        # The collectives run on the stream the collectors' kernels run on, so collectors see received
+        # buffers without this; the parser entry points work on their own stream, and received FASTQ
+        # text (border tiles) goes through them: wait once per exchange.
+        self._check(self._ctx.lib.sq_ctx_sync(self._ctx.h), "sq_ctx_sync")
+
+    # -- device buffers ---------------------------------------------------------------------------
+    def send(self, buf, dst):
+        self._check(self._ctx.lib.sq_comm_send(self.h, buf.data_ptr(), buf.nbytes, dst), "sq_comm_send")
+
+    def recv(self, buf, src):
+        self._check(self._ctx.lib.sq_comm_recv(self.h, buf.data_ptr(), buf.nbytes, src), "sq_comm_recv")
+
+    def bcast(self, buf, src):
+        self._check(self._ctx.lib.sq_comm_bcast(self.h, buf.data_ptr(), buf.nbytes, src), "sq_comm_bcast")
+
+    def allreduce_sum_u32(self, buf):
+        self._check(self._ctx.lib.sq_comm_allreduce_u32(self.h, buf.data_ptr(), buf.numel(), 0),
+                    "sq_comm_allreduce_u32")
+
+    def group(self):
+        comm_self = self
+
+        class _Group:
+            def __enter__(self):
+                comm_self._check(comm_self._ctx.lib.sq_comm_group_start(comm_self.h), "sq_comm_group_start")
+
+            def __exit__(self, *exc):
+                comm_self._check(comm_self._ctx.lib.sq_comm_group_end(comm_self.h), "sq_comm_group_end")
+                return False
+        return _Group()
+
+    def close(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            self._ctx.lib.sq_comm_destroy(h)
 
 
 def allreduce_max(value: int) -> int:
-    torch, dist, dev = _dist()
-    if dist is None:
-        return value
-    t = torch.tensor([value], dtype=torch.int64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return int(t.item())
+    return int(_COMM.allreduce_host_u64([int(value)], "max")[0])
+
+
+def allreduce_min(value: int) -> int:
+    return int(_COMM.allreduce_host_u64([int(value)], "min")[0])
 
 
 def allreduce_sum_tables(tables: list[np.ndarray]) -> list[np.ndarray]:
-    """One all-reduce(SUM) over a list of equally-shaped-per-rank u64 tables."""
-    torch, dist, dev = _dist()
-    if dist is None:
+    """One all-reduce(SUM) over a list of equally-shaped-per-rank u64 tables (host arrays)."""
+    if _COMM.world == 1 or not tables:
         return [np.asarray(t, dtype=np.uint64) for t in tables]
-    flat = np.concatenate([np.asarray(t, dtype=np.uint64).ravel() for t in tables]) if tables \
-        else np.zeros(0, np.uint64)
-    t = torch.from_numpy(flat.view(np.int64).copy()).to(dev)
-    dist.all_reduce(t)  # two's complement: the wrap-around of int64 equals the u64 sum
-    out = t.cpu().numpy().view(np.uint64)
+    flat = np.concatenate([np.asarray(t, dtype=np.uint64).ravel() for t in tables])
+    out = _COMM.allreduce_host_u64(flat, "sum")
     res, off = [], 0
     for src in tables:
         n = int(np.asarray(src).size)
@@ -113,11 +299,9 @@ def merge_adapter_counts(counts) -> list:
 
 def gather_nanostats(infos: np.ndarray) -> np.ndarray:
     """Per-read NanoStats records of all ranks, concatenated in rank (= read) order."""
-    torch, dist, dev = _dist()
-    if dist is None:
+    if _COMM.world == 1:
         return infos
-    parts = [None] * dist.get_world_size()
-    dist.all_gather_object(parts, infos.tobytes())
+    parts = _COMM.allgather_bytes(infos.tobytes())
     return np.concatenate([np.frombuffer(p, dtype=infos.dtype) for p in parts])
 
 
@@ -128,11 +312,9 @@ def merge_tile_counts(tiles) -> tuple[list, list]:
     partial sums are added in rank order, which is not the reference's rounding
     order; such tiles are returned in ``straddling`` so that the caller can shard
     at tile borders instead."""
-    torch, dist, dev = _dist()
-    if dist is None:
+    if _COMM.world == 1:
         return list(tiles), []
-    parts = [None] * dist.get_world_size()
-    dist.all_gather_object(parts, [(int(t), list(e), list(c)) for t, e, c in tiles])
+    parts = _allgather_obj([(int(t), list(e), list(c)) for t, e, c in tiles])
     merged, straddling = {}, []
     for part in parts:  # rank order = read order
         for t, e, c in part:
@@ -157,109 +339,75 @@ _NO_FAIL = (1 << 62)
 
 
 def _rank_world():
-    torch, dist, dev = _dist()
-    if dist is None:
-        return 0, 1
-    return dist.get_rank(), dist.get_world_size()
+    return _COMM.rank, _COMM.world
 
 
 def _bcast_ints(values, src: int) -> list[int]:
-    torch, dist, dev = _dist()
-    if dist is None:
+    if _COMM.world == 1:
         return [int(v) for v in values]
-    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
-    dist.broadcast(t, src=src)
-    return [int(v) for v in t.cpu().tolist()]
+    data = _COMM.bcast_bytes(np.array([int(v) for v in values], dtype=np.int64).tobytes(), src)
+    return [int(v) for v in np.frombuffer(data, dtype=np.int64)]
 
 
 def _allgather_obj(obj) -> list:
-    torch, dist, dev = _dist()
-    if dist is None:
+    if _COMM.world == 1:
         return [obj]
-    parts = [None] * dist.get_world_size()
-    dist.all_gather_object(parts, obj)
-    return parts
-
-
-def _bcast_obj(obj, src: int):
-    torch, dist, dev = _dist()
-    if dist is None:
-        return obj
-    box = [obj]
-    dist.broadcast_object_list(box, src=src)
-    return box[0]
+    return [pickle.loads(p) for p in _COMM.allgather_bytes(pickle.dumps(obj, protocol=4))]
 
 
 def _allgather_u64_rows(block: np.ndarray) -> list[np.ndarray]:
-    """All-gather of one 2-D uint64 block per rank (shapes may differ) as tensors: two collectives,
-    no pickling.  Returns the blocks of all ranks in rank order."""
-    torch, dist, dev = _dist()
+    """All-gather of one 2-D uint64 block per rank (shapes may differ); blocks of all ranks in rank order."""
     block = np.ascontiguousarray(block, dtype=np.uint64)
-    if dist is None:
+    if _COMM.world == 1:
         return [block]
-    world = dist.get_world_size()
-    shape = torch.tensor(list(block.shape), dtype=torch.int64, device=dev)
-    shapes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(shapes, shape)
-    shapes = [tuple(int(v) for v in t.cpu().tolist()) for t in shapes]
-    rows, cols = max(r for r, _ in shapes), max(c for _, c in shapes)
-    if rows == 0 or cols == 0:
-        return [np.zeros(sh, np.uint64) for sh in shapes]
-    padded = np.zeros((rows, cols), np.uint64)
-    padded[:block.shape[0], :block.shape[1]] = block
-    mine = torch.from_numpy(padded.view(np.int64)).to(dev)
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine)
-    return [t.cpu().numpy().view(np.uint64)[:r, :c].copy() for t, (r, c) in zip(parts, shapes)]
+    shapes = _allgather_obj(tuple(block.shape))
+    parts = _COMM.allgather_bytes(block.tobytes())
+    return [np.frombuffer(p, dtype=np.uint64).reshape(sh).copy() for p, sh in zip(parts, shapes)]
 
 
 def _bcast_u64(arr, src: int) -> np.ndarray:
-    """Broadcast of a 1-D uint64 array from `src` as a tensor (length first)."""
-    torch, dist, dev = _dist()
-    rank, _ = _rank_world()
-    if dist is None:
+    """Broadcast of a 1-D uint64 array from `src`."""
+    if _COMM.world == 1:
         return np.asarray(arr, dtype=np.uint64)
-    n = _bcast_ints([len(arr) if rank == src else 0], src)[0]
-    if rank == src:
-        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.uint64).view(np.int64)).to(dev)
-    else:
-        t = torch.empty(n, dtype=torch.int64, device=dev)
-    if n:
-        dist.broadcast(t, src=src)
-    return t.cpu().numpy().view(np.uint64).copy()
+    data = _COMM.bcast_bytes(np.ascontiguousarray(arr, dtype=np.uint64).tobytes() if _COMM.rank == src else b"", src)
+    return np.frombuffer(data, dtype=np.uint64).copy()
 
 
 def _comm_sync():
-    """Collectives on device tensors run on torch's streams, the collectors on the library's."""
-    torch, dist, dev = _dist()
-    if dist is not None and dev.type == "cuda":
-        torch.cuda.synchronize()
+    """Make received buffers visible to the collectors (a no-op when the collectives share their stream)."""
+    _COMM.sync()
 
 
 def merge_dedup(dd) -> tuple[np.ndarray, dict]:
     """DedupEstimator over all shards.  ``dd``: rank 0 a live estimator that has seen its shard,
     other ranks deferred ones.  Adapter interface: ``modulo_bits()``, ``deferred_hashes(bits) ->
-    int64 tensor`` (record order), ``consume(tensor)``, ``counts() -> np.ndarray``, ``info() ->
-    dict``, ``empty(n) -> tensor``.  Returns (duplication counts in slot order, info) on every rank."""
-    torch, dist, dev = _dist()
+    buffer of int64`` (record order), ``consume(buffer)``, ``counts() -> np.ndarray``, ``info() ->
+    dict``, ``empty(n) -> buffer``.  Returns (duplication counts in slot order, info) on every rank.
+
+    The hashes of all the other ranks land in ONE buffer on the owner, in rank (= read) order, and
+    are consumed in one go: what fails a later, higher sampling level is dropped by the table
+    maintenance itself (the mask only grows, _qcmodule.c:4429-4431)."""
     rank, world = _rank_world()
-    if world > 1:
-        bits = _bcast_ints([dd.modulo_bits() if rank == 0 else 0], 0)[0]
-        mine = dd.deferred_hashes(bits) if rank > 0 else None
-        sizes = _allgather_obj(0 if mine is None else int(mine.numel()))
-        for g in range(1, world):
-            if sizes[g] == 0:
-                continue
-            if rank == g:
-                dist.send(mine, dst=0)
-            elif rank == 0:
-                buf = dd.empty(sizes[g])
-                dist.recv(buf, src=g)
-                _comm_sync()
-                dd.consume(buf)
-        _comm_sync()
     if world == 1:
         return dd.counts(), dd.info()
+    bits = _bcast_ints([dd.modulo_bits() if rank == 0 else 0], 0)[0]
+    mine = dd.deferred_hashes(bits) if rank > 0 else None
+    sizes = [int(v) for v in _COMM.allreduce_host_u64(
+        [0 if (mine is None or g != rank) else int(mine.numel()) for g in range(world)], "sum")]
+    if rank == 0:
+        parts = [dd.empty(sizes[g]) if sizes[g] else None for g in range(world)]
+        with _COMM.group():
+            for g in range(1, world):
+                if sizes[g]:
+                    _COMM.recv(parts[g], g)
+        _comm_sync()
+        for g in range(1, world):  # rank order = read order
+            if sizes[g]:
+                dd.consume(parts[g])
+    elif sizes[rank]:
+        with _COMM.group():
+            _COMM.send(mine, 0)
+    _comm_sync()
     info = dd.info() if rank == 0 else None
     keys = ("modulo_bits", "hash_table_size", "tracked_sequences")
     vals = _bcast_ints([info[k] for k in keys] if rank == 0 else [0] * len(keys), 0)
@@ -273,7 +421,6 @@ def merge_overrep(ov) -> None:
     ``table() -> (keys int64 tensor, counts int32 tensor)``, ``load(keys, counts | None,
     n_unique)``, ``apply_deferred()``, ``local_counters() -> [n_seqs, n_sampled, total_fragments,
     warn_records, first_warn]``, ``set_counters(...)``, ``empty_table()``."""
-    torch, dist, dev = _dist()
     rank, world = _rank_world()
     if world == 1:
         return
@@ -284,19 +431,21 @@ def merge_overrep(ov) -> None:
             break
         if rank == cur:
             keys, counts = ov.table()
-            dist.send(keys, dst=cur + 1)
-            dist.send(counts, dst=cur + 1)
+            with _COMM.group():
+                _COMM.send(keys, cur + 1)
+                _COMM.send(counts, cur + 1)
         elif rank == cur + 1:
             keys, counts = ov.empty_table()
-            dist.recv(keys, src=cur)
-            dist.recv(counts, src=cur)
+            with _COMM.group():
+                _COMM.recv(keys, cur)
+                _COMM.recv(counts, cur)
             _comm_sync()
             ov.load(keys, counts, n_unique)
             ov.apply_deferred()
         cur += 1
     # `cur` holds the table of everything up to its own shard; behind it the key set is frozen
     keys, counts = ov.table() if rank == cur else ov.empty_table()
-    dist.broadcast(keys, src=cur)
+    _COMM.bcast(keys, cur)
     _comm_sync()
     if rank > cur:
         ov.load(keys, None, n_unique)
@@ -304,12 +453,12 @@ def merge_overrep(ov) -> None:
         _, counts = ov.table()
     elif rank < cur:
         counts.zero_()
-    dist.all_reduce(counts)  # int32 wrap-around = the reference's u32 counter
+    _COMM.allreduce_sum_u32(counts)  # wrap-around = the reference's u32 counter
     _comm_sync()
     ov.load(keys, counts, n_unique)
     local = ov.local_counters()  # reads, sampled reads, fragments, warnings of this shard only
     sums = allreduce_sum_tables([np.array(local[:4], dtype=np.uint64)])[0]
-    first_warn = -allreduce_max(-(int(local[4]) if local[4] >= 0 else _NO_FAIL))
+    first_warn = allreduce_min(int(local[4]) if local[4] >= 0 else _NO_FAIL)
     ov.set_counters(int(sums[0]), int(sums[1]), int(sums[2]), int(sums[3]),
                     -1 if first_warn == _NO_FAIL else first_warn)
 
@@ -337,7 +486,6 @@ def merge_pertile(pt, first_record: int) -> dict:
     each)``, ``add_text(tensor)``, ``tile_counts()`` (optionally ``tile_table()``, see
     ``_tile_table``), ``empty(n) -> uint8 tensor``.  Tables travel as numpy arrays; the Python
     lists of the result are built once at the end."""
-    torch, dist, dev = _dist()
     rank, world = _rank_world()
     if world == 1:
         tiles = pt.tile_counts()
@@ -345,7 +493,7 @@ def merge_pertile(pt, first_record: int) -> dict:
                     max_length=max([len(e) for _, e, _ in tiles], default=0), skipped_record=pt.fail_index())
     fail = pt.fail_index()
     fail_global = _NO_FAIL if fail is None else first_record + fail
-    F = -allreduce_max(-fail_global)
+    F = allreduce_min(fail_global)
     dropped = first_record >= F            # the whole shard lies behind the first unparsable header
     my_tiles = [] if dropped else sorted(int(t) for t in pt.tile_ids())
     my_reads = 0 if dropped else pt.number_of_reads()
@@ -365,19 +513,22 @@ def merge_pertile(pt, first_record: int) -> dict:
             if ids:
                 outgoing[o] = pt.select(ids, max(0, min(F - first_record, 1 << 62)))
         plan = _allgather_obj({o: [int(c.numel()) for c in chunks] for o, chunks in outgoing.items()})
-        for o in range(world):
-            for g in range(o + 1, world):
-                for i, nbytes in enumerate(plan[g].get(o, [])):
-                    if nbytes == 0:
-                        continue
-                    if rank == g:
-                        dist.send(outgoing[o][i], dst=o)
-                    elif rank == o:
-                        buf = pt.empty(nbytes)
-                        dist.recv(buf, src=g)
-                        _comm_sync()
-                        pt.add_text(buf)
+        incoming = []  # (sender, buffer), in sender (= read) order
+        with _COMM.group():
+            for o in range(world):
+                for g in range(o + 1, world):
+                    for i, nbytes in enumerate(plan[g].get(o, [])):
+                        if nbytes == 0:
+                            continue
+                        if rank == g:
+                            _COMM.send(outgoing[o][i], o)
+                        elif rank == o:
+                            buf = pt.empty(nbytes)
+                            _COMM.recv(buf, g)
+                            incoming.append(buf)
         _comm_sync()
+        for buf in incoming:
+            pt.add_text(buf)
     # one uint64 block per rank: [tile id | sums (bit patterns) | counts] per owned tile
     if dropped:
         block = np.zeros((0, 1), np.uint64)
@@ -418,8 +569,7 @@ class GpuDedup:
             check(estimator._ctx.lib.sq_dedup_set_deferred(estimator._h, 1), "sq_dedup_set_deferred")
 
     def empty(self, n):
-        import torch
-        return torch.empty(max(int(n), 1), dtype=torch.int64, device="cuda")[:int(n)]
+        return DevBuf(self.dd._ctx, int(n) * 8, 8)
 
     def modulo_bits(self):
         return self.dd._modulo_bits
@@ -464,11 +614,8 @@ class GpuOverrep:
         return int(i.collected_unique_fragments), int(i.collected_unique_fragments >= i.max_unique_fragments)
 
     def empty_table(self):
-        import torch
         size = int(self.ov._sync().table_size)
-        _comm_sync()
-        return (torch.empty(size, dtype=torch.int64, device="cuda"),
-                torch.empty(size, dtype=torch.int32, device="cuda"))
+        return DevBuf(self.ov._ctx, size * 8, 8), DevBuf(self.ov._ctx, size * 4, 4)
 
     def table(self):
         keys, counts = self.empty_table()
@@ -512,10 +659,7 @@ class GpuPerTile:
         self.pt.add_record_array(arr)
 
     def empty(self, n):
-        import torch
-        t = torch.empty(int(n) + 64, dtype=torch.uint8, device="cuda")
-        t[int(n):] = 0  # the parser's vector loads may look a few bytes past the text
-        return t[:int(n)]
+        return DevBuf(self.pt._ctx, int(n), 1)  # (sq_stream_alloc pads: the parser's vector loads look past the text)
 
     def tile_ids(self):
         return self.pt._tile_arrays()[0].tolist()
@@ -621,8 +765,14 @@ class ShardedCollectors:
 
     def merge(self) -> dict:
         """Merged results of all ranks, on every rank.  ``self.merge_ms`` afterwards: host wall time
-        of each merge on this rank (waiting for slower ranks included)."""
+        of each merge on this rank (waiting for slower ranks included).
+
+        QCMetrics, AdapterCounter and NanoStats are merged in place on the device (sq_qc_allreduce,
+        sq_adapters_allreduce, sq_nanostats_allgather): afterwards this rank's collectors answer the
+        usual getters with the tables of the whole stream."""
         import time
+        from . import _qc
+        from ._lib import check
         t = [time.perf_counter()]
         self.merge_ms = {}
 
@@ -630,15 +780,23 @@ class ShardedCollectors:
             t.append(time.perf_counter())
             self.merge_ms[name] = round((t[-1] - t[-2]) * 1e3, 2)
 
-        qc = self.qc
-        out = dict(qc=merge_qc(*[np.frombuffer(x, dtype=np.uint64) for x in (
-            qc.base_count_table(), qc.phred_count_table(), qc.end_anchored_base_count_table(),
-            qc.end_anchored_phred_count_table(), qc.gc_content(), qc.phred_scores())]))
-        out["qc"]["number_of_reads"] = int(allreduce_sum_tables(
-            [np.array([qc.number_of_reads], dtype=np.uint64)])[0][0])
-        out["adapters"] = merge_adapter_counts([(a, np.frombuffer(f, dtype=np.uint64), np.frombuffer(r, dtype=np.uint64))
-                                                for a, f, r in self.ad.get_counts()])
-        lap("qc+adapters (first getter: waits for the shard's kernels)")
+        c, qc = comm(), self.qc
+        _qc._flush()
+        if c.world > 1:
+            lib = qc._ctx.lib
+            check(lib.sq_qc_allreduce(qc._h, c.h), "sq_qc_allreduce")
+            check(lib.sq_adapters_allreduce(self.ad._h, c.h), "sq_adapters_allreduce")
+            check(lib.sq_nanostats_allgather(self.ns._h, c.h, self.first_record), "sq_nanostats_allgather")
+        keys = ("base_count_table", "phred_count_table", "end_anchored_base_count_table",
+                "end_anchored_phred_count_table", "gc_content", "phred_scores")
+        out = dict(qc={k: np.frombuffer(getattr(qc, k)(), dtype=np.uint64) for k in keys})
+        out["qc"]["number_of_reads"] = int(qc.number_of_reads)
+        out["qc"]["max_length"] = int(qc.max_length)
+        out["adapters"] = [(a, np.frombuffer(f, dtype=np.uint64), np.frombuffer(r, dtype=np.uint64))
+                           for a, f, r in self.ad.get_counts()]
+        out["adapters_number_of_sequences"] = int(self.ad.number_of_sequences)
+        out["nano"] = self.ns  # holds the records of all ranks in read order
+        lap("qc+adapters+nanostats (first getter: waits for the shard's kernels)")
         out["ptq"] = merge_pertile(self.pt, self.first_record)
         lap("pertile")
         counts, info = merge_dedup(self.dd)

@@ -9,6 +9,55 @@ import torch
 from oracle import oracle as orc
 
 
+class TorchComm:
+    """The communicator interface of sequali_b200.sharded over torch.distributed (gloo on CPU):
+    buffers are CPU tensors.  Test infrastructure: the product's communicator is NcclComm."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def allreduce_host_u64(self, arr, op="sum"):
+        a = np.ascontiguousarray(arr, dtype=np.uint64).copy()
+        t = torch.from_numpy(a.view(np.int64))
+        ops = {"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN}
+        self.dist.all_reduce(t, op=ops[op])  # (values stay below 2^63 in the tests; sums wrap like u64)
+        return a
+
+    def bcast_bytes(self, data, src):
+        box = [data]
+        self.dist.broadcast_object_list(box, src=src)
+        return box[0]
+
+    def allgather_bytes(self, data):
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, data)
+        return parts
+
+    def barrier(self):
+        self.dist.barrier()
+
+    def sync(self):
+        pass
+
+    def send(self, buf, dst):
+        self.dist.send(buf, dst=dst)
+
+    def recv(self, buf, src):
+        self.dist.recv(buf, src=src)
+
+    def bcast(self, buf, src):
+        self.dist.broadcast(buf, src=src)
+
+    def allreduce_sum_u32(self, buf):
+        self.dist.all_reduce(buf)
+
+    def group(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def _tile_of(name: bytes):
     parts = name.split(b":")
     if len(parts) < 6 or not parts[4].isdigit() or not 1 <= len(parts[4]) <= 18:

@@ -37,6 +37,8 @@ def _worker(rank, world, port, text, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests import sharded_adapters as A
+    sharded.use_comm(A.TorchComm())
     try:
         recs, _ = orc.parse_fastq(text)
         # shard at a tile border so that PerTileQuality stays exact
@@ -104,6 +106,7 @@ def _exact_worker(rank, world, port, text, cuts, dd_kw, ov_kw, out):
     from tests import sharded_adapters as A
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    sharded.use_comm(A.TorchComm())
     try:
         recs, _ = orc.parse_fastq(text)
         lo, hi = cuts[rank], cuts[rank + 1]
