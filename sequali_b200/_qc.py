@@ -155,20 +155,32 @@ class FastqRecordView:
 
 
 class _PinnedBuffer:
-    """A pinned staging buffer.  cudaMallocHost is slow (it page-locks), so
-    released buffers go back to a small per-size pool instead of the driver."""
-    __slots__ = ("ptr", "size", "_ctx")
-    _pool: dict = {}
+    """A pinned staging buffer.  cudaMallocHost is slow (it page-locks), so released buffers go back
+    to a pool: requests are rounded up to size classes (powers of two below 1 MiB, multiples of 1 MiB
+    above), the pool holds at most _POOL_BYTES in total and drops its least recently used blocks."""
+    __slots__ = ("ptr", "size", "_cls", "_ctx")
+    _pool: list = []      # [(class size, ptr)], oldest first
+    _pool_bytes = 0
     _POOL_BYTES = 1 << 30
+
+    @staticmethod
+    def _size_class(n: int) -> int:
+        n = max(n, 4096)
+        if n >= 1 << 20:
+            return (n + (1 << 20) - 1) & ~((1 << 20) - 1)
+        return 1 << (n - 1).bit_length()
 
     def __init__(self, ctx: Context, size: int):
         self._ctx = ctx
         self.size = size
-        free = _PinnedBuffer._pool.get(size)
-        if free:
-            self.ptr = free.pop()
-            return
-        self.ptr = ctx.lib.sq_pinned_alloc(ctx.h, size)
+        self._cls = cls = self._size_class(size)
+        pool = _PinnedBuffer._pool
+        for i in range(len(pool) - 1, -1, -1):
+            if pool[i][0] == cls:
+                self.ptr = pool.pop(i)[1]
+                _PinnedBuffer._pool_bytes -= cls
+                return
+        self.ptr = ctx.lib.sq_pinned_alloc(ctx.h, cls)
         if not self.ptr:
             raise MemoryError(_lib.last_error())
 
@@ -181,11 +193,13 @@ class _PinnedBuffer:
         if not ptr:
             return
         self.ptr = None
-        pool = _PinnedBuffer._pool.setdefault(self.size, [])
-        if (len(pool) + 1) * self.size <= _PinnedBuffer._POOL_BYTES or not pool:
-            pool.append(ptr)
-        else:
-            self._ctx.lib.sq_pinned_free(self._ctx.h, ptr)
+        P = _PinnedBuffer
+        P._pool.append((self._cls, ptr))
+        P._pool_bytes += self._cls
+        while P._pool_bytes > P._POOL_BYTES and P._pool:
+            cls, old = P._pool.pop(0)
+            P._pool_bytes -= cls
+            self._ctx.lib.sq_pinned_free(self._ctx.h, old)
 
 
 # ------------------------------------------------------------------------------
@@ -511,47 +525,51 @@ class BamParser:
         self._ctx = Context.get()
         self._file = fileobj
         self._read_in_size = size
-        self._leftover = b""
+        self._buf, self._filled = None, 0
 
     def __iter__(self):
         return self
 
     def __next__(self) -> FastqRecordArrayView:
+        # [leftover | newly read bytes] live in one pinned buffer kept between calls
         ctx, lib = self._ctx, self._ctx.lib
         step = self._read_in_size
-        data = bytearray(self._leftover)
         while True:
-            leftover = len(data)
-            if leftover >= 4:
-                want = max(int.from_bytes(data[:4], "little"), step)  # :1527-1531
+            have = self._filled
+            if have >= 4:
+                want = max(int.from_bytes(self._buf.view(0, 4), "little"), step)  # :1527-1531
             else:
-                want = step - leftover
-            chunk = bytearray(want)
-            got = self._file.readinto(chunk) or 0
-            if leftover + got == 0:
+                want = step - have
+            if self._buf is None or have + want > self._buf.size:
+                bigger = _PinnedBuffer(ctx, max(have + want, (self._buf.size * 3) // 2 if self._buf else 0))
+                if have:
+                    _C.memmove(bigger.ptr, self._buf.ptr, have)
+                self._buf = bigger
+            got = self._file.readinto(self._buf.view(have, have + want)) or 0
+            n = have + got
+            if n == 0:
                 raise StopIteration
             if got == 0:
-                raise EOFError(f"Incomplete record at the end of file {bytes(data)!r}")
-            data += chunk[:got]
+                raise EOFError(f"Incomplete record at the end of file {bytes(self._buf.view(0, have))!r}")
+            self._filled = n
             # walk the record chain (:1623-1637): sq_bam_walk, on the bytes read so far
-            n = len(data)
-            raw = np.frombuffer(data, dtype=np.uint8)
             offs = np.empty(n // 36 + 1, dtype=np.uint64)
             kept, skipped, used = _C.c_uint64(), _C.c_uint64(), _C.c_uint64()
-            check(lib.sq_bam_walk(_void(raw), n, _void(offs), len(offs), _C.byref(kept), _C.byref(skipped),
+            check(lib.sq_bam_walk(self._buf.ptr, n, _void(offs), len(offs), _C.byref(kept), _C.byref(skipped),
                                   _C.byref(used)), "sq_bam_walk")
-            pos = used.value
             if kept.value or skipped.value:
                 break
-            del raw
-        self._leftover = bytes(data[pos:])
-        if not kept.value:
-            return FastqRecordArrayView._empty()
-        offs = offs[:kept.value]
-        h, plen = _C.c_void_p(), _C.c_uint64()
-        check(lib.sq_batch_from_bam(ctx.h, _void(raw), pos, _void(offs), len(offs),
-                                    _C.byref(h), _C.byref(plen)), "sq_batch_from_bam")
-        return FastqRecordArrayView._from_parser(h, len(offs), None, plen.value)
+        pos, arr = used.value, None
+        if kept.value:
+            h, plen = _C.c_void_p(), _C.c_uint64()
+            check(lib.sq_batch_from_bam(ctx.h, self._buf.ptr, pos, _void(offs), kept.value,
+                                        _C.byref(h), _C.byref(plen)), "sq_batch_from_bam")  # (synchronises)
+            arr = FastqRecordArrayView._from_parser(h, kept.value, None, plen.value)
+        left = self._filled - pos
+        if left and pos:
+            _C.memmove(self._buf.ptr, self._buf.ptr + pos, left)
+        self._filled = left
+        return arr if arr is not None else FastqRecordArrayView._empty()
 
 
 # ------------------------------------------------------------------------------

@@ -114,6 +114,7 @@ extern "C" int sq_batch_from_bam(sq_ctx *ctx, const uint8_t *bam, uint64_t nbyte
         return SQ_E_LIMIT;
     }
     CUDA_TRY(cudaSetDevice(ctx->device));
+    SqParserScope on_parser_stream(ctx);
     // validate the chain the host walked before trusting the headers on the device
     for (uint64_t i = 0; i < n; i++) {
         if (rec_off[i] + 36 > nbytes) {
@@ -156,22 +157,22 @@ extern "C" int sq_batch_from_bam(sq_ctx *ctx, const uint8_t *bam, uint64_t nbyte
         b->tags_off = d + 5 * n4;
         b->tags_len = d + 6 * n4;
         b->err_sum = (double *)(d + 7 * n4);
-        CUDA_TRY(cudaMemcpyAsync(d_bam, bam, nbytes, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(d_off, rec_off, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemsetAsync(d_max, 0, 8, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_bam, bam, nbytes, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaMemcpyAsync(d_off, rec_off, n * 8, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaMemsetAsync(d_max, 0, 8, sq_cur_stream(ctx)));
         const int grid = sq_grid_for(ctx, n, BAM_TPB, 16);
         SQ_LAUNCH(ctx, k_bam_sizes, grid, BAM_TPB, 0, d_bam, d_off, (uint32_t)n, sizes, b->name_len, b->seq_len,
                   b->tags_len, d_max);
         rc = sq_scan_exclusive_u32(ctx, sizes, offs, (uint32_t)n, d_total);
         if (rc == SQ_OK) {
-            CUDA_TRY(cudaMemcpyAsync(h_res, d_max, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(h_res, d_max, 8, cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+            CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
             b->max_len = h_res[0];
             b->nbytes = h_res[1];
             rc = sq_dalloc(ctx, (void **)&b->text, b->nbytes + 64, false);
         }
         if (rc == SQ_OK) {
-            CUDA_TRY(cudaMemsetAsync(b->text + b->nbytes, 0, 64, ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(b->text + b->nbytes, 0, 64, sq_cur_stream(ctx)));
             const int wgrid = sq_grid_for(ctx, n * 32, BAM_TPB, 16);
             SQ_LAUNCH(ctx, k_bam_decode, wgrid, BAM_TPB, 0, d_bam, d_off, (uint32_t)n, offs, b->name_len, b->seq_len,
                       b->tags_len, b->text, b->name_off, b->seq_off, b->qual_off, b->tags_off);

@@ -312,6 +312,130 @@ k_qc_horizontal(BatchView bv, const double *__restrict__ err_tab, const double *
 }
 
 // --------------------------------------------------------------------------
+// horizontal pass for long reads (nanopore: mean 20 kb, up to 1 Mb): a warp per read.
+// The four error chains of a read (:2059-2099) are serial by construction -- a 1 Mb read is four
+// chains of 250 000 dependent additions -- so the point is to keep every chain step down to ONE
+// dependent DADD: all 32 lanes fetch the next 128 quality bytes with one coalesced word load each,
+// look the error rates up and park them in shared memory; lanes 0..3 then add their chain's 32
+// values in order (loads issued ahead, additions back to back).  GC content is counted on the same
+// trip with a coalesced word load of the sequence per lane.
+// --------------------------------------------------------------------------
+constexpr int QL_WARPS = QC_TPB / 32;
+__global__ void __launch_bounds__(QC_TPB)
+k_qc_horizontal_long(BatchView bv, const double *__restrict__ err_tab, const double *__restrict__ edges,
+                     uint64_t *g_gc, uint64_t *g_mean_phred, unsigned long long *err_key, uint64_t record_base) {
+    __shared__ double s_err[128], s_edge[94];
+    __shared__ uint32_t s_gc[101], s_mp[94];
+    __shared__ double s_val[QL_WARPS][2][128];  // error rates of 128 consecutive positions, double buffered
+    for (uint32_t i = threadIdx.x; i < 128; i += QC_TPB) s_err[i] = (i >= 33 && i < 127) ? err_tab[i - 33] : 0.0;
+    for (uint32_t i = threadIdx.x; i < 94; i += QC_TPB) {
+        s_edge[i] = edges[i];
+        s_mp[i] = 0;
+    }
+    for (uint32_t i = threadIdx.x; i < 101; i += QC_TPB) s_gc[i] = 0;
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t warps = gridDim.x * QL_WARPS;
+    for (uint32_t r = blockIdx.x * QL_WARPS + warp; r < bv.n; r += warps) {
+        const uint32_t L = bv.seq_len[r];
+        const uint8_t *s = bv.text + bv.seq_off[r];
+        const uint8_t *q = bv.text + bv.qual_off[r];
+        // ---- GC content: SWAR over coalesced words -----------------------------------------------------
+        uint32_t gc = 0, at = 0;
+        for (uint32_t i = lane * 4; i < L; i += 128) {
+            uint32_t w = load_u32_unaligned(s + i);
+            const uint32_t nvalid = min(4u, L - i);
+            if (nvalid < 4) w &= 0xFFFFFFFFu >> (8 * (4 - nvalid));
+            const uint32_t u = w | 0x20202020u;
+            gc += __popc(zero_bytes80(u ^ 0x63636363u) | zero_bytes80(u ^ 0x67676767u));
+            at += __popc(zero_bytes80(u ^ 0x61616161u) | zero_bytes80(u ^ 0x74747474u));
+        }
+        gc = warp_sum_u32(gc);
+        at = warp_sum_u32(at);
+        // ---- the four chains over positions [0, 4 * nit) ----------------------------------------------------
+        const uint32_t nit = L >= 5 ? (L - 1) / 4 : 0;  // groups of four while > 4 remain (:2068)
+        const uint32_t n_main = 4 * nit;
+        double acc = 0.0;
+        uint32_t bad = 0xFFFFFFFFu;  // first position holding a byte outside '!'..'~'
+        auto stage_block = [&](uint32_t base, int buf) {
+            // lane l: positions base + 4l .. base + 4l + 3 -> s_val[..][4l .. 4l+3] (0.0 past n_main)
+            const uint32_t i = base + lane * 4;
+            double e[4] = {0.0, 0.0, 0.0, 0.0};
+            if (i < n_main) {
+                const uint32_t w = load_u32_unaligned(q + i);  // n_main is a multiple of 4: whole words
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t c = (w >> (8 * k)) & 0xFF;
+                    if (c - 33u > 93u) bad = min(bad, i + k);
+                    e[k] = s_err[c & 0x7F];
+                }
+            }
+            double2 *dst = (double2 *)&s_val[warp][buf][lane * 4];
+            dst[0] = make_double2(e[0], e[1]);
+            dst[1] = make_double2(e[2], e[3]);
+        };
+        if (n_main) stage_block(0, 0);
+        __syncwarp();
+        int buf = 0;
+        for (uint32_t base = 0; base < n_main; base += 128) {
+            if (base + 128 < n_main) stage_block(base + 128, buf ^ 1);  // the next block travels meanwhile
+            if (lane < 4) {
+                const double *v = &s_val[warp][buf][lane];
+                const uint32_t steps = min(32u, (n_main - base) / 4);
+                if (steps == 32) {
+#pragma unroll
+                    for (int g = 0; g < 32; g++) acc += v[4 * g];
+                }
+                else
+                    for (uint32_t g = 0; g < steps; g++) acc += v[4 * g];
+            }
+            __syncwarp();
+            buf ^= 1;
+        }
+        bad = ~warp_max_u32(~bad);
+        const double a1 = __shfl_sync(0xffffffffu, acc, 1), a2 = __shfl_sync(0xffffffffu, acc, 2),
+                     a3 = __shfl_sync(0xffffffffu, acc, 3);
+        if (lane == 0) {
+            double sum = ((acc + a1) + a2) + a3;  // :2098-2099
+            if (bad == 0xFFFFFFFFu) {
+                for (uint32_t i = n_main; i < L; i++) {  // tail, in order (:2100-2112)
+                    const uint32_t v = (uint8_t)(q[i] - 33);
+                    if (v > 93) {
+                        bad = i;
+                        break;
+                    }
+                    sum += s_err[v + 33];
+                }
+            }
+            if (at + gc) {  // :2045-2058
+                const double pct = (double)gc * 100.0 / (double)(at + gc);
+                atomicAdd(&s_gc[(uint32_t)round(pct)], 1u);
+            }
+            if (bad != 0xFFFFFFFFu) atomicMin(err_key, (unsigned long long)((record_base + r) << 8 | q[bad]));
+            else {
+                bv.err_sum[r] = sum;
+                if (L) {  // floor(-10*log10(sum/L)) through host-derived bucket edges (:2127-2137)
+                    const double avg = sum / (double)L;
+                    uint32_t lo = 0, hi = 93;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi + 1) >> 1;
+                        if (avg <= s_edge[mid]) lo = mid;
+                        else hi = mid - 1;
+                    }
+                    atomicAdd(&s_mp[lo], 1u);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 101; i += QC_TPB)
+        if (s_gc[i]) atomic_add_u64(g_gc + i, s_gc[i]);
+    for (uint32_t i = threadIdx.x; i < 94; i += QC_TPB)
+        if (s_mp[i]) atomic_add_u64(g_mean_phred + i, s_mp[i]);
+}
+
+// --------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------
 extern "C" int sq_qc_create(sq_ctx *ctx, uint64_t end_anchor_length, sq_qc **out) {
@@ -422,9 +546,15 @@ extern "C" int sq_qc_add(sq_qc *m, sq_batch *b) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     SQ_TRY(qc_add_vertical(m, b));
     const uint32_t n = (uint32_t)b->n;
-    int grid_h = sq_grid_for(ctx, (uint64_t)n * 4, QC_TPB, 8);
-    SQ_LAUNCH(ctx, k_qc_horizontal, grid_h, QC_TPB, 0, b->view(), ctx->d_err_table, ctx->d_phred_thresholds, m->gc,
-              m->mean_phred, m->err_key, m->n_reads);
+    if (b->max_len > 2048) {  // long reads: a warp per read
+        SQ_LAUNCH(ctx, k_qc_horizontal_long, sq_grid_for(ctx, (uint64_t)n * 32, QC_TPB, 16), QC_TPB, 0, b->view(),
+                  ctx->d_err_table, ctx->d_phred_thresholds, m->gc, m->mean_phred, m->err_key, m->n_reads);
+    }
+    else {
+        int grid_h = sq_grid_for(ctx, (uint64_t)n * 4, QC_TPB, 8);
+        SQ_LAUNCH(ctx, k_qc_horizontal, grid_h, QC_TPB, 0, b->view(), ctx->d_err_table, ctx->d_phred_thresholds, m->gc,
+                  m->mean_phred, m->err_key, m->n_reads);
+    }
     m->n_reads += n;
     if (b->max_len > m->max_len) m->max_len = b->max_len;
     b->err_sum_valid = true;

@@ -1667,12 +1667,15 @@ struct Parser {
     PyObject *header;  // BamParser only
     Py_ssize_t read_in_size;
     std::vector<uint8_t> *leftover;
+    Pinned bam_buf;    // BamParser: staging buffer kept between calls, leftover at its front
+    size_t bam_filled;
 };
 void Parser_dealloc(Parser *self) {
     PyTypeObject *tp = Py_TYPE(self);
     Py_XDECREF(self->file);
     Py_XDECREF(self->header);
     delete self->leftover;
+    self->bam_buf.release();
     tp->tp_free((PyObject *)self);
     Py_DECREF(tp);
 }
@@ -1705,6 +1708,8 @@ PyObject *FQ_new(PyTypeObject *type, PyObject *args, PyObject *kwargs) {
     self->header = nullptr;
     self->read_in_size = size;
     self->leftover = new std::vector<uint8_t>();
+    new (&self->bam_buf) Pinned();
+    self->bam_filled = 0;
     return (PyObject *)self;
 }
 // fileobj.readinto(memoryview of [dst, dst + len)) -> bytes read, -1 on error
@@ -1932,50 +1937,64 @@ PyObject *BAM_new(PyTypeObject *type, PyObject *args, PyObject *kwargs) {
     self->header = header;
     self->read_in_size = size;
     self->leftover = new std::vector<uint8_t>();
+    new (&self->bam_buf) Pinned();
+    self->bam_filled = 0;
     return (PyObject *)self;
 }
 PyObject *BAM_next(Parser *self) {
-    std::vector<uint8_t> data;
-    data.swap(*self->leftover);
+    // [leftover | newly read bytes] live in one pinned buffer that is kept between calls: the
+    // host->device copy of sq_batch_from_bam runs at PCIe speed and nothing is re-allocated or zeroed
+    Pinned &buf = self->bam_buf;
     std::vector<uint64_t> offsets;
     const size_t step = (size_t)self->read_in_size;
     uint64_t consumed = 0, kept = 0, skipped = 0;
     for (;;) {
-        const size_t have = data.size();
-        const size_t want = have >= 4 ? std::max<size_t>(le32(data.data()), step) : step - have;  // :1527-1531
-        data.resize(have + want);
-        const Py_ssize_t got = call_readinto(self->file, data.data() + have, (Py_ssize_t)want);
+        const size_t have = self->bam_filled;
+        const size_t want = have >= 4 ? std::max<size_t>(le32(buf.ptr), step) : step - have;  // :1527-1531
+        if (have + want > buf.size) {
+            Pinned bigger;
+            if (!bigger.alloc(std::max(have + want, buf.size + buf.size / 2))) return nullptr;
+            if (have) memcpy(bigger.ptr, buf.ptr, have);
+            buf.release();
+            buf = bigger;
+        }
+        const Py_ssize_t got = call_readinto(self->file, buf.ptr + have, (Py_ssize_t)want);
         if (got < 0) return nullptr;
-        data.resize(have + (size_t)got);
-        if (data.empty()) return nullptr;  // StopIteration
+        const size_t n = have + (size_t)got;
+        if (n == 0) return nullptr;  // StopIteration
         if (got == 0) {
-            PyObject *b = PyBytes_FromStringAndSize((const char *)data.data(), (Py_ssize_t)data.size());
+            PyObject *b = PyBytes_FromStringAndSize((const char *)buf.ptr, (Py_ssize_t)have);
             if (b) PyErr_Format(PyExc_EOFError, "Incomplete record at the end of file %R", b);
             Py_XDECREF(b);
             return nullptr;
         }
+        self->bam_filled = n;
         // walk the record chain (:1623-1637)
-        offsets.resize(data.size() / 36 + 1);
-        SQ_CHECK(sq_bam_walk(data.data(), data.size(), offsets.data(), offsets.size(), &kept, &skipped, &consumed), "sq_bam_walk");
+        offsets.resize(n / 36 + 1);
+        SQ_CHECK(sq_bam_walk(buf.ptr, n, offsets.data(), offsets.size(), &kept, &skipped, &consumed), "sq_bam_walk");
         if (kept || skipped) break;
     }
-    self->leftover->assign(data.begin() + consumed, data.end());
-    if (!kept) return ArrayView_empty();
-    ArrayView *a = ArrayView_alloc();
-    if (!a) return nullptr;
-    uint64_t packed = 0;
-    int rc;
-    Py_BEGIN_ALLOW_THREADS
-    rc = sq_batch_from_bam(g_ctx, data.data(), consumed, offsets.data(), kept, &a->h, &packed);
-    Py_END_ALLOW_THREADS
-    if (rc != SQ_OK) {
-        a->h = nullptr;
-        Py_DECREF((PyObject *)a);
-        return raise_sq(rc, "sq_batch_from_bam");
+    ArrayView *a = nullptr;
+    if (kept) {
+        a = ArrayView_alloc();
+        if (!a) return nullptr;
+        uint64_t packed = 0;
+        int rc;
+        Py_BEGIN_ALLOW_THREADS
+        rc = sq_batch_from_bam(g_ctx, buf.ptr, consumed, offsets.data(), kept, &a->h, &packed);  // (synchronises)
+        Py_END_ALLOW_THREADS
+        if (rc != SQ_OK) {
+            a->h = nullptr;
+            Py_DECREF((PyObject *)a);
+            return raise_sq(rc, "sq_batch_from_bam");
+        }
+        a->n = kept;
+        a->nbytes = packed;
     }
-    a->n = kept;
-    a->nbytes = packed;
-    return (PyObject *)a;
+    const size_t left = self->bam_filled - (size_t)consumed;
+    if (left && consumed) memmove(buf.ptr, buf.ptr + consumed, left);
+    self->bam_filled = left;
+    return a ? (PyObject *)a : ArrayView_empty();
 }
 PyMemberDef BAM_members[] = {{"header", T_OBJECT, offsetof(Parser, header), READONLY, "the SAM header text"},
                              {nullptr, 0, 0, 0, nullptr}};
