@@ -182,6 +182,9 @@ extern "C" int sq_batch_from_bam(sq_ctx *ctx, const uint8_t *bam, uint64_t nbyte
     sq_dfree(ctx, d_off);
     sq_dfree(ctx, sizes);
     sq_dfree(ctx, offs);
+    // the record array is used on the launch stream from here on: the decode (parser stream) is done first
+    if (rc == SQ_OK && cudaStreamSynchronize(sq_cur_stream(ctx)) != cudaSuccess)
+        rc = sq_cuda_fail(cudaGetLastError(), "BAM decode", __FILE__, __LINE__);
     if (rc != SQ_OK) {
         sq_batch_free(b);
         return rc;

@@ -1130,6 +1130,8 @@ extern "C" int sq_fastq_stream_next(sq_fastq_stream *s, sq_batch **out, sq_parse
             s->tail_cap = left + left / 2 + 4096;
         }
         SQ_TRY(copy_bytes(ctx, s->tail, b->text + info->consumed, left));
+        // (the caller may free the record array on the launch stream at any time: the copy out of it is done first)
+        if (left) CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
         s->tail_len = left;
         if (info->n_records == 0) {  // no complete record yet: join with the next window
             sq_batch_free(b);
