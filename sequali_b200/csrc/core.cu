@@ -700,6 +700,8 @@ static int ensure_scratch(sq_ctx *ctx, void **ptr, size_t *cap, size_t need) {
     *cap = 0;
     need += need / 8;
     CUDA_TRY(cudaMalloc(ptr, need));
+    // (slot n_rec of the parser's field scratch is read back even when no partial record wrote it)
+    CUDA_TRY(cudaMemset(*ptr, 0, need));
     *cap = need;
     return SQ_OK;
 }
