@@ -281,6 +281,61 @@ def run_configs(gpu_mod, peak_gbs):
     return out
 
 
+def _bgzf_worker(chunk):
+    from sequali_b200 import synth
+    return synth.bgzf_compress(bytes(chunk), level=6, eof_marker=False)
+
+
+def e2e_bgzf(sq, hostq, HostFastq, feed, make_modules, read_results, ctx, args):
+    """End to end from BGZF-compressed HOST bytes: a prefix of the e2e text is compressed here with zlib
+    level 6 in 65 280-byte members (bgzip's layout; one process per core, outside the timed region), then
+    the timed loop is the reader of sq_fastq_stream_create_bgzf + the collectors + the getters."""
+    import multiprocessing as mp
+    text = np.frombuffer(hostq.view(), dtype=np.uint8)
+    limit = min(len(text), args.bgzf_bytes)
+    limit = int(np.flatnonzero(text[:limit] == 10)[-1]) + 1 if limit else 0      # whole lines ...
+    text = text[:limit]
+    n_lines = int((text == 10).sum())
+    reads = n_lines // 4
+    if n_lines % 4:                                                              # ... and whole records
+        ends = np.flatnonzero(text == 10)
+        text = text[:int(ends[reads * 4 - 1]) + 1]
+    step = 65280 * 256
+    chunks = [text[i:i + step].tobytes() for i in range(0, len(text), step)]
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(min(os.cpu_count() or 1, 32)) as pool:
+        parts = pool.map(_bgzf_worker, chunks)
+    comp = b"".join(parts)
+    compress_s = time.perf_counter() - t0
+    hz = HostFastq.from_bytes(comp)
+
+    def step_fn():
+        mods = make_modules(sq)
+        for arr in hz.record_arrays_bgzf(args.e2e_window):
+            feed(mods, arr)
+        _, nbytes, summary = read_results(mods)
+        assert summary["reads"] == reads, (summary["reads"], reads)
+        return nbytes
+
+    step_fn()
+    ctx.sync()
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        out_bytes = step_fn()
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    hz.free()
+    return {"value": round(reads * READ_LENGTH / best / 1e9, 4), "unit": "Gbases/s", "reads": reads,
+            "text_bytes": int(len(text)), "h2d_bytes_per_step": int(len(comp)), "d2h_bytes_per_step": int(out_bytes),
+            "compression_ratio": round(len(text) / len(comp), 3), "text_gbs": round(len(text) / best / 1e9, 2),
+            "h2d_gbs": round(len(comp) / best / 1e9, 2), "host_compress_s_outside_timed_region": round(compress_s, 2),
+            "path": "pinned host BGZF bytes (zlib level 6, 65280-byte members) -> H2D of the compressed windows on a copy "
+                    "stream -> k_bgzf_inflate (one warp per member) straight into the record array -> parser -> "
+                    "sq_fused_add -> getters"}
+
+
 def sharded_parity_check(sq, sharded, DeviceFastq, comm, rank, world, total_reads):
     """Every rank runs its shard of a `total_reads` stream through ShardedCollectors + merge(), then the
     whole stream alone with plain collectors; every table must be equal (doubles by bit pattern, the
@@ -562,6 +617,11 @@ def run_cuda(args):
                               "path": "sequali._qc extension: FastqParser(host file object).readinto (one host memcpy "
                                       "per byte, single thread) -> pinned staging -> H2D -> kernels -> getters"}
         del host
+
+        # (3) the same host text as BGZF members (what bgzip writes): the compressed bytes cross PCIe and are
+        #     inflated on the device (sq_fastq_stream_create_bgzf, csrc/inflate.cu) -- SURVEY.md 8(f)1
+        if world == 1:
+            e2e["bgzf"] = e2e_bgzf(sq, hostq, HostFastq, feed, make_modules, read_results, ctx, args)
         hostq.free()
 
     # ---- CPU baseline: the unmodified reference on one core, bounded sample ----
@@ -756,6 +816,7 @@ def main():
     ap.add_argument("--ref-reads", type=int, default=500_000)
     ap.add_argument("--parity-reads", type=int, default=2_000_000, help="N > 1: reads of the sharded-vs-single check")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 / C5 leg")
+    ap.add_argument("--bgzf-bytes", type=int, default=2 << 30, help="text bytes of the BGZF end-to-end leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -44,6 +44,7 @@ enum {
     SQ_PARSE_NO_PLUS = 2,  /* "Record second header does not start with + ..." :1121 */
     SQ_PARSE_LEN = 3,      /* "Record sequence and qualities do not have equal length" :1143 */
     SQ_PARSE_ASCII = 4,    /* "Found non-ASCII character in file: %c" :1062 */
+    SQ_PARSE_INFLATE = 5,  /* sq_fastq_stream over BGZF: a member failed to inflate (err_record = member index) */
 };
 
 typedef struct sq_ctx sq_ctx;     /* one CUDA device + stream + scratch      */
@@ -140,6 +141,34 @@ SQ_API int sq_fastq_stream_create(sq_ctx *ctx, const uint8_t *host_text, uint64_
 SQ_API int sq_fastq_stream_next(sq_fastq_stream *s, sq_batch **out, sq_parse_info *info);
 SQ_API uint64_t sq_fastq_stream_leftover(const sq_fastq_stream *s);
 SQ_API void sq_fastq_stream_destroy(sq_fastq_stream *s);
+/* ---- BGZF on the device ------------------------------------------------------
+ * In the reference decompression is xopen's job on host threads (src/sequali/util.py:108-123) and the
+ * documented bottleneck (README.rst:168-171).  A BGZF stream (bgzip'd FASTQ, every BAM) is a chain of
+ * independent gzip members of <= 64 KiB of text: the host hops over the member headers, the compressed
+ * bytes cross PCIe, one warp inflates one member. */
+typedef struct {
+    uint64_t comp_off; /* offset of the member's DEFLATE payload in the compressed stream */
+    uint64_t text_off; /* offset of its text in the inflated stream                         */
+    uint32_t comp_len, text_len;
+} sq_bgzf_block;
+/* member headers of host[0 .. nbytes): blocks[0 .. *n_blocks) (at most cap), *consumed = bytes covered by
+ * the complete members listed, *text_bytes = their inflated size.  SQ_E_FORMAT for anything that is not a
+ * BGZF member (a plain gzip stream has no block index and cannot be inflated in parallel). */
+SQ_API int sq_bgzf_scan(const uint8_t *host, uint64_t nbytes, sq_bgzf_block *blocks, uint64_t cap, uint64_t *n_blocks,
+                        uint64_t *consumed, uint64_t *text_bytes);
+/* inflate blocks[0 .. n) of the HOST stream `host_comp` into DEVICE memory: the text of block i lands at
+ * dev_out + (blocks[i].text_off - blocks[0].text_off).  SQ_E_FORMAT + *bad_block / *bad_code for a corrupt
+ * member.  CRC-32 is not checked; the trailer's text size and the decoder's consistency checks are. */
+SQ_API int sq_bgzf_inflate(sq_ctx *ctx, const uint8_t *host_comp, uint64_t nbytes, const sq_bgzf_block *blocks, uint64_t n,
+                           uint8_t *dev_out, uint64_t *bad_block, int *bad_code);
+/* sq_fastq_stream over BGZF-compressed FASTQ in (pinned) host memory: windows of whole members holding
+ * ~`window` bytes of TEXT travel compressed, are inflated straight into the record array's text buffer
+ * behind the leftover of the previous array, and parsed there.  Use with sq_fastq_stream_next / _leftover /
+ * _destroy. */
+SQ_API int sq_fastq_stream_create_bgzf(sq_ctx *ctx, const uint8_t *host_bgzf, uint64_t nbytes, uint64_t window,
+                                       sq_fastq_stream **out);
+/* the device decoder's code run on the host, for unit tests without a GPU (no product path calls it) */
+SQ_API int sq_selftest_inflate_host(const uint8_t *deflate, uint32_t len, uint8_t *out, uint32_t cap, uint32_t *out_len);
 SQ_API uint64_t sq_batch_size(const sq_batch *b);
 SQ_API uint64_t sq_batch_nbytes(const sq_batch *b);
 SQ_API uint32_t sq_batch_max_seq_len(const sq_batch *b);

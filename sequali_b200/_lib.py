@@ -77,6 +77,11 @@ class NanoStatsInfo(C.Structure):
                 ("tag_error_record", C.c_uint64), ("pi_warnings", C.c_uint64)]
 
 
+class BgzfBlock(C.Structure):
+    _fields_ = [("comp_off", C.c_uint64), ("text_off", C.c_uint64), ("comp_len", C.c_uint32),
+                ("text_len", C.c_uint32)]
+
+
 class InsertInfo(C.Structure):
     _fields_ = [("total_reads", C.c_uint64), ("number_of_adapters_read1", C.c_uint64),
                 ("number_of_adapters_read2", C.c_uint64), ("max_insert_size", C.c_uint64),
@@ -116,6 +121,10 @@ SIGNATURES = {
     "sq_fastq_stream_next": (_int, [_vp, _P(_vp), _P(ParseInfo)]),
     "sq_fastq_stream_leftover": (_u64, [_vp]),
     "sq_fastq_stream_destroy": (None, [_vp]),
+    "sq_bgzf_scan": (_int, [_vp, _u64, _vp, _u64, _P(_u64), _P(_u64), _P(_u64)]),
+    "sq_bgzf_inflate": (_int, [_vp, _vp, _u64, _vp, _u64, _vp, _P(_u64), _P(_int)]),
+    "sq_fastq_stream_create_bgzf": (_int, [_vp, _vp, _u64, _u64, _P(_vp)]),
+    "sq_selftest_inflate_host": (_int, [_vp, _u32, _vp, _u32, _P(_u32)]),
     "sq_dedup_set_deferred": (_int, [_vp, _int]),
     "sq_dedup_deferred_compact": (_int, [_vp, _u64, _P(_u64)]),
     "sq_dedup_deferred_fetch": (_int, [_vp, _vp]),

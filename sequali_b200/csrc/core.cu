@@ -1003,9 +1003,33 @@ struct sq_fastq_stream {
     uint8_t *tail = nullptr;           // bytes behind the last complete record of the previous array
     uint64_t tail_len = 0, tail_cap = 0;
     bool slots_from_ctx = false;
+    // BGZF input (sq_fastq_stream_create_bgzf): windows of whole members travel compressed
+    bool bgzf = false;
+    std::vector<sq_bgzf_block> blocks;  // every member of the stream (host)
+    sq_bgzf_block *d_blocks = nullptr;  // the same on the device
+    struct Win { uint64_t b0, b1, comp0, comp1, text; };  // members [b0, b1), their bytes in the stream, text bytes
+    std::vector<Win> wins;
+    uint64_t slot_win[SLOTS] = {0, 0, 0};
+    unsigned long long *d_bad = nullptr;  // first member that failed to inflate (block << 8 | code)
 };
 
+int bgzf_inflate_async(sq_ctx *ctx, const uint8_t *dev_comp, uint64_t comp_base, const sq_bgzf_block *dev_blocks, uint64_t n,
+                       uint64_t text_base, uint8_t *dev_out, unsigned long long *dev_first_bad);
+
 static int stream_issue(sq_fastq_stream *s) {
+    if (s->bgzf) {
+        while (s->n_issued - s->n_taken < (uint64_t)sq_fastq_stream::SLOTS && s->n_issued < s->wins.size()) {
+            const int k = (int)(s->n_issued % sq_fastq_stream::SLOTS);
+            const sq_fastq_stream::Win &w = s->wins[s->n_issued];
+            if (s->n_issued >= (uint64_t)sq_fastq_stream::SLOTS) CUDA_TRY(cudaStreamWaitEvent(s->copy, s->drained[k], 0));
+            CUDA_TRY(cudaMemcpyAsync(s->slot[k], s->host + w.comp0, w.comp1 - w.comp0, cudaMemcpyHostToDevice, s->copy));
+            CUDA_TRY(cudaEventRecord(s->filled[k], s->copy));
+            s->slot_len[k] = w.text;
+            s->slot_win[k] = s->n_issued;
+            s->n_issued++;
+        }
+        return SQ_OK;
+    }
     while (s->n_issued - s->n_taken < (uint64_t)sq_fastq_stream::SLOTS && s->issue_pos < s->nbytes) {
         const int k = (int)(s->n_issued % sq_fastq_stream::SLOTS);
         const uint64_t len = s->nbytes - s->issue_pos < s->window ? s->nbytes - s->issue_pos : s->window;
@@ -1032,8 +1056,45 @@ extern "C" void sq_fastq_stream_destroy(sq_fastq_stream *s) {
         if (s->drained[k]) cudaEventDestroy(s->drained[k]);
     }
     if (s->tail) cudaFree(s->tail);
+    if (s->d_blocks) cudaFree(s->d_blocks);
+    if (s->d_bad) cudaFree(s->d_bad);
     if (s->copy) cudaStreamDestroy(s->copy);
     delete s;
+}
+
+// staging ring + events of a reader whose slots hold `slot_bytes` each; starts the first copies
+static int stream_setup(sq_ctx *ctx, sq_fastq_stream *s, uint64_t slot_bytes) {
+    int rc = SQ_OK;
+    auto fail = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == SQ_OK) rc = sq_cuda_fail(e, what, __FILE__, __LINE__);
+    };
+    fail(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking), "copy stream");
+    // the staging ring lives in the context between readers (page-mapping 3 x window per pass is slow)
+    if (!ctx->stage_in_use) {
+        if (ctx->stage_cap < slot_bytes + 64) {
+            cudaStreamSynchronize(ctx->pstream);
+            cudaStreamSynchronize(ctx->stream);
+            for (int k = 0; k < 3; k++) {
+                if (ctx->stage_slot[k]) cudaFree(ctx->stage_slot[k]);
+                ctx->stage_slot[k] = nullptr;
+            }
+            ctx->stage_cap = 0;
+            for (int k = 0; k < 3; k++) fail(cudaMalloc(&ctx->stage_slot[k], slot_bytes + 64), "staging slot");
+            if (rc == SQ_OK) ctx->stage_cap = slot_bytes + 64;
+        }
+        if (rc == SQ_OK) {
+            for (int k = 0; k < 3; k++) s->slot[k] = (uint8_t *)ctx->stage_slot[k];
+            s->slots_from_ctx = true;
+            ctx->stage_in_use = true;
+        }
+    }
+    for (int k = 0; k < sq_fastq_stream::SLOTS && rc == SQ_OK; k++) {
+        if (!s->slots_from_ctx) fail(cudaMalloc(&s->slot[k], slot_bytes + 64), "staging slot");
+        fail(cudaEventCreateWithFlags(&s->filled[k], cudaEventDisableTiming), "event");
+        fail(cudaEventCreateWithFlags(&s->drained[k], cudaEventDisableTiming), "event");
+    }
+    if (rc == SQ_OK) rc = stream_issue(s);
+    return rc;
 }
 
 extern "C" int sq_fastq_stream_create(sq_ctx *ctx, const uint8_t *host_text, uint64_t nbytes, uint64_t window,
@@ -1049,36 +1110,68 @@ extern "C" int sq_fastq_stream_create(sq_ctx *ctx, const uint8_t *host_text, uin
     s->host = host_text;
     s->nbytes = nbytes;
     s->window = window;
-    int rc = SQ_OK;
+    int rc = stream_setup(ctx, s, window);
+    if (rc != SQ_OK) {
+        sq_fastq_stream_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return SQ_OK;
+}
+
+extern "C" int sq_fastq_stream_create_bgzf(sq_ctx *ctx, const uint8_t *host_bgzf, uint64_t nbytes, uint64_t window,
+                                           sq_fastq_stream **out) {
+    *out = nullptr;
+    if (window < 65536 || window >= 0xF0000000ULL) {
+        sq_set_error("window must be between 64 KiB and 3.75 GiB of text");
+        return SQ_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    sq_fastq_stream *s = new sq_fastq_stream();
+    s->ctx = ctx;
+    s->host = host_bgzf;
+    s->nbytes = nbytes;
+    s->window = window;
+    s->bgzf = true;
+    // every member header of the stream (a hop per member: ~64 KiB of text each)
+    s->blocks.resize(nbytes / 28 + 2);
+    uint64_t n_blocks = 0, consumed = 0, text = 0;
+    int rc = sq_bgzf_scan(host_bgzf, nbytes, s->blocks.data(), s->blocks.size(), &n_blocks, &consumed, &text);
+    if (rc == SQ_OK && consumed != nbytes) {
+        sq_set_error("truncated BGZF stream: %llu bytes behind the last complete member",
+                     (unsigned long long)(nbytes - consumed));
+        rc = SQ_E_FORMAT;
+    }
+    if (rc != SQ_OK) {
+        delete s;
+        return rc;
+    }
+    s->blocks.resize(n_blocks);
+    uint64_t max_comp = 0;
+    for (uint64_t b0 = 0; b0 < n_blocks;) {
+        uint64_t b1 = b0, t = 0;
+        while (b1 < n_blocks && (b1 == b0 || t + s->blocks[b1].text_len <= window)) t += s->blocks[b1++].text_len;
+        sq_fastq_stream::Win w;
+        w.b0 = b0;
+        w.b1 = b1;
+        w.comp0 = s->blocks[b0].comp_off;
+        w.comp1 = s->blocks[b1 - 1].comp_off + s->blocks[b1 - 1].comp_len;
+        w.text = t;
+        if (t) s->wins.push_back(w);  // (members without text -- the BGZF end marker -- carry nothing)
+        if (w.comp1 - w.comp0 > max_comp) max_comp = w.comp1 - w.comp0;
+        b0 = b1;
+    }
     auto fail = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess && rc == SQ_OK) rc = sq_cuda_fail(e, what, __FILE__, __LINE__);
     };
-    fail(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking), "copy stream");
-    // the staging ring lives in the context between readers (page-mapping 3 x window per pass is slow)
-    if (!ctx->stage_in_use) {
-        if (ctx->stage_cap < window + 64) {
-            cudaStreamSynchronize(ctx->pstream);
-            cudaStreamSynchronize(ctx->stream);
-            for (int k = 0; k < 3; k++) {
-                if (ctx->stage_slot[k]) cudaFree(ctx->stage_slot[k]);
-                ctx->stage_slot[k] = nullptr;
-            }
-            ctx->stage_cap = 0;
-            for (int k = 0; k < 3; k++) fail(cudaMalloc(&ctx->stage_slot[k], window + 64), "staging slot");
-            if (rc == SQ_OK) ctx->stage_cap = window + 64;
-        }
-        if (rc == SQ_OK) {
-            for (int k = 0; k < 3; k++) s->slot[k] = (uint8_t *)ctx->stage_slot[k];
-            s->slots_from_ctx = true;
-            ctx->stage_in_use = true;
-        }
+    if (n_blocks) {
+        fail(cudaMalloc(&s->d_blocks, n_blocks * sizeof(sq_bgzf_block)), "member table");
+        if (rc == SQ_OK)
+            fail(cudaMemcpy(s->d_blocks, s->blocks.data(), n_blocks * sizeof(sq_bgzf_block), cudaMemcpyHostToDevice), "member table");
     }
-    for (int k = 0; k < sq_fastq_stream::SLOTS && rc == SQ_OK; k++) {
-        if (!s->slots_from_ctx) fail(cudaMalloc(&s->slot[k], window + 64), "staging slot");
-        fail(cudaEventCreateWithFlags(&s->filled[k], cudaEventDisableTiming), "event");
-        fail(cudaEventCreateWithFlags(&s->drained[k], cudaEventDisableTiming), "event");
-    }
-    if (rc == SQ_OK) rc = stream_issue(s);
+    fail(cudaMalloc(&s->d_bad, 8), "status word");
+    if (rc == SQ_OK) fail(cudaMemset(s->d_bad, 0xFF, 8), "status word");
+    if (rc == SQ_OK) rc = stream_setup(ctx, s, max_comp ? max_comp : 4096);
     if (rc != SQ_OK) {
         sq_fastq_stream_destroy(s);
         return rc;
@@ -1112,12 +1205,31 @@ extern "C" int sq_fastq_stream_next(sq_fastq_stream *s, sq_batch **out, sq_parse
         }
         CUDA_TRY(cudaStreamWaitEvent(sq_cur_stream(ctx), s->filled[k], 0));
         SQ_TRY(copy_bytes(ctx, b->text, s->tail, s->tail_len));
-        SQ_TRY(copy_bytes(ctx, b->text + s->tail_len, s->slot[k], len));
+        if (s->bgzf) {
+            // the members of this window inflate straight behind the leftover of the previous array
+            const sq_fastq_stream::Win &w = s->wins[s->slot_win[k]];
+            SQ_TRY(bgzf_inflate_async(ctx, s->slot[k], w.comp0, s->d_blocks + w.b0, w.b1 - w.b0, s->blocks[w.b0].text_off,
+                                      b->text + s->tail_len, s->d_bad));
+        }
+        else SQ_TRY(copy_bytes(ctx, b->text + s->tail_len, s->slot[k], len));
         CUDA_TRY(cudaMemsetAsync(b->text + total, 0, 64, sq_cur_stream(ctx)));
         CUDA_TRY(cudaEventRecord(s->drained[k], sq_cur_stream(ctx)));
         s->n_taken++;
         SQ_TRY(stream_issue(s));  // the slot refills as soon as the copy above has run
         rc = parse_device_text(ctx, b, UINT64_MAX, info);
+        if (s->bgzf) {  // a member that failed to inflate explains (and outranks) whatever the parser saw
+            unsigned long long bad = ~0ULL;
+            cudaMemcpyAsync(&bad, s->d_bad, 8, cudaMemcpyDeviceToHost, sq_cur_stream(ctx));
+            cudaStreamSynchronize(sq_cur_stream(ctx));
+            if (bad != ~0ULL) {
+                sq_set_error("BGZF member %llu is corrupt (inflate error %d)", (unsigned long long)(bad >> 8), (int)(bad & 0xFF));
+                sq_batch_free(b);
+                memset(info, 0, sizeof(*info));
+                info->err_code = SQ_PARSE_INFLATE;
+                info->err_record = bad >> 8;
+                return SQ_E_FORMAT;
+            }
+        }
         if (rc != SQ_OK) {
             sq_batch_free(b);
             return rc;

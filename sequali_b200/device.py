@@ -134,6 +134,13 @@ class HostFastq:
             off += nbytes
         return self, reads
 
+    @classmethod
+    def from_bytes(cls, data) -> "HostFastq":
+        """Pinned copy of `data` (bytes-like)."""
+        self = cls(Context.get(), len(data))
+        self.view()[:] = data
+        return self
+
     def view(self) -> memoryview:
         return memoryview((C.c_char * self.nbytes).from_address(self.ptr)).cast("B")
 
@@ -143,15 +150,26 @@ class HostFastq:
         collectors)."""
         return _lib.prefetched(self._record_arrays(window))
 
-    def _record_arrays(self, window: int):
+    def record_arrays_bgzf(self, window: int = 256 << 20):
+        """The same for BGZF-compressed FASTQ in this buffer (bgzip output): the members travel
+        compressed and are inflated on the device (sq_fastq_stream_create_bgzf), `window` bytes of
+        text per record array."""
+        return _lib.prefetched(self._record_arrays(window, bgzf=True))
+
+    def _record_arrays(self, window: int, bgzf: bool = False):
         ctx = self._ctx
         stream = C.c_void_p()
-        check(ctx.lib.sq_fastq_stream_create(ctx.h, self.ptr, self.nbytes, window, C.byref(stream)),
-              "sq_fastq_stream_create")
+        create = ctx.lib.sq_fastq_stream_create_bgzf if bgzf else ctx.lib.sq_fastq_stream_create
+        rc = create(ctx.h, self.ptr, self.nbytes, window, C.byref(stream))
+        if rc == _lib.SQ_E_FORMAT:
+            raise ValueError(_lib.last_error())
+        check(rc, "sq_fastq_stream_create")
         try:
             while True:
                 h, info = C.c_void_p(), _lib.ParseInfo()
                 rc = ctx.lib.sq_fastq_stream_next(stream, C.byref(h), C.byref(info))
+                if rc == _lib.SQ_E_FORMAT and info.err_code == 5:
+                    raise ValueError(_lib.last_error())
                 if rc == _lib.SQ_E_FORMAT:
                     raise ValueError(f"malformed FASTQ text: parse error {info.err_code} in record "
                                      f"{info.err_record} at byte {info.err_pos} of its record array")

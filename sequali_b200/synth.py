@@ -211,3 +211,25 @@ def nanopore_ubam(n_reads: int, mean_length: int = 20000, max_length: int = 1_00
             tags += b"piZ" + _rand_uuid(rng).encode() + b"\0"
         out.write(bam_record(_rand_uuid(rng).encode(), s, q, tags))
     return out.getvalue()
+
+
+def bgzf_compress(data: bytes, level: int = 6, block_text: int = 65280, eof_marker: bool = True) -> bytes:
+    """`data` as a BGZF stream (SAM spec 4.1: what bgzip writes): independent gzip members of
+    `block_text` bytes of text each, every one with the 'BC' extra field giving its size."""
+    import zlib
+    out = io.BytesIO()
+
+    def member(chunk: bytes):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        payload = c.compress(chunk) + c.flush()
+        total = 12 + 6 + len(payload) + 8
+        assert total <= 65536, "pick a smaller block_text for incompressible data"
+        out.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", 6) +
+                  b"BC" + struct.pack("<HH", 2, total - 1) + payload +
+                  struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+    for i in range(0, len(data), block_text):
+        member(data[i:i + block_text])
+    if eof_marker:
+        member(b"")
+    return out.getvalue()

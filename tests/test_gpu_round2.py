@@ -114,3 +114,43 @@ def test_extension_parser_errors_and_record_access(ext, sq):
         for i in (0, len(a) - 1):
             assert (a[i].name(), a[i].sequence(), a[i].qualities(), a[i].tags()) == \
                    (b[i].name(), b[i].sequence(), b[i].qualities(), b[i].tags())
+
+
+# ---- BGZF members inflated on the device (sq_fastq_stream_create_bgzf, csrc/inflate.cu) ----------------
+@pytest.mark.parametrize("level,block_text,window", [(6, 65280, 1 << 20), (1, 20000, 300_000), (0, 60000, 65536),
+                                                     (9, 65280, 64 << 20)])
+def test_bgzf_fastq_stream_equals_plain_text(sq, level, block_text, window):
+    from sequali_b200.device import HostFastq
+    text = synth.illumina_fastq(12_000, length=150, seed=31, n_tiles=9)
+    comp = synth.bgzf_compress(text, level=level, block_text=block_text)
+    host = HostFastq.from_bytes(comp)
+    qc, ad, ptq = sq.QCMetrics(), sq.AdapterCounter(H.ILLUMINA_ADAPTERS), sq.PerTileQuality()
+    ov, ns = sq.OverrepresentedSequences(), sq.NanoStats()
+    dd = sq.DedupEstimator(front_sequence_offset=64, back_sequence_offset=0)
+    n, got_text = 0, []
+    for arr in host.record_arrays_bgzf(window):
+        n += len(arr)
+        got_text.append(arr.obj[:])  # the inflated bytes of this array (leftover of the previous one in front)
+        for m in (qc, ptq, ov, ns, ad, dd):
+            m.add_record_array(arr)
+    got = dict(qc=H.dump_qc(qc), adapters=H.dump_adapters(ad), ptq=H.dump_ptq(ptq), overrep=H.dump_overrep(ov),
+               dedup=H.dump_dedup(dd), nano=H.dump_nano(ns))
+    assert n == 12_000
+    H.assert_same(got, H.oracle_single_end(text, H.ILLUMINA_ADAPTERS, chunk_records=2500))
+    host.free()
+
+
+def test_bgzf_corrupt_member_is_an_error(sq):
+    from sequali_b200.device import HostFastq
+    text = synth.illumina_fastq(3000, length=150, seed=32, n_tiles=3)
+    comp = bytearray(synth.bgzf_compress(text, level=6, block_text=30000))
+    comp[len(comp) // 2] ^= 0x10  # inside the payload of a member in the middle
+    host = HostFastq.from_bytes(bytes(comp))
+    with pytest.raises((ValueError, EOFError)):
+        for _ in host.record_arrays_bgzf(1 << 20):
+            pass
+    host.free()
+    with pytest.raises(ValueError, match="BGZF"):  # plain gzip has no member index
+        import gzip
+        h2 = HostFastq.from_bytes(gzip.compress(text))
+        list(h2.record_arrays_bgzf(1 << 20))
