@@ -13,36 +13,78 @@
 #include "inflate_core.cuh"
 #include "modules.cuh"
 
-constexpr int INF_WARPS = 8;
+// One warp = one CTA = one member at a time.  The newest INF_WIN bytes of the member's text live in a ring in
+// shared memory: literals and matches are written there, matches read their source there (a match that
+// reaches further back than the ring reads the bytes this warp already flushed to global memory), and
+// the ring is flushed to global memory 1 KiB at a time with coalesced stores.  ~20 KiB of shared memory
+// per warp: eleven decoders per SM.
+constexpr uint32_t INF_WIN = 16384, INF_FLUSH = 1024;
 
-struct InfSmem {
-    InfTables t;
+struct WarpOut {
+    uint8_t *win;      // shared-memory ring
+    uint8_t *dst;      // the member's text in global memory
+    uint32_t flushed;  // bytes [0, flushed) are in global memory
+    uint32_t lane;
+
+    __device__ __forceinline__ void flush_to(uint32_t end) {  // bytes [flushed, end) -> global, all lanes
+        __syncwarp();
+        for (uint32_t i = flushed + lane; i < end; i += 32) dst[i] = win[i & (INF_WIN - 1)];
+        flushed = end;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void room(uint32_t op, uint32_t n) {
+        // keep the unflushed part short: the ring then always holds the last INF_WIN - INF_FLUSH - 258 bytes
+        if (op + n - flushed > INF_FLUSH) flush_to(op);
+    }
+    __device__ __forceinline__ void put(uint32_t op, uint8_t c) {
+        room(op, 1);
+        if (lane == 0) win[op & (INF_WIN - 1)] = c;
+    }
+    __device__ __forceinline__ void raw(uint32_t op, const uint8_t *src, uint32_t n) {
+        flush_to(op);
+        for (uint32_t i = lane; i < n; i += 32) dst[op + i] = src[i];  // stored block: straight to global ...
+        const uint32_t keep = n < INF_WIN ? n : INF_WIN;                // ... and its tail into the ring
+        for (uint32_t i = n - keep + lane; i < n; i += 32) win[(op + i) & (INF_WIN - 1)] = src[i];
+        flushed = op + n;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void match(uint32_t op, uint32_t dist, uint32_t n) {
+        room(op, n);
+        __syncwarp();
+        // out[op + i] = out[op - dist + (i mod dist)]: the source lies in front of `op` and is complete, so
+        // the lanes take the bytes of the match in any order
+        if (dist <= INF_WIN - INF_FLUSH - 258) {
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint32_t k = dist >= n ? i : i % dist;
+                win[(op + i) & (INF_WIN - 1)] = win[(op - dist + k) & (INF_WIN - 1)];
+            }
+        }
+        else {
+            // further back than the ring reaches: those bytes were flushed by this warp (dist >= n here)
+            flush_to(op);
+            for (uint32_t i = lane; i < n; i += 32) win[(op + i) & (INF_WIN - 1)] = dst[op - dist + i];
+        }
+        __syncwarp();
+    }
 };
 
-__global__ void __launch_bounds__(INF_WARPS * 32)
+__global__ void __launch_bounds__(32)
 k_bgzf_inflate(const uint8_t *__restrict__ comp, uint64_t comp_base, const sq_bgzf_block *__restrict__ blocks, uint32_t n_blocks,
                uint64_t text_base, uint8_t *__restrict__ out, unsigned long long *first_bad) {
-    __shared__ InfSmem sm[INF_WARPS];
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t warps = gridDim.x * INF_WARPS;
-    for (uint32_t bi = blockIdx.x * INF_WARPS + warp; bi < n_blocks; bi += warps) {
+    __shared__ InfTables tables;
+    __shared__ __align__(16) uint8_t win[INF_WIN];
+    for (uint32_t bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
         const sq_bgzf_block blk = blocks[bi];
-        uint8_t *dst = out + (blk.text_off - text_base);
+        WarpOut o;
+        o.win = win;
+        o.dst = out + (blk.text_off - text_base);
+        o.flushed = 0;
+        o.lane = lane_id();
         uint32_t produced = 0;
-        auto copy_match = [&](uint32_t op, uint32_t dist, uint32_t len) {
-            // out[op + i] = out[op - dist + (i mod dist)]: the source lies in front of `op` and is
-            // complete, so the lanes can take the bytes of the match in any order
-            __syncwarp();
-            const uint8_t *src = dst + op - dist;
-            if (dist >= len)
-                for (uint32_t i = lane; i < len; i += 32) dst[op + i] = src[i];
-            else
-                for (uint32_t i = lane; i < len; i += 32) dst[op + i] = src[i % dist];
-            __syncwarp();
-        };
-        int rc = inf_inflate(comp + (blk.comp_off - comp_base), blk.comp_len, dst, blk.text_len, &produced, sm[warp].t, copy_match);
+        int rc = inf_inflate(comp + (blk.comp_off - comp_base), blk.comp_len, blk.text_len, &produced, tables, o);
         if (rc == INF_OK && produced != blk.text_len) rc = INF_E_SIZE;
-        if (rc != INF_OK && lane == 0) atomicMin(first_bad, (unsigned long long)bi << 8 | (unsigned)rc);
+        if (rc == INF_OK) o.flush_to(produced);
+        else if (o.lane == 0) atomicMin(first_bad, (unsigned long long)bi << 8 | (unsigned)rc);
         __syncwarp();
     }
 }
@@ -111,11 +153,11 @@ extern "C" int sq_bgzf_scan(const uint8_t *host, uint64_t nbytes, sq_bgzf_block 
 int bgzf_inflate_async(sq_ctx *ctx, const uint8_t *dev_comp, uint64_t comp_base, const sq_bgzf_block *dev_blocks, uint64_t n,
                        uint64_t text_base, uint8_t *dev_out, unsigned long long *dev_first_bad) {
     if (n == 0) return SQ_OK;
-    uint64_t grid = (n + INF_WARPS - 1) / INF_WARPS;
-    const uint64_t cap = (uint64_t)ctx->num_sms * 8;  // 64 warps per SM: one decoder per warp slot
+    uint64_t grid = n;
+    const uint64_t cap = (uint64_t)ctx->num_sms * 11;  // eleven one-warp CTAs fit an SM (shared memory)
     if (grid > cap) grid = cap;
-    SQ_LAUNCH(ctx, k_bgzf_inflate, (unsigned)grid, INF_WARPS * 32, 0, dev_comp, comp_base, dev_blocks, (uint32_t)n, text_base,
-              dev_out, dev_first_bad);
+    SQ_LAUNCH(ctx, k_bgzf_inflate, (unsigned)grid, 32, 0, dev_comp, comp_base, dev_blocks, (uint32_t)n, text_base, dev_out,
+              dev_first_bad);
     return SQ_OK;
 }
 
@@ -159,8 +201,13 @@ extern "C" int sq_bgzf_inflate(sq_ctx *ctx, const uint8_t *host_comp, uint64_t n
 // the same decoder on the host, for the unit tests (no GPU needed); not used by any product path
 extern "C" int sq_selftest_inflate_host(const uint8_t *deflate, uint32_t len, uint8_t *out, uint32_t cap, uint32_t *out_len) {
     static thread_local InfTables t;
-    auto copy_match = [&](uint32_t op, uint32_t dist, uint32_t n) {
-        for (uint32_t i = 0; i < n; i++) out[op + i] = out[op - dist + (i % dist)];
-    };
-    return inf_inflate(deflate, len, out, cap, out_len, t, copy_match);
+    struct HostOut {
+        uint8_t *out;
+        void put(uint32_t op, uint8_t c) { out[op] = c; }
+        void raw(uint32_t op, const uint8_t *src, uint32_t n) { memcpy(out + op, src, n); }
+        void match(uint32_t op, uint32_t dist, uint32_t n) {
+            for (uint32_t i = 0; i < n; i++) out[op + i] = out[op - dist + (i % dist)];
+        }
+    } o{out};
+    return inf_inflate(deflate, len, cap, out_len, t, o);
 }

@@ -39,7 +39,16 @@ struct InfBits {
 };
 
 INF_HD void inf_refill(InfBits &b) {
-    // keep at least 32 bits when the input allows (byte loads: the input sits in L2 / L1)
+    // at least 32 valid bits afterwards (while the input lasts): four bytes at a time, single bytes at the very end
+    if (b.cnt > 32) return;
+    if (b.pos + 4 <= b.len) {
+        const uint8_t *p = b.in + b.pos;
+        const uint32_t w = (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
+        b.buf |= (uint64_t)w << b.cnt;
+        b.cnt += 32;
+        b.pos += 4;
+        return;
+    }
     while (b.cnt <= 56 && b.pos < b.len) {
         b.buf |= (uint64_t)b.in[b.pos++] << b.cnt;
         b.cnt += 8;
@@ -124,12 +133,12 @@ INF_HD int inf_symbol(InfBits &b, const uint16_t *primary, uint32_t primary_bits
     return -1;
 }
 
-// Inflates the raw deflate stream in[0 .. in_len) into out[0 .. out_cap); *out_len = bytes produced.
-// Copy: a callable (dst offset, distance, length) for matches, so that the device build can spread a long
-// match over the lanes of the warp; the host build and short matches copy byte by byte.
-template <typename Tables, typename Copy>
-INF_HD int inf_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, uint32_t *out_len, Tables &T,
-                       Copy copy_match) {
+// Inflates the raw deflate stream in[0 .. in_len) into at most out_cap bytes; *out_len = bytes produced.
+// Out: where the text goes -- put(op, byte), raw(op, src, n) for stored blocks, match(op, dist, n) for LZ77
+// copies.  The device build keeps a window of the text in shared memory and spreads every copy over the
+// lanes of the warp; the host build writes a plain array.
+template <typename Tables, typename Out>
+INF_HD int inf_inflate(const uint8_t *in, uint32_t in_len, uint32_t out_cap, uint32_t *out_len, Tables &T, Out &out) {
     const uint16_t len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115,
                                    131, 163, 195, 227, 258};
     const uint8_t len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -160,7 +169,7 @@ INF_HD int inf_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
             const uint32_t start = b.pos - b.cnt / 8;
             if (start + len > in_len) return INF_E_TRUNCATED;
             if (op + len > out_cap) return INF_E_OVERFLOW;
-            for (uint32_t i = 0; i < len; i++) out[op + i] = in[start + i];
+            out.raw(op, in + start, len);
             op += len;
             b.pos = start + len;
             b.buf = 0;
@@ -224,7 +233,7 @@ INF_HD int inf_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
                 if (sym < 0) return b.pos >= b.len ? INF_E_TRUNCATED : INF_E_CODE;
                 if (sym < 256) {
                     if (op >= out_cap) return INF_E_OVERFLOW;
-                    out[op++] = (uint8_t)sym;
+                    out.put(op++, (uint8_t)sym);
                     continue;
                 }
                 if (sym == 256) break;
@@ -240,7 +249,7 @@ INF_HD int inf_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
                 const uint32_t dist = dist_base[ds] + inf_take(b, dist_extra[ds]);
                 if (dist > op) return INF_E_DISTANCE;
                 if (op + len > out_cap) return INF_E_OVERFLOW;
-                copy_match(op, dist, len);
+                out.match(op, dist, len);
                 op += len;
             }
         }
