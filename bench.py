@@ -326,8 +326,15 @@ def e2e_bgzf(sq, hostq, HostFastq, feed, make_modules, read_results, ctx, args):
         ctx.sync()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
+    ctx.profile(True)
+    step_fn()
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    inflate_ms = prof.get("k_bgzf_inflate", (0, 0.0))[1]
     hz.free()
     return {"value": round(reads * READ_LENGTH / best / 1e9, 4), "unit": "Gbases/s", "reads": reads,
+            "inflate_kernel": {"ms": round(inflate_ms, 3), "text_gbs": round(len(text) / max(inflate_ms, 1e-9) / 1e6, 1),
+                               "launches": prof.get("k_bgzf_inflate", (0, 0.0))[0]},
             "text_bytes": int(len(text)), "h2d_bytes_per_step": int(len(comp)), "d2h_bytes_per_step": int(out_bytes),
             "compression_ratio": round(len(text) / len(comp), 3), "text_gbs": round(len(text) / best / 1e9, 2),
             "h2d_gbs": round(len(comp) / best / 1e9, 2), "host_compress_s_outside_timed_region": round(compress_s, 2),

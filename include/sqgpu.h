@@ -153,7 +153,8 @@ typedef struct {
 } sq_bgzf_block;
 /* member headers of host[0 .. nbytes): blocks[0 .. *n_blocks) (at most cap), *consumed = bytes covered by
  * the complete members listed, *text_bytes = their inflated size.  SQ_E_FORMAT for anything that is not a
- * BGZF member (a plain gzip stream has no block index and cannot be inflated in parallel). */
+ * BGZF member (a plain gzip stream has no block index and cannot be inflated in parallel).  blocks == NULL
+ * counts the members only. */
 SQ_API int sq_bgzf_scan(const uint8_t *host, uint64_t nbytes, sq_bgzf_block *blocks, uint64_t cap, uint64_t *n_blocks,
                         uint64_t *consumed, uint64_t *text_bytes);
 /* inflate blocks[0 .. n) of the HOST stream `host_comp` into DEVICE memory: the text of block i lands at

@@ -1134,9 +1134,12 @@ extern "C" int sq_fastq_stream_create_bgzf(sq_ctx *ctx, const uint8_t *host_bgzf
     s->window = window;
     s->bgzf = true;
     // every member header of the stream (a hop per member: ~64 KiB of text each)
-    s->blocks.resize(nbytes / 28 + 2);
     uint64_t n_blocks = 0, consumed = 0, text = 0;
-    int rc = sq_bgzf_scan(host_bgzf, nbytes, s->blocks.data(), s->blocks.size(), &n_blocks, &consumed, &text);
+    int rc = sq_bgzf_scan(host_bgzf, nbytes, nullptr, 0, &n_blocks, &consumed, &text);  // count, then list
+    if (rc == SQ_OK) {
+        s->blocks.resize(n_blocks + 1);
+        rc = sq_bgzf_scan(host_bgzf, nbytes, s->blocks.data(), s->blocks.size(), &n_blocks, &consumed, &text);
+    }
     if (rc == SQ_OK && consumed != nbytes) {
         sq_set_error("truncated BGZF stream: %llu bytes behind the last complete member",
                      (unsigned long long)(nbytes - consumed));

@@ -131,11 +131,13 @@ extern "C" int sq_bgzf_scan(const uint8_t *host, uint64_t nbytes, sq_bgzf_block 
             sq_set_error("BGZF member at byte %llu claims %u bytes of text (limit 65536)", (unsigned long long)pos, isize);
             return SQ_E_FORMAT;
         }
-        if (n == cap) break;
-        blocks[n].comp_off = pos + 12 + xlen;
-        blocks[n].comp_len = (uint32_t)(total - 12 - xlen - 8);
-        blocks[n].text_len = isize;
-        blocks[n].text_off = text;
+        if (blocks) {  // (blocks == NULL: count only)
+            if (n == cap) break;
+            blocks[n].comp_off = pos + 12 + xlen;
+            blocks[n].comp_len = (uint32_t)(total - 12 - xlen - 8);
+            blocks[n].text_len = isize;
+            blocks[n].text_off = text;
+        }
         text += isize;
         n++;
         pos += total;
