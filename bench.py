@@ -654,6 +654,7 @@ def run_cuda(args):
                                    "OverrepresentedSequences, NanoStats, AdapterCounter, DedupEstimator)",
                        "reads_per_gpu": n_reads, "read_length": READ_LENGTH,
                        "text_bytes_per_gpu": int(text_bytes), "record_arrays_per_step": n_chunks,
+                       "numa_node_of_rank0": ctx.numa_node,
                        "l2": "inputs larger than L2" if text_bytes > 200e6 else "input smaller than L2",
                        "parallelism": f"{world} x contiguous read shards" + (
                            "" if world == 1 else ", exact merges over NCCL inside libsqgpu (all-reduce of the additive "

@@ -75,6 +75,8 @@ typedef struct {
 /* ---- context ----------------------------------------------------------- */
 SQ_API int sq_device_count(void);
 SQ_API const char *sq_last_error(void);
+/* NUMA node of the device's PCIe root (-1: unknown): where pinned staging memory should be allocated */
+SQ_API int sq_device_numa_node(int device);
 SQ_API int sq_ctx_create(int device, sq_ctx **out);
 SQ_API void sq_ctx_destroy(sq_ctx *ctx);
 SQ_API int sq_ctx_sync(sq_ctx *ctx);

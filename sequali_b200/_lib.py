@@ -97,6 +97,7 @@ _P = C.POINTER
 SIGNATURES = {
     "sq_device_count": (_int, []),
     "sq_last_error": (C.c_char_p, []),
+    "sq_device_numa_node": (_int, [_int]),
     "sq_ctx_create": (_int, [_int, _P(_vp)]),
     "sq_ctx_destroy": (None, [_vp]),
     "sq_ctx_sync": (_int, [_vp]),
@@ -301,6 +302,34 @@ def prefetched(gen, depth: int = 1):
         gen.close()
 
 
+def bind_to_numa_node(lib, device: int):
+    """Run this process on the cores of the NUMA node the GPU hangs off, so that the pinned staging
+    buffers (first touch) and the threads that fill them sit next to the device: with eight ranks on a
+    two-socket box, host->device copies from the far socket run at less than half speed.  Only when
+    several ranks share the box (WORLD_SIZE > 1) or SEQUALI_B200_NUMA=1; SEQUALI_B200_NUMA=0 switches it
+    off.  Returns the node, or None."""
+    want = os.environ.get("SEQUALI_B200_NUMA")
+    if want == "0" or (want is None and int(os.environ.get("WORLD_SIZE", "1")) <= 1):
+        return None
+    try:
+        node = lib.sq_device_numa_node(device)
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except (OSError, ValueError, AttributeError):
+        pass
+    return None
+
+
 class Context:
     """One device context per process (device = $SEQUALI_B200_DEVICE, else
     $LOCAL_RANK, else 0)."""
@@ -315,8 +344,9 @@ class Context:
             raise SqGpuError("no CUDA device visible: sequali_b200 needs a GPU "
                              "(there is no CPU fallback)")
         h = C.c_void_p()
-        check(lib.sq_ctx_create(device % max(lib.sq_device_count(), 1), C.byref(h)),
-              "sq_ctx_create")
+        device = device % max(lib.sq_device_count(), 1)
+        self.numa_node = bind_to_numa_node(lib, device)
+        check(lib.sq_ctx_create(device, C.byref(h)), "sq_ctx_create")
         self.h, self.lib, self.device = h, lib, device
 
     @classmethod

@@ -11,6 +11,7 @@
 //                      closes (record k/4, line k%4) and checks '@' / '+'
 //   k_finish_records   one thread per record: sequence length, equal-length
 //                      check, longest sequence / record of the array
+#include <ctype.h>
 #include <math.h>
 #include <stdarg.h>
 
@@ -77,6 +78,25 @@ static double phred_bucket_edge(int k) {
     double r;
     memcpy(&r, &lo_bits, 8);
     return r;
+}
+
+// NUMA node the device's PCIe root hangs off (sysfs), -1 when unknown.  Pinned staging memory should live
+// there: host->device copies that cross the socket interconnect run at half speed or less.
+extern "C" int sq_device_numa_node(int device) {
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
 }
 
 extern "C" int sq_ctx_create(int device, sq_ctx **out) {
