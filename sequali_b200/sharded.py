@@ -105,9 +105,16 @@ class DevBuf:
         self._ctx.lib.sq_stream_memset(self._ctx.h, self.ptr, 0, self.nbytes)
         return self
 
+    def narrow(self, dim: int, start: int, length: int) -> "DevBuf":
+        """A view of `length` items from item `start` (torch.Tensor.narrow's signature); the parent owns the memory."""
+        view = object.__new__(DevBuf)
+        view._ctx, view.itemsize, view.nbytes = self._ctx, self.itemsize, int(length) * self.itemsize
+        view.ptr, view._parent = self.ptr + int(start) * self.itemsize, self
+        return view
+
     def __del__(self):
         ptr, self.ptr = getattr(self, "ptr", None), None
-        if ptr:
+        if ptr and getattr(self, "_parent", None) is None:
             try:
                 self._ctx.lib.sq_stream_free(self._ctx.h, ptr)
             except Exception:
@@ -395,15 +402,16 @@ def merge_dedup(dd) -> tuple[np.ndarray, dict]:
     sizes = [int(v) for v in _COMM.allreduce_host_u64(
         [0 if (mine is None or g != rank) else int(mine.numel()) for g in range(world)], "sum")]
     if rank == 0:
-        parts = [dd.empty(sizes[g]) if sizes[g] else None for g in range(world)]
-        with _COMM.group():
-            for g in range(1, world):
-                if sizes[g]:
-                    _COMM.recv(parts[g], g)
-        _comm_sync()
-        for g in range(1, world):  # rank order = read order
-            if sizes[g]:
-                dd.consume(parts[g])
+        total = sum(sizes[1:])
+        if total:
+            buf, at = dd.empty(total), 0
+            with _COMM.group():
+                for g in range(1, world):  # rank order = read order
+                    if sizes[g]:
+                        _COMM.recv(buf.narrow(0, at, sizes[g]), g)
+                        at += sizes[g]
+            _comm_sync()
+            dd.consume(buf)
     elif sizes[rank]:
         with _COMM.group():
             _COMM.send(mine, 0)
