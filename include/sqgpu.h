@@ -386,6 +386,15 @@ SQ_API int sq_adapters_allreduce(sq_adapters *a, sq_comm *c);
 /* NanoStats (:5314-5322): per-read records of all ranks in rank (= read) order, cut at the first header
  * of any rank that cannot be parsed; first_record = global index of this rank's first read */
 SQ_API int sq_nanostats_allgather(sq_nanostats *s, sq_comm *c, uint64_t first_record);
+/* InsertSizeMetrics (:5571-5611, 5883-5885): histogram and counters are sums (sq_insert_allreduce); the two
+ * capped adapter tables admit first come, first served, so the first rank owns them: a deferred collector
+ * keeps its adapter occurrences (32-byte key = length byte + <= 31 adapter bytes, and the hash) in pair
+ * order, the owner feeds them through sq_insert_add_keys rank by rank. */
+SQ_API int sq_insert_set_deferred(sq_insert *m, int deferred);
+SQ_API int sq_insert_deferred_count(sq_insert *m, int which, uint64_t *n);
+SQ_API int sq_insert_deferred_fetch(sq_insert *m, int which, uint8_t *dev_keys, uint64_t *dev_hashes);
+SQ_API int sq_insert_add_keys(sq_insert *m, int which, const uint8_t *dev_keys, const uint64_t *dev_hashes, uint64_t n);
+SQ_API int sq_insert_allreduce(sq_insert *m, sq_comm *c);
 /* stream-ordered device memory for exchange buffers (hash lists, table copies, border-tile text) */
 SQ_API void *sq_stream_alloc(sq_ctx *ctx, uint64_t nbytes);
 SQ_API void sq_stream_free(sq_ctx *ctx, void *p);

@@ -203,6 +203,11 @@ SIGNATURES = {
     "sq_qc_allreduce": (_int, [_vp, _vp]),
     "sq_adapters_allreduce": (_int, [_vp, _vp]),
     "sq_nanostats_allgather": (_int, [_vp, _vp, _u64]),
+    "sq_insert_set_deferred": (_int, [_vp, _int]),
+    "sq_insert_deferred_count": (_int, [_vp, _int, _P(_u64)]),
+    "sq_insert_deferred_fetch": (_int, [_vp, _int, _vp, _vp]),
+    "sq_insert_add_keys": (_int, [_vp, _int, _vp, _vp, _u64]),
+    "sq_insert_allreduce": (_int, [_vp, _vp]),
     "sq_stream_alloc": (_vp, [_vp, _u64]),
     "sq_stream_free": (None, [_vp, _vp]),
     "sq_stream_memset": (_int, [_vp, _vp, _int, _u64]),

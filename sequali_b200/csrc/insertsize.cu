@@ -42,6 +42,11 @@ struct sq_insert {
     uint64_t *sizes = nullptr;
     IsTable tab[2];
     IsCounters *cnt = nullptr;
+    // sharded runs (rank > 0): the adapter tables admit first come, first served (:5588-5610), so they live
+    // on the first rank; the other ranks keep their adapter occurrences (32-byte key + hash, pair order)
+    bool deferred = false;
+    struct Kept { uint8_t *keys; uint64_t *hashes; uint64_t n; };
+    std::vector<Kept> kept[2];
 };
 
 __device__ __forceinline__ uint8_t comp_upper(uint8_t c) {
@@ -164,7 +169,8 @@ __device__ __forceinline__ uint32_t is_scratch_slot(const IsScratch &S, uint64_t
 
 // adapter bytes of pair r for read `which`
 __device__ __forceinline__ const uint8_t *adapter_ptr(const BatchView &b, uint32_t r, uint32_t ins) {
-    return b.text + b.seq_off[r] + ins;
+    // (a list of 32-byte keys instead of a record array: sq_insert_add_keys)
+    return b.seq_off ? b.text + b.seq_off[r] + ins : b.text + (size_t)r * 32 + 1;
 }
 
 // cls[r]: 0xFFFFFFFF none / 0xFFFFFFFE new / slot of the existing entry (:5588-5610)
@@ -297,8 +303,19 @@ extern "C" int sq_insert_create(sq_ctx *ctx, uint64_t max_adapters, sq_insert **
     return SQ_OK;
 }
 
+static void is_free_kept(sq_insert *m) {
+    for (int w = 0; w < 2; w++) {
+        for (auto &k : m->kept[w]) {
+            sq_dfree(m->ctx, k.keys);
+            sq_dfree(m->ctx, k.hashes);
+        }
+        m->kept[w].clear();
+    }
+}
+
 extern "C" void sq_insert_destroy(sq_insert *m) {
     if (!m) return;
+    is_free_kept(m);
     cudaSetDevice(m->ctx->device);
     for (int w = 0; w < 2; w++) {
         sq_dfree(m->ctx, m->tab[w].hash);
@@ -309,6 +326,66 @@ extern "C" void sq_insert_destroy(sq_insert *m) {
     sq_dfree(m->ctx, m->cnt);
     sq_dfree(m->ctx, m->sizes);
     delete m;
+}
+
+// deferred mode: occurrences (len > 0) of one read side, packed in pair order
+__global__ void __launch_bounds__(256)
+k_is_has_adapter(const uint8_t *__restrict__ lens, uint32_t n, uint32_t *__restrict__ flag) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) flag[r] = lens[r] != 0;
+}
+__global__ void __launch_bounds__(256)
+k_is_pack_keys(BatchView b, const uint32_t *__restrict__ ins, const uint64_t *__restrict__ hs, const uint8_t *__restrict__ lens,
+               const uint32_t *__restrict__ rank, uint8_t *__restrict__ keys, uint64_t *__restrict__ hashes) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += gridDim.x * blockDim.x) {
+        const uint32_t len = lens[r];
+        if (!len) continue;
+        const uint32_t j = rank[r];
+        const uint8_t *a = adapter_ptr(b, r, ins[r]);
+        uint8_t *k = keys + (size_t)j * 32;
+        k[0] = (uint8_t)len;
+        for (uint32_t i = 0; i < 31; i++) k[1 + i] = i < len ? a[i] : 0;
+        hashes[j] = hs[r];
+    }
+}
+__global__ void __launch_bounds__(256)
+k_is_key_lens(const uint8_t *__restrict__ keys, uint32_t n, uint8_t *__restrict__ lens) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) lens[r] = keys[(size_t)r * 32];
+}
+
+// Table maintenance of read side `w` for n occurrences in arrival order (:5571-5611): count what is stored,
+// admit the first (cap - entries) new keys in order, place them by priority probing.
+static int is_table_update(sq_insert *m, int w, const BatchView &bv, uint32_t n, const uint32_t *ins, const uint64_t *hs,
+                           const uint8_t *lens, uint32_t *cls, uint32_t *flag, uint32_t *rank, IsScratch &S, uint32_t scap) {
+    sq_ctx *ctx = m->ctx;
+    const uint64_t tmask = m->table_size - 1;
+    const uint64_t prio_base = 1 + m->n_pairs_base;
+    const int grid = sq_grid_for(ctx, n, 256, 16);
+    IsCounters *hc = (IsCounters *)((char *)ctx->h_scratch + 3200);
+    const bool full = m->entries[w] >= m->max_adapters;
+    if (!full && !S.key) {
+        SQ_TRY(sq_dalloc(ctx, (void **)&S.key, (size_t)scap * 8, false));
+        SQ_TRY(sq_dalloc(ctx, (void **)&S.first, (size_t)scap * 4, false));
+        SQ_TRY(sq_dalloc(ctx, (void **)&S.cnt, (size_t)scap * 4, false));
+    }
+    if (!full) {
+        CUDA_TRY(cudaMemsetAsync(S.key, 0xFF, (size_t)scap * 8, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(S.first, 0xFF, (size_t)scap * 4, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(S.cnt, 0, (size_t)scap * 4, ctx->stream));
+    }
+    SQ_LAUNCH(ctx, k_is_classify, grid, 256, 0, bv, ins, hs, lens, m->tab[w], tmask, cls, S, full ? 0 : 1);
+    SQ_LAUNCH(ctx, k_is_count_existing, grid, 256, 0, cls, n, m->tab[w]);
+    if (full) return SQ_OK;
+    CUDA_TRY(cudaMemsetAsync(&m->cnt->n_new[w], 0, 4, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(&m->cnt->admitted[w], 0, 4, ctx->stream));
+    SQ_LAUNCH(ctx, k_is_flags, grid, 256, 0, hs, cls, n, S, flag, &m->cnt->n_new[w]);
+    SQ_TRY(sq_scan_exclusive_u32(ctx, flag, rank, n, nullptr));
+    const uint32_t K = (uint32_t)(m->max_adapters - m->entries[w]);
+    SQ_LAUNCH(ctx, k_is_admit, grid, 256, 0, hs, flag, rank, n, K, m->tab[w], tmask, prio_base, &m->cnt->admitted[w]);
+    SQ_LAUNCH(ctx, k_is_place, grid, 256, 0, bv, ins, hs, lens, flag, rank, K, m->tab[w], tmask, prio_base, S);
+    CUDA_TRY(cudaMemcpyAsync(hc, m->cnt, sizeof(IsCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    m->entries[w] += hc->admitted[w];
+    return SQ_OK;
 }
 
 extern "C" int sq_insert_add_pair(sq_insert *m, sq_batch *b1, sq_batch *b2) {
@@ -346,48 +423,38 @@ extern "C" int sq_insert_add_pair(sq_insert *m, sq_batch *b1, sq_batch *b2) {
     SQ_TRY(sq_dalloc(ctx, (void **)&rank, (size_t)n * 4, false));
     SQ_LAUNCH(ctx, k_is_overlap, sq_grid_for(ctx, n, IS_TPB, 16), IS_TPB, 0, b1->view(), b2->view(), ins, hs, lens,
               m->sizes, m->cnt);
-    const uint64_t tmask = m->table_size - 1;
-    const uint64_t prio_base = 1 + m->n_pairs_base;
-    const int grid = sq_grid_for(ctx, n, 256, 16);
     IsScratch S;
     uint32_t scap = 1024;
     while (scap < 2 * (uint64_t)n) scap <<= 1;
     S.mask = scap - 1;
     S.key = nullptr;
     S.first = S.cnt = nullptr;
-    IsCounters *hc = (IsCounters *)((char *)ctx->h_scratch + 3200);
     int rc = SQ_OK;
     for (int w = 0; w < 2 && rc == SQ_OK; w++) {
         sq_batch *b = w == 0 ? b1 : b2;
-        const bool full = m->entries[w] >= m->max_adapters;
-        if (!full && !S.key) {
-            rc = sq_dalloc(ctx, (void **)&S.key, (size_t)scap * 8, false);
-            if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&S.first, (size_t)scap * 4, false);
-            if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&S.cnt, (size_t)scap * 4, false);
+        if (m->deferred) {
+            // keep the occurrences of this side, packed in pair order, for the rank that owns the tables
+            const int grid = sq_grid_for(ctx, n, 256, 16);
+            uint32_t *d_total = (uint32_t *)((char *)ctx->d_scratch + 3300);
+            uint32_t *h_total = (uint32_t *)((char *)ctx->h_scratch + 3300);
+            SQ_LAUNCH(ctx, k_is_has_adapter, grid, 256, 0, lens + (size_t)w * n, n, flag);
+            rc = sq_scan_exclusive_u32(ctx, flag, rank, n, d_total);
             if (rc != SQ_OK) break;
+            CUDA_TRY(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            const uint64_t k = *h_total;
+            if (k) {
+                sq_insert::Kept kp = {nullptr, nullptr, k};
+                rc = sq_dalloc(ctx, (void **)&kp.keys, k * 32, false);
+                if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&kp.hashes, k * 8, false);
+                if (rc != SQ_OK) break;
+                SQ_LAUNCH(ctx, k_is_pack_keys, grid, 256, 0, b->view(), ins, hs + (size_t)w * n, lens + (size_t)w * n, rank,
+                          kp.keys, kp.hashes);
+                m->kept[w].push_back(kp);
+            }
+            continue;
         }
-        if (!full) {
-            CUDA_TRY(cudaMemsetAsync(S.key, 0xFF, (size_t)scap * 8, ctx->stream));
-            CUDA_TRY(cudaMemsetAsync(S.first, 0xFF, (size_t)scap * 4, ctx->stream));
-            CUDA_TRY(cudaMemsetAsync(S.cnt, 0, (size_t)scap * 4, ctx->stream));
-        }
-        SQ_LAUNCH(ctx, k_is_classify, grid, 256, 0, b->view(), ins, hs + (size_t)w * n, lens + (size_t)w * n,
-                  m->tab[w], tmask, cls, S, full ? 0 : 1);
-        SQ_LAUNCH(ctx, k_is_count_existing, grid, 256, 0, cls, n, m->tab[w]);
-        if (full) continue;
-        CUDA_TRY(cudaMemsetAsync(&m->cnt->n_new[w], 0, 4, ctx->stream));
-        CUDA_TRY(cudaMemsetAsync(&m->cnt->admitted[w], 0, 4, ctx->stream));
-        SQ_LAUNCH(ctx, k_is_flags, grid, 256, 0, hs + (size_t)w * n, cls, n, S, flag, &m->cnt->n_new[w]);
-        rc = sq_scan_exclusive_u32(ctx, flag, rank, n, nullptr);
-        if (rc != SQ_OK) break;
-        const uint32_t K = (uint32_t)(m->max_adapters - m->entries[w]);
-        SQ_LAUNCH(ctx, k_is_admit, grid, 256, 0, hs + (size_t)w * n, flag, rank, n, K, m->tab[w], tmask, prio_base,
-                  &m->cnt->admitted[w]);
-        SQ_LAUNCH(ctx, k_is_place, grid, 256, 0, b->view(), ins, hs + (size_t)w * n, lens + (size_t)w * n, flag, rank,
-                  K, m->tab[w], tmask, prio_base, S);
-        CUDA_TRY(cudaMemcpyAsync(hc, m->cnt, sizeof(IsCounters), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        m->entries[w] += hc->admitted[w];
+        rc = is_table_update(m, w, b->view(), n, ins, hs + (size_t)w * n, lens + (size_t)w * n, cls, flag, rank, S, scap);
     }
     m->total += n;
     m->n_pairs_base += n;
@@ -448,5 +515,97 @@ extern "C" int sq_insert_read_adapters(sq_insert *m, int which, uint8_t *seqs, u
             counts[w++] = hc[i];
         }
     *n = w;
+    return SQ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// sharded runs: the insert size histogram and the counters are sums; the two adapter
+// tables admit first come, first served, so the first rank owns them and the other ranks hand their
+// adapter occurrences over in pair order (32-byte key + hash each; a few percent of the pairs).
+// ---------------------------------------------------------------------------
+extern "C" int sq_insert_set_deferred(sq_insert *m, int deferred) {
+    m->deferred = deferred != 0;
+    return SQ_OK;
+}
+extern "C" int sq_insert_deferred_count(sq_insert *m, int which, uint64_t *n) {
+    uint64_t t = 0;
+    for (auto &k : m->kept[which & 1]) t += k.n;
+    *n = t;
+    return SQ_OK;
+}
+// the kept occurrences of read side `which`, concatenated in pair order, into caller-owned DEVICE buffers
+extern "C" int sq_insert_deferred_fetch(sq_insert *m, int which, uint8_t *dev_keys, uint64_t *dev_hashes) {
+    sq_ctx *ctx = m->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    uint64_t at = 0;
+    for (auto &k : m->kept[which & 1]) {
+        CUDA_TRY(cudaMemcpyAsync(dev_keys + at * 32, k.keys, k.n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(dev_hashes + at, k.hashes, k.n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        at += k.n;
+    }
+    return SQ_OK;
+}
+// the owner: n occurrences (arrival order) for the table of read side `which`
+extern "C" int sq_insert_add_keys(sq_insert *m, int which, const uint8_t *dev_keys, const uint64_t *dev_hashes, uint64_t n) {
+    sq_ctx *ctx = m->ctx;
+    if (n == 0) return SQ_OK;
+    if (n >= 0xFFFFFFFFULL || which < 0 || which > 1) {
+        sq_set_error("sq_insert_add_keys: bad arguments");
+        return SQ_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint32_t n32 = (uint32_t)n;
+    uint32_t *ins = nullptr, *cls = nullptr, *flag = nullptr, *rank = nullptr;
+    uint8_t *lens = nullptr;
+    int rc = sq_dalloc(ctx, (void **)&ins, n * 4, true);
+    if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&cls, n * 4, false);
+    if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&flag, n * 4, false);
+    if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&rank, n * 4, false);
+    if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&lens, n, false);
+    IsScratch S;
+    uint32_t scap = 1024;
+    while (scap < 2 * n) scap <<= 1;
+    S.mask = scap - 1;
+    S.key = nullptr;
+    S.first = S.cnt = nullptr;
+    if (rc == SQ_OK) {
+        BatchView bv;
+        memset(&bv, 0, sizeof(bv));
+        bv.text = dev_keys;  // seq_off == nullptr: adapter_ptr reads the 32-byte keys
+        bv.n = n32;
+        SQ_LAUNCH(ctx, k_is_key_lens, sq_grid_for(ctx, n, 256, 16), 256, 0, dev_keys, n32, lens);
+        rc = is_table_update(m, which, bv, n32, ins, dev_hashes, lens, cls, flag, rank, S, scap);
+        m->n_pairs_base += n;
+    }
+    void *ptrs[] = {ins, cls, flag, rank, lens, S.key, S.first, S.cnt};
+    for (void *q : ptrs) sq_dfree(ctx, q);
+    return rc;
+}
+// histogram, counters: sums over the ranks, in place on the device
+extern "C" int sq_insert_allreduce(sq_insert *m, sq_comm *c) {
+    sq_ctx *ctx = m->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    IsCounters *hc = (IsCounters *)((char *)ctx->h_scratch + 3200);
+    CUDA_TRY(cudaMemcpyAsync(hc, m->cnt, sizeof(IsCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint64_t mx[2] = {hc->max_insert, m->sizes_cap};
+    SQ_TRY(sq_comm_allreduce_host_u64(c, mx, 2, 1));
+    if (mx[1] > m->sizes_cap) {
+        uint64_t *ns = nullptr;
+        SQ_TRY(sq_dalloc(ctx, (void **)&ns, mx[1] * 8, true));
+        CUDA_TRY(cudaMemcpyAsync(ns, m->sizes, m->sizes_cap * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        sq_dfree(ctx, m->sizes);
+        m->sizes = ns;
+        m->sizes_cap = mx[1];
+    }
+    uint64_t sums[3] = {hc->n_ad[0], hc->n_ad[1], m->total};
+    SQ_TRY(sq_comm_allreduce_host_u64(c, sums, 3, 0));
+    SQ_TRY(sq_comm_allreduce_u64(c, m->sizes, mx[0] + 1, 0));
+    hc->n_ad[0] = sums[0];
+    hc->n_ad[1] = sums[1];
+    hc->max_insert = mx[0];
+    CUDA_TRY(cudaMemcpyAsync(m->cnt, hc, 24, cudaMemcpyHostToDevice, ctx->stream));  // n_ad[2], max_insert
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    m->total = sums[2];
     return SQ_OK;
 }

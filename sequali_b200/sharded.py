@@ -814,3 +814,124 @@ class ShardedCollectors:
         out["overrep"] = self.ov.ov  # the merged table answers the usual getters
         lap("overrep")
         return out
+
+
+# ------------------------------------------------------------------------------
+# paired end (src/sequali/__main__.py:284-303): InsertSizeMetrics + the pair fingerprints
+# ------------------------------------------------------------------------------
+class GpuInsert:
+    """InsertSizeMetrics of one shard; on ranks behind the first the adapter occurrences are kept for the
+    owner of the two first-come tables (sq_insert_set_deferred)."""
+
+    def __init__(self, collector, deferred: bool):
+        from ._lib import check
+        self.m, self._check = collector, check
+        if deferred:
+            check(collector._ctx.lib.sq_insert_set_deferred(collector._h, 1), "sq_insert_set_deferred")
+
+    def kept(self, which: int):
+        """(keys DevBuf of n x 32 bytes, hashes DevBuf of n x 8 bytes, n) in pair order."""
+        import ctypes as C
+        self.m._sync()
+        lib, ctx = self.m._ctx.lib, self.m._ctx
+        n = C.c_uint64()
+        self._check(lib.sq_insert_deferred_count(self.m._h, which, C.byref(n)), "sq_insert_deferred_count")
+        keys, hashes = DevBuf(ctx, n.value * 32, 32), DevBuf(ctx, n.value * 8, 8)
+        if n.value:
+            self._check(lib.sq_insert_deferred_fetch(self.m._h, which, keys.ptr, hashes.ptr), "sq_insert_deferred_fetch")
+        return keys, hashes, n.value
+
+    def add_keys(self, which: int, keys, hashes, n: int):
+        self._check(self.m._ctx.lib.sq_insert_add_keys(self.m._h, which, keys.data_ptr(), hashes.data_ptr(), n),
+                    "sq_insert_add_keys")
+
+
+def merge_insert(ins: GpuInsert) -> dict:
+    """InsertSizeMetrics over all shards, on every rank: the histogram and the counters are summed on the
+    device; the occurrences of the other ranks reach the owner of the adapter tables in rank (= pair) order."""
+    from ._lib import check
+    rank, world = _rank_world()
+    m = ins.m
+    if world > 1:
+        ctx = m._ctx
+        for which in (0, 1):
+            keys, hashes, n = ins.kept(which) if rank > 0 else (None, None, 0)
+            sizes = [int(v) for v in _COMM.allreduce_host_u64([n if g == rank else 0 for g in range(world)], "sum")]
+            total = sum(sizes[1:])
+            if total == 0:
+                continue
+            if rank == 0:
+                all_keys, all_hashes, at = DevBuf(ctx, total * 32, 32), DevBuf(ctx, total * 8, 8), 0
+                with _COMM.group():
+                    for g in range(1, world):
+                        if sizes[g]:
+                            _COMM.recv(all_keys.narrow(0, at, sizes[g]), g)
+                            _COMM.recv(all_hashes.narrow(0, at, sizes[g]), g)
+                            at += sizes[g]
+                ins.add_keys(which, all_keys, all_hashes, total)
+            elif n:
+                with _COMM.group():
+                    _COMM.send(keys, 0)
+                    _COMM.send(hashes, 0)
+        m._sync()
+        check(ctx.lib.sq_insert_allreduce(m._h, _COMM.h), "sq_insert_allreduce")
+    lists = _bcast_obj((m.adapters_read1(), m.adapters_read2()) if rank == 0 else None, 0)
+    return dict(sizes=np.frombuffer(m.insert_sizes(), dtype=np.uint64), adapters1=lists[0], adapters2=lists[1],
+                total_reads=int(m.total_reads), number_of_adapters_read1=int(m.number_of_adapters_read1),
+                number_of_adapters_read2=int(m.number_of_adapters_read2))
+
+
+def _bcast_obj(obj, src: int):
+    if _COMM.world == 1:
+        return obj
+    data = _COMM.bcast_bytes(pickle.dumps(obj, protocol=4) if _COMM.rank == src else b"", src)
+    return pickle.loads(data)
+
+
+class ShardedPairedCollectors:
+    """The paired-end hot loop on one shard of a pair of files, plus the merges: QCMetrics, PerTileQuality
+    and OverrepresentedSequences per read side, DedupEstimator on the pair fingerprints, InsertSizeMetrics."""
+
+    def __init__(self, mod, first_record: int = 0, dedup_kwargs=None, overrep_kwargs=None):
+        rank, _ = _rank_world()
+        self.first_record = first_record
+        self.qc = (mod.QCMetrics(), mod.QCMetrics())
+        self.pt = (GpuPerTile(mod.PerTileQuality()), GpuPerTile(mod.PerTileQuality()))
+        self.ov = tuple(GpuOverrep(mod.OverrepresentedSequences(**(overrep_kwargs or {})), rank > 0, first_record)
+                        for _ in range(2))
+        self.dd = GpuDedup(mod.DedupEstimator(**(dedup_kwargs or dict(front_sequence_offset=0,
+                                                                       back_sequence_offset=0))), rank > 0)
+        self.ins = GpuInsert(mod.InsertSizeMetrics(), rank > 0)
+
+    def add_record_array_pair(self, a, b) -> None:
+        self.qc[0].add_record_array(a)
+        self.pt[0].add_record_array(a)
+        self.ov[0].ov.add_record_array(a)
+        self.dd.dd.add_record_array_pair(a, b)
+        self.ins.m.add_record_array_pair(a, b)
+        self.qc[1].add_record_array(b)
+        self.pt[1].add_record_array(b)
+        self.ov[1].ov.add_record_array(b)
+
+    def merge(self) -> dict:
+        from . import _qc
+        from ._lib import check
+        c = comm()
+        _qc._flush()
+        out = {}
+        keys = ("base_count_table", "phred_count_table", "end_anchored_base_count_table",
+                "end_anchored_phred_count_table", "gc_content", "phred_scores")
+        for i, qc in enumerate(self.qc):
+            if c.world > 1:
+                check(qc._ctx.lib.sq_qc_allreduce(qc._h, c.h), "sq_qc_allreduce")
+            out[f"qc{i + 1}"] = {k: np.frombuffer(getattr(qc, k)(), dtype=np.uint64) for k in keys}
+            out[f"qc{i + 1}"]["number_of_reads"] = int(qc.number_of_reads)
+            out[f"qc{i + 1}"]["max_length"] = int(qc.max_length)
+        for i in range(2):
+            out[f"ptq{i + 1}"] = merge_pertile(self.pt[i], self.first_record)
+            merge_overrep(self.ov[i])
+            out[f"overrep{i + 1}"] = self.ov[i].ov
+        counts, info = merge_dedup(self.dd)
+        out["dedup"] = dict(counts=counts, **info)
+        out["insert"] = merge_insert(self.ins)
+        return out

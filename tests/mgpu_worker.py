@@ -13,6 +13,67 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def paired_case(sq, sharded, synth, orc, H, rank, world):
+    """Paired end over the ranks: InsertSizeMetrics (histogram + the two capped first-come adapter tables),
+    the pair fingerprints of DedupEstimator, both read sides of QCMetrics / PerTileQuality / Overrepresented."""
+    t1, t2 = synth.paired_fastq(24_000, seed=45)
+    r1, _ = orc.parse_fastq(t1)
+    r2, _ = orc.parse_fastq(t2)
+    n = len(r1)
+    cuts = [0] + [int(n * (g + 1) / world) + (5 if g + 1 < world else 0) for g in range(world)]
+    lo, hi = cuts[rank], cuts[rank + 1]
+
+    def piece(text, recs):
+        b0 = int(recs[lo]["name_off"]) - 1 if lo < n else len(text)
+        b1 = int(recs[hi]["name_off"]) - 1 if hi < n else len(text)
+        return text[b0:b1]
+    dd_kw = dict(max_stored_fingerprints=3000, front_sequence_offset=0, back_sequence_offset=0)
+    for max_adapters in (10_000, 300):  # never full / full inside the first shard
+        coll = sharded.ShardedPairedCollectors(sq, first_record=lo, dedup_kwargs=dd_kw)
+        coll.ins = sharded.GpuInsert(sq.InsertSizeMetrics(max_adapters), rank > 0)
+        rd1 = sq.FastqParser(io.BytesIO(piece(t1, r1)), 600_000)
+        rd2 = sq.FastqParser(io.BytesIO(piece(t2, r2)), 600_000)
+        for a in rd1:
+            b = rd2.read(len(a))
+            assert a.is_mate(b)
+            coll.add_record_array_pair(a, b)
+        got = coll.merge()
+        if rank == world - 1:
+            want = paired_oracle(orc, H, t1, t2, dd_kw, max_adapters)
+            ins, wi = got["insert"], want["insert"]
+            assert ins["sizes"].tolist() == wi["sizes"], "insert sizes"
+            assert ins["adapters1"] == wi["adapters1_slot_order"] and ins["adapters2"] == wi["adapters2_slot_order"], \
+                f"adapter tables (max_adapters={max_adapters})"
+            for k in ("total_reads", "number_of_adapters_read1", "number_of_adapters_read2"):
+                assert ins[k] == wi[k], (k, ins[k], wi[k])
+            assert got["dedup"]["counts"].tolist() == want["dedup"]["slot_order"], "pair dedup"
+            for side in ("1", "2"):
+                assert got["qc" + side]["base_count_table"].tolist() == want["qc" + side]["base"]
+                assert got["qc" + side]["phred_count_table"].tolist() == want["qc" + side]["phred"]
+                assert got["qc" + side]["number_of_reads"] == n
+                tiles = [(t, H.f64_bits(np.array(e, dtype=np.float64)), list(c)) for t, e, c in got["ptq" + side]["tiles"]]
+                assert tiles == want["ptq" + side]["tiles"], "per-tile sums, read " + side
+                H.assert_same(H.dump_overrep(got["overrep" + side]), want["overrep" + side])
+            print(f"paired case (max_adapters={max_adapters}): merged tables of {world} ranks equal the oracle", flush=True)
+        sharded.comm().barrier()
+
+
+def paired_oracle(orc, H, t1, t2, dd_kw, max_adapters):
+    r1, _ = orc.parse_fastq(t1)
+    r2, _ = orc.parse_fastq(t2)
+    b1, b2 = np.frombuffer(t1, np.uint8), np.frombuffer(t2, np.uint8)
+    qc1, qc2, p1, p2 = orc.QCMetrics(), orc.QCMetrics(), orc.PerTileQuality(), orc.PerTileQuality()
+    o1, o2 = orc.OverrepresentedSequences(), orc.OverrepresentedSequences()
+    dd, ins = orc.DedupEstimator(**dd_kw), orc.InsertSizeMetrics(max_adapters)
+    qc1.add(b1, r1); p1.add(b1, r1); o1.add(b1, r1)
+    dd.add_pair(b1, r1, b2, r2)
+    ins.add_pair(b1, r1, b2, r2)
+    qc2.add(b2, r2); p2.add(b2, r2); o2.add(b2, r2)
+    return dict(qc1=H.odump_qc(qc1), qc2=H.odump_qc(qc2), ptq1=H.odump_ptq(p1), ptq2=H.odump_ptq(p2),
+                overrep1=H.odump_overrep(o1), overrep2=H.odump_overrep(o2), dedup=H.odump_dedup(dd),
+                insert=H.odump_insert(ins))
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     os.environ["SEQUALI_B200_DEVICE"] = str(local)
@@ -84,6 +145,8 @@ def main():
                   f"(dedup bits {want['dedup']['modulo_bits']}, unique fragments "
                   f"{want['overrep']['collected_unique_fragments']})", flush=True)
         comm.barrier()
+    paired_case(sq, sharded, synth, orc, H, rank, world)
+    comm.barrier()
     if rank == world - 1:
         print("MGPU PARITY OK", flush=True)
     comm.close()
