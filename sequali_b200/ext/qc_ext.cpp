@@ -28,7 +28,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sqgpu.h"
@@ -1661,6 +1664,20 @@ PyType_Spec IS_spec = {"_qc.InsertSizeMetrics", sizeof(Collector), 0, Py_TPFLAGS
 constexpr Py_ssize_t DEFAULT_FASTQ_BUFFERSIZE = 32 << 20;
 constexpr Py_ssize_t DEFAULT_BAM_BUFFERSIZE = 24 << 20;
 
+// Read-ahead of the parsers' __next__: while the caller feeds the collectors with record array k, a helper
+// thread reads, copies and scans array k + 1 (readinto needs the GIL; the host->device copy and the
+// boundary scan run without it, on the context's parser stream).  This is the double buffering the
+// reference gets from xopen's reader threads (src/sequali/util.py:108-123).  Only for read steps of
+// 1 MiB and more: the small-buffer call patterns of the tests stay strictly synchronous.
+constexpr Py_ssize_t READ_AHEAD_MIN_STEP = 1 << 20;
+struct ReadAhead {
+    std::mutex mu;
+    std::condition_variable cv;
+    bool active = false, done = false;
+    PyObject *result = nullptr;                                  // new reference, or NULL with the exception below
+    PyObject *exc_type = nullptr, *exc_value = nullptr, *exc_tb = nullptr;
+};
+
 struct Parser {
     PyObject_HEAD
     PyObject *file;
@@ -1669,9 +1686,60 @@ struct Parser {
     std::vector<uint8_t> *leftover;
     Pinned bam_buf;    // BamParser: staging buffer kept between calls, leftover at its front
     size_t bam_filled;
+    ReadAhead *ra;
 };
+
+// start `produce(self)` on a helper thread; the thread owns a reference to the parser until it is done
+void read_ahead_start(Parser *self, PyObject *(*produce)(Parser *)) {
+    ReadAhead *ra = self->ra;
+    ra->active = true;
+    ra->done = false;
+    Py_INCREF((PyObject *)self);
+    std::thread([self, ra, produce]() {
+        PyGILState_STATE g = PyGILState_Ensure();
+        PyObject *r = produce(self);
+        PyObject *t = nullptr, *v = nullptr, *tb = nullptr;
+        if (!r) PyErr_Fetch(&t, &v, &tb);
+        {
+            std::lock_guard<std::mutex> lk(ra->mu);
+            ra->result = r;
+            ra->exc_type = t;
+            ra->exc_value = v;
+            ra->exc_tb = tb;
+            ra->done = true;
+        }
+        ra->cv.notify_all();
+        Py_DECREF((PyObject *)self);  // (may run the parser's dealloc: nothing of it is touched afterwards)
+        PyGILState_Release(g);
+    }).detach();
+}
+// wait for the helper thread (GIL released meanwhile) and take what it produced: a new reference, or NULL
+// with the exception set (NULL without exception = the producer's plain NULL, e.g. StopIteration)
+PyObject *read_ahead_take(Parser *self) {
+    ReadAhead *ra = self->ra;
+    Py_BEGIN_ALLOW_THREADS
+    {
+        std::unique_lock<std::mutex> lk(ra->mu);
+        ra->cv.wait(lk, [ra] { return ra->done; });
+    }
+    Py_END_ALLOW_THREADS
+    ra->active = false;
+    PyObject *r = ra->result;
+    ra->result = nullptr;
+    if (!r && ra->exc_type) PyErr_Restore(ra->exc_type, ra->exc_value, ra->exc_tb);
+    ra->exc_type = ra->exc_value = ra->exc_tb = nullptr;
+    return r;
+}
 void Parser_dealloc(Parser *self) {
     PyTypeObject *tp = Py_TYPE(self);
+    // (a helper thread holds a reference while it runs, so none is running here; what it left is dropped)
+    if (self->ra) {
+        Py_XDECREF(self->ra->result);
+        Py_XDECREF(self->ra->exc_type);
+        Py_XDECREF(self->ra->exc_value);
+        Py_XDECREF(self->ra->exc_tb);
+        delete self->ra;
+    }
     Py_XDECREF(self->file);
     Py_XDECREF(self->header);
     delete self->leftover;
@@ -1710,6 +1778,7 @@ PyObject *FQ_new(PyTypeObject *type, PyObject *args, PyObject *kwargs) {
     self->leftover = new std::vector<uint8_t>();
     new (&self->bam_buf) Pinned();
     self->bam_filled = 0;
+    self->ra = new ReadAhead();
     return (PyObject *)self;
 }
 // fileobj.readinto(memoryview of [dst, dst + len)) -> bytes read, -1 on error
@@ -1838,12 +1907,14 @@ PyObject *FQ_create_record_array(Parser *self, uint64_t min_records, uint64_t ma
     a->pinned = buf;
     return (PyObject *)a;
 }
+PyObject *FQ_produce(Parser *self) { return FQ_create_record_array(self, 1, UINT64_MAX); }
 PyObject *FQ_next(Parser *self) {
-    PyObject *a = FQ_create_record_array(self, 1, UINT64_MAX);
+    PyObject *a = self->ra->active ? read_ahead_take(self) : FQ_produce(self);
     if (a && ((ArrayView *)a)->n == 0) {
         Py_DECREF(a);
         return nullptr;  // StopIteration
     }
+    if (a && self->read_in_size >= READ_AHEAD_MIN_STEP) read_ahead_start(self, FQ_produce);
     return a;
 }
 PyObject *FQ_read(Parser *self, PyObject *n_o) {
@@ -1852,6 +1923,14 @@ PyObject *FQ_read(Parser *self, PyObject *n_o) {
     if (n < 1) {
         PyErr_Format(PyExc_ValueError, "number_of_records should be greater than 1, got %zd", n);
         return nullptr;
+    }
+    if (self->ra->active) {
+        // an array was read ahead by __next__: un-read it (its buffer = the leftover it started from + what it read)
+        PyObject *ahead = read_ahead_take(self);
+        if (!ahead) return nullptr;
+        ArrayView *av = (ArrayView *)ahead;
+        if (av->pinned.ptr) self->leftover->assign(av->pinned.ptr, av->pinned.ptr + av->nbytes);
+        Py_DECREF(ahead);
     }
     return FQ_create_record_array(self, (uint64_t)n, (uint64_t)n);
 }
@@ -1939,9 +2018,16 @@ PyObject *BAM_new(PyTypeObject *type, PyObject *args, PyObject *kwargs) {
     self->leftover = new std::vector<uint8_t>();
     new (&self->bam_buf) Pinned();
     self->bam_filled = 0;
+    self->ra = new ReadAhead();
     return (PyObject *)self;
 }
+PyObject *BAM_produce(Parser *self);
 PyObject *BAM_next(Parser *self) {
+    PyObject *a = self->ra->active ? read_ahead_take(self) : BAM_produce(self);
+    if (a && self->read_in_size >= READ_AHEAD_MIN_STEP) read_ahead_start(self, BAM_produce);
+    return a;
+}
+PyObject *BAM_produce(Parser *self) {
     // [leftover | newly read bytes] live in one pinned buffer that is kept between calls: the
     // host->device copy of sq_batch_from_bam runs at PCIe speed and nothing is re-allocated or zeroed
     Pinned &buf = self->bam_buf;

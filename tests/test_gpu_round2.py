@@ -154,3 +154,35 @@ def test_bgzf_corrupt_member_is_an_error(sq):
         import gzip
         h2 = HostFastq.from_bytes(gzip.compress(text))
         list(h2.record_arrays_bgzf(1 << 20))
+
+
+def test_extension_read_ahead_keeps_the_record_stream(ext, sq):
+    """The extension's parsers read one array ahead on a helper thread (read steps >= 1 MiB); mixing
+    __next__ and read(n) must still hand out every record exactly once and in order, errors at their place."""
+    text = synth.illumina_fastq(30_000, length=100, seed=41, n_tiles=5)  # ~7 MB: several 1 MiB steps
+
+    def names(arr):
+        return [arr[i].name() for i in (0, len(arr) - 1)] + [len(arr)]
+
+    def walk(mod):
+        p, out = mod.FastqParser(io.BytesIO(text), 1 << 20), []
+        out.append(names(next(p)))
+        out.append(names(p.read(7)))        # un-reads what was read ahead
+        out.append(names(next(p)))
+        out.append(names(p.read(50_000)))   # everything that is left
+        assert len(p.read(1)) == 0
+        return out
+    assert walk(ext) == walk(sq)
+    assert sum(len(a) for a in ext.FastqParser(io.BytesIO(text), 1 << 20)) == 30_000
+    bad = text[:3_000_000] + b"oops\n" + text[3_000_000:]
+    got = []
+    for mod in (ext, sq):
+        n = 0
+        try:
+            for arr in mod.FastqParser(io.BytesIO(bad), 1 << 20):
+                n += len(arr)
+        except ValueError as e:
+            got.append((n, str(e)))
+    assert len(got) == 2 and got[0] == got[1]
+    bam = synth.nanopore_ubam(400, mean_length=8000, max_length=100_000, seed=42)
+    assert [len(a) for a in ext.BamParser(io.BytesIO(bam), 1 << 20)] == [len(a) for a in sq.BamParser(io.BytesIO(bam), 1 << 20)]
