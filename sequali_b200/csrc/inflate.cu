@@ -16,11 +16,10 @@
 // One warp = one CTA = one member at a time.  The newest INF_WIN bytes of the member's text live in a ring in
 // shared memory: literals and matches are written there, matches read their source there (a match that
 // reaches further back than the ring reads the bytes this warp already flushed to global memory), and
-// the ring is flushed to global memory 1 KiB at a time with coalesced stores.  The ring spans DEFLATE's whole
-// 32 KiB history: zlib's matches into random DNA reach that far all the time (with a 16 KiB ring half of the
-// matches took the global-memory path, a dependent L2 round trip each: 7 GB/s instead of 13).  ~36 KiB of
-// shared memory per warp: six decoders per SM.
-constexpr uint32_t INF_WIN = 32768, INF_FLUSH = 1024;
+// the ring is flushed to global memory 1 KiB at a time with coalesced stores.  16 KiB of ring + 3 KiB of tables
+// per warp: ten decoders per SM.  (Measured with a ring spanning DEFLATE's whole 32 KiB history, which spares the
+// far matches their L2 round trip but leaves six decoders per SM: 6.6 GB/s of text against 8.9 GB/s.)
+constexpr uint32_t INF_WIN = 16384, INF_FLUSH = 1024;
 
 struct WarpOut {
     uint8_t *win;      // shared-memory ring
@@ -91,6 +90,10 @@ k_bgzf_inflate(const uint8_t *__restrict__ comp, uint64_t comp_base, const sq_bg
     }
 }
 
+// (Measured and dropped: one THREAD per member -- 32 members per warp, tables in local memory, text straight to
+// global memory.  Lanes of a warp take different branches at almost every symbol and serialise; with the few
+// thousand members a 256 MiB window holds it ran at 0.8 GB/s against 8.5 GB/s for the warp-per-member kernel.)
+
 // ---- host: hop over the member headers ---------------------------------------------------------------
 // RFC 1952 member with the BGZF extra subfield (SAM spec 4.1): ID1 ID2 CM FLG MTIME(4) XFL OS XLEN(2)
 // [SI1='B' SI2='C' SLEN=2 BSIZE(2)] ... CDATA CRC32(4) ISIZE(4); BSIZE = total member size - 1.
@@ -158,7 +161,7 @@ int bgzf_inflate_async(sq_ctx *ctx, const uint8_t *dev_comp, uint64_t comp_base,
                        uint64_t text_base, uint8_t *dev_out, unsigned long long *dev_first_bad) {
     if (n == 0) return SQ_OK;
     uint64_t grid = n;
-    const uint64_t cap = (uint64_t)ctx->num_sms * 6;  // six one-warp CTAs fit an SM (shared memory)
+    const uint64_t cap = (uint64_t)ctx->num_sms * 10;  // ten one-warp CTAs fit an SM (shared memory)
     if (grid > cap) grid = cap;
     SQ_LAUNCH(ctx, k_bgzf_inflate, (unsigned)grid, 32, 0, dev_comp, comp_base, dev_blocks, (uint32_t)n, text_base, dev_out,
               dev_first_bad);

@@ -21,6 +21,13 @@ def main():
         ctx.sync()
         dt = time.perf_counter() - t0
         print(f"pass {rep}: {n} reads, {len(text) / dt / 1e9:.2f} GB/s of text, ratio {len(text) / len(comp):.2f}")
+    ctx.profile(True)
+    n = sum(len(a) for a in host.record_arrays_bgzf(256 << 20))
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    for k, v in prof.items():
+        if "inflate" in k and not k.startswith("gap"):
+            print(f"{k}: {v[0]} launches, {v[1]:.3f} ms -> {len(text) / v[1] / 1e6:.1f} GB/s of text")
 
 
 if __name__ == "__main__":
