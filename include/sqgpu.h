@@ -130,6 +130,22 @@ SQ_API int sq_bam_walk(const uint8_t *bam, uint64_t nbytes, uint64_t *rec_off, u
 SQ_API int sq_batch_from_bam(sq_ctx *ctx, const uint8_t *bam, uint64_t nbytes,
                              const uint64_t *rec_off, uint64_t n, sq_batch **out,
                              uint64_t *packed_len);
+/* BamParser__next__ (_qcmodule.c:1506-1703) entirely on the device: `bam` = nbytes of alignment records starting
+ * at a record boundary (host memory, pinned for full copy speed), n_ref = the reference count of the BAM header.
+ * The bytes are copied once; the block_size chain (:1623-1637), the flag & 0x900 drop (:1633) and the decode
+ * run on the device, the host never reads a record.  *out = the record array of the kept complete records (NULL
+ * when there is none), *n_skipped = complete records dropped, *consumed = bytes covered by complete records (the
+ * rest is the caller's leftover).  The chain is found by testing every byte offset for a self-consistent record
+ * header and pointer doubling over the survivors; a chain that leaves them (a record the reference accepts
+ * although its header is not self-consistent) is followed by a plain one-thread walk from there, so the result
+ * is sq_bam_walk's for any input.  n_ref only sharpens the test. */
+SQ_API int sq_batch_from_bam_bytes(sq_ctx *ctx, const uint8_t *bam, uint64_t nbytes, int32_t n_ref,
+                                   sq_batch **out, uint64_t *n_kept, uint64_t *n_skipped,
+                                   uint64_t *consumed, uint64_t *packed_len);
+/* The device chain alone: same results as sq_bam_walk, offsets copied back to rec_off[0..cap). */
+SQ_API int sq_bam_walk_device(sq_ctx *ctx, const uint8_t *bam, uint64_t nbytes, int32_t n_ref,
+                              uint64_t *rec_off, uint64_t cap, uint64_t *n_kept, uint64_t *n_skipped,
+                              uint64_t *consumed);
 /* FastqParser's read loop (_qcmodule.c:985-1029: readinto + leftover carry,
  * :1187 __next__) for uncompressed text in (pinned) HOST memory: windows of
  * `window` bytes are copied host->device on a separate copy stream ahead of

@@ -118,6 +118,8 @@ SIGNATURES = {
     "sq_batch_from_packed": (_int, [_vp, _vp, _u64, _vp, _u64, _P(_vp)]),
     "sq_bam_walk": (_int, [_vp, _u64, _vp, _u64, _P(_u64), _P(_u64), _P(_u64)]),
     "sq_batch_from_bam": (_int, [_vp, _vp, _u64, _vp, _u64, _P(_vp), _P(_u64)]),
+    "sq_batch_from_bam_bytes": (_int, [_vp, _vp, _u64, C.c_int32, _P(_vp), _P(_u64), _P(_u64), _P(_u64), _P(_u64)]),
+    "sq_bam_walk_device": (_int, [_vp, _vp, _u64, C.c_int32, _vp, _u64, _P(_u64), _P(_u64), _P(_u64)]),
     "sq_fastq_stream_create": (_int, [_vp, _vp, _u64, _u64, _P(_vp)]),
     "sq_fastq_stream_next": (_int, [_vp, _P(_vp), _P(ParseInfo)]),
     "sq_fastq_stream_leftover": (_u64, [_vp]),

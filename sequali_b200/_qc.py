@@ -491,9 +491,10 @@ class FastqParser:
 class BamParser:
     """BamParser(fileobj, initial_buffersize) -- reference :1362-1725.
 
-    The host walks the block_size chain (one u32 per record); the 4-bit
-    sequence / raw quality decode into the packed record array runs on the
-    device (sq_batch_from_bam)."""
+    The bytes read from the file are copied to the device once; the block_size
+    chain, the drop of secondary / supplementary records and the 4-bit sequence /
+    raw quality decode into the packed record array all run there
+    (sq_batch_from_bam_bytes)."""
 
     def __init__(self, fileobj, initial_buffersize: Optional[int] = None):
         size = DEFAULT_BAM_BUFFERSIZE if initial_buffersize is None else initial_buffersize
@@ -514,7 +515,8 @@ class BamParser:
         n_ref_b = fileobj.read(4)
         if len(n_ref_b) != 4:
             raise EOFError("Truncated BAM file")
-        for _ in range(int.from_bytes(n_ref_b, "little")):
+        self._n_ref = int.from_bytes(n_ref_b, "little")
+        for _ in range(self._n_ref):
             l_name_b = fileobj.read(4)
             if len(l_name_b) != 4:
                 raise EOFError("Truncated BAM file")
@@ -552,18 +554,16 @@ class BamParser:
             if got == 0:
                 raise EOFError(f"Incomplete record at the end of file {bytes(self._buf.view(0, have))!r}")
             self._filled = n
-            # walk the record chain (:1623-1637): sq_bam_walk, on the bytes read so far
-            offs = np.empty(n // 36 + 1, dtype=np.uint64)
+            # record chain (:1623-1637) + decode of the bytes read so far, on the device
+            h, plen = _C.c_void_p(), _C.c_uint64()
             kept, skipped, used = _C.c_uint64(), _C.c_uint64(), _C.c_uint64()
-            check(lib.sq_bam_walk(self._buf.ptr, n, _void(offs), len(offs), _C.byref(kept), _C.byref(skipped),
-                                  _C.byref(used)), "sq_bam_walk")
+            check(lib.sq_batch_from_bam_bytes(ctx.h, self._buf.ptr, n, min(self._n_ref, 0x7fffffff), _C.byref(h),
+                                              _C.byref(kept), _C.byref(skipped), _C.byref(used), _C.byref(plen)),
+                  "sq_batch_from_bam_bytes")  # (synchronises)
             if kept.value or skipped.value:
                 break
         pos, arr = used.value, None
         if kept.value:
-            h, plen = _C.c_void_p(), _C.c_uint64()
-            check(lib.sq_batch_from_bam(ctx.h, self._buf.ptr, pos, _void(offs), kept.value,
-                                        _C.byref(h), _C.byref(plen)), "sq_batch_from_bam")  # (synchronises)
             arr = FastqRecordArrayView._from_parser(h, kept.value, None, plen.value)
         left = self._filled - pos
         if left and pos:

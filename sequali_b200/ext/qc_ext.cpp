@@ -1686,6 +1686,7 @@ struct Parser {
     std::vector<uint8_t> *leftover;
     Pinned bam_buf;    // BamParser: staging buffer kept between calls, leftover at its front
     size_t bam_filled;
+    int32_t bam_n_ref;  // reference count of the BAM header
     ReadAhead *ra;
 };
 
@@ -2018,6 +2019,7 @@ PyObject *BAM_new(PyTypeObject *type, PyObject *args, PyObject *kwargs) {
     self->leftover = new std::vector<uint8_t>();
     new (&self->bam_buf) Pinned();
     self->bam_filled = 0;
+    self->bam_n_ref = (int32_t)std::min<uint32_t>(n_ref, 0x7fffffffu);
     self->ra = new ReadAhead();
     return (PyObject *)self;
 }
@@ -2029,11 +2031,11 @@ PyObject *BAM_next(Parser *self) {
 }
 PyObject *BAM_produce(Parser *self) {
     // [leftover | newly read bytes] live in one pinned buffer that is kept between calls: the
-    // host->device copy of sq_batch_from_bam runs at PCIe speed and nothing is re-allocated or zeroed
+    // host->device copy of sq_batch_from_bam_bytes runs at PCIe speed and nothing is re-allocated or zeroed
     Pinned &buf = self->bam_buf;
-    std::vector<uint64_t> offsets;
     const size_t step = (size_t)self->read_in_size;
-    uint64_t consumed = 0, kept = 0, skipped = 0;
+    uint64_t consumed = 0, kept = 0, skipped = 0, packed = 0;
+    sq_batch *h = nullptr;
     for (;;) {
         const size_t have = self->bam_filled;
         const size_t want = have >= 4 ? std::max<size_t>(le32(buf.ptr), step) : step - have;  // :1527-1531
@@ -2055,25 +2057,22 @@ PyObject *BAM_produce(Parser *self) {
             return nullptr;
         }
         self->bam_filled = n;
-        // walk the record chain (:1623-1637)
-        offsets.resize(n / 36 + 1);
-        SQ_CHECK(sq_bam_walk(buf.ptr, n, offsets.data(), offsets.size(), &kept, &skipped, &consumed), "sq_bam_walk");
+        // record chain (:1623-1637), flag drop and decode of the bytes read so far: on the device
+        int rc;
+        Py_BEGIN_ALLOW_THREADS
+        rc = sq_batch_from_bam_bytes(g_ctx, buf.ptr, n, self->bam_n_ref, &h, &kept, &skipped, &consumed, &packed);  // (synchronises)
+        Py_END_ALLOW_THREADS
+        if (rc != SQ_OK) return raise_sq(rc, "sq_batch_from_bam_bytes");
         if (kept || skipped) break;
     }
     ArrayView *a = nullptr;
     if (kept) {
         a = ArrayView_alloc();
-        if (!a) return nullptr;
-        uint64_t packed = 0;
-        int rc;
-        Py_BEGIN_ALLOW_THREADS
-        rc = sq_batch_from_bam(g_ctx, buf.ptr, consumed, offsets.data(), kept, &a->h, &packed);  // (synchronises)
-        Py_END_ALLOW_THREADS
-        if (rc != SQ_OK) {
-            a->h = nullptr;
-            Py_DECREF((PyObject *)a);
-            return raise_sq(rc, "sq_batch_from_bam");
+        if (!a) {
+            sq_batch_free(h);
+            return nullptr;
         }
+        a->h = h;
         a->n = kept;
         a->nbytes = packed;
     }

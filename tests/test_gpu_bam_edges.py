@@ -119,3 +119,95 @@ def test_reference_fixture_files(sq, name):
     assert records(sq, raw) == records(REF, raw)
     H.assert_same(H.api_single_end(sq, b"", H.NANOPORE_ADAPTERS, fileobj=io.BytesIO(raw), bam=True),
                   H.api_single_end(REF, b"", H.NANOPORE_ADAPTERS, fileobj=io.BytesIO(raw), bam=True))
+
+
+# ---- the record chain on the device (sq_bam_walk_device) against the host walk (sq_bam_walk) ----
+def _walks(raw, n_ref=0):
+    """(kept offsets, n_skipped, consumed) of the host walk and of the device walk over the same bytes."""
+    import ctypes as C
+    from sequali_b200 import _lib
+    ctx = _lib.Context.get()
+    out = []
+    for device in (False, True):
+        offs = np.zeros(len(raw) // 36 + 2, dtype=np.uint64)
+        kept, skipped, used = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        buf = np.frombuffer(raw, dtype=np.uint8)
+        if device:
+            rc = ctx.lib.sq_bam_walk_device(ctx.h, buf.ctypes.data, len(raw), n_ref, offs.ctypes.data, len(offs),
+                                            C.byref(kept), C.byref(skipped), C.byref(used))
+        else:
+            rc = ctx.lib.sq_bam_walk(buf.ctypes.data, len(raw), offs.ctypes.data, len(offs), C.byref(kept),
+                                     C.byref(skipped), C.byref(used))
+        out.append((rc, offs[:kept.value].tolist(), skipped.value, used.value))
+    return out
+
+
+def _body(raw):
+    return raw[len(synth.bam_header()):]
+
+
+@pytest.mark.parametrize("cut", [0, 1, 3, 4, 5, 35, 36, 40, 100, -1, -5, -40])
+def test_device_walk_equals_host_walk_at_every_kind_of_end(cut):
+    rng = np.random.default_rng(41)
+    body = _body(make_bam(rng, 300, flags=(4, 0x104, 4, 0x804, 4, 4)))
+    raw = body if cut == 0 else body[:cut]
+    host, dev = _walks(raw)
+    assert host[0] == 0 and dev == host
+
+
+def test_device_walk_ignores_headers_that_only_look_like_records():
+    """A whole, self-consistent record header inside the tags of a record is a candidate the chain never reaches."""
+    rng = np.random.default_rng(42)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    inner = synth.bam_record(b"decoy", letters[rng.integers(0, 4, 40)], np.full(40, 53, np.uint8), b"")
+    recs = []
+    for i in range(200):
+        seq = letters[rng.integers(0, 4, 60 + i)]
+        tags = b"xxZ" + inner * (1 + i % 3) + b"\0" if i % 2 else b"chS\x01\x00"
+        recs.append(synth.bam_record(b"r%d" % i, seq, np.full(len(seq), 60, np.uint8), tags, flag=4 if i % 7 else 0x904))
+    raw = b"".join(recs)
+    host, dev = _walks(raw)
+    assert host[0] == 0 and len(host[1]) + host[2] == 200 and dev == host
+
+
+def test_device_walk_follows_records_whose_header_is_not_self_consistent():
+    """The reference only trusts block_size: records with an odd reference id, no NUL behind the name or no name
+    at all are part of the chain; the device falls back to the plain walk from the first such record."""
+    rng = np.random.default_rng(43)
+    body = bytearray(_body(make_bam(rng, 120, lengths=(50, 151, 7))))
+    host0, _ = _walks(bytes(body))
+    offs = host0[1]
+    r = offs[40]
+    body[r + 4:r + 8] = struct.pack("<i", 77)          # refID beyond n_ref = 0
+    r = offs[80]
+    name_end = r + 36 + body[r + 12] - 1
+    body[name_end] = ord("x")                          # name not NUL terminated
+    host, dev = _walks(bytes(body))
+    assert host[0] == 0 and host[1] == offs and dev == host
+    # with a reference dictionary that covers the id, record 40 is an ordinary candidate again
+    host, dev = _walks(bytes(body[:offs[80]]), n_ref=100)
+    assert dev == host and len(dev[1]) == 80
+
+
+def test_device_walk_of_a_chain_that_starts_with_an_odd_record():
+    rng = np.random.default_rng(44)
+    body = bytearray(_body(make_bam(rng, 50)))
+    body[4:8] = struct.pack("<i", 5)
+    host, dev = _walks(bytes(body))
+    assert host[0] == 0 and len(host[1]) == 50 and dev == host
+
+
+def test_device_walk_large(sq):
+    raw = _body(synth.nanopore_ubam(400, mean_length=3000, max_length=60_000, seed=9))
+    host, dev = _walks(raw + raw[:1000])
+    assert host[0] == 0 and len(host[1]) == 400 and dev == host
+
+
+def test_long_records_decode_in_tiles(sq):
+    """Reads of 0 .. 3 tiles and every alignment of the output words, against the unmodified reference."""
+    rng = np.random.default_rng(45)
+    lengths = (0, 1, 4095, 4096, 4097, 8191, 8192, 8193, 12289, 3, 20000, 5)
+    raw = make_bam(rng, 36, flags=(4,), missing_every=5, lengths=lengths)
+    want = records(REF, raw)
+    assert records(sq, raw) == want
+    assert records(sq, raw, 1000) == want
