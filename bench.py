@@ -281,6 +281,83 @@ def run_configs(gpu_mod, peak_gbs):
     return out
 
 
+def run_next_rows():
+    """SURVEY.md 8(f) rows beside the hot path, each against the unmodified reference on one core:
+    seqident (8(f)4): Smith-Waterman identity of 21-mers against contaminant-sized targets, one launch for all
+    pairs / one call per pair; bam_chain (8(f)3): the block_size chain of a short-read uBAM, host bytes in."""
+    import ctypes as C
+    import importlib
+    from sequali_b200 import _lib, synth
+    from sequali_b200._qc import _PinnedBuffer
+    from sequali_b200.ext import _seqident
+    out = {}
+    rng = np.random.default_rng(11)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    pairs = []
+    for k in range(20_000):
+        target = letters[rng.integers(0, 4, size=int(rng.integers(200, 2000)))]
+        at = int(rng.integers(0, len(target) - 21))
+        q = target[at:at + 21].copy()
+        q[int(rng.integers(0, 21))] = letters[int(rng.integers(0, 4))]
+        pairs.append((target.tobytes().decode(), q.tobytes().decode()))
+    cells = sum(len(t) * len(q) for t, q in pairs)
+    _seqident.sequence_identities(pairs[:100])
+    t0 = time.perf_counter()
+    got = _seqident.sequence_identities(pairs)
+    dt = time.perf_counter() - t0
+    row = {"workload": "20k (target 200-2000 nt, 21-mer query) pairs, one launch, host strings in, floats out",
+           "value": round(cells / dt / 1e9, 3), "unit": "Gcells/s", "ms": round(dt * 1e3, 2)}
+    ref, _ = import_cpu_impl()
+    if ref is not None:
+        ref_si = importlib.import_module("sequali._seqident")
+        t0 = time.perf_counter()
+        want = [ref_si.sequence_identity(t, q) for t, q in pairs]
+        cdt = time.perf_counter() - t0
+        assert got == want
+        row["cpu_reference"] = {"value": round(cells / cdt / 1e9, 3), "unit": "Gcells/s", "cores": 1, "kind": "reference",
+                                "sample": "the identical pairs, one call per pair"}
+        row["speedup_vs_1_core"] = round(cdt / dt, 1)
+    out["seqident"] = row
+
+    ctx = _lib.Context.get()
+    n_rec, length, name_w, tags = 2_000_000, 150, 12, b"RGZrg1\0"
+    body = 32 + name_w + (length + 1) // 2 + length + len(tags)
+    rec = np.zeros((n_rec, 4 + body), dtype=np.uint8)
+    import struct
+    rec[:, :36] = np.frombuffer(struct.pack("<IiiBBHHHIiii", body, -1, -1, name_w, 0, 4680, 0, 4, length, -1, -1, 0), dtype=np.uint8)
+    rec[:, 36:47] = np.frombuffer(np.char.zfill(np.arange(n_rec).astype("S11"), 11).tobytes(), dtype=np.uint8).reshape(n_rec, 11)
+    rec[:, 48:48 + (length + 1) // 2] = rng.integers(0, 256, size=(n_rec, (length + 1) // 2), dtype=np.uint8)
+    rec[:, 48 + (length + 1) // 2:48 + (length + 1) // 2 + length] = rng.integers(2, 41, size=(n_rec, length), dtype=np.uint8)
+    rec[:, -len(tags):] = np.frombuffer(tags, dtype=np.uint8)
+    n = rec.size
+    pinned = _PinnedBuffer(ctx, n)
+    C.memmove(pinned.ptr, rec.ctypes.data, n)
+    del rec
+    offs = np.zeros(n // 36 + 2, dtype=np.uint64)
+    kept, skipped, used = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    res = {}
+    for what in ("host", "device"):
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            if what == "host":
+                rc = ctx.lib.sq_bam_walk(pinned.ptr, n, offs.ctypes.data, len(offs), C.byref(kept), C.byref(skipped), C.byref(used))
+            else:
+                rc = ctx.lib.sq_bam_walk_device(ctx.h, pinned.ptr, n, 0, offs.ctypes.data, len(offs), C.byref(kept),
+                                                C.byref(skipped), C.byref(used))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            assert rc == 0
+        res[what] = (best, kept.value, used.value, int(offs[:kept.value].sum()))
+    assert res["host"][1:] == res["device"][1:] and res["host"][1] == n_rec
+    out["bam_chain"] = {"workload": f"block_size chain of {n_rec} unaligned 150 bp BAM records ({n >> 20} MiB, pinned host bytes)",
+                        "value": round(n / res["device"][0] / 1e9, 2), "unit": "GB/s",
+                        "path": "sq_bam_walk_device: H2D copy + candidate test + pointer doubling + offsets back to the host",
+                        "cpu_walk": {"value": round(n / res["host"][0] / 1e9, 2), "unit": "GB/s", "cores": 1,
+                                     "kind": "port", "sample": "the identical bytes (sq_bam_walk: the reference's loop, :1623-1637)"}}
+    return out
+
+
 def _bgzf_worker(chunk):
     from sequali_b200 import synth
     return synth.bgzf_compress(bytes(chunk), level=6, eof_marker=False)
@@ -637,11 +714,12 @@ def run_cuda(args):
         cpu = cpu_baseline(data, args.cpu_reads)
 
     # ---- the other configurations BASELINE.json names (bounded sizes, single GPU) -------------
-    configs = None
+    configs = next_rows = None
     if rank == 0 and world == 1 and not args.no_configs:
         import sequali_b200.ext as sqx
         data.free()  # the 100 M reads leave HBM first
         configs = run_configs(sqx, measured_peak_gbs()[0])
+        next_rows = run_next_rows()
 
     if rank == 0:
         line = {
@@ -673,6 +751,8 @@ def run_cuda(args):
             line["cpu_baseline"] = cpu
         if configs:
             line["configs"] = configs
+        if next_rows:
+            line["next_rows"] = next_rows
         print(json.dumps(line), flush=True)
     if comm is not None:
         comm.barrier()

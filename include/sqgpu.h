@@ -424,6 +424,18 @@ SQ_API int sq_synth_illumina(sq_ctx *ctx, uint8_t *dev_text, uint64_t cap, uint6
                              uint32_t read_length, uint64_t seed, uint64_t first_read,
                              uint64_t reads_per_tile, uint64_t *nbytes);
 
+/* ---- _seqident (reference _seqidentmodule.c) ---------------------------------------------------------- */
+/* sequence_identity (_seqidentmodule.c:32-101, 279-343) for n (target, query) pairs in one launch: pair p is
+ * targets[target_off[p] .. target_off[p+1]) against queries[query_off[p] .. query_off[p+1]) (at most 31 letters,
+ * else SQ_E_ARG; host buffers).  matches_out[p] = the reference's most_matches: the largest count of matched query
+ * letters among the Smith-Waterman cells with the highest score; identity = matches / len(query).  Scores are
+ * added as 32-bit integers (the reference's portable loop uses Py_ssize_t, its AVX2 loop 8-bit lanes: equal
+ * whenever the 8-bit lanes do not overflow, e.g. for the default scores).  Synchronous. */
+SQ_API int sq_sequence_identity_batch(sq_ctx *ctx, const uint8_t *targets, const uint64_t *target_off,
+                                      const uint8_t *queries, const uint32_t *query_off, uint64_t n,
+                                      int match_score, int mismatch_penalty, int deletion_penalty,
+                                      int insertion_penalty, int32_t *matches_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,7 @@ SIGNATURES = {
     "sq_bam_walk": (_int, [_vp, _u64, _vp, _u64, _P(_u64), _P(_u64), _P(_u64)]),
     "sq_batch_from_bam": (_int, [_vp, _vp, _u64, _vp, _u64, _P(_vp), _P(_u64)]),
     "sq_batch_from_bam_bytes": (_int, [_vp, _vp, _u64, C.c_int32, _P(_vp), _P(_u64), _P(_u64), _P(_u64), _P(_u64)]),
+    "sq_sequence_identity_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _int, _int, _int, _int, _vp]),
     "sq_bam_walk_device": (_int, [_vp, _vp, _u64, C.c_int32, _vp, _u64, _P(_u64), _P(_u64), _P(_u64)]),
     "sq_fastq_stream_create": (_int, [_vp, _vp, _u64, _u64, _P(_vp)]),
     "sq_fastq_stream_next": (_int, [_vp, _P(_vp), _P(ParseInfo)]),
