@@ -355,7 +355,86 @@ def run_next_rows():
                         "path": "sq_bam_walk_device: H2D copy + candidate test + pointer doubling + offsets back to the host",
                         "cpu_walk": {"value": round(n / res["host"][0] / 1e9, 2), "unit": "GB/s", "cores": 1,
                                      "kind": "port", "sample": "the identical bytes (sq_bam_walk: the reference's loop, :1623-1637)"}}
+    out["report"] = report_row()
     return out
+
+
+_REF_REPORT = r'''
+import json, sys, time
+from sequali import report_modules as rm
+from sequali._qc import FastqParser, QCMetrics, NanoStats
+metrics, nano = QCMetrics(), NanoStats()
+with open(sys.argv[1], "rb") as f:
+    for arr in FastqParser(f):
+        metrics.add_record_array(arr)
+        nano.add_record_array(arr)
+ml = metrics.max_length
+ranges = list(rm.logarithmic_ranges(ml)) if ml > 500 else list(rm.equidistant_ranges(ml, 200))
+t0 = time.perf_counter()
+mods = rm.qc_metrics_modules(metrics, ranges)
+t1 = time.perf_counter()
+ns = rm.NanoStatsReport.from_nanostats(nano)
+t2 = time.perf_counter()
+print(json.dumps({"qc_ms": (t1 - t0) * 1e3, "nano_ms": (t2 - t1) * 1e3, "n50": mods[1].n50, "total_bases": mods[0].total_bases,
+                  "time_reads": sum(ns.time_reads), "channels": len(ns.per_channel_bases)}))
+'''
+
+
+def report_row():
+    """8(f)2: the aggregation the report does on the collectors' results -- qc_metrics_modules' table sums and length
+    walk (report_modules.py:2537-2605) and NanoStatsReport.from_nanostats' loop over every read (:1952-2046) --
+    on the device tables (sequali_b200.report) against the reference's Python on one core, same input."""
+    import shutil
+    import tempfile
+    import sequali_b200.ext as sqx
+    from sequali_b200 import report, synth
+    text = synth.nanopore_fastq(100_000, mean_length=300, max_length=1_000_000, seed=12)
+    big = synth.nanopore_fastq(1, mean_length=900_000, max_length=1_000_000, seed=13)  # one read near 1 Mb: long tables
+    text = text + big
+    metrics, nano = sqx.QCMetrics(), sqx.NanoStats()
+    for arr in sqx.FastqParser(io.BytesIO(text), 64 << 20):
+        metrics.add_record_array(arr)
+        nano.add_record_array(arr)
+    ranges = report.data_ranges_for(metrics.max_length)
+    report.qc_metrics_tables(metrics, ranges), report.nanostats_report(nano)  # warm-up
+    t0 = time.perf_counter()
+    qc = report.qc_metrics_tables(metrics, ranges)
+    t1 = time.perf_counter()
+    ns = report.nanostats_report(nano)
+    t2 = time.perf_counter()
+    row = {"workload": f"{nano.number_of_reads} nanopore reads, longest {metrics.max_length} nt ({len(ranges)} position ranges): "
+                       "table sums + length walk of qc_metrics_modules, per-read loop of NanoStatsReport.from_nanostats",
+           "qc_tables_ms": round((t1 - t0) * 1e3, 2), "nanostats_ms": round((t2 - t1) * 1e3, 2),
+           "path": "sequali_b200.report on the collectors' device tables (results to Python objects included)"}
+    pkg_src = os.path.join(ROOT, "oracle", "_ref", "pkg_src")
+    ref_dir = os.path.join(ROOT, "oracle", "_ref", "sequali")
+    if os.path.exists(os.path.join(pkg_src, "report_modules.py")) and os.path.exists(os.path.join(ref_dir, "_qc.abi3.so")):
+        tmp = tempfile.mkdtemp(prefix="sq_report_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            shutil.copytree(pkg_src, os.path.join(tmp, "sequali"))
+            for so in os.listdir(ref_dir):
+                if so.endswith(".so"):
+                    shutil.copy(os.path.join(ref_dir, so), os.path.join(tmp, "sequali", so))
+            with open(os.path.join(tmp, "in.fastq"), "wb") as f:
+                f.write(text)
+            env = dict(os.environ)
+            env["PYTHONPATH"] = os.pathsep.join([tmp, os.path.join(ROOT, "oracle", "_ref", "tests", "shim")])
+            proc = subprocess.run([sys.executable, "-c", _REF_REPORT, os.path.join(tmp, "in.fastq")], env=env,
+                                  capture_output=True, text=True, timeout=900)
+            if proc.returncode == 0:
+                ref = json.loads(proc.stdout)
+                assert ref["n50"] == qc["sequence_length_distribution"]["n50"] and ref["total_bases"] == qc["summary"]["total_bases"]
+                assert ref["time_reads"] == sum(ns["time_reads"]) and ref["channels"] == len(ns["per_channel_bases"])
+                row["cpu_reference"] = {"qc_tables_ms": round(ref["qc_ms"], 1), "nanostats_ms": round(ref["nano_ms"], 1), "cores": 1,
+                                        "kind": "reference", "sample": "the identical reads; report_modules.py unchanged "
+                                        "(pygal stubbed: nothing is plotted in either arm)"}
+                row["speedup_vs_1_core"] = {"qc_tables": round(ref["qc_ms"] / max(row["qc_tables_ms"], 1e-3), 1),
+                                            "nanostats": round(ref["nano_ms"] / max(row["nanostats_ms"], 1e-3), 1)}
+            else:
+                row["cpu_reference"] = {"unavailable": proc.stderr.strip().splitlines()[-1][:200] if proc.stderr.strip() else "failed"}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return row
 
 
 def _bgzf_worker(chunk):

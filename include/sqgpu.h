@@ -424,6 +424,43 @@ SQ_API int sq_synth_illumina(sq_ctx *ctx, uint8_t *dev_text, uint64_t cap, uint6
                              uint32_t read_length, uint64_t seed, uint64_t first_read,
                              uint64_t reads_per_tile, uint64_t *nbytes);
 
+/* ---- report aggregation on device-resident tables (reference report_modules.py) ----------------------- */
+typedef struct {
+    uint64_t total_bases;            /* sum(base_count_tables), :620 */
+    uint64_t minimum_length;         /* qc_metrics_modules :2563-2566 */
+    uint64_t n50, n90;               /* :621-634 */
+    uint64_t threshold_lengths[16];  /* the percentile walk of :598-617, one length per count threshold */
+} sq_qc_length_summary;
+/* aggregate_count_matrix (report_modules.py:307-322) of base_count_table and phred_count_table over the data
+ * ranges [starts[k], stops[k]) (positions; clipped to max_length like a Python slice), and
+ * SequenceLengthDistribution.from_base_count_tables (:575-637) without moving the tables to the host:
+ * base_matrix[n_ranges][5], phred_matrix[n_ranges][12], length_counts[k] = reads with starts[k] < length <=
+ * stops[k]; summary->threshold_lengths[j] = the first length at which more than count_thresholds[j] reads (of
+ * at least one letter) are at most that long, 0 if there is none (the caller passes int(p * total / 100) for
+ * its percentiles; n_thresholds <= 16); total_sequences = QCMetrics.number_of_reads. */
+SQ_API int sq_qc_aggregate(sq_qc *m, const uint64_t *starts, const uint64_t *stops, uint64_t n_ranges,
+                           uint64_t *base_matrix, uint64_t *phred_matrix, uint64_t *length_counts,
+                           const uint64_t *count_thresholds, uint64_t n_thresholds,
+                           uint64_t total_sequences, sq_qc_length_summary *summary);
+typedef struct {
+    int32_t kind;     /* 0 none; 1 / 2: length / duration is infinite / NaN (Python: OverflowError / ValueError
+                         from round()); 3: a list index out of range (IndexError) */
+    uint64_t record;  /* the first read it happens at */
+} sq_nano_report_error;
+/* NanoStatsReport.from_nanostats (report_modules.py:1952-2046) over the per-read records on the device.  The
+ * caller computes run_start = minimum_time, interval and n_slots like :1968-1980.  time_bases / time_reads /
+ * time_active_channels [n_slots], time_qualities [n_slots][12] (class = min(round(-10 log10(error / length)),
+ * 47) >> 2 with the host's log10), translocation_speeds [81], *reads_with_parent; *n_channels = distinct
+ * channel ids, whose sorted ids / base totals / error sums (added in read order) are then fetched with
+ * sq_nanostats_report_channels. */
+SQ_API int sq_nanostats_report(sq_nanostats *s, int64_t run_start, int64_t interval, uint64_t n_slots,
+                               uint64_t *time_bases, uint64_t *time_reads, uint64_t *time_active_channels,
+                               uint64_t *time_qualities, uint64_t *translocation_speeds,
+                               uint64_t *reads_with_parent, uint64_t *n_channels,
+                               sq_nano_report_error *error);
+SQ_API int sq_nanostats_report_channels(sq_nanostats *s, int32_t *channel_ids, uint64_t *bases,
+                                        double *cumulative_error, uint64_t cap);
+
 /* ---- _seqident (reference _seqidentmodule.c) ---------------------------------------------------------- */
 /* sequence_identity (_seqidentmodule.c:32-101, 279-343) for n (target, query) pairs in one launch: pair p is
  * targets[target_off[p] .. target_off[p+1]) against queries[query_off[p] .. query_off[p+1]) (at most 31 letters,

@@ -70,6 +70,15 @@ class NanoInfo(C.Structure):
                 ("parent_id_hash", C.c_uint64)]
 
 
+class QcLengthSummary(C.Structure):
+    _fields_ = [("total_bases", C.c_uint64), ("minimum_length", C.c_uint64), ("n50", C.c_uint64), ("n90", C.c_uint64),
+                ("threshold_lengths", C.c_uint64 * 16)]
+
+
+class NanoReportError(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("record", C.c_uint64)]
+
+
 class NanoStatsInfo(C.Structure):
     _fields_ = [("number_of_reads", C.c_uint64), ("minimum_time", C.c_int64),
                 ("maximum_time", C.c_int64), ("skipped", C.c_int32),
@@ -119,6 +128,9 @@ SIGNATURES = {
     "sq_bam_walk": (_int, [_vp, _u64, _vp, _u64, _P(_u64), _P(_u64), _P(_u64)]),
     "sq_batch_from_bam": (_int, [_vp, _vp, _u64, _vp, _u64, _P(_vp), _P(_u64)]),
     "sq_batch_from_bam_bytes": (_int, [_vp, _vp, _u64, C.c_int32, _P(_vp), _P(_u64), _P(_u64), _P(_u64), _P(_u64)]),
+    "sq_qc_aggregate": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _u64, _u64, _vp]),
+    "sq_nanostats_report": (_int, [_vp, C.c_int64, C.c_int64, _u64, _vp, _vp, _vp, _vp, _vp, _P(_u64), _P(_u64), _vp]),
+    "sq_nanostats_report_channels": (_int, [_vp, _vp, _vp, _vp, _u64]),
     "sq_sequence_identity_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _int, _int, _int, _int, _vp]),
     "sq_bam_walk_device": (_int, [_vp, _vp, _u64, C.c_int32, _vp, _u64, _P(_u64), _P(_u64), _P(_u64)]),
     "sq_fastq_stream_create": (_int, [_vp, _vp, _u64, _u64, _P(_vp)]),

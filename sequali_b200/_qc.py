@@ -645,6 +645,27 @@ class QCMetrics(_Collector):
         check(self._ctx.lib.sq_qc_read(self._h, *[_void(x) for x in t]), "sq_qc_read")
         return t
 
+    def aggregate(self, data_ranges, count_thresholds=()):
+        """Extension of the B200 build: what the report derives from base_count_table() and
+        phred_count_table() for the given (start, stop) position ranges -- aggregate_count_matrix of both tables
+        and the length distribution walk of SequenceLengthDistribution (report_modules.py:307-322, 575-637) --
+        computed on the device tables; only the aggregated numbers come back.  See sequali_b200.report."""
+        info = self._sync()
+        ranges = np.asarray(list(data_ranges), dtype=np.uint64).reshape(-1, 2)
+        starts, stops = np.ascontiguousarray(ranges[:, 0]), np.ascontiguousarray(ranges[:, 1])
+        thr = np.asarray(list(count_thresholds), dtype=np.uint64)
+        n = len(starts)
+        base, phred = np.zeros(n * NUMBER_OF_NUCS, dtype=np.uint64), np.zeros(n * NUMBER_OF_PHREDS, dtype=np.uint64)
+        lengths = np.zeros(n, dtype=np.uint64)
+        summary = _lib.QcLengthSummary()
+        check(self._ctx.lib.sq_qc_aggregate(self._h, _void(starts), _void(stops), n, _void(base), _void(phred),
+                                            _void(lengths), _void(thr), len(thr), info.number_of_reads,
+                                            _C.byref(summary)), "sq_qc_aggregate")
+        return {"base_matrix": array.array("Q", base.tobytes()), "phred_matrix": array.array("Q", phred.tobytes()),
+                "length_counts": lengths.tolist(), "total_bases": summary.total_bases,
+                "minimum_length": summary.minimum_length, "n50": summary.n50, "n90": summary.n90,
+                "threshold_lengths": list(summary.threshold_lengths[:len(thr)])}
+
     def base_count_table(self):
         return _u64_array(self._tables()[0])
 
@@ -1079,6 +1100,33 @@ class NanoStats(_Collector):
             return
         if len(arr):
             _defer("ns", self, arr)
+
+    def report_tables(self, run_start_time: int, time_interval: int, time_slots: int) -> dict:
+        """Extension of the B200 build: the per-read loop of NanoStatsReport.from_nanostats
+        (report_modules.py:1990-2024) over the records on the device.  See sequali_b200.report."""
+        self._sync()
+        lib = self._ctx.lib
+        n = time_slots
+        t_bases, t_reads, t_active = (np.zeros(n, dtype=np.uint64) for _ in range(3))
+        t_quals, speeds = np.zeros(n * 12, dtype=np.uint64), np.zeros(81, dtype=np.uint64)
+        parents, n_ch, err = _C.c_uint64(), _C.c_uint64(), _lib.NanoReportError()
+        check(lib.sq_nanostats_report(self._h, run_start_time, time_interval, n, _void(t_bases), _void(t_reads),
+                                      _void(t_active), _void(t_quals), _void(speeds), _C.byref(parents),
+                                      _C.byref(n_ch), _C.byref(err)), "sq_nanostats_report")
+        ch = np.zeros(n_ch.value, dtype=np.int32)
+        ch_bases, ch_err = np.zeros(n_ch.value, dtype=np.uint64), np.zeros(n_ch.value, dtype=np.float64)
+        check(lib.sq_nanostats_report_channels(self._h, _void(ch), _void(ch_bases), _void(ch_err), n_ch.value),
+              "sq_nanostats_report_channels")
+        if err.kind == 1:
+            raise OverflowError("cannot convert float infinity to integer")
+        if err.kind == 2:
+            raise ValueError("cannot convert float NaN to integer")
+        if err.kind == 3:
+            raise IndexError("list index out of range")
+        return {"time_bases": t_bases.tolist(), "time_reads": t_reads.tolist(), "time_active_channels": t_active.tolist(),
+                "time_qualities": t_quals.reshape(n, 12).tolist(), "translocation_speed": speeds.tolist(),
+                "reads_with_parent": parents.value, "channels": ch.tolist(), "channel_bases": ch_bases.tolist(),
+                "channel_cumulative_error": ch_err.tolist()}
 
     def nano_info_iterator(self) -> NanoStatsIterator:
         info = self._sync()

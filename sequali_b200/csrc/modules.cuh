@@ -172,3 +172,30 @@ struct sq_dedup {
 
 // Takes `hashes` in record order.  In deferred mode the buffer is KEPT (the caller must not free it).
 int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n);
+
+// ---- NanoStats (nanostats.cu, report.cu) -----------------------------------------
+struct NsState {  // device
+    unsigned long long fail_idx;      // global index of the first unparsable header
+    unsigned long long tag_err_idx;   // global index of the first malformed aux block
+    unsigned long long pi_warnings;
+    long long min_time, max_time;
+    unsigned int nonpositive_time;    // a timestamp <= 0 exists (order-dependent min, see k_ns_minmax_ordered)
+    unsigned int pad;
+};
+
+struct sq_nanostats {
+    sq_ctx *ctx = nullptr;
+    uint64_t n_added = 0, cap = 0;
+    sq_nanoinfo *infos = nullptr;
+    NsState *st = nullptr;
+    bool skipped = false;          // known on the host after a sync
+    uint64_t skipped_record = 0;
+    std::vector<uint8_t> skipped_name;
+    // names of the newest arrays are needed for skipped_reason: keep (batch ptr, base) of pending adds
+    std::vector<std::pair<sq_batch *, uint64_t>> pending;
+    // per-channel results of the last sq_nanostats_report, until sq_nanostats_report_channels fetches them
+    uint64_t rp_n = 0;
+    int32_t *rp_channel = nullptr;
+    unsigned long long *rp_bases = nullptr;
+    double *rp_error = nullptr;
+};

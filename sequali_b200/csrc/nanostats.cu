@@ -8,29 +8,9 @@
 // at read-out.  The per-read error sum is the one QCMetrics stored on the
 // record array (same stream, so it is already there when this kernel runs).
 #include "common.cuh"
+#include "modules.cuh"
 
 constexpr int NS_TPB = 128;
-
-struct NsState {  // device
-    unsigned long long fail_idx;      // global index of the first unparsable header
-    unsigned long long tag_err_idx;   // global index of the first malformed aux block
-    unsigned long long pi_warnings;
-    long long min_time, max_time;
-    unsigned int nonpositive_time;    // a timestamp <= 0 exists (order-dependent min, see k_ns_minmax_ordered)
-    unsigned int pad;
-};
-
-struct sq_nanostats {
-    sq_ctx *ctx = nullptr;
-    uint64_t n_added = 0, cap = 0;
-    sq_nanoinfo *infos = nullptr;
-    NsState *st = nullptr;
-    bool skipped = false;          // known on the host after a sync
-    uint64_t skipped_record = 0;
-    std::vector<uint8_t> skipped_name;
-    // names of the newest arrays are needed for skipped_reason: keep (batch ptr, base) of pending adds
-    std::vector<std::pair<sq_batch *, uint64_t>> pending;
-};
 
 __device__ __forceinline__ long long dec_field(const uint8_t *s, const uint8_t *end, uint32_t len) {
     if (len < 1 || len > 18 || s + len > end) return -1;
@@ -301,6 +281,9 @@ extern "C" void sq_nanostats_destroy(sq_nanostats *s) {
     cudaSetDevice(s->ctx->device);
     sq_dfree(s->ctx, s->infos);
     sq_dfree(s->ctx, s->st);
+    sq_dfree(s->ctx, s->rp_channel);
+    sq_dfree(s->ctx, s->rp_bases);
+    sq_dfree(s->ctx, s->rp_error);
     delete s;
 }
 

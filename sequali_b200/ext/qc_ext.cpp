@@ -162,6 +162,60 @@ PyObject *u64_array(const uint64_t *data, size_t n) {
     return arr;
 }
 
+// list of Python ints / floats from a plain array
+PyObject *u64_list(const uint64_t *v, size_t n) {
+    PyObject *l = PyList_New((Py_ssize_t)n);
+    for (size_t i = 0; l && i < n; i++) {
+        PyObject *o = PyLong_FromUnsignedLongLong(v[i]);
+        if (!o) {
+            Py_CLEAR(l);
+            break;
+        }
+        PyList_SET_ITEM(l, (Py_ssize_t)i, o);
+    }
+    return l;
+}
+// dict from "key", value, ... (values are stolen; a NULL value fails the whole dict)
+PyObject *dict_of(std::initializer_list<std::pair<const char *, PyObject *>> items) {
+    PyObject *d = PyDict_New();
+    bool ok = d != nullptr;
+    for (auto &kv : items) {
+        if (ok && (!kv.second || PyDict_SetItemString(d, kv.first, kv.second) < 0)) ok = false;
+        Py_XDECREF(kv.second);
+    }
+    if (!ok) Py_CLEAR(d);
+    return d;
+}
+// uint64 values of an iterable of ints (flattening one level of pairs when `pairs`)
+int u64_from_iterable(PyObject *obj, bool pairs, std::vector<uint64_t> &out) {
+    PyObject *it = PyObject_GetIter(obj);
+    if (!it) return -1;
+    while (PyObject *item = PyIter_Next(it)) {
+        if (pairs) {
+            unsigned long long a, b;
+            if (!PyArg_ParseTuple(item, "KK", &a, &b)) {
+                Py_DECREF(item);
+                Py_DECREF(it);
+                return -1;
+            }
+            out.push_back(a);
+            out.push_back(b);
+        }
+        else {
+            const unsigned long long a = PyLong_AsUnsignedLongLong(item);
+            if (a == (unsigned long long)-1 && PyErr_Occurred()) {
+                Py_DECREF(item);
+                Py_DECREF(it);
+                return -1;
+            }
+            out.push_back(a);
+        }
+        Py_DECREF(item);
+    }
+    Py_DECREF(it);
+    return PyErr_Occurred() ? -1 : 0;
+}
+
 const double *error_rates() {
     static double tab[94];
     static bool done = false;
@@ -709,6 +763,31 @@ PyObject *QC_get(Collector *self, void *closure) {
     const intptr_t k = (intptr_t)closure;
     return PyLong_FromUnsignedLongLong(k == 0 ? info.max_length : k == 1 ? info.number_of_reads : info.end_anchor_length);
 }
+// extension of the B200 build: aggregate(data_ranges, count_thresholds=()) -> dict, see sequali_b200/report.py
+PyObject *QC_aggregate(Collector *self, PyObject *args) {
+    PyObject *ranges_obj = nullptr, *thr_obj = nullptr;
+    if (!PyArg_ParseTuple(args, "O|O:aggregate", &ranges_obj, &thr_obj)) return nullptr;
+    std::vector<uint64_t> flat, thr;
+    if (u64_from_iterable(ranges_obj, true, flat) < 0) return nullptr;
+    if (thr_obj && u64_from_iterable(thr_obj, false, thr) < 0) return nullptr;
+    sq_qc_info info;
+    if (QC_sync(self, &info) < 0) return nullptr;
+    const size_t n = flat.size() / 2;
+    std::vector<uint64_t> starts(n + 1), stops(n + 1), base(n * 5 + 1), phred(n * 12 + 1), lengths(n + 1);
+    for (size_t i = 0; i < n; i++) starts[i] = flat[2 * i], stops[i] = flat[2 * i + 1];
+    sq_qc_length_summary sum;
+    SQ_CHECK(sq_qc_aggregate((sq_qc *)self->h, starts.data(), stops.data(), n, base.data(), phred.data(), lengths.data(),
+                             thr.data(), thr.size(), info.number_of_reads, &sum),
+             "sq_qc_aggregate");
+    return dict_of({{"base_matrix", u64_array(base.data(), n * 5)},
+                    {"phred_matrix", u64_array(phred.data(), n * 12)},
+                    {"length_counts", u64_list(lengths.data(), n)},
+                    {"total_bases", PyLong_FromUnsignedLongLong(sum.total_bases)},
+                    {"minimum_length", PyLong_FromUnsignedLongLong(sum.minimum_length)},
+                    {"n50", PyLong_FromUnsignedLongLong(sum.n50)},
+                    {"n90", PyLong_FromUnsignedLongLong(sum.n90)},
+                    {"threshold_lengths", u64_list(sum.threshold_lengths, thr.size())}});
+}
 PyMethodDef QC_methods[] = {
     {"add_read", (PyCFunction)QC_add_read, METH_O, "Add a read to the count metrics."},
     {"add_record_array", (PyCFunction)QC_add_record_array, METH_O, "Add a record_array to the count metrics."},
@@ -718,6 +797,9 @@ PyMethodDef QC_methods[] = {
     {"end_anchored_phred_count_table", (PyCFunction)QC_ea_phred, METH_NOARGS, "end anchored phred counts"},
     {"gc_content", (PyCFunction)QC_gc, METH_NOARGS, "array.array('Q') of 101 GC percentage counts"},
     {"phred_scores", (PyCFunction)QC_scores, METH_NOARGS, "array.array('Q') of PHRED_MAX + 1 mean phred counts"},
+    {"aggregate", (PyCFunction)QC_aggregate, METH_VARARGS,
+     "aggregate(data_ranges, count_thresholds=()) -> dict: the report's sums over position ranges and its length\n"
+     "distribution walk, computed on the device tables (extension of the B200 build)"},
     {nullptr, nullptr, 0, nullptr}};
 PyGetSetDef QC_getset[] = {{"max_length", (getter)QC_get, nullptr, "length of the longest read", (void *)0},
                            {"number_of_reads", (getter)QC_get, nullptr, "number of reads processed", (void *)1},
@@ -1530,9 +1612,77 @@ PyObject *NS_get(Skippable *self, void *closure) {
     }
     }
 }
+// extension of the B200 build: report_tables(run_start_time, time_interval, time_slots) -> dict
+PyObject *NS_report_tables(Skippable *self, PyObject *args) {
+    long long run_start, interval;
+    unsigned long long n_slots;
+    if (!PyArg_ParseTuple(args, "LLK:report_tables", &run_start, &interval, &n_slots)) return nullptr;
+    sq_nanostats_info info;
+    if (NS_sync(self, &info) < 0) return nullptr;
+    if (n_slots < 1 || n_slots > (1u << 24)) {
+        PyErr_SetString(PyExc_ValueError, "time_slots out of range");
+        return nullptr;
+    }
+    std::vector<uint64_t> t_bases(n_slots), t_reads(n_slots), t_active(n_slots), t_quals(n_slots * 12), speeds(81);
+    uint64_t parents = 0, n_ch = 0;
+    sq_nano_report_error err;
+    sq_nanostats *h = (sq_nanostats *)self->h;
+    SQ_CHECK(sq_nanostats_report(h, run_start, interval, n_slots, t_bases.data(), t_reads.data(), t_active.data(),
+                                 t_quals.data(), speeds.data(), &parents, &n_ch, &err),
+             "sq_nanostats_report");
+    std::vector<int32_t> ch(n_ch + 1);
+    std::vector<uint64_t> ch_bases(n_ch + 1);
+    std::vector<double> ch_err(n_ch + 1);
+    SQ_CHECK(sq_nanostats_report_channels(h, ch.data(), ch_bases.data(), ch_err.data(), n_ch), "sq_nanostats_report_channels");
+    if (err.kind == 1) {
+        PyErr_SetString(PyExc_OverflowError, "cannot convert float infinity to integer");
+        return nullptr;
+    }
+    if (err.kind == 2) {
+        PyErr_SetString(PyExc_ValueError, "cannot convert float NaN to integer");
+        return nullptr;
+    }
+    if (err.kind == 3) {
+        PyErr_SetString(PyExc_IndexError, "list index out of range");
+        return nullptr;
+    }
+    PyObject *quals = PyList_New((Py_ssize_t)n_slots);
+    for (size_t i = 0; quals && i < n_slots; i++) {
+        PyObject *row = u64_list(t_quals.data() + i * 12, 12);
+        if (!row) {
+            Py_CLEAR(quals);
+            break;
+        }
+        PyList_SET_ITEM(quals, (Py_ssize_t)i, row);
+    }
+    PyObject *channels = PyList_New((Py_ssize_t)n_ch), *errors = PyList_New((Py_ssize_t)n_ch);
+    for (size_t i = 0; channels && errors && i < n_ch; i++) {
+        PyObject *c = PyLong_FromLong(ch[i]), *e = PyFloat_FromDouble(ch_err[i]);
+        if (!c || !e) {
+            Py_XDECREF(c);
+            Py_XDECREF(e);
+            Py_CLEAR(channels);
+            break;
+        }
+        PyList_SET_ITEM(channels, (Py_ssize_t)i, c);
+        PyList_SET_ITEM(errors, (Py_ssize_t)i, e);
+    }
+    return dict_of({{"time_bases", u64_list(t_bases.data(), n_slots)},
+                    {"time_reads", u64_list(t_reads.data(), n_slots)},
+                    {"time_active_channels", u64_list(t_active.data(), n_slots)},
+                    {"time_qualities", quals},
+                    {"translocation_speed", u64_list(speeds.data(), 81)},
+                    {"reads_with_parent", PyLong_FromUnsignedLongLong(parents)},
+                    {"channels", channels},
+                    {"channel_bases", u64_list(ch_bases.data(), n_ch)},
+                    {"channel_cumulative_error", errors}});
+}
 PyMethodDef NS_methods[] = {{"add_read", (PyCFunction)NS_add_read, METH_O, "Add a read to the NanoStats module."},
                             {"add_record_array", (PyCFunction)NS_add_record_array, METH_O, "Add a record_array."},
                             {"nano_info_iterator", (PyCFunction)NS_iterator, METH_NOARGS, "iterator over NanoporeReadInfo"},
+                            {"report_tables", (PyCFunction)NS_report_tables, METH_VARARGS,
+                             "report_tables(run_start_time, time_interval, time_slots) -> dict: the per-read loop of the\n"
+                             "report's NanoStats module on the device (extension of the B200 build)"},
                             {nullptr, nullptr, 0, nullptr}};
 PyGetSetDef NS_getset[] = {{"number_of_reads", (getter)NS_get, nullptr, "reads processed", (void *)0},
                            {"minimum_time", (getter)NS_get, nullptr, "earliest start time", (void *)1},
