@@ -335,9 +335,14 @@ typedef struct {
     int64_t minimum_time, maximum_time;
     int32_t skipped;
     uint64_t skipped_record;
-    int32_t tag_error;        /* malformed BAM aux data (the reference raises)   */
+    int32_t tag_error;        /* malformed BAM aux data (the reference raises, _qcmodule.c:5078-5259): 0 none,
+                                 1 "truncated tags", 2 "Invalid type for array %c", 3 "Unknown tag type %c"
+                                 (ValueError), 4 "Wrong tag type for '%s' expected '%c' got '%c'" (RuntimeError),
+                                 5 ch with a non-integer type (the reference returns NULL with no exception set) */
     uint64_t tag_error_record;
     uint64_t pi_warnings;     /* pi:Z tags that are not 36 characters long        */
+    uint32_t tag_error_detail; /* kinds 2, 3: the type character; kind 4: tag (0 st, 1 du, 2 pi) << 8 | type found */
+    uint32_t pi_first_length;  /* length of the first such pi tag (the "Counted %zu" of the warning, :5245) */
 } sq_nanostats_info;
 SQ_API int sq_nanostats_create(sq_ctx *ctx, sq_nanostats **out);
 SQ_API void sq_nanostats_destroy(sq_nanostats *s);

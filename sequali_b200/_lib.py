@@ -83,7 +83,8 @@ class NanoStatsInfo(C.Structure):
     _fields_ = [("number_of_reads", C.c_uint64), ("minimum_time", C.c_int64),
                 ("maximum_time", C.c_int64), ("skipped", C.c_int32),
                 ("skipped_record", C.c_uint64), ("tag_error", C.c_int32),
-                ("tag_error_record", C.c_uint64), ("pi_warnings", C.c_uint64)]
+                ("tag_error_record", C.c_uint64), ("pi_warnings", C.c_uint64),
+                ("tag_error_detail", C.c_uint32), ("pi_first_length", C.c_uint32)]
 
 
 class BgzfBlock(C.Structure):

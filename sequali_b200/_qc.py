@@ -1064,12 +1064,22 @@ class NanoStats(_Collector):
         _flush()
         info = _lib.NanoStatsInfo()
         check(self._ctx.lib.sq_nanostats_sync(self._h, _C.byref(info)), "sq_nanostats_sync")
-        if info.tag_error:
+        if info.tag_error:  # the reference's exceptions for malformed aux data (:5078-5259)
+            kind, detail = info.tag_error, info.tag_error_detail
+            if kind == 2:
+                raise ValueError(f"Invalid type for array {chr(detail & 0xff)}")
+            if kind == 3:
+                raise ValueError(f"Unknown tag type {chr(detail & 0xff)}")
+            if kind == 4:
+                tag, expected = (("st", "Z"), ("du", "f"), ("pi", "Z"))[min(detail >> 8, 2)]
+                raise RuntimeError(f"Wrong tag type for '{tag}' expected '{expected}' got '{chr(detail & 0xff)}'")
+            if kind == 5:
+                raise SystemError("error return without exception set")
             raise ValueError("truncated tags")
         if info.pi_warnings > self._pi_warned:
             self._pi_warned = info.pi_warnings
             warnings.warn("pi tag should have a valid uuid4 format with 36 characters. "
-                          "Skipping tag.", UserWarning, stacklevel=3)
+                          f"Counted {info.pi_first_length}. Skipping tag.", UserWarning, stacklevel=3)
         if info.skipped and self._reason is None:
             buf = np.zeros(1 << 16, np.uint8)
             ln = _C.c_uint64()

@@ -135,6 +135,31 @@ int sq_batch_get_name(sq_batch *b, uint64_t r, std::vector<uint8_t> &out);
 int sq_dalloc(sq_ctx *ctx, void **p, size_t nbytes, bool zero);
 void sq_dfree(sq_ctx *ctx, void *p);
 
+// Stream-ordered scratch that goes back to the pool on EVERY way out of a function (early error returns
+// included); keep(p) hands a block over to the caller / a longer-lived owner.
+struct SqScratch {
+    sq_ctx *ctx;
+    std::vector<void *> owned;
+    explicit SqScratch(sq_ctx *c) : ctx(c) {}
+    SqScratch(const SqScratch &) = delete;
+    SqScratch &operator=(const SqScratch &) = delete;
+    ~SqScratch() {
+        for (void *p : owned) sq_dfree(ctx, p);
+    }
+    template <class T> int get(T **p, size_t nbytes, bool zero = false) {
+        const int rc = sq_dalloc(ctx, (void **)p, nbytes, zero);
+        if (rc == SQ_OK && *p) owned.push_back((void *)*p);
+        return rc;
+    }
+    void keep(const void *p) {
+        for (size_t i = 0; i < owned.size(); i++)
+            if (owned[i] == p) {
+                owned.erase(owned.begin() + i);
+                return;
+            }
+    }
+};
+
 // device-wide exclusive scan (scan.cu)
 int sq_scan_exclusive_u32(sq_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total_dev);
 

@@ -419,8 +419,9 @@ int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n) {
     if (d->mod_bits >= 2 && n >= 4096) {
         uint32_t *flag = nullptr, *rank = nullptr;
         uint64_t *kept = nullptr;
-        SQ_TRY(sq_dalloc(ctx, (void **)&flag, (size_t)n * 4, false));
-        SQ_TRY(sq_dalloc(ctx, (void **)&rank, (size_t)n * 4 + 4, false));
+        SqScratch scratch(ctx);
+        SQ_TRY(scratch.get(&flag, (size_t)n * 4));
+        SQ_TRY(scratch.get(&rank, (size_t)n * 4 + 4));
         const int grid = sq_grid_for(ctx, n, DD_TPB, 16);
         SQ_LAUNCH(ctx, k_dd_pass_flags, grid, DD_TPB, 0, hashes, n, (1ULL << d->mod_bits) - 1, flag);
         SQ_TRY(sq_scan_exclusive_u32(ctx, flag, rank, n, rank + n));
@@ -428,12 +429,9 @@ int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n) {
         CUDA_TRY(cudaMemcpyAsync(h_total, rank + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         const uint32_t n_kept = *h_total;
-        SQ_TRY(sq_dalloc(ctx, (void **)&kept, ((size_t)n_kept + 1) * 8, false));
+        SQ_TRY(scratch.get(&kept, ((size_t)n_kept + 1) * 8));
         SQ_LAUNCH(ctx, k_dd_pass_scatter, grid, DD_TPB, 0, hashes, flag, rank, n, kept);
         rc = n_kept ? dedup_consume_range(d, kept, n_kept) : SQ_OK;
-        sq_dfree(ctx, flag);
-        sq_dfree(ctx, rank);
-        sq_dfree(ctx, kept);
     }
     else rc = dedup_consume_range(d, hashes, n);
     d->n_records += n;
@@ -445,17 +443,18 @@ static int dedup_consume_range(sq_dedup *d, const uint64_t *hashes, uint32_t n) 
     const uint64_t tmask = d->table_size - 1;
     const uint64_t prio_base = d->table_size + 1 + d->n_records;  // above every rebuild priority
     uint32_t *cls = nullptr, *flag = nullptr, *rank = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&cls, (size_t)n * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&flag, (size_t)n * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&rank, (size_t)n * 4, false));
+    SqScratch scratch(ctx);
+    SQ_TRY(scratch.get(&cls, (size_t)n * 4));
+    SQ_TRY(scratch.get(&flag, (size_t)n * 4));
+    SQ_TRY(scratch.get(&rank, (size_t)n * 4));
     // scratch sized for the worst case (every record a distinct new key)
     uint32_t scap = 1024;
     while (scap < 2 * (uint64_t)n) scap <<= 1;
     Scratch S;
     S.mask = scap - 1;
-    SQ_TRY(sq_dalloc(ctx, (void **)&S.key, (size_t)scap * 8, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&S.first, (size_t)scap * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&S.cnt, (size_t)scap * 4, false));
+    SQ_TRY(scratch.get(&S.key, (size_t)scap * 8));
+    SQ_TRY(scratch.get(&S.first, (size_t)scap * 4));
+    SQ_TRY(scratch.get(&S.cnt, (size_t)scap * 4));
     DdCounters *hc = (DdCounters *)((char *)ctx->h_scratch + 2048);
     int rc = SQ_OK;
     uint32_t lo = 0;
@@ -523,12 +522,6 @@ static int dedup_consume_range(sq_dedup *d, const uint64_t *hashes, uint32_t n) 
         d->mod_bits = m + 1;
         lo = r_star + 1;
     }
-    sq_dfree(ctx, cls);
-    sq_dfree(ctx, flag);
-    sq_dfree(ctx, rank);
-    sq_dfree(ctx, S.key);
-    sq_dfree(ctx, S.first);
-    sq_dfree(ctx, S.cnt);
     return rc;
 }
 
@@ -541,11 +534,12 @@ extern "C" int sq_dedup_add(sq_dedup *d, sq_batch *b) {
     if (b->n == 0) return SQ_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
     uint64_t *hashes = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&hashes, b->n * 8, false));
+    SqScratch scratch(ctx);
+    SQ_TRY(scratch.get(&hashes, b->n * 8));
     SQ_LAUNCH(ctx, k_dd_hash, sq_grid_for(ctx, b->n, DD_TPB, 16), DD_TPB, 0, b->view(), d->front_len,
               d->back_len, d->front_off, d->back_off, hashes);
     int rc = dedup_consume(d, hashes, (uint32_t)b->n);
-    if (!d->deferred) sq_dfree(ctx, hashes);
+    if (d->deferred && rc == SQ_OK) scratch.keep(hashes);  // a deferred estimator holds on to them
     return rc;
 }
 
@@ -564,11 +558,9 @@ extern "C" int sq_dedup_add_pair(sq_dedup *d, sq_batch *b1, sq_batch *b2) {
     const uint32_t n = (uint32_t)b1->n;
     uint64_t *hashes = nullptr;
     uint32_t *short_flag = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&hashes, (size_t)n * 8, false));
-    if (int rc = sq_dalloc(ctx, (void **)&short_flag, (size_t)n * 4, false)) {
-        sq_dfree(ctx, hashes);
-        return rc;
-    }
+    SqScratch scratch(ctx);
+    SQ_TRY(scratch.get(&hashes, (size_t)n * 8));
+    SQ_TRY(scratch.get(&short_flag, (size_t)n * 4));
     SQ_LAUNCH(ctx, k_dd_hash_pair, sq_grid_for(ctx, n, DD_TPB, 16), DD_TPB, 0, b1->view(), b2->view(),
               d->front_len, d->back_len, d->front_off, d->back_off, hashes, short_flag, d->pair_range);
     // short pairs hash what the previous pair left in the reference's scratch buffer (:4503-4516): one warp
@@ -576,8 +568,7 @@ extern "C" int sq_dedup_add_pair(sq_dedup *d, sq_batch *b1, sq_batch *b2) {
     SQ_LAUNCH(ctx, k_dd_hash_pair_ordered, 1, 1024, 0, b1->view(), b2->view(), d->front_len, d->back_len,
               d->front_off, d->back_off, hashes, short_flag, d->pair_range, d->stale_fp);
     int rc = dedup_consume(d, hashes, n);
-    if (!d->deferred) sq_dfree(ctx, hashes);
-    sq_dfree(ctx, short_flag);
+    if (d->deferred && rc == SQ_OK) scratch.keep(hashes);
     return rc;
 }
 
@@ -610,10 +601,11 @@ extern "C" int sq_dedup_read(sq_dedup *d, uint64_t *counts, uint64_t *n) {
     const uint32_t size = (uint32_t)d->table_size;
     uint32_t *flag = nullptr, *rank = nullptr, *total = nullptr;
     uint64_t *out = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&flag, (size_t)size * 4, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&rank, (size_t)size * 4 + 4, false));
+    SqScratch scratch(ctx);
+    SQ_TRY(scratch.get(&flag, (size_t)size * 4));
+    SQ_TRY(scratch.get(&rank, (size_t)size * 4 + 4));
     total = rank + size;
-    SQ_TRY(sq_dalloc(ctx, (void **)&out, (size_t)(d->stored + 1) * 8, false));
+    SQ_TRY(scratch.get(&out, (size_t)(d->stored + 1) * 8));
     const int grid = sq_grid_for(ctx, size, DD_TPB, 16);
     SQ_LAUNCH(ctx, k_dd_occupied, grid, DD_TPB, 0, d->tab.count, size, flag);
     SQ_TRY(sq_scan_exclusive_u32(ctx, flag, rank, size, total));
@@ -629,9 +621,6 @@ extern "C" int sq_dedup_read(sq_dedup *d, uint64_t *counts, uint64_t *n) {
     }
     if (got) SQ_TRY(sq_d2h_bounced(ctx, counts, out, got * 8));
     *n = got;
-    sq_dfree(ctx, flag);
-    sq_dfree(ctx, rank);
-    sq_dfree(ctx, out);
     return SQ_OK;
 }
 
@@ -664,11 +653,12 @@ extern "C" int sq_dedup_deferred_compact(sq_dedup *d, uint64_t mod_bits, uint64_
     const size_t n_arr = d->kept.size();
     std::vector<uint32_t *> flags(n_arr, nullptr), ranks(n_arr, nullptr);
     uint32_t *totals = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&totals, (n_arr + 1) * 4, true));
+    SqScratch scratch(ctx);
+    SQ_TRY(scratch.get(&totals, (n_arr + 1) * 4, true));
     for (size_t a = 0; a < n_arr; a++) {
         const uint32_t len = d->kept[a].n;
-        SQ_TRY(sq_dalloc(ctx, (void **)&flags[a], (size_t)len * 4, false));
-        SQ_TRY(sq_dalloc(ctx, (void **)&ranks[a], (size_t)len * 4, false));
+        SQ_TRY(scratch.get(&flags[a], (size_t)len * 4));
+        SQ_TRY(scratch.get(&ranks[a], (size_t)len * 4));
         SQ_LAUNCH(ctx, k_dd_pass_flags, sq_grid_for(ctx, len, DD_TPB, 16), DD_TPB, 0, d->kept[a].hashes, len, mask,
                   flags[a]);
         SQ_TRY(sq_scan_exclusive_u32(ctx, flags[a], ranks[a], len, totals + a));
@@ -687,12 +677,9 @@ extern "C" int sq_dedup_deferred_compact(sq_dedup *d, uint64_t mod_bits, uint64_
         SQ_LAUNCH(ctx, k_dd_pass_scatter, sq_grid_for(ctx, len, DD_TPB, 16), DD_TPB, 0, d->kept[a].hashes, flags[a],
                   ranks[a], len, d->compact + off);
         off += h_tot[a];
-        sq_dfree(ctx, flags[a]);
-        sq_dfree(ctx, ranks[a]);
         sq_dfree(ctx, d->kept[a].hashes);
     }
     d->kept.clear();
-    sq_dfree(ctx, totals);
     d->compact_n = total;
     *n = total;
     return SQ_OK;

@@ -1752,10 +1752,11 @@ static int fused_add_onewalk(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt
     long long *tile = nullptr;
     uint64_t *hashes = nullptr;
     uint8_t *cta_mixed = nullptr, *qh = nullptr, *oob = nullptr;
+    SqScratch scratch(ctx);
     int rc = SQ_OK;
     if (qc) {
         rc = qc_grow(qc, b->max_len);
-        if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&cta_mixed, g.grid, true);
+        if (rc == SQ_OK) rc = scratch.get(&cta_mixed, g.grid, true);
         A.do_qc = 1;
         A.gc = qc->gc;
         A.mean_phred = qc->mean_phred;
@@ -1778,7 +1779,7 @@ static int fused_add_onewalk(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt
         A.ad_cap_len = ad->cap_len;
     }
     if (rc == SQ_OK && dd) {
-        rc = sq_dalloc(ctx, (void **)&hashes, (size_t)n * 8, false);
+        rc = scratch.get(&hashes, (size_t)n * 8);
         A.do_dd = 1;
         A.front_len = dd->front_len;
         A.back_len = dd->back_len;
@@ -1788,14 +1789,14 @@ static int fused_add_onewalk(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt
     }
     const uint64_t pt_base = pt ? pt->n_added : 0;
     if (rc == SQ_OK && pt) {
-        rc = sq_dalloc(ctx, (void **)&tile, (size_t)n * 8, false);
+        rc = scratch.get(&tile, (size_t)n * 8);
         A.do_pt = 1;
         A.tile = tile;
         A.pt_base = pt_base;
         A.pt_st = pt->st;
         if (rc == SQ_OK && A.pt_rows) {
-            rc = sq_dalloc(ctx, (void **)&qh, (size_t)g.n_segs * g.hg.seg_bytes, false);
-            if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&oob, g.n_segs, true);
+            rc = scratch.get(&qh, (size_t)g.n_segs * g.hg.seg_bytes);
+            if (rc == SQ_OK) rc = scratch.get(&oob, g.n_segs, true);
             A.qh = qh;
             A.seg_oob = oob;
         }
@@ -1819,12 +1820,10 @@ static int fused_add_onewalk(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt
     // ---- table maintenance, in the reference's module order ------------------------------------
     if (pt) {
         PtPlan plan;
-        // (the plan takes over qh / oob and frees them)
-        if (rc == SQ_OK) rc = pt_prepare(pt, b, tile, A.pt_rows ? g.R * g.TS : 0, g.n_segs, g.W, g.hg, &plan, qh, oob);
-        else {
-            sq_dfree(ctx, qh);
-            sq_dfree(ctx, oob);
-            plan = PtPlan();
+        if (rc == SQ_OK) {  // (the plan takes over qh / oob and frees them)
+            scratch.keep(qh);
+            scratch.keep(oob);
+            rc = pt_prepare(pt, b, tile, A.pt_rows ? g.R * g.TS : 0, g.n_segs, g.W, g.hg, &plan, qh, oob);
         }
         if (rc == SQ_OK) rc = pt_finish(pt, b, &plan);
         else pt_plan_free(ctx, &plan);
@@ -1835,14 +1834,10 @@ static int fused_add_onewalk(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt
         ad->n_seqs += n;
         if (b->max_len > ad->max_len) ad->max_len = b->max_len;
     }
-    bool hashes_kept = false;
     if (rc == SQ_OK && dd) {
         rc = dedup_consume(dd, hashes, n);
-        hashes_kept = dd->deferred && rc == SQ_OK;  // a deferred estimator keeps them
+        if (dd->deferred && rc == SQ_OK) scratch.keep(hashes);  // a deferred estimator keeps them
     }
-    sq_dfree(ctx, tile);
-    if (!hashes_kept) sq_dfree(ctx, hashes);
-    sq_dfree(ctx, cta_mixed);
     return rc;
 }
 
@@ -1885,8 +1880,9 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     long long *tile = nullptr;
     uint64_t *hashes = nullptr;
     uint8_t *cta_mixed = nullptr, *all_acgt = nullptr;
+    SqScratch scratch(ctx);  // tile / hashes / cta_mixed / all_acgt leave with the function, whichever way
     if (qc) {
-        SQ_TRY(sq_dalloc(ctx, (void **)&all_acgt, n, false));
+        SQ_TRY(scratch.get(&all_acgt, n));
         A.all_acgt = all_acgt;
         A.do_qc = 1;
         A.gc = qc->gc;
@@ -1904,7 +1900,7 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
         A.ad_cap_len = ad->cap_len;
     }
     if (dd) {
-        SQ_TRY(sq_dalloc(ctx, (void **)&hashes, (size_t)n * 8, false));
+        SQ_TRY(scratch.get(&hashes, (size_t)n * 8));
         A.do_dd = 1;
         A.front_len = dd->front_len;
         A.back_len = dd->back_len;
@@ -1913,7 +1909,7 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
         A.hashes = hashes;
     }
     if (pt) {
-        SQ_TRY(sq_dalloc(ctx, (void **)&tile, (size_t)n * 8, false));
+        SQ_TRY(scratch.get(&tile, (size_t)n * 8));
         A.do_pt = 1;
         A.tile = tile;
         A.pt_base = pt->n_added;
@@ -1930,6 +1926,11 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     // and without (QCMetrics alone, or tiles in random order -> sort-based PerTileQuality)
     ColGeom g = col_geometry(ctx, b, 1, 0);
     PtPlan plan;
+    struct PlanGuard {
+        sq_ctx *ctx;
+        PtPlan *plan;
+        ~PlanGuard() { pt_plan_free(ctx, plan); }  // (a plan that pt_finish consumed is empty by then)
+    } plan_guard{ctx, &plan};
     const uint64_t pt_base = pt ? pt->n_added : 0;
     if (rc == SQ_OK && pt) {
         uint32_t qmin = 1, qmax = 0;
@@ -1958,7 +1959,7 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
         C.buf_bytes = g.buf_bytes;
         if (qc) {
             rc = qc_grow(qc, b->max_len);
-            if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&cta_mixed, g.grid, true);
+            if (rc == SQ_OK) rc = scratch.get(&cta_mixed, g.grid, true);
             C.do_qc = 1;
             C.base = qc->base;
             C.phred = qc->phred;
@@ -2006,9 +2007,6 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
         if (b->max_len > ad->max_len) ad->max_len = b->max_len;
     }
     if (rc == SQ_OK && dd) rc = dedup_consume(dd, hashes, n);
-    sq_dfree(ctx, tile);
-    if (!(dd && dd->deferred && rc == SQ_OK)) sq_dfree(ctx, hashes);  // a deferred estimator keeps them
-    sq_dfree(ctx, cta_mixed);
-    sq_dfree(ctx, all_acgt);
+    if (dd && dd->deferred && rc == SQ_OK) scratch.keep(hashes);  // a deferred estimator keeps them
     return rc;
 }

@@ -174,13 +174,16 @@ struct sq_dedup {
 int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n);
 
 // ---- NanoStats (nanostats.cu, report.cu) -----------------------------------------
+constexpr uint32_t NS_NAME_CAP = 1u << 16;
+
 struct NsState {  // device
     unsigned long long fail_idx;      // global index of the first unparsable header
-    unsigned long long tag_err_idx;   // global index of the first malformed aux block
+    unsigned long long tag_err_idx;   // first malformed aux block: record << 24 | kind << 16 | detail (NS_TAG_*), min
     unsigned long long pi_warnings;
     long long min_time, max_time;
     unsigned int nonpositive_time;    // a timestamp <= 0 exists (order-dependent min, see k_ns_minmax_ordered)
     unsigned int pad;
+    unsigned long long pi_first;      // first pi:Z tag that is not 36 characters long: record << 24 | its length, min
 };
 
 struct sq_nanostats {
@@ -191,8 +194,13 @@ struct sq_nanostats {
     bool skipped = false;          // known on the host after a sync
     uint64_t skipped_record = 0;
     std::vector<uint8_t> skipped_name;
-    // names of the newest arrays are needed for skipped_reason: keep (batch ptr, base) of pending adds
-    std::vector<std::pair<sq_batch *, uint64_t>> pending;
+    // the header that switches the module off is copied aside on the device while its record array is alive
+    // (k_ns_capture_name); the host learns about it without waiting: a copy of the state trails every add
+    uint8_t *d_name = nullptr;          // [NS_NAME_CAP]
+    uint32_t *d_name_len = nullptr;
+    NsState *h_peek = nullptr;          // pinned
+    cudaEvent_t peek_ev = nullptr;
+    bool peek_pending = false;
     // per-channel results of the last sq_nanostats_report, until sq_nanostats_report_channels fetches them
     uint64_t rp_n = 0;
     int32_t *rp_channel = nullptr;

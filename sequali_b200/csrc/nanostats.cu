@@ -85,31 +85,41 @@ __device__ __forceinline__ uint32_t rd32(const uint8_t *p) {
     return p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
 }
 
+// what went wrong in an aux block, as -(kind << 16 | detail): the reference's exceptions (:5080-5137, 5188-5195)
+constexpr int NS_TAG_TRUNCATED = 1;   // ValueError("truncated tags")
+constexpr int NS_TAG_ARRAY_TYPE = 2;  // ValueError("Invalid type for array %c"), detail = the type
+constexpr int NS_TAG_UNKNOWN = 3;     // ValueError("Unknown tag type %c"), detail = the type
+constexpr int NS_TAG_WRONG_TYPE = 4;  // RuntimeError("Wrong tag type for 'st' ..."), detail = tag (0 st, 1 du, 2 pi) << 8 | type
+constexpr int NS_TAG_CH_TYPE = 5;     // ch with a non-integer type: the reference returns -1 without an exception set
+__device__ __forceinline__ long long ns_tag_error(int kind, uint32_t detail = 0) { return -(long long)(kind << 16 | detail); }
+
 __device__ long long aux_len(const uint8_t *t, uint64_t avail) {  // :5078-5140
-    if (avail < 4) return -1;
+    if (avail < 4) return ns_tag_error(NS_TAG_TRUNCATED);
     uint8_t ty = t[2];
     uint64_t head = 3, count = 1, width;
+    bool is_array = false;
     if (ty == 'B') {
-        if (avail < 8) return -1;
+        if (avail < 8) return ns_tag_error(NS_TAG_TRUNCATED);
         ty = t[3];
         count = rd32(t + 4);
         head = 8;
-        if (ty == 'Z' || ty == 'H') return -1;
+        is_array = true;
     }
     switch (ty) {
         case 'A': case 'c': case 'C': width = 1; break;
         case 's': case 'S': width = 2; break;
         case 'i': case 'I': case 'f': width = 4; break;
         case 'Z': case 'H': {
+            if (is_array) return ns_tag_error(NS_TAG_ARRAY_TYPE, ty);
             const uint8_t *z = find_byte(t + 3, t + avail, 0);
-            if (!z) return -1;
+            if (!z) return ns_tag_error(NS_TAG_TRUNCATED);
             width = (uint64_t)(z - (t + 3)) + 1;
             break;
         }
-        default: return -1;
+        default: return ns_tag_error(NS_TAG_UNKNOWN, ty);
     }
     uint64_t len = head + count * width;
-    return len > avail ? -1 : (long long)len;
+    return len > avail ? ns_tag_error(NS_TAG_TRUNCATED) : (long long)len;
 }
 
 // strtoull(s, &end, 16) consuming exactly 8 bytes (blanks, sign, 0x prefix accepted like libc)
@@ -143,14 +153,15 @@ __device__ uint64_t uuid4_hash(const uint8_t *u) {  // :5153-5179
     return a << 32 | (b & 0xffffffffULL);
 }
 
-__device__ int nano_tags(const uint8_t *t, uint64_t n, sq_nanoinfo *o, unsigned long long *pi_warn) {
+// 0, or kind << 16 | detail of the first defect
+__device__ int nano_tags(const uint8_t *t, uint64_t n, sq_nanoinfo *o, NsState *st, uint64_t record) {
     o->channel_id = -1;
     o->duration = 0.0f;
     o->start_time = 0;
     o->parent_id_hash = 0;
     while (n) {
         long long len = aux_len(t, n);
-        if (len < 0) return -1;
+        if (len < 0) return (int)-len;
         uint8_t ty = t[2];
         if (t[0] == 'c' && t[1] == 'h') {
             const uint8_t *v = t + 3;
@@ -160,20 +171,23 @@ __device__ int nano_tags(const uint8_t *t, uint64_t n, sq_nanoinfo *o, unsigned 
                 case 's': o->channel_id = (int16_t)rd16(v); break;
                 case 'S': o->channel_id = (int32_t)rd16(v); break;
                 case 'i': case 'I': o->channel_id = (int32_t)rd32(v); break;
-                default: return -1;
+                default: return NS_TAG_CH_TYPE << 16;
             }
         }
         else if (t[0] == 's' && t[1] == 't') {
-            if (ty != 'Z') return -1;
+            if (ty != 'Z') return NS_TAG_WRONG_TYPE << 16 | 0 << 8 | ty;
             o->start_time = nanopore_time(t + 3, t + len);
         }
         else if (t[0] == 'd' && t[1] == 'u') {
-            if (ty != 'f') return -1;
+            if (ty != 'f') return NS_TAG_WRONG_TYPE << 16 | 1 << 8 | ty;
             o->duration = __uint_as_float(rd32(t + 3));
         }
         else if (t[0] == 'p' && t[1] == 'i') {
-            if (ty != 'Z') return -1;
-            if (len - 4 != 36) atomicAdd(pi_warn, 1ULL);
+            if (ty != 'Z') return NS_TAG_WRONG_TYPE << 16 | 2 << 8 | ty;
+            if (len - 4 != 36) {
+                atomicAdd(&st->pi_warnings, 1ULL);
+                atomicMin(&st->pi_first, (unsigned long long)record << 24 | (unsigned long long)min((long long)0xffffff, len - 4));
+            }
             else o->parent_id_hash = uuid4_hash(t + 3);
         }
         t += len;
@@ -197,8 +211,8 @@ k_ns_parse(BatchView bv, sq_nanoinfo *out, uint64_t base, NsState *st) {
         info.parent_id_hash = 0;
         const uint32_t tl = bv.tags_len ? bv.tags_len[r] : 0;
         if (tl) {
-            if (nano_tags(bv.text + bv.tags_off[r], tl, &info, &st->pi_warnings))
-                atomicMin(&st->tag_err_idx, (unsigned long long)(base + r));
+            const int defect = nano_tags(bv.text + bv.tags_off[r], tl, &info, st, base + r);
+            if (defect) atomicMin(&st->tag_err_idx, (unsigned long long)(base + r) << 24 | (unsigned)defect);
         }
         else {
             const uint32_t nl = bv.name_len ? bv.name_len[r] : bv.seq_off[r] - 1 - bv.name_off[r];
@@ -215,6 +229,18 @@ k_ns_parse(BatchView bv, sq_nanoinfo *out, uint64_t base, NsState *st) {
         info.cumulative_error_rate = bv.err_sum[r];
         out[base + r] = info;
     }
+}
+
+// the header that switched the module off, if it lies in this record array: copied aside for skipped_reason
+__global__ void __launch_bounds__(256)
+k_ns_capture_name(BatchView bv, uint64_t base, const NsState *st, uint8_t *name, uint32_t *name_len) {
+    const unsigned long long fail = st->fail_idx;
+    if (fail < base || fail >= base + bv.n) return;
+    const uint32_t r = (uint32_t)(fail - base);
+    const uint32_t nl = min(NS_NAME_CAP, bv.name_len ? bv.name_len[r] : bv.seq_off[r] - 1 - bv.name_off[r]);
+    const uint8_t *src = bv.text + bv.name_off[r];
+    for (uint32_t i = threadIdx.x; i < nl; i += blockDim.x) name[i] = src[i];
+    if (threadIdx.x == 0) *name_len = nl;
 }
 
 // min/max start time over the first n kept records
@@ -258,11 +284,16 @@ extern "C" int sq_nanostats_create(sq_ctx *ctx, sq_nanostats **out) {
     sq_nanostats *s = new sq_nanostats();
     s->ctx = ctx;
     int rc = sq_dalloc(ctx, (void **)&s->st, sizeof(NsState), true);
+    if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&s->d_name, NS_NAME_CAP, false);
+    if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&s->d_name_len, 4, true);
+    if (rc == SQ_OK && cudaMallocHost((void **)&s->h_peek, sizeof(NsState)) != cudaSuccess) rc = SQ_E_CUDA;
+    if (rc == SQ_OK && cudaEventCreateWithFlags(&s->peek_ev, cudaEventDisableTiming) != cudaSuccess) rc = SQ_E_CUDA;
     if (rc == SQ_OK) {
         NsState init;
         memset(&init, 0, sizeof(init));
         init.fail_idx = ~0ULL;
         init.tag_err_idx = ~0ULL;
+        init.pi_first = ~0ULL;
         // same stream as the zero-fill above, so the two cannot swap
         rc = cudaMemcpyAsync(s->st, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
                      cudaStreamSynchronize(ctx->stream) == cudaSuccess
@@ -281,10 +312,40 @@ extern "C" void sq_nanostats_destroy(sq_nanostats *s) {
     cudaSetDevice(s->ctx->device);
     sq_dfree(s->ctx, s->infos);
     sq_dfree(s->ctx, s->st);
+    sq_dfree(s->ctx, s->d_name);
+    sq_dfree(s->ctx, s->d_name_len);
+    if (s->peek_ev) {
+        cudaEventSynchronize(s->peek_ev);
+        cudaEventDestroy(s->peek_ev);
+    }
+    if (s->h_peek) cudaFreeHost(s->h_peek);
     sq_dfree(s->ctx, s->rp_channel);
     sq_dfree(s->ctx, s->rp_bases);
     sq_dfree(s->ctx, s->rp_error);
     delete s;
+}
+
+// the device has met a header it cannot parse: record index and the header itself to the host (synchronises)
+static int ns_learn_skip(sq_nanostats *s, unsigned long long fail_idx) {
+    sq_ctx *ctx = s->ctx;
+    uint32_t len = 0;
+    SQ_TRY(sq_memcpy_d2h(ctx, &len, s->d_name_len, 4));
+    s->skipped_name.resize(len);
+    if (len) SQ_TRY(sq_memcpy_d2h(ctx, s->skipped_name.data(), s->d_name, len));
+    s->skipped = true;
+    s->skipped_record = fail_idx;
+    return SQ_OK;
+}
+
+// everything enqueued so far is done and the host knows whether the module switched itself off
+static int ns_settle(sq_nanostats *s) {
+    sq_ctx *ctx = s->ctx;
+    NsState *h = (NsState *)((char *)ctx->h_scratch + 2560);
+    CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    s->peek_pending = false;
+    if (!s->skipped && h->fail_idx != ~0ULL) SQ_TRY(ns_learn_skip(s, h->fail_idx));
+    return SQ_OK;
 }
 
 extern "C" int sq_nanostats_add(sq_nanostats *s, sq_batch *b) {
@@ -295,8 +356,13 @@ extern "C" int sq_nanostats_add(sq_nanostats *s, sq_batch *b) {
     }
     if (s->skipped || b->n == 0) return SQ_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    // Cheap early out for non-nanopore input: once the device has reported an
-    // unparsable header there is nothing left to do.  Peek without blocking.
+    if (s->peek_pending && cudaEventQuery(s->peek_ev) == cudaSuccess) {  // what an earlier add found out
+        s->peek_pending = false;
+        if (s->h_peek->fail_idx != ~0ULL) {
+            SQ_TRY(ns_learn_skip(s, s->h_peek->fail_idx));
+            return SQ_OK;
+        }
+    }
     if (s->n_added + b->n > s->cap) {
         uint64_t cap = s->cap ? s->cap : 16384;
         while (cap < s->n_added + b->n) cap *= 2;
@@ -309,16 +375,14 @@ extern "C" int sq_nanostats_add(sq_nanostats *s, sq_batch *b) {
         s->cap = cap;
     }
     SQ_LAUNCH(ctx, k_ns_parse, sq_grid_for(ctx, b->n, NS_TPB, 16), NS_TPB, 0, b->view(), s->infos, s->n_added, s->st);
-    // the name of the record that switches the module off is wanted for
-    // skipped_reason: find out now while the array is still alive
-    NsState *h = (NsState *)((char *)ctx->h_scratch + 2560);
-    CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (h->fail_idx != ~0ULL) {
-        s->skipped = true;
-        s->skipped_record = h->fail_idx;
-        uint64_t r = h->fail_idx - s->n_added;
-        SQ_TRY(sq_batch_get_name(b, r, s->skipped_name));
+    // the name of the record that switches the module off is wanted for skipped_reason: copied aside on the
+    // device while the array is alive; a copy of the state trails behind so that a later add can tell, without
+    // waiting, that there is nothing left to do
+    SQ_LAUNCH(ctx, k_ns_capture_name, 1, 256, 0, b->view(), s->n_added, s->st, s->d_name, s->d_name_len);
+    if (!s->peek_pending) {
+        CUDA_TRY(cudaMemcpyAsync(s->h_peek, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaEventRecord(s->peek_ev, ctx->stream));
+        s->peek_pending = true;
     }
     s->n_added += b->n;
     return SQ_OK;
@@ -328,6 +392,7 @@ extern "C" int sq_nanostats_sync(sq_nanostats *s, sq_nanostats_info *info) {
     sq_ctx *ctx = s->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     memset(info, 0, sizeof(*info));
+    SQ_TRY(ns_settle(s));
     const uint64_t n = s->skipped ? s->skipped_record : s->n_added;
     NsState *h = (NsState *)((char *)ctx->h_scratch + 2560);
     // recompute min/max over the kept prefix
@@ -348,9 +413,11 @@ extern "C" int sq_nanostats_sync(sq_nanostats *s, sq_nanostats_info *info) {
     info->maximum_time = n ? h->max_time : 0;
     info->skipped = s->skipped;
     info->skipped_record = s->skipped_record;
-    info->tag_error = h->tag_err_idx != ~0ULL;
-    info->tag_error_record = h->tag_err_idx;
+    info->tag_error = h->tag_err_idx != ~0ULL ? (int32_t)(h->tag_err_idx >> 16 & 0xff) : 0;
+    info->tag_error_record = h->tag_err_idx >> 24;
+    info->tag_error_detail = (uint32_t)(h->tag_err_idx & 0xffff);
     info->pi_warnings = h->pi_warnings;
+    info->pi_first_length = h->pi_first != ~0ULL ? (uint32_t)(h->pi_first & 0xffffff) : 0;
     return SQ_OK;
 }
 
@@ -364,6 +431,7 @@ extern "C" int sq_nanostats_skipped_name(sq_nanostats *s, uint8_t *out, uint64_t
 extern "C" int sq_nanostats_read(sq_nanostats *s, sq_nanoinfo *out) {
     sq_ctx *ctx = s->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    SQ_TRY(ns_settle(s));
     const uint64_t n = s->skipped ? s->skipped_record : s->n_added;
     if (n) CUDA_TRY(cudaMemcpyAsync(out, s->infos, n * sizeof(sq_nanoinfo), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -378,7 +446,7 @@ extern "C" int sq_nanostats_read(sq_nanostats *s, sq_nanoinfo *out) {
 extern "C" int sq_nanostats_allgather(sq_nanostats *s, sq_comm *c, uint64_t first_record) {
     sq_ctx *ctx = s->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SQ_TRY(ns_settle(s));
     const int rank = sq_comm_rank(c), world = sq_comm_world(c);
     const uint64_t NONE = 1ULL << 62;
     uint64_t fail = s->skipped ? first_record + s->skipped_record : NONE;
@@ -419,12 +487,18 @@ extern "C" int sq_nanostats_allgather(sq_nanostats *s, sq_comm *c, uint64_t firs
     NsState *h = (NsState *)((char *)ctx->h_scratch + 2560);
     CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    uint64_t pi = h->pi_warnings, tag_err = h->tag_err_idx == ~0ULL ? NONE : first_record + h->tag_err_idx;
+    auto global_key = [&](unsigned long long key) {  // record index of this shard -> of the whole stream
+        return key == ~0ULL ? NONE : ((first_record + (key >> 24)) << 24 | (key & 0xffffff));
+    };
+    uint64_t pi = h->pi_warnings, tag_err = global_key(h->tag_err_idx), pi_first = global_key(h->pi_first);
     SQ_TRY(sq_comm_allreduce_host_u64(c, &pi, 1, 0));
     SQ_TRY(sq_comm_allreduce_host_u64(c, &tag_err, 1, 2));
+    SQ_TRY(sq_comm_allreduce_host_u64(c, &pi_first, 1, 2));
     h->pi_warnings = pi;
     h->tag_err_idx = tag_err == NONE ? ~0ULL : tag_err;
+    h->pi_first = pi_first == NONE ? ~0ULL : pi_first;
     CUDA_TRY(cudaMemcpyAsync(&s->st->tag_err_idx, &h->tag_err_idx, 16, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&s->st->pi_first, &h->pi_first, 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     sq_dfree(ctx, s->infos);
     s->infos = merged;

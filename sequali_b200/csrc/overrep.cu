@@ -477,19 +477,19 @@ extern "C" int sq_overrep_add(sq_overrep *o, sq_batch *b) {
     }
     uint64_t *frag_hash = nullptr;
     uint32_t *frag_n = nullptr;
-    SQ_TRY(sq_dalloc(ctx, (void **)&frag_hash, occ * 8, false));
-    SQ_TRY(sq_dalloc(ctx, (void **)&frag_n, n_sampled * 4, false));
+    SqScratch scratch(ctx);
+    SQ_TRY(scratch.get(&frag_hash, occ * 8));
+    SQ_TRY(scratch.get(&frag_n, n_sampled * 4));
     SQ_LAUNCH(ctx, k_ov_fragments, sq_grid_for(ctx, n_sampled, OV_TPB, 16), OV_TPB, 0, b->view(), (uint32_t)first,
               (uint32_t)se, (uint32_t)n_sampled, (uint32_t)o->k, o->frags_front, o->frags_back, fcap, frag_hash,
               frag_n, o->cnt, record_base);
     if (o->deferred) {
         o->kept.push_back({frag_hash, frag_n, n_sampled, total, fcap});
+        scratch.keep(frag_hash);
+        scratch.keep(frag_n);
         return SQ_OK;
     }
-    int rc = ov_apply(o, frag_hash, frag_n, n_sampled, total, fcap);
-    sq_dfree(ctx, frag_hash);
-    sq_dfree(ctx, frag_n);
-    return rc;
+    return ov_apply(o, frag_hash, frag_n, n_sampled, total, fcap);
 }
 
 extern "C" int sq_overrep_sync(sq_overrep *o, sq_overrep_info *info) {

@@ -1540,13 +1540,26 @@ int NS_sync(Skippable *self, sq_nanostats_info *info) {
     rc = sq_nanostats_sync((sq_nanostats *)self->h, info);
     Py_END_ALLOW_THREADS
     SQ_CHECK_INT(rc, "sq_nanostats_sync");
-    if (info->tag_error) {
-        PyErr_SetString(PyExc_ValueError, "truncated tags");
+    if (info->tag_error) {  // the reference's exceptions for malformed aux data (:5078-5259)
+        const int got = (int)(info->tag_error_detail & 0xff);
+        static const char *tags[] = {"st", "du", "pi"};
+        static const char expected[] = {'Z', 'f', 'Z'};
+        const unsigned which = std::min<unsigned>(info->tag_error_detail >> 8, 2);
+        switch (info->tag_error) {
+        case 2: PyErr_Format(PyExc_ValueError, "Invalid type for array %c", got); break;
+        case 3: PyErr_Format(PyExc_ValueError, "Unknown tag type %c", got); break;
+        case 4: PyErr_Format(PyExc_RuntimeError, "Wrong tag type for '%s' expected '%c' got '%c'", tags[which], expected[which], got); break;
+        case 5:
+            PyErr_SetString(PyExc_SystemError, "error return without exception set");
+            break;
+        default: PyErr_SetString(PyExc_ValueError, "truncated tags");
+        }
         return -1;
     }
     if (info->pi_warnings > self->warned) {
         self->warned = info->pi_warnings;
-        if (PyErr_WarnEx(PyExc_UserWarning, "pi tag should have a valid uuid4 format with 36 characters. Skipping tag.", 1) < 0)
+        if (PyErr_WarnFormat(PyExc_UserWarning, 1, "pi tag should have a valid uuid4 format with 36 characters. Counted %u. Skipping tag.",
+                             info->pi_first_length) < 0)
             return -1;
     }
     if (info->skipped && !self->reason) {

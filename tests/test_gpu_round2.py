@@ -189,3 +189,81 @@ def test_extension_read_ahead_keeps_the_record_stream(ext, sq):
     assert len(got) == 2 and got[0] == got[1]
     bam = synth.nanopore_ubam(400, mean_length=8000, max_length=100_000, seed=42)
     assert [len(a) for a in ext.BamParser(io.BytesIO(bam), 1 << 20)] == [len(a) for a in sq.BamParser(io.BytesIO(bam), 1 << 20)]
+
+
+def _impl(name):
+    if name == "extension":
+        import sequali_b200.ext
+        return sequali_b200.ext
+    import sequali_b200
+    return sequali_b200
+
+
+# ---- NanoStats: malformed aux data raises what the reference raises (_qcmodule.c:5078-5259) ----
+@pytest.mark.parametrize("impl", ["ctypes", "extension"])
+@pytest.mark.parametrize("tags", [b"xxX\1", b"xxBZ\1\0\0\0a\0", b"sti\1\0\0\0", b"duZabc\0", b"pii\1\0\0\0",
+                                  b"chf\0\0\0\0", b"chi\1\0", b"xxZabc", b"xxBi\xff\0\0\0"])
+def test_nanostats_tag_errors_are_the_references(impl, tags):
+    import struct  # noqa: F401
+    import warnings
+    from sequali_b200 import synth
+    ref = H.import_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref is not built")
+    sq = _impl(impl)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)
+    good = b"chS\x05\x00" + b"stZ2024-01-01T00:00:00Z\0"
+    raw = synth.bam_header() + b"".join(
+        synth.bam_record(b"r%d" % i, seq, np.full(4, 50, np.uint8), tags if i == 3 else good) for i in range(6))
+    outcomes = []
+    for mod in (ref, sq):
+        ns = mod.NanoStats()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                for arr in mod.BamParser(io.BytesIO(raw)):
+                    ns.add_record_array(arr)
+                outcomes.append(("ok", ns.number_of_reads))
+            except BaseException as e:  # noqa: BLE001
+                outcomes.append((type(e).__name__, str(e)))
+    assert outcomes[0] == outcomes[1] and outcomes[0][0] != "ok"
+
+
+@pytest.mark.parametrize("impl", ["ctypes", "extension"])
+def test_nanostats_pi_warning_names_the_length(impl):
+    import warnings
+    from sequali_b200 import synth
+    sq = _impl(impl)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)
+    raw = synth.bam_header() + b"".join(
+        synth.bam_record(b"r%d" % i, seq, np.full(4, 50, np.uint8), b"chS\x05\x00" + (b"piZabcdef\0" if i == 2 else b""))
+        for i in range(4))
+    ns = sq.NanoStats()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        for arr in sq.BamParser(io.BytesIO(raw)):
+            ns.add_record_array(arr)
+        assert ns.number_of_reads == 4
+    assert [str(x.message) for x in w] == ["pi tag should have a valid uuid4 format with 36 characters. Counted 6. Skipping tag."]
+
+
+@pytest.mark.parametrize("impl", ["ctypes", "extension"])
+def test_nanostats_skipped_reason_is_learned_without_waiting(impl):
+    """Record arrays keep arriving after the header that switches NanoStats off: the reason names that header and
+    the counters stop there, whichever add notices it."""
+    from sequali_b200 import synth
+    ref = H.import_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref is not built")
+    sq = _impl(impl)
+    nano = synth.nanopore_fastq(300, mean_length=400, max_length=3000, seed=81)
+    lines = nano.split(b"\n")
+    lines[4 * 170] = b"@not a nanopore header"
+    text = b"\n".join(lines)
+    got = []
+    for mod in (ref, sq):
+        ns = mod.NanoStats()
+        for arr in mod.FastqParser(io.BytesIO(text), 20_000):
+            ns.add_record_array(arr)
+        got.append((ns.skipped_reason, ns.number_of_reads, ns.minimum_time, ns.maximum_time))
+    assert got[0] == got[1] and "not a nanopore header" in got[0][0]
