@@ -225,7 +225,8 @@ def test_nanostats_tag_errors_are_the_references(impl, tags):
                     ns.add_record_array(arr)
                 outcomes.append(("ok", ns.number_of_reads))
             except BaseException as e:  # noqa: BLE001
-                outcomes.append((type(e).__name__, str(e)))
+                # (the text of a SystemError is CPython's, and depends on how the method was called)
+                outcomes.append((type(e).__name__, "" if isinstance(e, SystemError) else str(e)))
     assert outcomes[0] == outcomes[1] and outcomes[0][0] != "ok"
 
 
