@@ -45,6 +45,13 @@ struct sq_ctx {
     // (SqParserScope below), so their host synchronisations do not wait for the collectors' kernels.
     // One collector thread + one parser thread per context is the supported concurrency.
     cudaStream_t pstream = nullptr;
+    // Table stream: PerTileQuality's ordered-sum kernel of a record array (a string of dependent round trips:
+    // latency bound) runs here beside the hash-table kernels of OverrepresentedSequences / DedupEstimator on
+    // the launch stream (latency and atomics bound as well); sq_fused_add forks after the per-position pass
+    // and joins before it returns, so everything else stays ordered on the launch stream.
+    cudaStream_t tstream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool pool_primed = false;  // sq_prime_pool ran
     std::atomic<uint64_t> launches{0};
     std::mutex prof_mutex;
     // pinned scratch for small device->host result structs
@@ -78,6 +85,14 @@ void sq_prof_end(sq_ctx *ctx);
 // parser entry point
 extern thread_local cudaStream_t sq_tls_stream;
 inline cudaStream_t sq_cur_stream(const sq_ctx *ctx) { return sq_tls_stream ? sq_tls_stream : ctx->stream; }
+// work of the calling thread goes to stream `s` inside the scope (nullptr: no change)
+struct SqStreamScope {
+    cudaStream_t prev;
+    explicit SqStreamScope(cudaStream_t s) : prev(sq_tls_stream) {
+        if (s) sq_tls_stream = s;
+    }
+    ~SqStreamScope() { sq_tls_stream = prev; }
+};
 struct SqParserScope {
     cudaStream_t prev;
     // (while per-kernel profiling is on everything stays on the launch stream: its events are ordered)
@@ -130,6 +145,12 @@ int sq_d2h_bounced(sq_ctx *ctx, void *dst, const void *dev_src, size_t nbytes);
 
 // name bytes of record r of a record array (host copy; rare paths only)
 int sq_batch_get_name(sq_batch *b, uint64_t r, std::vector<uint8_t> &out);
+
+// Large inputs: reserve device memory for the stream-ordered pool in ONE piece before the first big record
+// array is processed.  The pool otherwise grows in many steps over the first passes, whenever a scratch block
+// does not fit the fragments it holds, and a growth step costs 10-800 ms of host time on a virtualised box
+// (measured: cudaMallocAsync of 121 MB taking 832 ms in the eighth pass over the same data).
+int sq_prime_pool(sq_ctx *ctx, uint64_t records_per_array);
 
 // stream-ordered allocation helpers (cudaMallocAsync on the context stream)
 int sq_dalloc(sq_ctx *ctx, void **p, size_t nbytes, bool zero);

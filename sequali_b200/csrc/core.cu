@@ -15,6 +15,8 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <chrono>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -51,11 +53,48 @@ extern "C" int sq_device_count(void) {
 int sq_dalloc(sq_ctx *ctx, void **p, size_t nbytes, bool zero) {
     *p = nullptr;
     if (nbytes == 0) nbytes = 16;
+    static const bool trace = getenv("SQ_TRACE_ALLOC") != nullptr;
+    if (trace) {
+        const auto t0 = std::chrono::steady_clock::now();
+        cudaError_t e = cudaMallocAsync(p, nbytes, sq_cur_stream(ctx));
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 2.0) fprintf(stderr, "[sq] cudaMallocAsync(%zu bytes) took %.1f ms\n", nbytes, ms);
+        if (e != cudaSuccess) return sq_cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+    }
+    else
     CUDA_TRY(cudaMallocAsync(p, nbytes, sq_cur_stream(ctx)));
     if (zero) CUDA_TRY(cudaMemsetAsync(*p, 0, nbytes, sq_cur_stream(ctx)));
     return SQ_OK;
 }
+int sq_prime_pool(sq_ctx *ctx, uint64_t records_per_array) {
+    if (ctx->pool_primed || records_per_array < (1u << 20)) return SQ_OK;
+    ctx->pool_primed = true;
+    static const bool off = getenv("SQ_NO_POOL_PRIME") != nullptr;
+    if (off) return SQ_OK;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    // scratch of one record array is ~300 B per record over all collectors; three arrays are in flight
+    uint64_t want = records_per_array * 1024;
+    if (want > free_b / 4) want = free_b / 4;
+    if (want < (256u << 20)) return SQ_OK;
+    void *p = nullptr;
+    if (cudaMallocAsync(&p, want, ctx->stream) != cudaSuccess) {
+        cudaGetLastError();  // not fatal: the pool grows on demand instead
+        return SQ_OK;
+    }
+    CUDA_TRY(cudaFreeAsync(p, ctx->stream));
+    return SQ_OK;
+}
+
 void sq_dfree(sq_ctx *ctx, void *p) {
+    static const bool trace = getenv("SQ_TRACE_ALLOC") != nullptr;
+    if (p && trace) {
+        const auto t0 = std::chrono::steady_clock::now();
+        cudaFreeAsync(p, sq_cur_stream(ctx));
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 2.0) fprintf(stderr, "[sq] cudaFreeAsync took %.1f ms\n", ms);
+        return;
+    }
     if (p) cudaFreeAsync(p, sq_cur_stream(ctx));
 }
 
@@ -116,8 +155,13 @@ extern "C" int sq_ctx_create(int device, sq_ctx **out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->num_sms = prop.multiProcessorCount;
+    // (equal priorities on purpose: with the parser stream below the launch stream the scan of the next record
+    // array never overlaps the collectors' kernels and the read-ahead hides nothing -- measured)
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->pstream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->tstream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     // keep freed blocks in the pool: record arrays come and go every batch
     cudaMemPool_t pool;
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -140,7 +184,16 @@ extern "C" int sq_ctx_create(int device, sq_ctx **out) {
 extern "C" void sq_ctx_destroy(sq_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (getenv("SQ_TRACE_ALLOC")) {
+        cudaMemPool_t pool;
+        uint64_t reserved = 0, used = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemHigh, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &used) == cudaSuccess)
+            fprintf(stderr, "[sq] memory pool high water marks: reserved %.2f GB, in use %.2f GB\n", reserved / 1e9, used / 1e9);
+    }
     cudaStreamSynchronize(ctx->pstream);
+    cudaStreamSynchronize(ctx->tstream);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_err_table);
     cudaFree(ctx->d_phred_thresholds);
@@ -151,7 +204,10 @@ extern "C" void sq_ctx_destroy(sq_ctx *ctx) {
     if (ctx->h_bounce) cudaFreeHost(ctx->h_bounce);
     for (int k = 0; k < 3; k++) cudaFree(ctx->stage_slot[k]);
     cudaFreeHost(ctx->h_scratch);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
     cudaStreamDestroy(ctx->pstream);
+    cudaStreamDestroy(ctx->tstream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -1850,6 +1850,7 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     }
     if (b->n == 0) return SQ_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    SQ_TRY(sq_prime_pool(ctx, b->n));
     if (pt && pt->skipped) pt = nullptr;
     if (!fused_eligible(b, ad) || !(qc || pt || ad || dd)) {
         // the reference's module order (__main__.py:280-306)
@@ -1996,8 +1997,23 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
         b->err_sum_valid = true;
     }
     // ---- table maintenance, in the reference's module order ------------------------------------
+    // PerTileQuality's chain kernel (run path) forks to the table stream and runs beside the hash-table kernels
+    // below; the launch stream joins it before this function returns (nothing else ever sees the fork)
+    static const bool no_fork = getenv("SQ_NO_TABLE_STREAM") != nullptr;
+    bool forked = false;
     if (pt) {
-        if (rc == SQ_OK) rc = pt_finish(pt, b, &plan);
+        if (rc == SQ_OK) {
+            forked = plan.work && plan.runs && !ctx->profile && !no_fork && sq_cur_stream(ctx) == ctx->stream && (ov || dd);
+            if (forked) {
+                CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+                CUDA_TRY(cudaStreamWaitEvent(ctx->tstream, ctx->ev_fork, 0));
+            }
+            {
+                SqStreamScope on_table_stream(forked ? ctx->tstream : nullptr);
+                rc = pt_finish(pt, b, &plan);
+            }
+            if (forked) CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->tstream));
+        }
         else pt_plan_free(ctx, &plan);
     }
     if (rc == SQ_OK && ov) rc = sq_overrep_add(ov, b);
@@ -2008,5 +2024,7 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     }
     if (rc == SQ_OK && dd) rc = dedup_consume(dd, hashes, n);
     if (dd && dd->deferred && rc == SQ_OK) scratch.keep(hashes);  // a deferred estimator keeps them
+    if (forked && cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0) != cudaSuccess && rc == SQ_OK)
+        rc = sq_cuda_fail(cudaGetLastError(), "join of the table stream", __FILE__, __LINE__);
     return rc;
 }
