@@ -51,7 +51,7 @@ struct sq_ctx {
     // and joins before it returns, so everything else stays ordered on the launch stream.
     cudaStream_t tstream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool pool_primed = false;  // sq_prime_pool ran
+    std::atomic<bool> pool_primed{false};  // sq_prime_pool ran
     std::atomic<uint64_t> launches{0};
     std::mutex prof_mutex;
     // pinned scratch for small device->host result structs

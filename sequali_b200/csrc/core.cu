@@ -67,8 +67,7 @@ int sq_dalloc(sq_ctx *ctx, void **p, size_t nbytes, bool zero) {
     return SQ_OK;
 }
 int sq_prime_pool(sq_ctx *ctx, uint64_t records_per_array) {
-    if (ctx->pool_primed || records_per_array < (1u << 20)) return SQ_OK;
-    ctx->pool_primed = true;
+    if (records_per_array < (1u << 20) || ctx->pool_primed.exchange(true)) return SQ_OK;
     static const bool off = getenv("SQ_NO_POOL_PRIME") != nullptr;
     if (off) return SQ_OK;
     size_t free_b = 0, total_b = 0;
@@ -898,6 +897,7 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
         rc = SQ_E_FORMAT;
     }
     b->n = n_rec;
+    if (rc == SQ_OK) rc = sq_prime_pool(ctx, n_rec);  // (large inputs: before the collectors' scratch comes and goes)
     b->max_len = info->max_seq_len;
     b->max_rec_bytes = hst->max_rec_bytes;
     b->text_end = info->consumed;
