@@ -643,10 +643,15 @@ def run_cuda(args):
     launches0 = ctx.launch_count
     ctx.timer_start()
     t0 = time.perf_counter()
+    step_ends = []
     for _ in range(args.steps):
         d2h, summary = step_resident()
+        step_ends.append(time.perf_counter())  # (a step ends with its getters: the host has waited for the device)
     barrier()
     ms = ctx.timer_stop()
+    ms_each_step = [round((b - a) * 1e3, 2) for a, b in zip([t0] + step_ends[:-1], step_ends)]
+    if world > 1:
+        print(f"[bench] rank {rank}: ms of each timed step (host clock): {ms_each_step}", file=sys.stderr, flush=True)
     wall = time.perf_counter() - t0
     sharded_resident = dict(sharded_ms)
     clocks = sampler.finish()
@@ -774,11 +779,43 @@ def run_cuda(args):
             tables, nbytes, _ = read_results(mods)
             return nbytes
 
+        step_fileobj()  # warm-up (staging buffers, the pool's reserve)
         dt2, _ = timed(step_fileobj, 1)
         e2e["fileobj_api"] = {"value": round(world * e2e_reads * READ_LENGTH / dt2 / 1e9, 4), "unit": "Gbases/s",
                               "buffersize": args.buffersize,
-                              "path": "sequali._qc extension: FastqParser(host file object).readinto (one host memcpy "
+                              "path": ("sequali._qc extension: " if world == 1 else "ctypes mirror + sharded merges: ") +
+                                      "FastqParser(in-memory file object).readinto (one host memcpy "
                                       "per byte, single thread) -> pinned staging -> H2D -> kernels -> getters"}
+        # (2b) the same through a REGULAR FILE, open(path, "rb"), what the CLI hands the parser for an uncompressed
+        #      input: the extension fetches the bytes with pread() from several threads (page cache -> pinned staging)
+        if world == 1:
+            import shutil
+            import tempfile
+            where = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+            room = shutil.disk_usage(where).free
+            n_file = len(host) if room > len(host) + (2 << 30) else 0
+            if n_file:
+                fd, path = tempfile.mkstemp(prefix="sq_bench_", suffix=".fastq", dir=where)
+                try:
+                    with os.fdopen(fd, "wb") as f:
+                        f.write(memoryview(host))
+
+                    def step_file():
+                        mods = make_modules(sqx)
+                        with open(path, "rb") as f:
+                            for arr in sqx.FastqParser(f, args.buffersize):
+                                feed(mods, arr)
+                        return read_results(mods)[1]
+
+                    step_file()
+                    dt3, _ = timed(step_file, 2)
+                    e2e["fileobj_api"]["regular_file"] = {
+                        "value": round(e2e_reads * READ_LENGTH / dt3 / 1e9, 4), "unit": "Gbases/s",
+                        "file_gbs": round(n_file / dt3 / 1e9, 2),
+                        "path": f"open(path, 'rb') on {where} (page cache) -> FastqParser: pread from up to 8 threads into "
+                                "pinned staging, one record array read ahead -> H2D -> kernels -> getters"}
+                finally:
+                    os.unlink(path)
         del host
 
         # (3) the same host text as BGZF members (what bgzip writes): the compressed bytes cross PCIe and are
@@ -804,6 +841,7 @@ def run_cuda(args):
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": "Gbases/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
+            "ms_each_step_rank0_host_clock": ms_each_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 (+f64 ordered sums)",
             "data": "synthetic",
             "config": {"workload": f"{n_reads} synthetic NovaSeq {READ_LENGTH} bp single-end reads per GPU, "

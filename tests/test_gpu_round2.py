@@ -268,3 +268,61 @@ def test_nanostats_skipped_reason_is_learned_without_waiting(impl):
             ns.add_record_array(arr)
         got.append((ns.skipped_reason, ns.number_of_reads, ns.minimum_time, ns.maximum_time))
     assert got[0] == got[1] and "not a nanopore header" in got[0][0]
+
+
+# ---- regular files: the extension reads them with pread() from several threads (qc_ext.cpp parser_read) ----
+def _names(arrays):
+    return [arr[i].name() for arr in arrays for i in range(len(arr))]
+
+
+def test_extension_reads_regular_files_directly(tmp_path):
+    """open(path, 'rb') (BufferedReader), buffering=0 (FileIO) and gzip objects (never direct: their fileno() is
+    the compressed file's) give the record stream of an in-memory object; the file object ends up where the
+    parser stopped reading."""
+    import gzip
+    import sequali_b200.ext as ext
+    text = synth.illumina_fastq(120_000, 151, seed=91, n_tiles=6)       # ~41 MB: several direct reads of 8 MiB
+    want = _names(ext.FastqParser(io.BytesIO(text), 8 << 20))
+    assert len(want) == 120_000
+    path = tmp_path / "reads.fastq"
+    path.write_bytes(text)
+    for buffering in (-1, 0, 1 << 16):
+        with open(path, "rb", buffering=buffering) as f:
+            assert _names(ext.FastqParser(f, 8 << 20)) == want
+            assert f.tell() == len(text) and f.read(1) == b""
+    gz = tmp_path / "reads.fastq.gz"
+    with gzip.open(gz, "wb", compresslevel=1) as f:
+        f.write(text)
+    with gzip.open(gz, "rb") as f:
+        assert _names(ext.FastqParser(f, 8 << 20)) == want
+    # read(n) and iteration mixed on a regular file; a partial last record is still an error
+    with open(path, "rb") as f:
+        p = ext.FastqParser(f, 8 << 20)
+        first = p.read(1000)
+        rest = _names(p)
+        assert _names([first]) + rest == want
+    (tmp_path / "cut.fastq").write_bytes(text[:-7])
+    with open(tmp_path / "cut.fastq", "rb") as f, pytest.raises(EOFError):
+        _names(ext.FastqParser(f, 8 << 20))
+
+
+def test_extension_reads_regular_bam_files_directly(tmp_path):
+    """BamParser has consumed the header through read(): the descriptor's own position is somewhere else than the
+    object's, the direct reads start at tell()."""
+    import sequali_b200.ext as ext
+    raw = synth.nanopore_ubam(3000, mean_length=4000, max_length=60_000, seed=92)   # ~20 MB
+    assert len(raw) > (12 << 20)
+
+    def dump(fileobj, size):
+        parser = ext.BamParser(fileobj, size)
+        return parser.header, [(a[i].name(), a[i].sequence()[:50], len(a[i].qualities()), a[i].tags()[:20])
+                               for a in parser for i in range(len(a))]
+
+    want = dump(io.BytesIO(raw), 4 << 20)
+    assert len(want[1]) == 3000
+    path = tmp_path / "reads.bam"
+    path.write_bytes(raw)
+    for buffering in (-1, 0):
+        with open(path, "rb", buffering=buffering) as f:
+            assert dump(f, 4 << 20) == want
+            assert f.tell() == len(raw)
