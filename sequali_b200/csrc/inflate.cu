@@ -210,9 +210,12 @@ extern "C" int sq_selftest_inflate_host(const uint8_t *deflate, uint32_t len, ui
     static thread_local InfTables t;
     struct HostOut {
         uint8_t *out;
-        void put(uint32_t op, uint8_t c) { out[op] = c; }
-        void raw(uint32_t op, const uint8_t *src, uint32_t n) { memcpy(out + op, src, n); }
-        void match(uint32_t op, uint32_t dist, uint32_t n) {
+        // (__host__ __device__ only because inf_inflate is: this instantiation runs on the host)
+        __host__ __device__ void put(uint32_t op, uint8_t c) { out[op] = c; }
+        __host__ __device__ void raw(uint32_t op, const uint8_t *src, uint32_t n) {
+            for (uint32_t i = 0; i < n; i++) out[op + i] = src[i];
+        }
+        __host__ __device__ void match(uint32_t op, uint32_t dist, uint32_t n) {
             for (uint32_t i = 0; i < n; i++) out[op + i] = out[op - dist + (i % dist)];
         }
     } o{out};
