@@ -8,6 +8,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/sqgpu.h"
@@ -51,7 +52,17 @@ struct sq_ctx {
     // and joins before it returns, so everything else stays ordered on the launch stream.
     cudaStream_t tstream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    std::atomic<bool> pool_primed{false};  // sq_prime_pool ran
+    // cache of large scratch blocks (sq_dalloc / sq_dfree)
+    struct BigBlock {
+        void *p = nullptr;
+        size_t cls = 0;
+        cudaEvent_t ev = nullptr;        // recorded where the block was freed
+        cudaStream_t freed_on = nullptr;
+    };
+    std::mutex big_mutex;
+    std::vector<BigBlock> big_free;      // oldest first
+    size_t big_free_bytes = 0, big_free_cap = (size_t)16 << 30;
+    std::unordered_map<void *, BigBlock> big_live;
     std::atomic<uint64_t> launches{0};
     std::mutex prof_mutex;
     // pinned scratch for small device->host result structs
@@ -146,13 +157,8 @@ int sq_d2h_bounced(sq_ctx *ctx, void *dst, const void *dev_src, size_t nbytes);
 // name bytes of record r of a record array (host copy; rare paths only)
 int sq_batch_get_name(sq_batch *b, uint64_t r, std::vector<uint8_t> &out);
 
-// Large inputs: reserve device memory for the stream-ordered pool in ONE piece before the first big record
-// array is processed.  The pool otherwise grows in many steps over the first passes, whenever a scratch block
-// does not fit the fragments it holds, and a growth step costs 10-800 ms of host time on a virtualised box
-// (measured: cudaMallocAsync of 121 MB taking 832 ms in the eighth pass over the same data).
-int sq_prime_pool(sq_ctx *ctx, uint64_t records_per_array);
-
-// stream-ordered allocation helpers (cudaMallocAsync on the context stream)
+// stream-ordered allocation helpers (cudaMallocAsync on the calling thread's stream; blocks of 8 MiB and more are
+// cached by the context, see core.cu)
 int sq_dalloc(sq_ctx *ctx, void **p, size_t nbytes, bool zero);
 void sq_dfree(sq_ctx *ctx, void *p);
 

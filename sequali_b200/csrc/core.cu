@@ -50,51 +50,128 @@ extern "C" int sq_device_count(void) {
 // ---------------------------------------------------------------------------
 // allocation
 // ---------------------------------------------------------------------------
+// Large scratch blocks (descriptor blocks, hashes, tile ids, segment histograms: 16-170 MB each, several per
+// record array) are kept by the context instead of going back to the stream-ordered pool.  The pool serves a large
+// request by re-mapping free physical granules into one address range when none of its fragments fits, and on a
+// virtualised box that step takes 10-800 ms of host time inside cudaMallocAsync, at random, for dozens of passes
+// (`SQ_TRACE_ALLOC=1`, tools/step_times.py: single passes of 160-1350 ms among 88 ms ones, with the pool's
+// reserved size unchanged).  Here a freed block of >= 8 MiB keeps its size class and the event of its last use;
+// the next request of that class takes it and, on another stream, waits for that event on the device.  After
+// the first record arrays no allocation reaches the driver any more.
+constexpr size_t SQ_BIG_MIN = (size_t)8 << 20;
+static size_t sq_big_class(size_t nbytes) {
+    const size_t step = nbytes < ((size_t)256 << 20) ? (size_t)16 << 20 : (size_t)64 << 20;
+    return (nbytes + step - 1) / step * step;
+}
+
+static int sq_dalloc_traced(sq_ctx *ctx, void **p, size_t nbytes) {
+    static const bool trace = getenv("SQ_TRACE_ALLOC") != nullptr;
+    if (!trace) {
+        CUDA_TRY(cudaMallocAsync(p, nbytes, sq_cur_stream(ctx)));
+        return SQ_OK;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaError_t e = cudaMallocAsync(p, nbytes, sq_cur_stream(ctx));
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (ms > 2.0) {
+        cudaMemPool_t pool;
+        uint64_t reserved = 0, used = 0;
+        cudaDeviceGetDefaultMemPool(&pool, ctx->device);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        fprintf(stderr, "[sq] cudaMallocAsync(%zu bytes) took %.1f ms on the %s stream; pool: reserved %.2f GB, in use %.2f GB\n",
+                nbytes, ms, sq_cur_stream(ctx) == ctx->stream ? "launch" : sq_cur_stream(ctx) == ctx->pstream ? "parser" : "table",
+                reserved / 1e9, used / 1e9);
+    }
+    if (e != cudaSuccess) return sq_cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+    return SQ_OK;
+}
+
 int sq_dalloc(sq_ctx *ctx, void **p, size_t nbytes, bool zero) {
     *p = nullptr;
     if (nbytes == 0) nbytes = 16;
-    static const bool trace = getenv("SQ_TRACE_ALLOC") != nullptr;
-    if (trace) {
-        const auto t0 = std::chrono::steady_clock::now();
-        cudaError_t e = cudaMallocAsync(p, nbytes, sq_cur_stream(ctx));
-        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        if (ms > 2.0) fprintf(stderr, "[sq] cudaMallocAsync(%zu bytes) took %.1f ms\n", nbytes, ms);
-        if (e != cudaSuccess) return sq_cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+    static const bool no_cache = getenv("SQ_NO_BLOCK_CACHE") != nullptr;
+    cudaStream_t cur = sq_cur_stream(ctx);
+    if (nbytes >= SQ_BIG_MIN && !no_cache) {
+        const size_t cls = sq_big_class(nbytes);
+        sq_ctx::BigBlock blk;
+        bool found = false;
+        {
+            std::lock_guard<std::mutex> lk(ctx->big_mutex);
+            int pick = -1;
+            for (int i = (int)ctx->big_free.size() - 1; i >= 0; i--)
+                if (ctx->big_free[i].cls == cls) {
+                    if (pick < 0) pick = i;
+                    if (ctx->big_free[i].freed_on == cur) {  // last used on this very stream: nothing to wait for
+                        pick = i;
+                        break;
+                    }
+                }
+            if (pick >= 0) {
+                blk = ctx->big_free[pick];
+                ctx->big_free.erase(ctx->big_free.begin() + pick);
+                ctx->big_free_bytes -= blk.cls;
+                found = true;
+            }
+        }
+        if (found) {
+            if (blk.freed_on != cur) CUDA_TRY(cudaStreamWaitEvent(cur, blk.ev, 0));
+        }
+        else {
+            SQ_TRY(sq_dalloc_traced(ctx, &blk.p, cls));
+            blk.cls = cls;
+            blk.freed_on = nullptr;
+            CUDA_TRY(cudaEventCreateWithFlags(&blk.ev, cudaEventDisableTiming));
+        }
+        {
+            std::lock_guard<std::mutex> lk(ctx->big_mutex);
+            ctx->big_live[blk.p] = blk;
+        }
+        *p = blk.p;
     }
-    else
-    CUDA_TRY(cudaMallocAsync(p, nbytes, sq_cur_stream(ctx)));
-    if (zero) CUDA_TRY(cudaMemsetAsync(*p, 0, nbytes, sq_cur_stream(ctx)));
-    return SQ_OK;
-}
-int sq_prime_pool(sq_ctx *ctx, uint64_t records_per_array) {
-    if (records_per_array < (1u << 20) || ctx->pool_primed.exchange(true)) return SQ_OK;
-    static const bool off = getenv("SQ_NO_POOL_PRIME") != nullptr;
-    if (off) return SQ_OK;
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    // scratch of one record array is ~300 B per record over all collectors; three arrays are in flight
-    uint64_t want = records_per_array * 1024;
-    if (want > free_b / 4) want = free_b / 4;
-    if (want < (256u << 20)) return SQ_OK;
-    void *p = nullptr;
-    if (cudaMallocAsync(&p, want, ctx->stream) != cudaSuccess) {
-        cudaGetLastError();  // not fatal: the pool grows on demand instead
-        return SQ_OK;
-    }
-    CUDA_TRY(cudaFreeAsync(p, ctx->stream));
+    else SQ_TRY(sq_dalloc_traced(ctx, p, nbytes));
+    if (zero) CUDA_TRY(cudaMemsetAsync(*p, 0, nbytes, cur));
     return SQ_OK;
 }
 
 void sq_dfree(sq_ctx *ctx, void *p) {
-    static const bool trace = getenv("SQ_TRACE_ALLOC") != nullptr;
-    if (p && trace) {
-        const auto t0 = std::chrono::steady_clock::now();
-        cudaFreeAsync(p, sq_cur_stream(ctx));
-        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        if (ms > 2.0) fprintf(stderr, "[sq] cudaFreeAsync took %.1f ms\n", ms);
-        return;
+    if (!p) return;
+    cudaStream_t cur = sq_cur_stream(ctx);
+    {
+        std::lock_guard<std::mutex> lk(ctx->big_mutex);
+        auto it = ctx->big_live.find(p);
+        if (it != ctx->big_live.end()) {
+            sq_ctx::BigBlock blk = it->second;
+            ctx->big_live.erase(it);
+            blk.freed_on = cur;
+            cudaEventRecord(blk.ev, cur);  // everything that used the block was enqueued on `cur` before this point
+            ctx->big_free.push_back(blk);
+            ctx->big_free_bytes += blk.cls;
+            // idle blocks beyond the cap go back to the driver, oldest first (inputs whose array sizes drift)
+            while (ctx->big_free_bytes > ctx->big_free_cap && ctx->big_free.size() > 1) {
+                sq_ctx::BigBlock old = ctx->big_free.front();
+                ctx->big_free.erase(ctx->big_free.begin());
+                ctx->big_free_bytes -= old.cls;
+                cudaFreeAsync(old.p, old.freed_on);
+                cudaEventDestroy(old.ev);
+            }
+            return;
+        }
     }
-    if (p) cudaFreeAsync(p, sq_cur_stream(ctx));
+    cudaFreeAsync(p, cur);
+}
+
+// blocks of the cache back to the driver (context teardown)
+static void sq_big_release(sq_ctx *ctx) {
+    std::lock_guard<std::mutex> lk(ctx->big_mutex);
+    for (auto &blk : ctx->big_free) {
+        cudaFreeAsync(blk.p, ctx->stream);
+        cudaEventDestroy(blk.ev);
+    }
+    ctx->big_free.clear();
+    ctx->big_free_bytes = 0;
+    for (auto &kv : ctx->big_live) cudaEventDestroy(kv.second.ev);  // (their owners never freed them)
+    ctx->big_live.clear();
 }
 
 // Largest x with floor(-10*log10(x)) >= k, found on the bit pattern of the
@@ -166,6 +243,9 @@ extern "C" int sq_ctx_create(int device, sq_ctx **out) {
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = UINT64_MAX;
     CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    ctx->big_free_cap = std::min<size_t>(total_b / 8, (size_t)16 << 30);
     CUDA_TRY(cudaMallocHost(&ctx->h_scratch, 4096));
     CUDA_TRY(cudaMalloc(&ctx->d_scratch, 4096));
     double tab[94], edges[94];
@@ -193,6 +273,8 @@ extern "C" void sq_ctx_destroy(sq_ctx *ctx) {
     }
     cudaStreamSynchronize(ctx->pstream);
     cudaStreamSynchronize(ctx->tstream);
+    cudaStreamSynchronize(ctx->stream);
+    sq_big_release(ctx);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_err_table);
     cudaFree(ctx->d_phred_thresholds);
@@ -897,7 +979,6 @@ static int parse_device_text(sq_ctx *ctx, sq_batch *b, uint64_t max_records, sq_
         rc = SQ_E_FORMAT;
     }
     b->n = n_rec;
-    if (rc == SQ_OK) rc = sq_prime_pool(ctx, n_rec);  // (large inputs: before the collectors' scratch comes and goes)
     b->max_len = info->max_seq_len;
     b->max_rec_bytes = hst->max_rec_bytes;
     b->text_end = info->consumed;

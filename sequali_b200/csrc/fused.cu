@@ -1850,7 +1850,6 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     }
     if (b->n == 0) return SQ_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    SQ_TRY(sq_prime_pool(ctx, b->n));
     if (pt && pt->skipped) pt = nullptr;
     if (!fused_eligible(b, ad) || !(qc || pt || ad || dd)) {
         // the reference's module order (__main__.py:280-306)
