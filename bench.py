@@ -301,7 +301,7 @@ def run_next_rows():
         q[int(rng.integers(0, 21))] = letters[int(rng.integers(0, 4))]
         pairs.append((target.tobytes().decode(), q.tobytes().decode()))
     cells = sum(len(t) * len(q) for t, q in pairs)
-    _seqident.sequence_identities(pairs[:100])
+    _seqident.sequence_identities(pairs)  # warm-up: context of the extension module, its device buffers
     t0 = time.perf_counter()
     got = _seqident.sequence_identities(pairs)
     dt = time.perf_counter() - t0
