@@ -79,6 +79,11 @@ SQ_API const char *sq_last_error(void);
 SQ_API int sq_device_numa_node(int device);
 SQ_API int sq_ctx_create(int device, sq_ctx **out);
 SQ_API void sq_ctx_destroy(sq_ctx *ctx);
+/* Scratch blocks of 8 MiB and more are kept by the context after their first use instead of going back to the
+ * stream-ordered pool (size classes; reuse ordered by the event of the last use): how many such requests went to
+ * cudaMallocAsync, how many were served from the cache, and the bytes idle in the cache right now. */
+SQ_API int sq_ctx_block_cache_stats(sq_ctx *ctx, uint64_t *from_driver, uint64_t *from_cache,
+                                    uint64_t *idle_bytes);
 SQ_API int sq_ctx_sync(sq_ctx *ctx);
 /* raw stream handle (cudaStream_t) for callers that time with CUDA events */
 SQ_API void *sq_ctx_stream(sq_ctx *ctx);

@@ -110,6 +110,7 @@ SIGNATURES = {
     "sq_device_numa_node": (_int, [_int]),
     "sq_ctx_create": (_int, [_int, _P(_vp)]),
     "sq_ctx_destroy": (None, [_vp]),
+    "sq_ctx_block_cache_stats": (_int, [_vp, _P(_u64), _P(_u64), _P(_u64)]),
     "sq_ctx_sync": (_int, [_vp]),
     "sq_ctx_stream": (_vp, [_vp]),
     "sq_ctx_launch_count": (_u64, [_vp]),

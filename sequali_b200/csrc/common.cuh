@@ -62,6 +62,7 @@ struct sq_ctx {
     std::mutex big_mutex;
     std::vector<BigBlock> big_free;      // oldest first
     size_t big_free_bytes = 0, big_free_cap = (size_t)16 << 30;
+    std::atomic<uint64_t> big_from_driver{0}, big_from_cache{0};  // requests of >= 8 MiB served by cudaMallocAsync / by the cache
     std::unordered_map<void *, BigBlock> big_live;
     std::atomic<uint64_t> launches{0};
     std::mutex prof_mutex;

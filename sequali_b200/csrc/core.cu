@@ -116,9 +116,11 @@ int sq_dalloc(sq_ctx *ctx, void **p, size_t nbytes, bool zero) {
         }
         if (found) {
             if (blk.freed_on != cur) CUDA_TRY(cudaStreamWaitEvent(cur, blk.ev, 0));
+            ctx->big_from_cache++;
         }
         else {
             SQ_TRY(sq_dalloc_traced(ctx, &blk.p, cls));
+            ctx->big_from_driver++;
             blk.cls = cls;
             blk.freed_on = nullptr;
             CUDA_TRY(cudaEventCreateWithFlags(&blk.ev, cudaEventDisableTiming));
@@ -159,6 +161,14 @@ void sq_dfree(sq_ctx *ctx, void *p) {
         }
     }
     cudaFreeAsync(p, cur);
+}
+
+extern "C" int sq_ctx_block_cache_stats(sq_ctx *ctx, uint64_t *from_driver, uint64_t *from_cache, uint64_t *idle_bytes) {
+    std::lock_guard<std::mutex> lk(ctx->big_mutex);
+    *from_driver = ctx->big_from_driver;
+    *from_cache = ctx->big_from_cache;
+    *idle_bytes = ctx->big_free_bytes;
+    return SQ_OK;
 }
 
 // blocks of the cache back to the driver (context teardown)

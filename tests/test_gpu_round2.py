@@ -326,3 +326,41 @@ def test_extension_reads_regular_bam_files_directly(tmp_path):
         with open(path, "rb", buffering=buffering) as f:
             assert dump(f, 4 << 20) == want
             assert f.tell() == len(raw)
+
+
+def test_large_scratch_blocks_are_reused_after_the_first_passes():
+    """Steady state: passes over the same input make no driver allocation of 8 MiB or more any more (sq_dalloc's
+    block cache), and the results do not depend on which pass it is."""
+    import ctypes as C
+    import sequali_b200 as sq
+    from sequali_b200 import _lib
+    from sequali_b200.device import DeviceFastq
+    ctx = _lib.Context.get()
+    data = DeviceFastq.synth_illumina(3_000_000, 151, seed=5, chunk_reads=1 << 20)
+
+    def stats():
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _lib.check(ctx.lib.sq_ctx_block_cache_stats(ctx.h, C.byref(a), C.byref(b), C.byref(c)), "stats")
+        return a.value, b.value, c.value
+
+    def one_pass():
+        qc, pt, ov, dd = sq.QCMetrics(), sq.PerTileQuality(), sq.OverrepresentedSequences(), sq.DedupEstimator()
+        ad = sq.AdapterCounter(["AGATCGGAAGAGC", "CTGTCTCTTATA"])
+        for arr in data.record_arrays():
+            for m in (qc, pt, ov, ad, dd):
+                m.add_record_array(arr)
+        return (bytes(qc.base_count_table()), bytes(qc.phred_count_table()), pt.get_tile_counts(),
+                bytes(dd.duplication_counts()), ov.sequence_counts(), ad.get_counts())
+
+    first = one_pass()
+    one_pass()
+    one_pass()
+    ctx.sync()
+    before = stats()
+    again = one_pass()
+    ctx.sync()
+    after = stats()
+    assert again == first
+    assert after[0] == before[0], (before, after)      # nothing new from the driver
+    assert after[1] > before[1] and after[2] > 0       # the pass lived off the cache
+    data.free()
