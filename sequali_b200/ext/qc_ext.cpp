@@ -376,6 +376,7 @@ struct ArrayView {
     sq_batch *h;        // device record array, or NULL (not uploaded yet)
     uint64_t n, nbytes;
     Pinned pinned;      // staging buffer a parser-made array was read into
+    size_t pinned_off;  // where the text starts in it
     bool metas_stale;   // err_sum changed on the device (QCMetrics ran)
 };
 
@@ -394,6 +395,7 @@ ArrayView *ArrayView_alloc() {
     a->h = nullptr;
     a->n = a->nbytes = 0;
     new (&a->pinned) Pinned();
+    a->pinned_off = 0;
     a->metas_stale = false;
     return a;
 }
@@ -499,7 +501,7 @@ int ArrayView_fetch_metas(ArrayView *a) {
 }
 PyObject *ArrayView_obj(ArrayView *a, void *) {
     if (!a->obj) {
-        if (a->pinned.ptr) a->obj = PyBytes_FromStringAndSize((const char *)a->pinned.ptr, (Py_ssize_t)a->nbytes);
+        if (a->pinned.ptr) a->obj = PyBytes_FromStringAndSize((const char *)a->pinned.ptr + a->pinned_off, (Py_ssize_t)a->nbytes);
         else {
             a->obj = PyBytes_FromStringAndSize(nullptr, (Py_ssize_t)a->nbytes);
             if (a->obj && a->nbytes) {
@@ -1856,10 +1858,14 @@ struct Parser {
     size_t bam_filled;
     int32_t bam_n_ref;  // reference count of the BAM header
     int direct_fd;      // >= 0: `file` is a plain io.BufferedReader / io.FileIO over a regular file (parser_read)
+    struct FileReader *reader;  // FastqParser iterating over such a file: blocks read ahead of the parser
+    bool reader_done;           // ... has handed out its last block (or was stopped): the classic path continues
     ReadAhead *ra;
 };
 int direct_fd_of(PyObject *file);
 Py_ssize_t parser_read(Parser *self, uint8_t *dst, Py_ssize_t len);
+long long parallel_pread(int fd, uint8_t *dst, size_t len, long long pos, int *err);
+void reader_stop(Parser *self, bool seek);
 
 // start `produce(self)` on a helper thread; the thread owns a reference to the parser until it is done
 void read_ahead_start(Parser *self, PyObject *(*produce)(Parser *)) {
@@ -1912,6 +1918,7 @@ void Parser_dealloc(Parser *self) {
         Py_XDECREF(self->ra->exc_tb);
         delete self->ra;
     }
+    reader_stop(self, true);
     Py_XDECREF(self->file);
     Py_XDECREF(self->header);
     delete self->leftover;
@@ -1951,6 +1958,8 @@ PyObject *FQ_new(PyTypeObject *type, PyObject *args, PyObject *kwargs) {
     new (&self->bam_buf) Pinned();
     self->bam_filled = 0;
     self->direct_fd = size >= (Py_ssize_t)READ_AHEAD_MIN_STEP ? direct_fd_of(file) : -1;
+    self->reader = nullptr;
+    self->reader_done = false;
     self->ra = new ReadAhead();
     return (PyObject *)self;
 }
@@ -2018,6 +2027,46 @@ int direct_fd_of(PyObject *file) {
     return fd;
 }
 
+// bytes [pos, pos + len) of a regular file into dst from up to eight threads; what was read in one piece from
+// `pos` on (short at the end of the file), or -1 with *err = errno
+long long parallel_pread(int fd, uint8_t *dst, size_t len, long long pos, int *err) {
+    unsigned n_threads = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency() / 2));
+    n_threads = (unsigned)std::min<size_t>(n_threads, std::max<size_t>(1, len / DIRECT_MIN_BYTES));
+    const size_t piece = ((len + n_threads - 1) / n_threads + 4095) & ~(size_t)4095;
+    std::vector<long long> got(n_threads, 0);
+    std::vector<int> errs(n_threads, 0);
+    auto work = [&](unsigned k) {
+        const size_t lo = std::min(len, k * piece), hi = std::min(len, lo + piece);
+        size_t at = lo;
+        while (at < hi) {
+            const ssize_t r = pread(fd, dst + at, hi - at, (off_t)(pos + (long long)at));
+            if (r < 0) {
+                if (errno == EINTR) continue;
+                errs[k] = errno;
+                break;
+            }
+            if (r == 0) break;  // end of the file
+            at += (size_t)r;
+        }
+        got[k] = (long long)(at - lo);
+    };
+    std::vector<std::thread> pool;
+    for (unsigned k = 1; k < n_threads; k++) pool.emplace_back(work, k);
+    work(0);
+    for (auto &t : pool) t.join();
+    long long total = 0;
+    for (unsigned k = 0; k < n_threads; k++) {
+        if (errs[k]) {
+            *err = errs[k];
+            return -1;
+        }
+        const size_t lo = std::min(len, k * piece), hi = std::min(len, lo + piece);
+        total += got[k];
+        if ((size_t)got[k] < hi - lo) break;  // the file ends inside this piece: later pieces lie behind the end
+    }
+    return total;
+}
+
 // fills dst[0..len) from the parser's file: the number of bytes read (0 at the end of the file), -1 with an exception
 Py_ssize_t parser_read(Parser *self, uint8_t *dst, Py_ssize_t len) {
     if (self->direct_fd < 0 || (size_t)len < DIRECT_MIN_BYTES) return call_readinto(self->file, dst, len);
@@ -2029,49 +2078,190 @@ Py_ssize_t parser_read(Parser *self, uint8_t *dst, Py_ssize_t len) {
         if (!PyErr_Occurred()) PyErr_SetString(PyExc_OSError, "negative file position");
         return -1;
     }
-    const int fd = self->direct_fd;
-    unsigned n_threads = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency() / 2));
-    n_threads = (unsigned)std::min<size_t>(n_threads, std::max<size_t>(1, (size_t)len / DIRECT_MIN_BYTES));
-    const size_t piece = (((size_t)len + n_threads - 1) / n_threads + 4095) & ~(size_t)4095;
-    std::vector<long long> got(n_threads, 0);
-    std::vector<int> err(n_threads, 0);
-    auto work = [&](unsigned k) {
-        const size_t lo = std::min((size_t)len, k * piece), hi = std::min((size_t)len, lo + piece);
-        size_t at = lo;
-        while (at < hi) {
-            const ssize_t r = pread(fd, dst + at, hi - at, (off_t)(pos + (long long)at));
-            if (r < 0) {
-                if (errno == EINTR) continue;
-                err[k] = errno;
-                break;
-            }
-            if (r == 0) break;  // end of the file
-            at += (size_t)r;
-        }
-        got[k] = (long long)(at - lo);
-    };
-    Py_BEGIN_ALLOW_THREADS
-    std::vector<std::thread> pool;
-    for (unsigned k = 1; k < n_threads; k++) pool.emplace_back(work, k);
-    work(0);
-    for (auto &t : pool) t.join();
-    Py_END_ALLOW_THREADS
+    int err = 0;
     long long total = 0;
-    for (unsigned k = 0; k < n_threads; k++) {
-        if (err[k]) {
-            errno = err[k];
-            PyErr_SetFromErrno(PyExc_OSError);
-            return -1;
-        }
-        const size_t lo = std::min((size_t)len, k * piece), hi = std::min((size_t)len, lo + piece);
-        total += got[k];
-        if ((size_t)got[k] < hi - lo) break;  // the file ends inside this piece: what later pieces read lies behind the end
+    Py_BEGIN_ALLOW_THREADS
+    total = parallel_pread(self->direct_fd, dst, (size_t)len, pos, &err);
+    Py_END_ALLOW_THREADS
+    if (total < 0) {
+        errno = err;
+        PyErr_SetFromErrno(PyExc_OSError);
+        return -1;
     }
     PyObject *r = PyObject_CallMethod(self->file, "seek", "L", pos + total);
     if (!r) return -1;
     Py_DECREF(r);
     return (Py_ssize_t)total;
 }
+// ---- FastqParser iterating over a regular file: the file is read AHEAD of the parser -------------------------
+// A third thread fetches the file block by block (parallel_pread) into pinned buffers while the read-ahead thread
+// copies the previous block to the device and scans it and the caller's thread feeds the collectors with the one
+// before: read, copy + scan and the collectors' kernels run side by side instead of one after the other.  A block
+// is read RES bytes into its buffer, so that the unfinished record the previous block ended with is copied in
+// front of it, not the block behind it.  The Python file object is not touched while the reader runs; when the
+// reader ends (end of file, read(n), the parser's end) the object is moved behind the last block handed out.
+struct FileReader {
+    static constexpr size_t RES = (size_t)1 << 20;  // room in front of a block for the previous block's leftover
+    static constexpr int SLOTS = 3;
+    struct Slot {
+        Pinned buf;      // RES + step bytes, allocated by the consumer (the pinned pool belongs to the GIL holder)
+        size_t got = 0;
+        bool full = false;
+    };
+    int fd = -1;
+    size_t step = 0;
+    long long next_off = 0;      // where the worker reads next
+    long long consumed_off = 0;  // the file position behind the last block handed out
+    Slot slots[SLOTS];
+    unsigned head = 0, tail = 0;  // next slot to hand out / to fill
+    bool eof = false, stop = false;
+    int err = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::thread worker;
+
+    void run() {
+        for (;;) {
+            Slot *s;
+            long long off;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || (!slots[tail % SLOTS].full && slots[tail % SLOTS].buf.ptr && tail - head < SLOTS); });
+                if (stop) return;
+                s = &slots[tail % SLOTS];
+                off = next_off;
+            }
+            int e = 0;
+            const long long got = parallel_pread(fd, s->buf.ptr + RES, step, off, &e);
+            std::lock_guard<std::mutex> lk(mu);
+            if (got < 0) {
+                err = e;
+                eof = true;
+            }
+            else {
+                s->got = (size_t)got;
+                s->full = true;
+                next_off += got;
+                tail++;
+                if ((size_t)got < step) eof = true;
+            }
+            cv.notify_all();
+            if (eof) return;
+        }
+    }
+};
+
+// stops the reader and moves the file object behind what the parser has been given (seek: with the GIL held)
+void reader_stop(Parser *self, bool seek) {
+    FileReader *r = self->reader;
+    if (!r) return;
+    self->reader = nullptr;
+    self->reader_done = true;
+    {
+        std::lock_guard<std::mutex> lk(r->mu);
+        r->stop = true;
+    }
+    r->cv.notify_all();
+    Py_BEGIN_ALLOW_THREADS
+    if (r->worker.joinable()) r->worker.join();
+    Py_END_ALLOW_THREADS
+    for (auto &s : r->slots) s.buf.release();
+    if (seek) {
+        PyObject *t = nullptr, *v = nullptr, *tb = nullptr;
+        PyErr_Fetch(&t, &v, &tb);  // (may run while an exception travels)
+        PyObject *res = PyObject_CallMethod(self->file, "seek", "L", r->consumed_off);
+        if (!res) PyErr_Clear();  // best effort: a closed file cannot be moved, and nobody will read it either
+        Py_XDECREF(res);
+        PyErr_Restore(t, v, tb);
+    }
+    delete r;
+}
+
+// first call: reader from the file object's position.  false with an exception set, or with none when this file
+// is read the classic way
+bool reader_start(Parser *self) {
+    PyObject *pos_o = PyObject_CallMethod(self->file, "tell", nullptr);
+    if (!pos_o) return false;
+    const long long pos = PyLong_AsLongLong(pos_o);
+    Py_DECREF(pos_o);
+    if (pos < 0) {
+        PyErr_Clear();
+        self->reader_done = true;
+        return false;
+    }
+    FileReader *r = new FileReader();
+    r->fd = self->direct_fd;
+    r->step = (size_t)self->read_in_size;
+    r->next_off = r->consumed_off = pos;
+    for (auto &s : r->slots)
+        if (!s.buf.alloc(FileReader::RES + r->step)) {
+            for (auto &t : r->slots) t.buf.release();
+            delete r;
+            return false;
+        }
+    r->worker = std::thread([r] { r->run(); });
+    self->reader = r;
+    return true;
+}
+
+// the next block, with `leftover` copied in front of it: text = buf.ptr + off, n bytes, `last` when the file ends
+// with it.  0 on success, -1 with an exception, 1 when the reader has nothing more (it is stopped then).
+int reader_take(Parser *self, const std::vector<uint8_t> &leftover, Pinned *buf, size_t *off, size_t *n, bool *last) {
+    FileReader *r = self->reader;
+    FileReader::Slot *s = nullptr;
+    bool drained = false;
+    int err = 0;
+    Py_BEGIN_ALLOW_THREADS
+    {
+        std::unique_lock<std::mutex> lk(r->mu);
+        r->cv.wait(lk, [&] { return r->slots[r->head % FileReader::SLOTS].full || (r->eof && r->head == r->tail); });
+        if (r->slots[r->head % FileReader::SLOTS].full) s = &r->slots[r->head % FileReader::SLOTS];
+        else drained = true;
+        err = r->err;
+    }
+    Py_END_ALLOW_THREADS
+    if (!s || drained) {
+        reader_stop(self, true);
+        if (err) {
+            errno = err;
+            PyErr_SetFromErrno(PyExc_OSError);
+            return -1;
+        }
+        return 1;
+    }
+    if (leftover.size() > FileReader::RES) {  // a record longer than RES: its block moves behind it in a buffer of its own
+        Pinned big;
+        if (!big.alloc(leftover.size() + s->got)) return -1;
+        memcpy(big.ptr, leftover.data(), leftover.size());
+        memcpy(big.ptr + leftover.size(), s->buf.ptr + FileReader::RES, s->got);
+        *buf = big;
+        *off = 0;
+        *n = leftover.size() + s->got;
+        *last = s->got < r->step;
+        std::lock_guard<std::mutex> lk(r->mu);  // the slot keeps its buffer
+        r->consumed_off += (long long)s->got;
+        s->full = false;
+        r->head++;
+        r->cv.notify_all();
+        return 0;
+    }
+    Pinned fresh;  // the block's buffer goes with the record array; the slot gets a new one
+    const bool more = s->got == r->step;
+    if (more && !fresh.alloc(FileReader::RES + r->step)) return -1;
+    if (!leftover.empty()) memcpy(s->buf.ptr + FileReader::RES - leftover.size(), leftover.data(), leftover.size());
+    *buf = s->buf;
+    *off = FileReader::RES - leftover.size();
+    *n = leftover.size() + s->got;
+    *last = !more;
+    std::lock_guard<std::mutex> lk(r->mu);
+    r->consumed_off += (long long)s->got;
+    s->buf = fresh;
+    s->full = false;
+    r->head++;
+    r->cv.notify_all();
+    return 0;
+}
+
 PyObject *raise_format_error(const uint8_t *data, uint64_t nbytes, const sq_parse_info &info) {
     const uint64_t pos = info.err_pos < nbytes ? info.err_pos : 0;
     switch (info.err_code) {
@@ -2097,8 +2287,70 @@ PyObject *raise_format_error(const uint8_t *data, uint64_t nbytes, const sq_pars
     }
     }
 }
+// iteration over a regular file: blocks from the FileReader.  nullptr + no exception: go on the classic way
+PyObject *FQ_from_reader(Parser *self) {
+    sq_ctx *ctx = g_ctx;
+    std::vector<uint8_t> &leftover = *self->leftover;
+    for (;;) {
+        Pinned buf;
+        size_t off = 0, n = 0;
+        bool last = false;
+        const int st = reader_take(self, leftover, &buf, &off, &n, &last);
+        if (st != 0) return nullptr;  // an exception (-1), or the end of the file (1: the classic path sees it too)
+        if (last) {
+            // the last block: it becomes the leftover and the classic path finishes (it reads the end of the file
+            // and words the errors of an unfinished record)
+            leftover.assign(buf.ptr + off, buf.ptr + off + n);
+            buf.release();
+            reader_stop(self, true);
+            return nullptr;
+        }
+        sq_batch *handle = nullptr;
+        sq_parse_info info;
+        memset(&info, 0, sizeof(info));
+        int rc;
+        Py_BEGIN_ALLOW_THREADS
+        rc = sq_batch_from_fastq(ctx, buf.ptr + off, n, UINT64_MAX, &handle, &info);
+        Py_END_ALLOW_THREADS
+        if (rc != SQ_OK) {
+            if (rc == SQ_E_FORMAT) raise_format_error(buf.ptr + off, n, info);
+            else raise_sq(rc, "sq_batch_from_fastq");
+            buf.release();
+            reader_stop(self, true);
+            return nullptr;
+        }
+        if (info.n_records == 0) {  // no whole record yet (a record longer than a block): on with the next block behind it
+            if (handle) sq_batch_free(handle);
+            leftover.assign(buf.ptr + off, buf.ptr + off + n);
+            buf.release();
+            continue;
+        }
+        leftover.assign(buf.ptr + off + info.consumed, buf.ptr + off + n);
+        ArrayView *a = ArrayView_alloc();
+        if (!a) {
+            sq_batch_free(handle);
+            buf.release();
+            return nullptr;
+        }
+        a->h = handle;
+        a->n = info.n_records;
+        a->nbytes = n;
+        a->pinned = buf;
+        a->pinned_off = off;
+        return (PyObject *)a;
+    }
+}
+
 PyObject *FQ_create_record_array(Parser *self, uint64_t min_records, uint64_t max_records) {
     sq_ctx *ctx = g_ctx;
+    if (min_records == 1 && max_records == UINT64_MAX && self->direct_fd >= 0 && !self->reader_done &&
+        (size_t)self->read_in_size >= DIRECT_MIN_BYTES) {
+        if (!self->reader && !reader_start(self) && PyErr_Occurred()) return nullptr;
+        if (self->reader) {
+            PyObject *a = FQ_from_reader(self);
+            if (a || PyErr_Occurred()) return a;
+        }
+    }
     std::vector<uint8_t> &leftover = *self->leftover;
     const size_t step = (size_t)self->read_in_size;
     const size_t size = std::max(step, leftover.size() + (leftover.size() < step ? 0 : step));
@@ -2198,9 +2450,10 @@ PyObject *FQ_read(Parser *self, PyObject *n_o) {
         PyObject *ahead = read_ahead_take(self);
         if (!ahead) return nullptr;
         ArrayView *av = (ArrayView *)ahead;
-        if (av->pinned.ptr) self->leftover->assign(av->pinned.ptr, av->pinned.ptr + av->nbytes);
+        if (av->pinned.ptr) self->leftover->assign(av->pinned.ptr + av->pinned_off, av->pinned.ptr + av->pinned_off + av->nbytes);
         Py_DECREF(ahead);
     }
+    reader_stop(self, true);  // (blocks read ahead of the parser are dropped: the file object goes back behind the last one used)
     return FQ_create_record_array(self, (uint64_t)n, (uint64_t)n);
 }
 PyMethodDef FQ_methods[] = {{"read", (PyCFunction)FQ_read, METH_O, "Read up to number_of_records records."},
@@ -2289,6 +2542,8 @@ PyObject *BAM_new(PyTypeObject *type, PyObject *args, PyObject *kwargs) {
     self->bam_filled = 0;
     self->bam_n_ref = (int32_t)std::min<uint32_t>(n_ref, 0x7fffffffu);
     self->direct_fd = size >= (Py_ssize_t)READ_AHEAD_MIN_STEP ? direct_fd_of(file) : -1;
+    self->reader = nullptr;
+    self->reader_done = false;
     self->ra = new ReadAhead();
     return (PyObject *)self;
 }

@@ -306,6 +306,34 @@ def test_extension_reads_regular_files_directly(tmp_path):
         _names(ext.FastqParser(f, 8 << 20))
 
 
+def test_extension_file_reader_with_records_longer_than_a_block(tmp_path):
+    """Reads of up to 9 Mb with 4 MiB blocks: blocks without a whole record, leftovers longer than the room in front
+    of a block; and a parser that is dropped half way leaves the file where its last record array ended."""
+    import sequali_b200.ext as ext
+    rng = np.random.default_rng(93)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    out = io.BytesIO()
+    for i, ln in enumerate([300, 9_000_000, 50, 2_000_000, 5_000_000, 120, 4_194_304, 7, 1_100_000, 60] * 2):
+        out.write(b"@read%d ch=%d start_time=2024-01-01T00:00:%02dZ\n" % (i, i + 1, i))
+        out.write(letters[rng.integers(0, 4, ln)].tobytes() + b"\n+\n" + (rng.integers(0, 40, ln).astype(np.uint8) + 33).tobytes() + b"\n")
+    text = out.getvalue()
+    want = [(a[i].name(), len(a[i].sequence()), a[i].sequence()[:30], a[i].qualities()[-30:])
+            for a in ext.FastqParser(io.BytesIO(text), 4 << 20) for i in range(len(a))]
+    assert len(want) == 20
+    path = tmp_path / "long.fastq"
+    path.write_bytes(text)
+    with open(path, "rb") as f:
+        got = [(a[i].name(), len(a[i].sequence()), a[i].sequence()[:30], a[i].qualities()[-30:])
+               for a in ext.FastqParser(f, 4 << 20) for i in range(len(a))]
+        assert got == want and f.tell() == len(text)
+    with open(path, "rb") as f:
+        parser = ext.FastqParser(f, 4 << 20)
+        first = next(parser)
+        used = len(first.obj)
+        del parser
+        assert 0 < f.tell() <= len(text) and f.tell() % (4 << 20) == 0 and f.tell() >= used
+
+
 def test_extension_reads_regular_bam_files_directly(tmp_path):
     """BamParser has consumed the header through read(): the descriptor's own position is somewhere else than the
     object's, the direct reads start at tell()."""
