@@ -97,7 +97,7 @@ struct PinnedPool {
     struct Item { void *ptr; size_t size; };
     std::vector<Item> free_list;  // oldest first
     size_t bytes = 0;
-    static constexpr size_t CAP = (size_t)1 << 30;
+    static constexpr size_t CAP = (size_t)2 << 30;  // idle bytes kept; the oldest blocks go first
     static size_t size_class(size_t n) {
         if (n < 4096) n = 4096;
         if (n >= ((size_t)1 << 20)) return (n + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
@@ -2102,7 +2102,7 @@ Py_ssize_t parser_read(Parser *self, uint8_t *dst, Py_ssize_t len) {
 // reader ends (end of file, read(n), the parser's end) the object is moved behind the last block handed out.
 struct FileReader {
     static constexpr size_t RES = (size_t)1 << 20;  // room in front of a block for the previous block's leftover
-    static constexpr int SLOTS = 3;
+    static constexpr int SLOTS = 2;  // one block being read, one waiting for the parser
     struct Slot {
         Pinned buf;      // RES + step bytes, allocated by the consumer (the pinned pool belongs to the GIL holder)
         size_t got = 0;

@@ -330,7 +330,14 @@ def test_extension_file_reader_with_records_longer_than_a_block(tmp_path):
         parser = ext.FastqParser(f, 4 << 20)
         first = next(parser)
         used = len(first.obj)
-        del parser
+        del parser, first
+        # (the array read ahead on the helper thread holds the parser until it is done; then the reader stops and
+        # moves the file object behind the last block it handed out)
+        import time
+        for _ in range(200):
+            if f.tell():
+                break
+            time.sleep(0.01)
         assert 0 < f.tell() <= len(text) and f.tell() % (4 << 20) == 0 and f.tell() >= used
 
 
