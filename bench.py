@@ -226,8 +226,9 @@ def loop_paired(mod, f1, f2, buffersize=None):
 
 def run_configs(gpu_mod, peak_gbs):
     """C1 / C3 / C4 / C5 of BASELINE.json at bounded sizes: the B200 build through the reference-shaped
-    API on host bytes (device copies inside the timed region), the unmodified reference on the identical
-    bytes with one thread, and text bytes / time / HBM peak for the B200 run."""
+    API on regular files in the page cache (file reads and device copies inside the timed region), the
+    unmodified reference on the identical files with one thread, and text bytes / time / HBM peak for the
+    B200 run."""
     from sequali_b200 import synth
     ref, _ = import_cpu_impl()
     big = 64 << 20
@@ -246,38 +247,65 @@ def run_configs(gpu_mod, peak_gbs):
         dt, bases = timed(gpu_fn, 2)
         row = {"workload": workload, "bases": bases, "text_bytes": int(nbytes),
                "value": round(bases / dt / 1e9, 3), "unit": "Gbases/s", "ms": round(dt * 1e3, 2),
-               "path": "sequali._qc extension on host bytes (H2D inside the timed region)",
+               "path": "sequali._qc extension on a regular file in the page cache, open(path, 'rb') (read + H2D inside the "
+                       "timed region)",
                "roofline": {"bound": "hbm", "frac_step": round(nbytes / dt / 1e9 / peak_gbs, 5),
                             "step_gbs": round(nbytes / dt / 1e9, 2), "peak": peak_gbs}}
         if ref is not None:
             cdt, cbases = timed(cpu_fn, 1)
             assert cbases == bases, (workload, cbases, bases)
             row["cpu_reference"] = {"value": round(cbases / cdt / 1e9, 4), "unit": "Gbases/s", "cores": 1,
-                                    "kind": "reference", "sample": "the identical bytes, whole"}
+                                    "kind": "reference", "sample": "the identical file, whole"}
             row["speedup_vs_1_core"] = round(cdt / dt, 1)
         return row
 
+    import tempfile
+    where = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    tmp = tempfile.mkdtemp(prefix="sq_configs_", dir=where)
+
+    def on_disk(name, data):
+        """The input as a regular file (page cache): what the CLI hands the parsers for an uncompressed input."""
+        path = os.path.join(tmp, name)
+        with open(path, "wb") as f:
+            f.write(data)
+        return path
+
+    def single(mod, path, adapters, bam=False, **kw):
+        with open(path, "rb") as f:
+            return loop_single_end(mod, f, adapters, bam=bam, **kw)
+
+    def paired(mod, p1, p2, **kw):
+        with open(p1, "rb") as f1, open(p2, "rb") as f2:
+            return loop_paired(mod, f1, f2, **kw)
+
     out = {}
-    text = synth.illumina_fastq(1_000_000, READ_LENGTH, seed=1, n_tiles=192)
-    out["C1"] = entry("1M synthetic Illumina 150 bp single-end reads, all default modules", len(text),
-                      lambda: loop_single_end(gpu_mod, io.BytesIO(text), ILLUMINA_ADAPTERS, buffersize=big),
-                      lambda: loop_single_end(ref, io.BytesIO(text), ILLUMINA_ADAPTERS))
-    t1, t2 = synth.paired_fastq(400_000, seed=3)
-    out["C3"] = entry("paired-end 2x150 bp, 400k pairs (BASELINE: 50M pairs; scaled 1/125): adapter overlap "
-                      "detection and InsertSizeMetrics", len(t1) + len(t2),
-                      lambda: loop_paired(gpu_mod, io.BytesIO(t1), io.BytesIO(t2), buffersize=big),
-                      lambda: loop_paired(ref, io.BytesIO(t1), io.BytesIO(t2)))
-    del t1, t2
-    text = synth.nanopore_fastq(20_000, mean_length=20_000, max_length=1_000_000, seed=4)
-    out["C4"] = entry("synthetic ultra-long Nanopore reads (mean 20 kb, max 1 Mb), 20k reads (BASELINE: 10 Gbases; "
-                      "scaled ~1/25) with guppy headers: NanoStats, 14 adapters, 21-mer overrepresentation", len(text),
-                      lambda: loop_single_end(gpu_mod, io.BytesIO(text), NANOPORE_ADAPTERS, buffersize=big),
-                      lambda: loop_single_end(ref, io.BytesIO(text), NANOPORE_ADAPTERS))
-    bam = synth.nanopore_ubam(20_000, mean_length=20_000, max_length=1_000_000, seed=5)
-    out["C5"] = entry("dorado-style unaligned BAM, 20k reads (BASELINE: 10 Gbases; scaled ~1/25) with channel / "
-                      "duration tags via BamParser", len(bam),
-                      lambda: loop_single_end(gpu_mod, io.BytesIO(bam), NANOPORE_ADAPTERS, bam=True, buffersize=big),
-                      lambda: loop_single_end(ref, io.BytesIO(bam), NANOPORE_ADAPTERS, bam=True))
+    try:
+        text = synth.illumina_fastq(1_000_000, READ_LENGTH, seed=1, n_tiles=192)
+        path = on_disk("c1.fastq", text)
+        out["C1"] = entry("1M synthetic Illumina 150 bp single-end reads, all default modules", len(text),
+                          lambda: single(gpu_mod, path, ILLUMINA_ADAPTERS, buffersize=big),
+                          lambda: single(ref, path, ILLUMINA_ADAPTERS))
+        t1, t2 = synth.paired_fastq(400_000, seed=3)
+        p1, p2 = on_disk("c3_1.fastq", t1), on_disk("c3_2.fastq", t2)
+        out["C3"] = entry("paired-end 2x150 bp, 400k pairs (BASELINE: 50M pairs; scaled 1/125): adapter overlap "
+                          "detection and InsertSizeMetrics", len(t1) + len(t2),
+                          lambda: paired(gpu_mod, p1, p2, buffersize=big), lambda: paired(ref, p1, p2))
+        del t1, t2
+        text = synth.nanopore_fastq(20_000, mean_length=20_000, max_length=1_000_000, seed=4)
+        p4 = on_disk("c4.fastq", text)
+        out["C4"] = entry("synthetic ultra-long Nanopore reads (mean 20 kb, max 1 Mb), 20k reads (BASELINE: 10 Gbases; "
+                          "scaled ~1/25) with guppy headers: NanoStats, 14 adapters, 21-mer overrepresentation", len(text),
+                          lambda: single(gpu_mod, p4, NANOPORE_ADAPTERS, buffersize=big),
+                          lambda: single(ref, p4, NANOPORE_ADAPTERS))
+        bam = synth.nanopore_ubam(20_000, mean_length=20_000, max_length=1_000_000, seed=5)
+        p5 = on_disk("c5.bam", bam)
+        out["C5"] = entry("dorado-style unaligned BAM, 20k reads (BASELINE: 10 Gbases; scaled ~1/25) with channel / "
+                          "duration tags via BamParser", len(bam),
+                          lambda: single(gpu_mod, p5, NANOPORE_ADAPTERS, bam=True, buffersize=big),
+                          lambda: single(ref, p5, NANOPORE_ADAPTERS, bam=True))
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
     return out
 
 
