@@ -46,6 +46,7 @@ struct sq_ctx {
     // (SqParserScope below), so their host synchronisations do not wait for the collectors' kernels.
     // One collector thread + one parser thread per context is the supported concurrency.
     cudaStream_t pstream = nullptr;
+    std::recursive_mutex parse_mutex;  // one parser entry point at a time (SqParserScope)
     // Table stream: PerTileQuality's ordered-sum kernel of a record array (a string of dependent round trips:
     // latency bound) runs here beside the hash-table kernels of OverrepresentedSequences / DedupEstimator on
     // the launch stream (latency and atomics bound as well); sq_fused_add forks after the per-position pass
@@ -105,10 +106,17 @@ struct SqStreamScope {
     }
     ~SqStreamScope() { sq_tls_stream = prev; }
 };
+// A parser entry point: its work goes to the parser stream, and it has the context's parser scratch (field
+// buffers, look-back words, result slots) to itself -- two parsers of one process may be driven from two threads
+// (the paired loop: one parser reads ahead on a helper thread while the caller asks the other for read(n)); their
+// scans take turns.
 struct SqParserScope {
     cudaStream_t prev;
+    std::unique_lock<std::recursive_mutex> turn;
     // (while per-kernel profiling is on everything stays on the launch stream: its events are ordered)
-    explicit SqParserScope(const sq_ctx *ctx) : prev(sq_tls_stream) { sq_tls_stream = ctx->profile ? nullptr : ctx->pstream; }
+    explicit SqParserScope(sq_ctx *ctx) : prev(sq_tls_stream), turn(ctx->parse_mutex) {
+        sq_tls_stream = ctx->profile ? nullptr : ctx->pstream;
+    }
     ~SqParserScope() { sq_tls_stream = prev; }
 };
 

@@ -399,3 +399,31 @@ def test_large_scratch_blocks_are_reused_after_the_first_passes():
     assert after[0] == before[0], (before, after)      # nothing new from the driver
     assert after[1] > before[1] and after[2] > 0       # the pass lived off the cache
     data.free()
+
+
+@pytest.mark.parametrize("which", ["both files", "read() side a file", "iterated side a file"])
+def test_extension_paired_reads_from_regular_files(tmp_path, which):
+    """The paired loop of the CLI: one parser iterated, the other asked for exactly as many records with read(n)."""
+    import sequali_b200.ext as ext
+    t1, t2 = synth.paired_fastq(60_000, seed=94)                      # ~21 MB each
+    p1, p2 = tmp_path / "r1.fastq", tmp_path / "r2.fastq"
+    p1.write_bytes(t1)
+    p2.write_bytes(t2)
+
+    def run(f1, f2):
+        names = []
+        rd1, rd2 = ext.FastqParser(f1, 4 << 20), ext.FastqParser(f2, 4 << 20)
+        for a in rd1:
+            b = rd2.read(len(a))
+            assert len(b) == len(a) and a.is_mate(b)
+            names.append((a[0].name(), b[len(b) - 1].name(), len(a)))
+        assert len(rd2.read(1)) == 0
+        return names
+
+    want = run(io.BytesIO(t1), io.BytesIO(t2))
+    assert sum(n for _, _, n in want) == 60_000
+    with open(p1, "rb") as f1, open(p2, "rb") as f2:
+        got = run(f1 if which != "read() side a file" else io.BytesIO(t1),
+                  f2 if which != "iterated side a file" else io.BytesIO(t2))
+    assert [(a, b) for a, b, _ in got][0] == [(a, b) for a, b, _ in want][0]
+    assert sum(n for _, _, n in got) == 60_000
