@@ -2553,7 +2553,68 @@ PyObject *BAM_next(Parser *self) {
     if (a && self->read_in_size >= READ_AHEAD_MIN_STEP) read_ahead_start(self, BAM_produce);
     return a;
 }
+// iteration over a regular file: blocks from the FileReader (see FQ_from_reader).  nullptr + no exception: the
+// classic path below goes on (with what is left of the last block in bam_buf)
+PyObject *BAM_from_reader(Parser *self) {
+    std::vector<uint8_t> &leftover = *self->leftover;
+    for (;;) {
+        Pinned buf;
+        size_t off = 0, n = 0;
+        bool last = false;
+        const int st = reader_take(self, leftover, &buf, &off, &n, &last);
+        if (st != 0) return nullptr;
+        sq_batch *h = nullptr;
+        uint64_t kept = 0, skipped = 0, consumed = 0, packed = 0;
+        int rc;
+        Py_BEGIN_ALLOW_THREADS
+        rc = sq_batch_from_bam_bytes(g_ctx, buf.ptr + off, n, self->bam_n_ref, &h, &kept, &skipped, &consumed, &packed);
+        Py_END_ALLOW_THREADS
+        if (rc != SQ_OK) {
+            buf.release();
+            reader_stop(self, true);
+            return raise_sq(rc, "sq_batch_from_bam_bytes");
+        }
+        leftover.assign(buf.ptr + off + consumed, buf.ptr + off + n);
+        buf.release();
+        if (last) {  // the classic path ends the file: nothing left -> StopIteration, an unfinished record -> EOFError
+            Pinned &bb = self->bam_buf;
+            if (bb.size < leftover.size()) {
+                bb.release();
+                if (!bb.alloc(leftover.size())) {
+                    if (h) sq_batch_free(h);
+                    return nullptr;
+                }
+            }
+            if (!leftover.empty()) memcpy(bb.ptr, leftover.data(), leftover.size());
+            self->bam_filled = leftover.size();
+            leftover.clear();
+            reader_stop(self, true);
+        }
+        if (!kept && !skipped && !last) continue;  // no whole record yet: on with the next block behind it
+        if (!kept) {
+            if (h) sq_batch_free(h);
+            return last && !skipped ? nullptr : ArrayView_empty();
+        }
+        ArrayView *a = ArrayView_alloc();
+        if (!a) {
+            sq_batch_free(h);
+            return nullptr;
+        }
+        a->h = h;
+        a->n = kept;
+        a->nbytes = packed;
+        return (PyObject *)a;
+    }
+}
+
 PyObject *BAM_produce(Parser *self) {
+    if (self->direct_fd >= 0 && !self->reader_done && (size_t)self->read_in_size >= DIRECT_MIN_BYTES && self->bam_filled == 0) {
+        if (!self->reader && !reader_start(self) && PyErr_Occurred()) return nullptr;
+        if (self->reader) {
+            PyObject *a = BAM_from_reader(self);
+            if (a || PyErr_Occurred()) return a;
+        }
+    }
     // [leftover | newly read bytes] live in one pinned buffer that is kept between calls: the
     // host->device copy of sq_batch_from_bam_bytes runs at PCIe speed and nothing is re-allocated or zeroed
     Pinned &buf = self->bam_buf;

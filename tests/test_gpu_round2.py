@@ -361,6 +361,18 @@ def test_extension_reads_regular_bam_files_directly(tmp_path):
         with open(path, "rb", buffering=buffering) as f:
             assert dump(f, 4 << 20) == want
             assert f.tell() == len(raw)
+    # a file that ends inside a record; a file whose records are all secondary alignments
+    (tmp_path / "cut.bam").write_bytes(raw[:-11])
+    with open(tmp_path / "cut.bam", "rb") as f, pytest.raises(EOFError, match="ncomplete record"):
+        dump(f, 4 << 20)
+    with pytest.raises(EOFError, match="ncomplete record"):
+        dump(io.BytesIO(raw[:-11]), 4 << 20)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[np.random.default_rng(1).integers(0, 4, 3000)]
+    skipped = synth.bam_header() + b"".join(
+        synth.bam_record(b"s%d" % i, seq, np.full(3000, 60, np.uint8), b"", flag=0x100) for i in range(2500))
+    (tmp_path / "skipped.bam").write_bytes(skipped)
+    with open(tmp_path / "skipped.bam", "rb") as f:
+        assert dump(f, 4 << 20)[1] == dump(io.BytesIO(skipped), 4 << 20)[1] == []
 
 
 def test_large_scratch_blocks_are_reused_after_the_first_passes():
