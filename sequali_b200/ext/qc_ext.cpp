@@ -2464,8 +2464,8 @@ PyType_Slot FQ_slots[] = {{Py_tp_new, (void *)FQ_new},           {Py_tp_dealloc,
 PyType_Spec FQ_spec = {"_qc.FastqParser", sizeof(Parser), 0, Py_TPFLAGS_DEFAULT, FQ_slots};
 
 // ---------------------------------------------------------------------------------------------
-// BamParser (reference :1362-1725): header skip and the block_size walk on the host (sq_bam_walk),
-// 4-bit sequence / raw quality decode on the device (sq_batch_from_bam)
+// BamParser (reference :1362-1725): header skip here; the block_size chain, the flag drop and the 4-bit sequence /
+// raw quality decode on the device (sq_batch_from_bam_bytes)
 // ---------------------------------------------------------------------------------------------
 PyObject *read_exact(PyObject *file, Py_ssize_t n, bool first) {
     PyObject *b = PyObject_CallMethod(file, "read", "n", n);
