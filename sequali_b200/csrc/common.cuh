@@ -47,10 +47,10 @@ struct sq_ctx {
     // One collector thread + one parser thread per context is the supported concurrency.
     cudaStream_t pstream = nullptr;
     std::recursive_mutex parse_mutex;  // one parser entry point at a time (SqParserScope)
-    // Table stream: PerTileQuality's ordered-sum kernel of a record array (a string of dependent round trips:
-    // latency bound) runs here beside the hash-table kernels of OverrepresentedSequences / DedupEstimator on
-    // the launch stream (latency and atomics bound as well); sq_fused_add forks after the per-position pass
-    // and joins before it returns, so everything else stays ordered on the launch stream.
+    // Table stream: the hash-table modules of a record array (OverrepresentedSequences, NanoStats, DedupEstimator:
+    // latency and atomics bound kernels with host waits in between) run here from the end of k_fused_reads on, beside
+    // the per-position pass and PerTileQuality's chain kernel on the launch stream; sq_fused_add forks and joins, so
+    // everything else stays ordered on the launch stream.
     cudaStream_t tstream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // cache of large scratch blocks (sq_dalloc / sq_dfree)

@@ -331,13 +331,13 @@ static int table_alloc(sq_ctx *ctx, DdTable *t, uint64_t size) {
     SQ_TRY(sq_dalloc(ctx, (void **)&t->hash, size * 8, true));
     SQ_TRY(sq_dalloc(ctx, (void **)&t->count, size * 4, true));
     SQ_TRY(sq_dalloc(ctx, (void **)&t->prio, size * 8, false));
-    CUDA_TRY(cudaMemsetAsync(t->prio, 0xFF, size * 8, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(t->prio, 0xFF, size * 8, sq_cur_stream(ctx)));
     return SQ_OK;
 }
 static int table_clear(sq_ctx *ctx, DdTable *t, uint64_t size) {
-    CUDA_TRY(cudaMemsetAsync(t->hash, 0, size * 8, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(t->count, 0, size * 4, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(t->prio, 0xFF, size * 8, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(t->hash, 0, size * 8, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaMemsetAsync(t->count, 0, size * 4, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaMemsetAsync(t->prio, 0xFF, size * 8, sq_cur_stream(ctx)));
     return SQ_OK;
 }
 static void table_free(sq_ctx *ctx, DdTable *t) {
@@ -368,7 +368,7 @@ extern "C" int sq_dedup_create(sq_ctx *ctx, uint64_t max_stored_fingerprints, ui
     if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&d->cnt, sizeof(DdCounters), true);
     if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&d->stale_fp, front_len + back_len + 16, true);
     if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&d->pair_range, 8, true);
-    if (rc == SQ_OK) rc = cudaMemsetAsync(d->pair_range, 0xFF, 4, ctx->stream) == cudaSuccess ? SQ_OK : SQ_E_CUDA;
+    if (rc == SQ_OK) rc = cudaMemsetAsync(d->pair_range, 0xFF, 4, sq_cur_stream(ctx)) == cudaSuccess ? SQ_OK : SQ_E_CUDA;
     if (rc != SQ_OK) {
         sq_dedup_destroy(d);
         return rc;
@@ -426,8 +426,8 @@ int dedup_consume(sq_dedup *d, const uint64_t *hashes, uint32_t n) {
         SQ_LAUNCH(ctx, k_dd_pass_flags, grid, DD_TPB, 0, hashes, n, (1ULL << d->mod_bits) - 1, flag);
         SQ_TRY(sq_scan_exclusive_u32(ctx, flag, rank, n, rank + n));
         uint32_t *h_total = (uint32_t *)((char *)ctx->h_scratch + 3088);
-        CUDA_TRY(cudaMemcpyAsync(h_total, rank + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_total, rank + n, 4, cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
         const uint32_t n_kept = *h_total;
         SQ_TRY(scratch.get(&kept, ((size_t)n_kept + 1) * 8));
         SQ_LAUNCH(ctx, k_dd_pass_scatter, grid, DD_TPB, 0, hashes, flag, rank, n, kept);
@@ -465,15 +465,15 @@ static int dedup_consume_range(sq_dedup *d, const uint64_t *hashes, uint32_t n) 
         for (;;) {  // at most two passes: whole segment, then the part before the trigger
             const uint32_t len = hi - lo;
             const int grid = sq_grid_for(ctx, len, DD_TPB, 16);
-            CUDA_TRY(cudaMemsetAsync(S.key, 0xFF, (size_t)scap * 8, ctx->stream));
-            CUDA_TRY(cudaMemsetAsync(S.first, 0xFF, (size_t)scap * 4, ctx->stream));
-            CUDA_TRY(cudaMemsetAsync(S.cnt, 0, (size_t)scap * 4, ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(S.key, 0xFF, (size_t)scap * 8, sq_cur_stream(ctx)));
+            CUDA_TRY(cudaMemsetAsync(S.first, 0xFF, (size_t)scap * 4, sq_cur_stream(ctx)));
+            CUDA_TRY(cudaMemsetAsync(S.cnt, 0, (size_t)scap * 4, sq_cur_stream(ctx)));
             DdCounters init;
             init.r_full = ~0ULL;
             init.r_star = ~0ULL;
             init.n_new = init.kept = init.inserted_one = init.pad = 0;
             *hc = init;
-            CUDA_TRY(cudaMemcpyAsync(d->cnt, hc, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(d->cnt, hc, sizeof(init), cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
             SQ_LAUNCH(ctx, k_dd_classify, grid, DD_TPB, 0, hashes, lo, hi, m, d->tab, tmask, cls, S);
             SQ_LAUNCH(ctx, k_dd_flags, grid, DD_TPB, 0, hashes, cls, lo, hi, S, flag, d->cnt);
             if (truncated) break;  // range ends before the trigger: no escalation inside
@@ -485,8 +485,8 @@ static int dedup_consume_range(sq_dedup *d, const uint64_t *hashes, uint32_t n) 
                     SQ_LAUNCH(ctx, k_dd_trigger_full, grid, DD_TPB, 0, flag, rank, lo, hi, (uint32_t)K, d->cnt);
             }
             SQ_LAUNCH(ctx, k_dd_trigger_star, grid, DD_TPB, 0, cls, lo, hi, already_full ? 1 : 0, d->cnt);
-            CUDA_TRY(cudaMemcpyAsync(hc, d->cnt, sizeof(DdCounters), cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(hc, d->cnt, sizeof(DdCounters), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+            CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
             if (hc->r_star == ~0ULL) break;  // no add meets a full table
             hi = (uint32_t)hc->r_star;
             truncated = true;
@@ -497,8 +497,8 @@ static int dedup_consume_range(sq_dedup *d, const uint64_t *hashes, uint32_t n) 
             const uint32_t len = hi - lo;
             const int grid = sq_grid_for(ctx, len, DD_TPB, 16);
             if (truncated) {  // n_new of the truncated range
-                CUDA_TRY(cudaMemcpyAsync(hc, d->cnt, sizeof(DdCounters), cudaMemcpyDeviceToHost, ctx->stream));
-                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                CUDA_TRY(cudaMemcpyAsync(hc, d->cnt, sizeof(DdCounters), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+                CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
             }
             SQ_LAUNCH(ctx, k_dd_apply_existing, grid, DD_TPB, 0, cls, lo, hi, d->tab);
             SQ_LAUNCH(ctx, k_dd_insert_new, grid, DD_TPB, 0, hashes, flag, lo, hi, m, d->tab, tmask, prio_base);
@@ -508,7 +508,7 @@ static int dedup_consume_range(sq_dedup *d, const uint64_t *hashes, uint32_t n) 
         if (!truncated) break;
         // ---- escalation at record r_star ---------------------------------------------------
         SQ_TRY(table_clear(ctx, &d->spare, d->table_size));
-        CUDA_TRY(cudaMemsetAsync(&d->cnt->kept, 0, 8, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(&d->cnt->kept, 0, 8, sq_cur_stream(ctx)));
         const int tgrid = sq_grid_for(ctx, d->table_size, DD_TPB, 16);
         SQ_LAUNCH(ctx, k_dd_rebuild_insert, tgrid, DD_TPB, 0, d->tab, d->spare, d->table_size, m + 1, d->cnt);
         SQ_LAUNCH(ctx, k_dd_rebuild_place, tgrid, DD_TPB, 0, d->tab, d->spare, d->table_size, m + 1);
@@ -516,8 +516,8 @@ static int dedup_consume_range(sq_dedup *d, const uint64_t *hashes, uint32_t n) 
         d->tab = d->spare;
         d->spare = t;
         SQ_LAUNCH(ctx, k_dd_insert_one, 1, 32, 0, hashes, r_star, m, d->tab, tmask, prio_base, d->cnt);
-        CUDA_TRY(cudaMemcpyAsync(hc, d->cnt, sizeof(DdCounters), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(hc, d->cnt, sizeof(DdCounters), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
         d->stored = (uint64_t)hc->kept + hc->inserted_one;
         d->mod_bits = m + 1;
         lo = r_star + 1;
@@ -574,7 +574,7 @@ extern "C" int sq_dedup_add_pair(sq_dedup *d, sq_batch *b1, sq_batch *b2) {
 
 extern "C" int sq_dedup_sync(sq_dedup *d, sq_dedup_info *info) {
     CUDA_TRY(cudaSetDevice(d->ctx->device));
-    CUDA_TRY(cudaStreamSynchronize(d->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(d->ctx)));
     info->modulo_bits = d->mod_bits;
     info->hash_table_size = d->table_size;
     info->tracked_sequences = d->stored;
@@ -611,8 +611,8 @@ extern "C" int sq_dedup_read(sq_dedup *d, uint64_t *counts, uint64_t *n) {
     SQ_TRY(sq_scan_exclusive_u32(ctx, flag, rank, size, total));
     SQ_LAUNCH(ctx, k_dd_compact, grid, DD_TPB, 0, d->tab.count, rank, size, out);
     uint32_t *h_total = (uint32_t *)((char *)ctx->h_scratch + 3080);
-    CUDA_TRY(cudaMemcpyAsync(h_total, total, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h_total, total, 4, cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     const uint64_t got = *h_total;
     if (got > d->stored) {
         sq_set_error("dedup table holds %llu entries, expected at most %llu", (unsigned long long)got,
@@ -664,8 +664,8 @@ extern "C" int sq_dedup_deferred_compact(sq_dedup *d, uint64_t mod_bits, uint64_
         SQ_TRY(sq_scan_exclusive_u32(ctx, flags[a], ranks[a], len, totals + a));
     }
     std::vector<uint32_t> h_tot(n_arr + 1, 0);
-    if (n_arr) CUDA_TRY(cudaMemcpyAsync(h_tot.data(), totals, n_arr * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (n_arr) CUDA_TRY(cudaMemcpyAsync(h_tot.data(), totals, n_arr * 4, cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     uint64_t total = 0;
     for (size_t a = 0; a < n_arr; a++) total += h_tot[a];
     sq_dfree(ctx, d->compact);
@@ -690,8 +690,8 @@ extern "C" int sq_dedup_deferred_fetch(sq_dedup *d, uint64_t *dev_out) {
     sq_ctx *ctx = d->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (d->compact_n)
-        CUDA_TRY(cudaMemcpyAsync(dev_out, d->compact, d->compact_n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(dev_out, d->compact, d->compact_n * 8, cudaMemcpyDeviceToDevice, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     sq_dfree(ctx, d->compact);
     d->compact = nullptr;
     d->compact_n = 0;
@@ -711,6 +711,6 @@ extern "C" int sq_dedup_add_hashes(sq_dedup *d, const uint64_t *dev_hashes, uint
         const uint64_t len = n - lo < step ? n - lo : step;
         SQ_TRY(dedup_consume(d, dev_hashes + lo, (uint32_t)len));
     }
-    CUDA_TRY(cudaStreamSynchronize(d->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(d->ctx)));
     return SQ_OK;
 }

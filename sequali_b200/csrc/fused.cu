@@ -1920,6 +1920,12 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     else if (b->max_len <= 160) rc = launch_fused<5>(ctx, A);
     else if (b->max_len <= 256) rc = launch_fused<8>(ctx, A);
     else rc = launch_fused<10>(ctx, A);
+    // The hash-table modules (OverrepresentedSequences, NanoStats, DedupEstimator) need nothing but what this kernel
+    // leaves (fingerprint hashes, error sums) and the text: from here on they can run on the table stream, beside
+    // the per-position pass and PerTileQuality's chain kernel, which are enqueued first (see the end of the function)
+    static const bool no_fork = getenv("SQ_NO_TABLE_STREAM") != nullptr;
+    const bool forked = rc == SQ_OK && !ctx->profile && !no_fork && sq_cur_stream(ctx) == ctx->stream && (ov || dd || ns);
+    if (forked) CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
 
     // ---- PerTileQuality: slots and segments (needs the tile ids) ---------------------------------
     // two plans for the per-position pass: with per-segment quality histograms (reads in tile runs)
@@ -1995,33 +2001,29 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
         if (b->max_len > qc->max_len) qc->max_len = b->max_len;
         b->err_sum_valid = true;
     }
-    // ---- table maintenance, in the reference's module order ------------------------------------
-    // PerTileQuality's chain kernel (run path) forks to the table stream and runs beside the hash-table kernels
-    // below; the launch stream joins it before this function returns (nothing else ever sees the fork)
-    static const bool no_fork = getenv("SQ_NO_TABLE_STREAM") != nullptr;
-    bool forked = false;
+    // ---- table maintenance ---------------------------------------------------------------------------
+    // PerTileQuality's ordered sums stay on the launch stream, behind the per-position pass that feeds them
     if (pt) {
-        if (rc == SQ_OK) {
-            forked = plan.work && plan.runs && !ctx->profile && !no_fork && sq_cur_stream(ctx) == ctx->stream && (ov || dd);
-            if (forked) {
-                CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
-                CUDA_TRY(cudaStreamWaitEvent(ctx->tstream, ctx->ev_fork, 0));
-            }
-            {
-                SqStreamScope on_table_stream(forked ? ctx->tstream : nullptr);
-                rc = pt_finish(pt, b, &plan);
-            }
-            if (forked) CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->tstream));
-        }
+        if (rc == SQ_OK) rc = pt_finish(pt, b, &plan);
         else pt_plan_free(ctx, &plan);
     }
-    if (rc == SQ_OK && ov) rc = sq_overrep_add(ov, b);
-    if (rc == SQ_OK && ns) rc = sq_nanostats_add(ns, b);
+    // ... and everything above is only ENQUEUED by now (the last host wait was in pt_prepare): while the host goes
+    // through the table modules below, with their waits, on the table stream, the device works on both streams.
+    // The launch stream joins before this function returns, so nothing else ever sees the fork.  Module order as in
+    // the reference's loop (the modules do not read each other's state).
+    {
+        if (forked) CUDA_TRY(cudaStreamWaitEvent(ctx->tstream, ctx->ev_fork, 0));
+        SqStreamScope on_table_stream(forked ? ctx->tstream : nullptr);
+        if (rc == SQ_OK && ov) rc = sq_overrep_add(ov, b);
+        if (rc == SQ_OK && ns) rc = sq_nanostats_add(ns, b);
+        if (rc == SQ_OK && dd) rc = dedup_consume(dd, hashes, n);
+        if (forked && cudaEventRecord(ctx->ev_join, ctx->tstream) != cudaSuccess && rc == SQ_OK)
+            rc = sq_cuda_fail(cudaGetLastError(), "end of the table stream's part", __FILE__, __LINE__);
+    }
     if (ad) {
         ad->n_seqs += n;
         if (b->max_len > ad->max_len) ad->max_len = b->max_len;
     }
-    if (rc == SQ_OK && dd) rc = dedup_consume(dd, hashes, n);
     if (dd && dd->deferred && rc == SQ_OK) scratch.keep(hashes);  // a deferred estimator keeps them
     if (forked && cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0) != cudaSuccess && rc == SQ_OK)
         rc = sq_cuda_fail(cudaGetLastError(), "join of the table stream", __FILE__, __LINE__);

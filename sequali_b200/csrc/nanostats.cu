@@ -295,8 +295,8 @@ extern "C" int sq_nanostats_create(sq_ctx *ctx, sq_nanostats **out) {
         init.tag_err_idx = ~0ULL;
         init.pi_first = ~0ULL;
         // same stream as the zero-fill above, so the two cannot swap
-        rc = cudaMemcpyAsync(s->st, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
-                     cudaStreamSynchronize(ctx->stream) == cudaSuccess
+        rc = cudaMemcpyAsync(s->st, &init, sizeof(init), cudaMemcpyHostToDevice, sq_cur_stream(ctx)) == cudaSuccess &&
+                     cudaStreamSynchronize(sq_cur_stream(ctx)) == cudaSuccess
                  ? SQ_OK : SQ_E_CUDA;
     }
     if (rc != SQ_OK) {
@@ -341,8 +341,8 @@ static int ns_learn_skip(sq_nanostats *s, unsigned long long fail_idx) {
 static int ns_settle(sq_nanostats *s) {
     sq_ctx *ctx = s->ctx;
     NsState *h = (NsState *)((char *)ctx->h_scratch + 2560);
-    CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     s->peek_pending = false;
     if (!s->skipped && h->fail_idx != ~0ULL) SQ_TRY(ns_learn_skip(s, h->fail_idx));
     return SQ_OK;
@@ -369,7 +369,7 @@ extern "C" int sq_nanostats_add(sq_nanostats *s, sq_batch *b) {
         sq_nanoinfo *ni = nullptr;
         SQ_TRY(sq_dalloc(ctx, (void **)&ni, cap * sizeof(sq_nanoinfo), false));
         if (s->n_added)
-            CUDA_TRY(cudaMemcpyAsync(ni, s->infos, s->n_added * sizeof(sq_nanoinfo), cudaMemcpyDeviceToDevice, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(ni, s->infos, s->n_added * sizeof(sq_nanoinfo), cudaMemcpyDeviceToDevice, sq_cur_stream(ctx)));
         sq_dfree(ctx, s->infos);
         s->infos = ni;
         s->cap = cap;
@@ -380,8 +380,8 @@ extern "C" int sq_nanostats_add(sq_nanostats *s, sq_batch *b) {
     // waiting, that there is nothing left to do
     SQ_LAUNCH(ctx, k_ns_capture_name, 1, 256, 0, b->view(), s->n_added, s->st, s->d_name, s->d_name_len);
     if (!s->peek_pending) {
-        CUDA_TRY(cudaMemcpyAsync(s->h_peek, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaEventRecord(s->peek_ev, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->h_peek, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaEventRecord(s->peek_ev, sq_cur_stream(ctx)));
         s->peek_pending = true;
     }
     s->n_added += b->n;
@@ -396,17 +396,17 @@ extern "C" int sq_nanostats_sync(sq_nanostats *s, sq_nanostats_info *info) {
     const uint64_t n = s->skipped ? s->skipped_record : s->n_added;
     NsState *h = (NsState *)((char *)ctx->h_scratch + 2560);
     // recompute min/max over the kept prefix
-    CUDA_TRY(cudaMemsetAsync(&s->st->max_time, 0, 8, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(&s->st->max_time, 0, 8, sq_cur_stream(ctx)));
     long long big = 0x7fffffffffffffffLL;
-    CUDA_TRY(cudaMemcpyAsync(&s->st->min_time, &big, 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(&s->st->nonpositive_time, 0, 4, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&s->st->min_time, &big, 8, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaMemsetAsync(&s->st->nonpositive_time, 0, 4, sq_cur_stream(ctx)));
     if (n) SQ_LAUNCH(ctx, k_ns_minmax, sq_grid_for(ctx, n, 256, 8), 256, 0, s->infos, n, s->st);
-    CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     if (n && h->nonpositive_time) {
         SQ_LAUNCH(ctx, k_ns_minmax_ordered, 1, 32, 0, s->infos, n, s->st);
-        CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     }
     info->number_of_reads = n;
     info->minimum_time = n ? h->min_time : 0;
@@ -433,8 +433,8 @@ extern "C" int sq_nanostats_read(sq_nanostats *s, sq_nanoinfo *out) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     SQ_TRY(ns_settle(s));
     const uint64_t n = s->skipped ? s->skipped_record : s->n_added;
-    if (n) CUDA_TRY(cudaMemcpyAsync(out, s->infos, n * sizeof(sq_nanoinfo), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (n) CUDA_TRY(cudaMemcpyAsync(out, s->infos, n * sizeof(sq_nanoinfo), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     return SQ_OK;
 }
 
@@ -466,7 +466,7 @@ extern "C" int sq_nanostats_allgather(sq_nanostats *s, sq_comm *c, uint64_t firs
     SQ_TRY(sq_dalloc(ctx, (void **)&merged, (total ? total : 1) * sizeof(sq_nanoinfo), false));
     if (kept)
         CUDA_TRY(cudaMemcpyAsync(merged + my_off, s->infos, kept * sizeof(sq_nanoinfo), cudaMemcpyDeviceToDevice,
-                                 ctx->stream));
+                                 sq_cur_stream(ctx)));
     uint64_t off = 0;
     SQ_TRY(sq_comm_group_start(c));
     for (int g = 0; g < world; g++) {
@@ -485,8 +485,8 @@ extern "C" int sq_nanostats_allgather(sq_nanostats *s, sq_comm *c, uint64_t firs
     }
     // pi warnings / tag errors: counters of all ranks
     NsState *h = (NsState *)((char *)ctx->h_scratch + 2560);
-    CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h, s->st, sizeof(NsState), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     auto global_key = [&](unsigned long long key) {  // record index of this shard -> of the whole stream
         return key == ~0ULL ? NONE : ((first_record + (key >> 24)) << 24 | (key & 0xffffff));
     };
@@ -497,9 +497,9 @@ extern "C" int sq_nanostats_allgather(sq_nanostats *s, sq_comm *c, uint64_t firs
     h->pi_warnings = pi;
     h->tag_err_idx = tag_err == NONE ? ~0ULL : tag_err;
     h->pi_first = pi_first == NONE ? ~0ULL : pi_first;
-    CUDA_TRY(cudaMemcpyAsync(&s->st->tag_err_idx, &h->tag_err_idx, 16, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(&s->st->pi_first, &h->pi_first, 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&s->st->tag_err_idx, &h->tag_err_idx, 16, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaMemcpyAsync(&s->st->pi_first, &h->pi_first, 8, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     sq_dfree(ctx, s->infos);
     s->infos = merged;
     s->cap = total ? total : 1;

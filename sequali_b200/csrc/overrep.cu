@@ -346,7 +346,7 @@ extern "C" int sq_overrep_create(sq_ctx *ctx, uint64_t max_unique_fragments, uin
     if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&o->counts, o->table_size * 4, true);
     if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&o->cnt, sizeof(OvCounters), true);
     if (rc == SQ_OK)
-        rc = cudaMemsetAsync(&o->cnt->first_warn, 0xFF, 8, ctx->stream) == cudaSuccess ? SQ_OK : SQ_E_CUDA;
+        rc = cudaMemsetAsync(&o->cnt->first_warn, 0xFF, 8, sq_cur_stream(ctx)) == cudaSuccess ? SQ_OK : SQ_E_CUDA;
     if (rc != SQ_OK) {
         sq_overrep_destroy(o);
         return rc;
@@ -372,8 +372,8 @@ extern "C" void sq_overrep_destroy(sq_overrep *o) {
 static int ov_refresh_unique(sq_overrep *o) {
     sq_ctx *ctx = o->ctx;
     OvCounters *h = (OvCounters *)((char *)ctx->h_scratch + 1536);
-    CUDA_TRY(cudaMemcpyAsync(h, o->cnt, sizeof(OvCounters), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h, o->cnt, sizeof(OvCounters), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     o->unique_known = o->unique_upper = h->n_unique;
     o->full = o->unique_known >= o->max_unique;
     return SQ_OK;
@@ -395,7 +395,7 @@ static int ov_apply(sq_overrep *o, const uint64_t *frag_hash, const uint32_t *fr
             if (!o->filter_valid) {
                 const size_t fbytes = (size_t)1 << (OV_FILTER_BITS - 3);
                 if (!o->filter) SQ_TRY(sq_dalloc(ctx, (void **)&o->filter, fbytes, false));
-                CUDA_TRY(cudaMemsetAsync(o->filter, 0, fbytes, ctx->stream));
+                CUDA_TRY(cudaMemsetAsync(o->filter, 0, fbytes, sq_cur_stream(ctx)));
                 SQ_LAUNCH(ctx, k_ov_filter_build, sq_grid_for(ctx, o->table_size, 256, 16), 256, 0, o->keys,
                           o->table_size, o->filter);
                 o->filter_valid = true;
@@ -422,8 +422,8 @@ static int ov_apply(sq_overrep *o, const uint64_t *frag_hash, const uint32_t *fr
             if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&S.key, (size_t)scap * 8, false);
             if (rc == SQ_OK) rc = sq_dalloc(ctx, (void **)&S.first, (size_t)scap * 4, false);
             if (rc == SQ_OK) {
-                CUDA_TRY(cudaMemsetAsync(S.key, 0xFF, (size_t)scap * 8, ctx->stream));
-                CUDA_TRY(cudaMemsetAsync(S.first, 0xFF, (size_t)scap * 4, ctx->stream));
+                CUDA_TRY(cudaMemsetAsync(S.key, 0xFF, (size_t)scap * 8, sq_cur_stream(ctx)));
+                CUDA_TRY(cudaMemsetAsync(S.first, 0xFF, (size_t)scap * 4, sq_cur_stream(ctx)));
                 SQ_LAUNCH(ctx, k_ov_classify, grid, 256, 0, frag_hash, frag_n, (uint32_t)n_sampled, fcap, o->keys,
                           mask, cls, S);
                 SQ_LAUNCH(ctx, k_ov_flags, grid, 256, 0, frag_hash, cls, occ, S, flag);
@@ -496,8 +496,8 @@ extern "C" int sq_overrep_sync(sq_overrep *o, sq_overrep_info *info) {
     sq_ctx *ctx = o->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     OvCounters *h = (OvCounters *)((char *)ctx->h_scratch + 1536);
-    CUDA_TRY(cudaMemcpyAsync(h, o->cnt, sizeof(OvCounters), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h, o->cnt, sizeof(OvCounters), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     o->unique_known = o->unique_upper = h->n_unique;
     o->full = o->unique_known >= o->max_unique;
     info->number_of_sequences = o->n_seqs;
@@ -555,13 +555,13 @@ extern "C" int sq_overrep_read_min(sq_overrep *o, uint32_t min_count, uint64_t *
     SQ_LAUNCH(ctx, k_ov_compact, sq_grid_for(ctx, o->table_size + 31, 256, 16), 256, 0, o->keys, o->counts,
               o->table_size, min_count, cap, dk, dc, dn);
     unsigned long long *hn = (unsigned long long *)((char *)ctx->h_scratch + 1792);
-    CUDA_TRY(cudaMemcpyAsync(hn, dn, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(hn, dn, 8, cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     const uint64_t got = *hn < cap ? *hn : cap;
     if (got) {
-        CUDA_TRY(cudaMemcpyAsync(kmers, dk, got * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(counts, dc, got * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(kmers, dk, got * 8, cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaMemcpyAsync(counts, dc, got * 4, cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     }
     *n = *hn;  // > cap tells the caller to retry with a larger buffer
     sq_dfree(ctx, dk);
@@ -617,10 +617,10 @@ extern "C" int sq_overrep_apply_deferred(sq_overrep *o) {
 extern "C" int sq_overrep_copy_table(sq_overrep *o, uint64_t *dev_keys, uint32_t *dev_counts) {
     sq_ctx *ctx = o->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    if (dev_keys) CUDA_TRY(cudaMemcpyAsync(dev_keys, o->keys, o->table_size * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (dev_keys) CUDA_TRY(cudaMemcpyAsync(dev_keys, o->keys, o->table_size * 8, cudaMemcpyDeviceToDevice, sq_cur_stream(ctx)));
     if (dev_counts)
-        CUDA_TRY(cudaMemcpyAsync(dev_counts, o->counts, o->table_size * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(dev_counts, o->counts, o->table_size * 4, cudaMemcpyDeviceToDevice, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     return SQ_OK;
 }
 
@@ -630,14 +630,14 @@ extern "C" int sq_overrep_load_table(sq_overrep *o, const uint64_t *dev_keys, co
                                      uint64_t n_unique) {
     sq_ctx *ctx = o->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    if (dev_keys) CUDA_TRY(cudaMemcpyAsync(o->keys, dev_keys, o->table_size * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (dev_keys) CUDA_TRY(cudaMemcpyAsync(o->keys, dev_keys, o->table_size * 8, cudaMemcpyDeviceToDevice, sq_cur_stream(ctx)));
     if (dev_counts)
-        CUDA_TRY(cudaMemcpyAsync(o->counts, dev_counts, o->table_size * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    else CUDA_TRY(cudaMemsetAsync(o->counts, 0, o->table_size * 4, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(o->counts, dev_counts, o->table_size * 4, cudaMemcpyDeviceToDevice, sq_cur_stream(ctx)));
+    else CUDA_TRY(cudaMemsetAsync(o->counts, 0, o->table_size * 4, sq_cur_stream(ctx)));
     unsigned int *h = (unsigned int *)((char *)ctx->h_scratch + 1664);
     *h = (unsigned int)n_unique;
-    CUDA_TRY(cudaMemcpyAsync(&o->cnt->n_unique, h, 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&o->cnt->n_unique, h, 4, cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     o->unique_known = o->unique_upper = n_unique;
     o->full = n_unique >= o->max_unique;
     o->filter_valid = false;  // another key set
@@ -652,12 +652,12 @@ extern "C" int sq_overrep_set_counters(sq_overrep *o, uint64_t number_of_sequenc
     o->n_seqs = number_of_sequences;
     o->n_sampled = sampled_sequences;
     OvCounters *h = (OvCounters *)((char *)ctx->h_scratch + 1536);
-    CUDA_TRY(cudaMemcpyAsync(h, o->cnt, sizeof(OvCounters), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h, o->cnt, sizeof(OvCounters), cudaMemcpyDeviceToHost, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     h->total_frags = total_fragments;
     h->warn_records = warn_records;
     h->first_warn = first_warn_record;
-    CUDA_TRY(cudaMemcpyAsync(o->cnt, h, sizeof(OvCounters), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(o->cnt, h, sizeof(OvCounters), cudaMemcpyHostToDevice, sq_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(sq_cur_stream(ctx)));
     return SQ_OK;
 }

@@ -77,8 +77,8 @@ int sq_radix_sort_pairs(sq_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *t
         t = vi; vi = vo; vo = t;
     }
     if (ki != keys) {
-        CUDA_TRY(cudaMemcpyAsync(keys, ki, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(vals, vi, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(keys, ki, (size_t)n * 4, cudaMemcpyDeviceToDevice, sq_cur_stream(ctx)));
+        CUDA_TRY(cudaMemcpyAsync(vals, vi, (size_t)n * 4, cudaMemcpyDeviceToDevice, sq_cur_stream(ctx)));
     }
     sq_dfree(ctx, hist);
     return SQ_OK;
