@@ -1925,7 +1925,22 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     // the per-position pass and PerTileQuality's chain kernel, which are enqueued first (see the end of the function)
     static const bool no_fork = getenv("SQ_NO_TABLE_STREAM") != nullptr;
     const bool forked = rc == SQ_OK && !ctx->profile && !no_fork && sq_cur_stream(ctx) == ctx->stream && (ov || dd || ns);
-    if (forked) CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    OvPendingAdd ov_pending;
+    struct OvGuard {  // (an error on the way out must not leave the fragment buffers behind)
+        sq_overrep *o;
+        OvPendingAdd *pa;
+        ~OvGuard() {
+            if (o) ov_add_abandon(o, pa);
+        }
+    } ov_guard{ov, &ov_pending};
+    if (forked) {
+        CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->tstream, ctx->ev_fork, 0));
+        if (ov) {  // the fragment kernel goes to the device now: it runs while the host waits in pt_prepare
+            SqStreamScope on_table_stream(ctx->tstream);
+            rc = ov_add_begin(ov, b, &ov_pending);
+        }
+    }
 
     // ---- PerTileQuality: slots and segments (needs the tile ids) ---------------------------------
     // two plans for the per-position pass: with per-segment quality histograms (reads in tile runs)
@@ -2012,9 +2027,11 @@ extern "C" int sq_fused_add(sq_ctx *ctx, sq_batch *b, sq_qc *qc, sq_pertile *pt,
     // The launch stream joins before this function returns, so nothing else ever sees the fork.  Module order as in
     // the reference's loop (the modules do not read each other's state).
     {
-        if (forked) CUDA_TRY(cudaStreamWaitEvent(ctx->tstream, ctx->ev_fork, 0));
         SqStreamScope on_table_stream(forked ? ctx->tstream : nullptr);
-        if (rc == SQ_OK && ov) rc = sq_overrep_add(ov, b);
+        if (rc == SQ_OK && ov) {
+            if (!forked) rc = ov_add_begin(ov, b, &ov_pending);
+            if (rc == SQ_OK) rc = ov_add_end(ov, &ov_pending);
+        }
         if (rc == SQ_OK && ns) rc = sq_nanostats_add(ns, b);
         if (rc == SQ_OK && dd) rc = dedup_consume(dd, hashes, n);
         if (forked && cudaEventRecord(ctx->ev_join, ctx->tstream) != cudaSuccess && rc == SQ_OK)

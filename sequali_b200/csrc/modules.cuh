@@ -207,3 +207,14 @@ struct sq_nanostats {
     unsigned long long *rp_bases = nullptr;
     double *rp_error = nullptr;
 };
+
+// ---- OverrepresentedSequences: an add in two halves (overrep.cu; sq_fused_add puts other work between them) ----
+struct OvPendingAdd {
+    uint64_t *frag_hash = nullptr;
+    uint32_t *frag_n = nullptr;
+    uint64_t n_sampled = 0, total = 0;
+    uint32_t fcap = 0;
+};
+int ov_add_begin(sq_overrep *o, sq_batch *b, OvPendingAdd *pa);
+int ov_add_end(sq_overrep *o, OvPendingAdd *pa);
+void ov_add_abandon(sq_overrep *o, OvPendingAdd *pa);

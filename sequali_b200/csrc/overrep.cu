@@ -17,6 +17,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "modules.cuh"
 
 constexpr int OV_TPB = 128;
 constexpr int OV_STAGE_MAX = 128;  // per-read staging slots kept in local memory
@@ -446,7 +447,11 @@ static int ov_apply(sq_overrep *o, const uint64_t *frag_hash, const uint32_t *fr
 }
 
 
-extern "C" int sq_overrep_add(sq_overrep *o, sq_batch *b) {
+// First half of an add: the sampled reads' fragment hashes (no host wait); ov_add_end applies them to the table.
+// Split so that sq_fused_add can put the fragment kernel on the device right behind k_fused_reads, in front of the
+// host wait of PerTileQuality's planning.
+int ov_add_begin(sq_overrep *o, sq_batch *b, OvPendingAdd *pa) {
+    *pa = OvPendingAdd();
     sq_ctx *ctx = o->ctx;
     if (b->ctx != ctx) {
         sq_set_error("record array belongs to another context");
@@ -483,13 +488,42 @@ extern "C" int sq_overrep_add(sq_overrep *o, sq_batch *b) {
     SQ_LAUNCH(ctx, k_ov_fragments, sq_grid_for(ctx, n_sampled, OV_TPB, 16), OV_TPB, 0, b->view(), (uint32_t)first,
               (uint32_t)se, (uint32_t)n_sampled, (uint32_t)o->k, o->frags_front, o->frags_back, fcap, frag_hash,
               frag_n, o->cnt, record_base);
+    scratch.keep(frag_hash);
+    scratch.keep(frag_n);
+    pa->frag_hash = frag_hash;
+    pa->frag_n = frag_n;
+    pa->n_sampled = n_sampled;
+    pa->total = total;
+    pa->fcap = fcap;
+    return SQ_OK;
+}
+
+// Second half: table update (or, deferred, the hashes are kept).  Always releases what the first half allocated.
+int ov_add_end(sq_overrep *o, OvPendingAdd *pa) {
+    if (!pa->frag_hash) return SQ_OK;
+    sq_ctx *ctx = o->ctx;
     if (o->deferred) {
-        o->kept.push_back({frag_hash, frag_n, n_sampled, total, fcap});
-        scratch.keep(frag_hash);
-        scratch.keep(frag_n);
+        o->kept.push_back({pa->frag_hash, pa->frag_n, pa->n_sampled, pa->total, pa->fcap});
+        *pa = OvPendingAdd();
         return SQ_OK;
     }
-    return ov_apply(o, frag_hash, frag_n, n_sampled, total, fcap);
+    const int rc = ov_apply(o, pa->frag_hash, pa->frag_n, pa->n_sampled, pa->total, pa->fcap);
+    sq_dfree(ctx, pa->frag_hash);
+    sq_dfree(ctx, pa->frag_n);
+    *pa = OvPendingAdd();
+    return rc;
+}
+
+void ov_add_abandon(sq_overrep *o, OvPendingAdd *pa) {
+    sq_dfree(o->ctx, pa->frag_hash);
+    sq_dfree(o->ctx, pa->frag_n);
+    *pa = OvPendingAdd();
+}
+
+extern "C" int sq_overrep_add(sq_overrep *o, sq_batch *b) {
+    OvPendingAdd pa;
+    SQ_TRY(ov_add_begin(o, b, &pa));
+    return ov_add_end(o, &pa);
 }
 
 extern "C" int sq_overrep_sync(sq_overrep *o, sq_overrep_info *info) {
