@@ -723,10 +723,14 @@ def run_cuda(args):
                "getters_each": getter_ms}
 
     # ---- per-kernel times of one step (CUDA events around every launch) --------
+    # (profiled pass: everything on the launch stream, one host thread -- with the read-ahead thread enqueueing the
+    # next array's scan on the same stream the gaps between kernels would measure the interleaving, not the idle time)
+    os.environ["SEQUALI_B200_NO_PREFETCH"] = "1"
     ctx.profile(True)
     step_resident()
     prof = ctx.profile_report()
     ctx.profile(False)
+    del os.environ["SEQUALI_B200_NO_PREFETCH"]
     gaps = {k[4:]: v for k, v in prof.items() if k.startswith("gap>")}
     prof = {k: v for k, v in prof.items() if not k.startswith("gap>")}
     kernel_ms = sum(v[1] for v in prof.values())
