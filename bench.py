@@ -259,23 +259,31 @@ def run_configs(gpu_mod, peak_gbs):
             row["speedup_vs_1_core"] = round(cdt / dt, 1)
         return row
 
+    import shutil
     import tempfile
-    where = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
-    tmp = tempfile.mkdtemp(prefix="sq_configs_", dir=where)
+    where = next((d for d in ("/dev/shm", tempfile.gettempdir())
+                  if os.path.isdir(d) and shutil.disk_usage(d).free > (6 << 30)), None)
+    tmp = tempfile.mkdtemp(prefix="sq_configs_", dir=where) if where else None
 
     def on_disk(name, data):
-        """The input as a regular file (page cache): what the CLI hands the parsers for an uncompressed input."""
+        """The input as a regular file (page cache): what the CLI hands the parsers for an uncompressed input.
+        (No room for files on this box: the bytes themselves, read through an in-memory file object.)"""
+        if tmp is None:
+            return data
         path = os.path.join(tmp, name)
         with open(path, "wb") as f:
             f.write(data)
         return path
 
+    def opened(src):
+        return open(src, "rb") if isinstance(src, str) else io.BytesIO(src)
+
     def single(mod, path, adapters, bam=False, **kw):
-        with open(path, "rb") as f:
+        with opened(path) as f:
             return loop_single_end(mod, f, adapters, bam=bam, **kw)
 
     def paired(mod, p1, p2, **kw):
-        with open(p1, "rb") as f1, open(p2, "rb") as f2:
+        with opened(p1) as f1, opened(p2) as f2:
             return loop_paired(mod, f1, f2, **kw)
 
     out = {}
@@ -304,8 +312,8 @@ def run_configs(gpu_mod, peak_gbs):
                           lambda: single(gpu_mod, p5, NANOPORE_ADAPTERS, bam=True, buffersize=big),
                           lambda: single(ref, p5, NANOPORE_ADAPTERS, bam=True))
     finally:
-        import shutil
-        shutil.rmtree(tmp, ignore_errors=True)
+        if tmp:
+            shutil.rmtree(tmp, ignore_errors=True)
     return out
 
 
